@@ -1,0 +1,190 @@
+/*
+ * rsvio_b200.h -- C ABI of the B200-native stereo patch tracker (librsvio_b200.so).
+ *
+ * Drop-in boundary for RS-VIO's tracker A, `src/feature_tracker/` of the reference
+ * (all file:line citations are relative to the reference repository root).  The Rust
+ * side (rs-vio_b200/rust/feature_tracker) keeps `StereoPatchTracker<N>` / `PatchTracker<N>`
+ * with the reference's signatures and forwards to the functions below; INTEGRATION.md shows
+ * the binding.  Plain pointers and sizes only; no CUDA, torch or C++ types cross this line.
+ *
+ * Conventions
+ *  - every function returns an rsvio_status (0 = ok, < 0 = error); nothing unwinds or aborts
+ *    across the boundary; rsvio_tracker_last_error() gives the text of the last failure.
+ *  - per-point tracking failures are NOT errors: they are reported as status codes per point
+ *    (stateless entry points) or by the point disappearing from the track table (stateful),
+ *    exactly as the reference drops them (feature_tracker.rs:259-287, 316-330, 362-391).
+ *  - images are row-major 8-bit luma, `stride` bytes between rows (GrayImage: stride == width).
+ *  - a transform is the 6 free entries of the reference's `na::Affine2<f32>`:
+ *    T = [m11, m12, m13(tx), m21, m22, m23(ty)]; the third row is (0, 0, 1).
+ *  - one handle == one CUDA device + one CUDA stream; a handle is not re-entrant, distinct
+ *    handles may be driven from distinct threads (mirrors `&mut self`, feature_tracker.rs:116).
+ *  - there is no CPU fallback: without a usable CUDA device every entry point fails with
+ *    RSVIO_ERR_CUDA.
+ */
+#ifndef RSVIO_B200_H
+#define RSVIO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSVIO_ABI_VERSION 1
+#define RSVIO_PATTERN_SIZE 52 /* patch.rs:7 PATTERN52_SIZE */
+#define RSVIO_MAX_LEVELS 8
+
+typedef int32_t rsvio_status;
+enum {
+    RSVIO_OK = 0,
+    RSVIO_ERR_INVALID_ARG = -1,
+    RSVIO_ERR_CUDA = -2,      /* CUDA runtime error or no device */
+    RSVIO_ERR_CAPACITY = -3,  /* a track table or output array was too small */
+    RSVIO_ERR_STATE = -4,     /* call order violated (e.g. sync without submit) */
+    RSVIO_ERR_ALLOC = -5
+};
+
+/* per-point outcome of one track_points element (feature_tracker.rs:259-287) */
+enum {
+    RSVIO_TRACK_OK = 0,
+    RSVIO_FAIL_TEMPLATE = 1,  /* Pattern52::new invalid             patch.rs:146,156-158 */
+    RSVIO_FAIL_RESIDUAL = 2,  /* residual() == None                 patch.rs:212,227 */
+    RSVIO_FAIL_NONFINITE = 3, /* non-finite increment               feature_tracker.rs:366 */
+    RSVIO_FAIL_DIVERGED = 4,  /* |inc| > 1e6                        feature_tracker.rs:369 */
+    RSVIO_FAIL_OOB = 5,       /* left the image after an update     feature_tracker.rs:380-388 */
+    RSVIO_FAIL_FB = 6,        /* forward-backward distance^2 >= 0.4 feature_tracker.rs:277-281 */
+    RSVIO_FAIL_BACKWARD = 16  /* added to 1..5 when the backward pass was the one that failed */
+};
+
+enum { RSVIO_MODE_STEREO = 0, RSVIO_MODE_MONO = 1 };
+
+/* Replaces the constructor arguments of StereoPatchTracker::<N>::new(grid_size,
+ * optical_flow_max_iterations, optical_flow_convergence_threshold) (feature_tracker.rs:103-114,
+ * called from estimator.rs:85-89) plus the const generic N (estimator.rs:27). */
+typedef struct rsvio_config {
+    int32_t width;                 /* image width in pixels (fixed for the handle's lifetime) */
+    int32_t height;
+    int32_t levels;                /* N of StereoPatchTracker<N>; level i is (w >> i, h >> i) */
+    uint32_t grid_size;            /* feature_detection.grid_size (config/euroc_vio.yaml:42) */
+    int32_t max_iterations;        /* optical_flow_max_iterations */
+    float convergence_threshold;   /* optical_flow_convergence_threshold */
+    int32_t mode;                  /* RSVIO_MODE_STEREO | RSVIO_MODE_MONO (PatchTracker<N>) */
+    int32_t n_streams;             /* independent sequences batched on this handle; 1 == reference */
+    int32_t device;                /* CUDA device ordinal */
+    int32_t max_tracks;            /* capacity per stream and camera; 0 = 4 * cells + 64 */
+    void *cuda_stream;             /* optional cudaStream_t to run on; NULL = handle creates its own */
+} rsvio_config;
+
+typedef struct rsvio_tracker rsvio_tracker;
+
+/* ---- library ------------------------------------------------------------------------- */
+int32_t rsvio_abi_version(void);
+const char *rsvio_status_string(rsvio_status s);
+/* number of visible CUDA devices (0 and RSVIO_ERR_CUDA text in *err if none) */
+rsvio_status rsvio_device_count(int32_t *n);
+/* fills the defaults of PatchTracker (30 iterations, 0.005, grid 30: feature_tracker.rs:51-52,65) */
+void rsvio_config_default(rsvio_config *cfg);
+
+/* pinned host memory for image hand-off without a staging copy (ingest row f-3;
+ * replaces the `to_vec()` copies at estimator.rs:131,143) */
+rsvio_status rsvio_host_alloc(void **ptr, size_t bytes);
+rsvio_status rsvio_host_free(void *ptr);
+
+/* ---- stateful tracker: StereoPatchTracker<N> / PatchTracker<N> ------------------------- */
+/* StereoPatchTracker::new (feature_tracker.rs:103) / PatchTracker::default (:35-41) */
+rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out);
+void rsvio_tracker_destroy(rsvio_tracker *t);
+const char *rsvio_tracker_last_error(const rsvio_tracker *t);
+/* drops all tracks and the previous pyramids; ids restart at 0 */
+rsvio_status rsvio_tracker_reset(rsvio_tracker *t);
+
+/* StereoPatchTracker::process_frame (feature_tracker.rs:116-187) for stream 0 of a
+ * 1-stream handle: upload, 2 pyramids, temporal L->L and R->R, replenish, stereo L->R,
+ * id merge.  Host pointers (pinned or pageable).  Synchronous. */
+rsvio_status rsvio_tracker_process_stereo(rsvio_tracker *t, const uint8_t *left, const uint8_t *right,
+                                          size_t stride);
+/* PatchTracker::process_frame (feature_tracker.rs:43-77) */
+rsvio_status rsvio_tracker_process_mono(rsvio_tracker *t, const uint8_t *image, size_t stride);
+
+/* the same for all n_streams sequences of the handle in one batched pass: left[s], right[s]
+ * are the images of stream s (right may be NULL in mono mode) */
+rsvio_status rsvio_tracker_process_batch(rsvio_tracker *t, const uint8_t *const *left,
+                                         const uint8_t *const *right, size_t stride);
+/* asynchronous form: submit enqueues upload + kernels and returns; sync waits for the oldest
+ * submitted frame.  At most 2 frames may be in flight (double-buffered inputs). */
+rsvio_status rsvio_tracker_submit_batch(rsvio_tracker *t, const uint8_t *const *left,
+                                        const uint8_t *const *right, size_t stride);
+rsvio_status rsvio_tracker_sync(rsvio_tracker *t);
+/* inputs already resident in HBM: n_streams images back to back, `pitch` bytes apart,
+ * `stride` bytes between rows.  Asynchronous on the handle's stream; rsvio_tracker_sync waits. */
+rsvio_status rsvio_tracker_submit_device(rsvio_tracker *t, const void *d_left, const void *d_right,
+                                         size_t stride, size_t pitch);
+
+/* get_track_points (feature_tracker.rs:188-200): ids ascending, xy = n x (x, y) */
+rsvio_status rsvio_tracker_num_tracks(rsvio_tracker *t, int32_t stream, int32_t cam, int32_t *n);
+rsvio_status rsvio_tracker_get_tracks(rsvio_tracker *t, int32_t stream, int32_t cam, uint64_t *ids,
+                                      float *xy, size_t cap, size_t *n);
+/* the full Affine2 of every track (tracked_points_map_cam{0,1}, feature_tracker.rs:93,95) */
+rsvio_status rsvio_tracker_get_transforms(rsvio_tracker *t, int32_t stream, int32_t cam, uint64_t *ids,
+                                          float *T6, size_t cap, size_t *n);
+/* remove_id (feature_tracker.rs:201-206): removes from both cameras */
+rsvio_status rsvio_tracker_remove_ids(rsvio_tracker *t, int32_t stream, const uint64_t *ids, size_t n);
+
+/* counters since create/reset, summed over streams:
+ * [0] tracks attempted (track_points elements)  [1] frames (per stream)
+ * [2] LK iterations evaluated                   [3] Pattern52 templates built
+ * [4] kernels launched by this handle           [5] points detected by grid replenishment */
+rsvio_status rsvio_tracker_counters(rsvio_tracker *t, uint64_t out[6]);
+
+/* per-stage device time (CUDA events on the handle's stream), accumulated since the last call
+ * with reset != 0.  ms[0..7]: upload, pyramid, temporal LK, compaction+occupancy, detection,
+ * stereo LK, merge, download.  launches[i] = kernel launches (or copies) in that stage. */
+#define RSVIO_N_STAGES 8
+rsvio_status rsvio_tracker_set_profiling(rsvio_tracker *t, int32_t enabled);
+rsvio_status rsvio_tracker_stage_times(rsvio_tracker *t, float ms[RSVIO_N_STAGES],
+                                       uint64_t launches[RSVIO_N_STAGES], int32_t reset);
+
+/* ---- stateless entry points (parity tests, kernel benchmarks) -------------------------- */
+/* bytes of a pyramid stored level after level, each level dense (stride == width) */
+size_t rsvio_pyramid_bytes(int32_t width, int32_t height, int32_t levels);
+
+/* bytes between two pyramids in the device layout (every level start aligned to 256 B) */
+size_t rsvio_pyramid_device_bytes(int32_t width, int32_t height, int32_t levels);
+
+/* build_image_pyramid (feature_tracker.rs:209-220) for n_images images that are `pitch`
+ * bytes apart; out receives n_images pyramids back to back.  Host pointers. */
+rsvio_status rsvio_build_pyramid_u8(int32_t device, const uint8_t *images, int32_t n_images,
+                                    int32_t width, int32_t height, size_t stride, size_t pitch,
+                                    int32_t levels, uint8_t *out);
+/* same on device pointers; d_out holds n_images * rsvio_pyramid_device_bytes() (device layout).
+ * `repeats` back-to-back launches timed with CUDA events on the launching stream;
+ * kernel_ms = average milliseconds per launch (NULL to skip) */
+rsvio_status rsvio_build_pyramid_u8_device(int32_t device, const void *d_images, int32_t n_images,
+                                           int32_t width, int32_t height, size_t stride, size_t pitch,
+                                           int32_t levels, void *d_out, int32_t repeats, float *kernel_ms);
+
+/* track_points (feature_tracker.rs:252-291): n points from pyramid A to pyramid B
+ * (rsvio_pyramid_bytes layout, host pointers), forward + backward + FB test.
+ * out_T6: forward result (valid when status == 0); status: RSVIO_TRACK_* / RSVIO_FAIL_*;
+ * iters (may be NULL): n x 2 LK iterations evaluated forward / backward. */
+rsvio_status rsvio_track_points(int32_t device, const uint8_t *pyr_a, const uint8_t *pyr_b,
+                                int32_t width, int32_t height, int32_t levels, int32_t n,
+                                const float *in_T6, int32_t max_iterations, float convergence_threshold,
+                                float *out_T6, int32_t *status, int32_t *iters);
+
+/* detect_key_points with one point per cell (image_utilities.rs:108-175; add_points
+ * feature_tracker.rs:222-251).  cur_xy: n_cur x 2 rounded positions of the tracked points.
+ * out_xy / out_score hold up to cap corners in the reference's visiting order. */
+rsvio_status rsvio_detect_keypoints(int32_t device, const uint8_t *image, int32_t width, int32_t height,
+                                    size_t stride, uint32_t grid_size, const uint32_t *cur_xy, int32_t n_cur,
+                                    uint32_t *out_xy, float *out_score, size_t cap, size_t *n);
+
+/* se2_exp_matrix (image_utilities.rs:82-106) evaluated by the device code: n twists
+ * [vx, vy, theta] -> n row-major 3x3 matrices */
+rsvio_status rsvio_se2_exp(int32_t device, const float *twists, int32_t n, float *out9);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSVIO_B200_H */

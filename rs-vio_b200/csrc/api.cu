@@ -1,0 +1,915 @@
+// api.cu -- the extern "C" boundary declared in include/rsvio_b200.h.
+//
+// Mirrors the reference's StereoPatchTracker<N> / PatchTracker<N>
+// (src/feature_tracker/feature_tracker.rs:36-207) as an opaque handle that owns all device
+// state: two ping-pong sets of pyramids (previous / current), the per-camera track tables, the
+// detection scratch and a host-mapped output ring.  One frame is one stream-ordered sequence
+//   upload -> pyramid -> temporal LK (both cameras, all streams, one launch) -> compaction +
+//   occupancy -> FAST detection -> collect -> stereo LK -> merge + packed output
+// with no host round trip in between.  There is no CPU fallback anywhere in this file.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace rsvio;
+
+namespace {
+
+constexpr int kSlots = 2;
+
+#define CU_TRY(t, expr)                                                                        \
+    do {                                                                                       \
+        cudaError_t e__ = (expr);                                                              \
+        if (e__ != cudaSuccess) return fail_cuda((t), e__, #expr, __LINE__);                   \
+    } while (0)
+
+}  // namespace
+
+struct rsvio_tracker {
+    rsvio_config cfg{};
+    int S = 1, groups = 2, cap = 0, new_cap = 0, stereo = 1;
+    size_t img_bytes = 0;
+    cudaStream_t st = nullptr, copy_st = nullptr;
+    bool own_stream = false;
+    PyrPlan *plan = nullptr;
+    PyrDesc pd{};
+    GridDesc gd{};
+    uint8_t *d_in[kSlots] = {nullptr, nullptr};
+    uint8_t *h_stage[kSlots] = {nullptr, nullptr};
+    uint8_t *d_pyr[2] = {nullptr, nullptr};
+    int pcur = 0;  // index of the set that will receive the next frame's pyramids
+    bool have_prev = false;
+    TableView tab[2]{};
+    int tcur = 0;  // table holding the current tracks
+    float *d_lk_T6 = nullptr;
+    int32_t *d_lk_status = nullptr;
+    uint8_t *d_occ = nullptr;
+    uint32_t *d_cell_pt = nullptr;
+    float *d_cell_score = nullptr;
+    float *d_new_T6 = nullptr, *d_st_T6 = nullptr;
+    int *d_new_count = nullptr;
+    int32_t *d_st_status = nullptr;
+    unsigned long long *d_last_id = nullptr, *d_counters = nullptr, *d_rm = nullptr;
+    int rm_cap = 0;
+    int *d_err = nullptr;
+    // host-mapped output ring: records [groups][cap] and counts [groups] (+1 error flag)
+    OutRecord *h_out[kSlots] = {nullptr, nullptr}, *d_out[kSlots] = {nullptr, nullptr};
+    int *h_cnt[kSlots] = {nullptr, nullptr}, *d_cnt[kSlots] = {nullptr, nullptr};
+    cudaEvent_t ev_h2d[kSlots]{}, ev_in_free[kSlots]{}, ev_done[kSlots]{};
+    int next_slot = 0, oldest_slot = 0, inflight = 0, result_slot = -1;
+    uint64_t host_launches = 0;
+    // profiling
+    bool profiling = false;
+    cudaEvent_t ev_stage[kSlots][RSVIO_N_STAGES + 1]{};
+    cudaEvent_t ev_up[kSlots][2]{};
+    bool stage_valid[kSlots] = {false, false}, up_valid[kSlots] = {false, false};
+    double stage_ms[RSVIO_N_STAGES] = {0};
+    uint64_t stage_launches[RSVIO_N_STAGES] = {0};
+    std::string err;
+};
+
+namespace {
+
+rsvio_status fail_cuda(rsvio_tracker *t, cudaError_t e, const char *what, int line) {
+    if (t) {
+        char buf[512];
+        snprintf(buf, sizeof(buf), "CUDA error %d (%s) at api.cu:%d: %s", (int)e, cudaGetErrorString(e), line, what);
+        t->err = buf;
+    }
+    return RSVIO_ERR_CUDA;
+}
+
+rsvio_status fail(rsvio_tracker *t, rsvio_status s, const char *msg) {
+    if (t) t->err = msg;
+    return s;
+}
+
+bool is_device_accessible_host(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+template <typename T>
+cudaError_t dmalloc(T **p, size_t n) {
+    return cudaMalloc((void **)p, n * sizeof(T) > 0 ? n * sizeof(T) : 16);
+}
+
+void free_all(rsvio_tracker *t) {
+    if (!t) return;
+    cudaSetDevice(t->cfg.device);
+    if (t->st) cudaStreamSynchronize(t->st);
+    if (t->copy_st) cudaStreamSynchronize(t->copy_st);
+    pyr_plan_destroy(t->plan);
+    for (int i = 0; i < kSlots; ++i) {
+        cudaFree(t->d_in[i]);
+        if (t->h_stage[i]) cudaFreeHost(t->h_stage[i]);
+        if (t->h_out[i]) cudaFreeHost(t->h_out[i]);
+        if (t->h_cnt[i]) cudaFreeHost(t->h_cnt[i]);
+        if (t->ev_h2d[i]) cudaEventDestroy(t->ev_h2d[i]);
+        if (t->ev_in_free[i]) cudaEventDestroy(t->ev_in_free[i]);
+        if (t->ev_done[i]) cudaEventDestroy(t->ev_done[i]);
+        for (int k = 0; k <= RSVIO_N_STAGES; ++k)
+            if (t->ev_stage[i][k]) cudaEventDestroy(t->ev_stage[i][k]);
+        for (int k = 0; k < 2; ++k)
+            if (t->ev_up[i][k]) cudaEventDestroy(t->ev_up[i][k]);
+    }
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(t->d_pyr[i]);
+        cudaFree(t->tab[i].ids);
+        cudaFree(t->tab[i].T6);
+        cudaFree(t->tab[i].counts);
+    }
+    cudaFree(t->d_lk_T6);
+    cudaFree(t->d_lk_status);
+    cudaFree(t->d_occ);
+    cudaFree(t->d_cell_pt);
+    cudaFree(t->d_cell_score);
+    cudaFree(t->d_new_T6);
+    cudaFree(t->d_st_T6);
+    cudaFree(t->d_new_count);
+    cudaFree(t->d_st_status);
+    cudaFree(t->d_last_id);
+    cudaFree(t->d_counters);
+    cudaFree(t->d_rm);
+    cudaFree(t->d_err);
+    if (t->copy_st) cudaStreamDestroy(t->copy_st);
+    if (t->own_stream && t->st) cudaStreamDestroy(t->st);
+    cudaGetLastError();
+    delete t;
+}
+
+rsvio_status clear_state(rsvio_tracker *t) {
+    for (int i = 0; i < 2; ++i) CU_TRY(t, cudaMemsetAsync(t->tab[i].counts, 0, sizeof(int) * t->groups, t->st));
+    CU_TRY(t, cudaMemsetAsync(t->d_last_id, 0, sizeof(unsigned long long) * t->S, t->st));
+    CU_TRY(t, cudaMemsetAsync(t->d_counters, 0, sizeof(unsigned long long) * CNT_N, t->st));
+    CU_TRY(t, cudaMemsetAsync(t->d_err, 0, sizeof(int), t->st));
+    CU_TRY(t, cudaMemsetAsync(t->d_new_count, 0, sizeof(int) * t->S, t->st));
+    CU_TRY(t, cudaStreamSynchronize(t->st));
+    for (int i = 0; i < kSlots; ++i) memset(t->h_cnt[i], 0, sizeof(int) * (t->groups + 1));
+    t->have_prev = false;
+    t->tcur = 0;
+    t->pcur = 0;
+    t->inflight = 0;
+    t->next_slot = t->oldest_slot = 0;
+    t->result_slot = -1;
+    t->host_launches = 0;
+    return RSVIO_OK;
+}
+
+// one frame, enqueued on t->st.  src0/src1: device images of camera 0 / 1 (S each).
+rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, const uint8_t *src1, size_t stride,
+                           size_t pitch) {
+    cudaStream_t st = t->st;
+    const bool prof = t->profiling;
+    int stage = 1;  // stage 0 (upload) is timed on the copy stream
+    auto mark = [&](int k) {
+        if (prof) cudaEventRecord(t->ev_stage[slot][k], st);
+    };
+    auto count = [&](int stg, int n) {
+        t->host_launches += (uint64_t)n;
+        t->stage_launches[stg] += (uint64_t)n;
+    };
+    uint8_t *cur = t->d_pyr[t->pcur], *prev = t->d_pyr[t->pcur ^ 1];
+    const int n_img = t->stereo ? 2 * t->S : t->S;
+    const TableView &tin = t->tab[t->tcur], &tout = t->tab[t->tcur ^ 1];
+
+    mark(stage);  // 1: pyramid
+    int nl = 0;
+    CU_TRY(t, pyr_build(t->plan, src0, src1, t->S, n_img, stride, pitch, cur, st, &nl));
+    count(1, nl);
+    CU_TRY(t, cudaEventRecord(t->ev_in_free[slot], st));
+    mark(++stage);  // 2: temporal LK
+    if (t->have_prev) {
+        LkBatch b{};
+        b.pyr_a = prev;
+        b.pyr_b = cur;
+        b.counts = tin.counts;
+        b.in_T6 = tin.T6;
+        b.out_T6 = t->d_lk_T6;
+        b.status = t->d_lk_status;
+        b.iters = nullptr;
+        b.counters = t->d_counters;
+        b.groups = t->stereo ? t->groups : t->S;
+        b.cap = t->cap;
+        b.max_it = t->cfg.max_iterations;
+        b.thr = t->cfg.convergence_threshold;
+        CU_TRY(t, lk_track(t->pd, b, st));
+        count(2, 1);
+    }
+    mark(++stage);  // 3: compaction + occupancy
+    CU_TRY(t, compact_tracks(tin, t->d_lk_T6, t->d_lk_status, tout, t->groups, t->cap, t->S, t->gd, t->d_occ,
+                             t->have_prev ? 1 : 0, t->d_counters, st));
+    count(3, 1);
+    mark(++stage);  // 4: detection (level 0 of the current left pyramid is the input image)
+    CU_TRY(t, detect_cells(t->gd, cur + t->pd.lv[0].off, (size_t)t->pd.lv[0].w, (size_t)t->pd.pyr_stride, t->S,
+                           t->d_occ, t->d_cell_pt, t->d_cell_score, st));
+    CU_TRY(t, collect_new_points(t->gd, t->S, t->d_cell_pt, t->d_cell_score, t->d_new_T6, nullptr, t->d_new_count,
+                                 t->new_cap, t->d_counters, st));
+    count(4, 2);
+    mark(++stage);  // 5: stereo LK (left -> right of the current frame)
+    if (t->stereo) {
+        LkBatch b{};
+        b.pyr_a = cur;
+        b.pyr_b = cur + (size_t)t->S * t->pd.pyr_stride;
+        b.counts = t->d_new_count;
+        b.in_T6 = t->d_new_T6;
+        b.out_T6 = t->d_st_T6;
+        b.status = t->d_st_status;
+        b.iters = nullptr;
+        b.counters = t->d_counters;
+        b.groups = t->S;
+        b.cap = t->new_cap;
+        b.max_it = t->cfg.max_iterations;
+        b.thr = t->cfg.convergence_threshold;
+        CU_TRY(t, lk_track(t->pd, b, st));
+        count(5, 1);
+    }
+    mark(++stage);  // 6: merge + packed output
+    CU_TRY(t, merge_new_points(tout, t->S, t->cap, t->stereo, t->d_new_T6, t->d_st_T6, t->d_st_status,
+                               t->d_new_count, t->new_cap, t->d_last_id, t->d_err, t->d_out[slot], t->d_cnt[slot],
+                               t->d_counters, st));
+    count(6, 1);
+    mark(++stage);  // 7: download (error flag; the records were written to mapped host memory above)
+    CU_TRY(t, cudaMemcpyAsync(t->h_cnt[slot] + t->groups, t->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    t->stage_launches[7] += 1;  // a copy, not a kernel: not added to host_launches
+    mark(++stage);  // end
+    t->stage_valid[slot] = prof;
+    CU_TRY(t, cudaEventRecord(t->ev_done[slot], st));
+    t->tcur ^= 1;
+    t->pcur ^= 1;
+    t->have_prev = true;
+    return RSVIO_OK;
+}
+
+rsvio_status upload(rsvio_tracker *t, int slot, const uint8_t *const *left, const uint8_t *const *right,
+                    size_t stride) {
+    const int w = t->cfg.width, h = t->cfg.height, S = t->S;
+    const int ncam = t->stereo ? 2 : 1;
+    // the copy engine must not overwrite d_in[slot] while the pyramid kernel of the frame that
+    // last used this slot may still read it
+    CU_TRY(t, cudaStreamWaitEvent(t->copy_st, t->ev_in_free[slot], 0));
+    if (t->profiling) cudaEventRecord(t->ev_up[slot][0], t->copy_st);
+    for (int cam = 0; cam < ncam; ++cam) {
+        const uint8_t *const *src = cam == 0 ? left : right;
+        uint8_t *dst = t->d_in[slot] + (size_t)cam * S * t->img_bytes;
+        const bool pinned = is_device_accessible_host(src[0]);
+        // contiguous batch: constant pitch between consecutive images
+        bool uniform = true;
+        const ptrdiff_t pitch = S > 1 ? src[1] - src[0] : (ptrdiff_t)(stride * h);
+        for (int s = 1; s < S && uniform; ++s) uniform = (src[s] - src[s - 1]) == pitch;
+        if (!pinned) {
+            // pageable source: gather into the slot's pinned staging buffer (the caller may free
+            // or overwrite its images as soon as this call returns), then one DMA.
+            CU_TRY(t, cudaEventSynchronize(t->ev_h2d[slot]));
+            if (!t->h_stage[slot])  // allocated on first use: callers with pinned images never need it
+                CU_TRY(t, cudaHostAlloc((void **)&t->h_stage[slot], 2 * (size_t)S * t->img_bytes, cudaHostAllocDefault));
+            uint8_t *stage = t->h_stage[slot] + (size_t)cam * S * t->img_bytes;
+            for (int s = 0; s < S; ++s)
+                for (int y = 0; y < h; ++y)
+                    memcpy(stage + (size_t)s * t->img_bytes + (size_t)y * w, src[s] + (size_t)y * stride, (size_t)w);
+            CU_TRY(t, cudaMemcpyAsync(dst, stage, (size_t)S * t->img_bytes, cudaMemcpyHostToDevice, t->copy_st));
+            t->stage_launches[0] += 1;
+        } else if (uniform && stride == (size_t)w && pitch == (ptrdiff_t)t->img_bytes) {
+            CU_TRY(t, cudaMemcpyAsync(dst, src[0], (size_t)S * t->img_bytes, cudaMemcpyHostToDevice, t->copy_st));
+            t->stage_launches[0] += 1;
+        } else {
+            for (int s = 0; s < S; ++s)
+                CU_TRY(t, cudaMemcpy2DAsync(dst + (size_t)s * t->img_bytes, (size_t)w, src[s], stride, (size_t)w,
+                                            (size_t)h, cudaMemcpyHostToDevice, t->copy_st));
+            t->stage_launches[0] += (uint64_t)S;
+        }
+    }
+    if (t->profiling) cudaEventRecord(t->ev_up[slot][1], t->copy_st);
+    t->up_valid[slot] = t->profiling;
+    CU_TRY(t, cudaEventRecord(t->ev_h2d[slot], t->copy_st));
+    CU_TRY(t, cudaStreamWaitEvent(t->st, t->ev_h2d[slot], 0));
+    return RSVIO_OK;
+}
+
+rsvio_status check_batch_args(rsvio_tracker *t, const uint8_t *const *left, const uint8_t *const *right,
+                              size_t stride) {
+    if (!t) return RSVIO_ERR_INVALID_ARG;
+    if (!left || (t->stereo && !right)) return fail(t, RSVIO_ERR_INVALID_ARG, "null image array");
+    if (stride < (size_t)t->cfg.width) return fail(t, RSVIO_ERR_INVALID_ARG, "stride smaller than width");
+    for (int s = 0; s < t->S; ++s)
+        if (!left[s] || (t->stereo && !right[s])) return fail(t, RSVIO_ERR_INVALID_ARG, "null image pointer");
+    if (t->inflight >= kSlots) return fail(t, RSVIO_ERR_STATE, "two frames already in flight: call rsvio_tracker_sync");
+    return RSVIO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t rsvio_abi_version(void) { return RSVIO_ABI_VERSION; }
+
+const char *rsvio_status_string(rsvio_status s) {
+    switch (s) {
+        case RSVIO_OK: return "ok";
+        case RSVIO_ERR_INVALID_ARG: return "invalid argument";
+        case RSVIO_ERR_CUDA: return "CUDA error or no usable device";
+        case RSVIO_ERR_CAPACITY: return "capacity exceeded";
+        case RSVIO_ERR_STATE: return "invalid call order";
+        case RSVIO_ERR_ALLOC: return "allocation failed";
+        default: return "unknown status";
+    }
+}
+
+rsvio_status rsvio_device_count(int32_t *n) {
+    if (!n) return RSVIO_ERR_INVALID_ARG;
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) {
+        cudaGetLastError();
+        *n = 0;
+        return RSVIO_ERR_CUDA;
+    }
+    *n = c;
+    return c > 0 ? RSVIO_OK : RSVIO_ERR_CUDA;
+}
+
+void rsvio_config_default(rsvio_config *cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->levels = 6;                       /* estimator.rs:27 */
+    cfg->grid_size = 30;                   /* feature_tracker.rs:65 */
+    cfg->max_iterations = 30;              /* feature_tracker.rs:51 */
+    cfg->convergence_threshold = 0.005f;   /* feature_tracker.rs:52 */
+    cfg->mode = RSVIO_MODE_STEREO;
+    cfg->n_streams = 1;
+}
+
+rsvio_status rsvio_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return RSVIO_ERR_INVALID_ARG;
+    if (cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        *ptr = nullptr;
+        return RSVIO_ERR_CUDA;
+    }
+    return RSVIO_OK;
+}
+
+rsvio_status rsvio_host_free(void *ptr) {
+    if (!ptr) return RSVIO_OK;
+    if (cudaFreeHost(ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return RSVIO_ERR_CUDA;
+    }
+    return RSVIO_OK;
+}
+
+rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) {
+    if (!cfg || !out) return RSVIO_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (cfg->width < 8 || cfg->height < 8 || cfg->width > 65535 || cfg->height > 65535 || cfg->levels < 1 ||
+        cfg->levels > RSVIO_MAX_LEVELS || (cfg->width >> (cfg->levels - 1)) < 1 ||
+        (cfg->height >> (cfg->levels - 1)) < 1 || cfg->grid_size < 7 || cfg->grid_size > 1024 ||
+        cfg->max_iterations < 0 || cfg->n_streams < 1 || cfg->max_tracks < 0 ||
+        (cfg->mode != RSVIO_MODE_STEREO && cfg->mode != RSVIO_MODE_MONO))
+        return RSVIO_ERR_INVALID_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device < 0 || cfg->device >= ndev) {
+        cudaGetLastError();
+        return RSVIO_ERR_CUDA;
+    }
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return RSVIO_ERR_CUDA;
+    rsvio_tracker *t = new (std::nothrow) rsvio_tracker();
+    if (!t) return RSVIO_ERR_ALLOC;
+    t->cfg = *cfg;
+    t->S = cfg->n_streams;
+    t->groups = 2 * t->S;
+    t->stereo = cfg->mode == RSVIO_MODE_STEREO ? 1 : 0;
+    t->gd = make_grid_desc(cfg->width, cfg->height, cfg->grid_size);
+    const int cells = t->gd.ncx * t->gd.ncy;
+    t->new_cap = cells > 0 ? cells : 1;
+    t->cap = cfg->max_tracks > 0 ? cfg->max_tracks : 4 * cells + 64;
+    t->img_bytes = (size_t)cfg->width * cfg->height;
+    rsvio_status rs = RSVIO_OK;
+    auto body = [&]() -> rsvio_status {
+        if (cfg->cuda_stream) {
+            t->st = (cudaStream_t)cfg->cuda_stream;
+        } else {
+            CU_TRY(t, cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking));
+            t->own_stream = true;
+        }
+        CU_TRY(t, cudaStreamCreateWithFlags(&t->copy_st, cudaStreamNonBlocking));
+        CU_TRY(t, pyr_plan_create(cfg->width, cfg->height, cfg->levels, t->st, &t->plan));
+        t->pd = pyr_plan_desc(t->plan);
+        const size_t G = (size_t)t->groups, cap = (size_t)t->cap, S = (size_t)t->S;
+        for (int i = 0; i < kSlots; ++i) {
+            CU_TRY(t, dmalloc(&t->d_in[i], 2 * S * t->img_bytes));
+            CU_TRY(t, cudaHostAlloc((void **)&t->h_out[i], G * cap * sizeof(OutRecord), cudaHostAllocMapped));
+            CU_TRY(t, cudaHostGetDevicePointer((void **)&t->d_out[i], t->h_out[i], 0));
+            CU_TRY(t, cudaHostAlloc((void **)&t->h_cnt[i], (G + 1) * sizeof(int), cudaHostAllocMapped));
+            CU_TRY(t, cudaHostGetDevicePointer((void **)&t->d_cnt[i], t->h_cnt[i], 0));
+            CU_TRY(t, cudaEventCreateWithFlags(&t->ev_h2d[i], cudaEventDisableTiming));
+            CU_TRY(t, cudaEventCreateWithFlags(&t->ev_in_free[i], cudaEventDisableTiming));
+            CU_TRY(t, cudaEventCreateWithFlags(&t->ev_done[i], cudaEventDisableTiming));
+            for (int k = 0; k <= RSVIO_N_STAGES; ++k) CU_TRY(t, cudaEventCreate(&t->ev_stage[i][k]));
+            for (int k = 0; k < 2; ++k) CU_TRY(t, cudaEventCreate(&t->ev_up[i][k]));
+        }
+        for (int i = 0; i < 2; ++i) {
+            CU_TRY(t, dmalloc(&t->d_pyr[i], G * (size_t)t->pd.pyr_stride));
+            CU_TRY(t, dmalloc(&t->tab[i].ids, G * cap));
+            CU_TRY(t, dmalloc(&t->tab[i].T6, G * cap * 6));
+            CU_TRY(t, dmalloc(&t->tab[i].counts, G));
+        }
+        CU_TRY(t, dmalloc(&t->d_lk_T6, G * cap * 6));
+        CU_TRY(t, dmalloc(&t->d_lk_status, G * cap));
+        CU_TRY(t, dmalloc(&t->d_occ, S * (size_t)t->gd.occ_rows * t->gd.occ_cols));
+        CU_TRY(t, dmalloc(&t->d_cell_pt, S * (size_t)t->new_cap));
+        CU_TRY(t, dmalloc(&t->d_cell_score, S * (size_t)t->new_cap));
+        CU_TRY(t, dmalloc(&t->d_new_T6, S * (size_t)t->new_cap * 6));
+        CU_TRY(t, dmalloc(&t->d_st_T6, S * (size_t)t->new_cap * 6));
+        CU_TRY(t, dmalloc(&t->d_new_count, S));
+        CU_TRY(t, dmalloc(&t->d_st_status, S * (size_t)t->new_cap));
+        CU_TRY(t, dmalloc(&t->d_last_id, S));
+        CU_TRY(t, dmalloc(&t->d_counters, (size_t)CNT_N));
+        CU_TRY(t, dmalloc(&t->d_err, (size_t)1));
+        return clear_state(t);
+    };
+    rs = body();
+    if (rs != RSVIO_OK) {
+        fprintf(stderr, "rsvio_tracker_create failed: %s\n", t->err.c_str());
+        free_all(t);
+        return rs;
+    }
+    *out = t;
+    return RSVIO_OK;
+}
+
+void rsvio_tracker_destroy(rsvio_tracker *t) { free_all(t); }
+
+const char *rsvio_tracker_last_error(const rsvio_tracker *t) { return t ? t->err.c_str() : "null handle"; }
+
+rsvio_status rsvio_tracker_reset(rsvio_tracker *t) {
+    if (!t) return RSVIO_ERR_INVALID_ARG;
+    CU_TRY(t, cudaSetDevice(t->cfg.device));
+    CU_TRY(t, cudaStreamSynchronize(t->copy_st));
+    CU_TRY(t, cudaStreamSynchronize(t->st));
+    return clear_state(t);
+}
+
+rsvio_status rsvio_tracker_submit_batch(rsvio_tracker *t, const uint8_t *const *left, const uint8_t *const *right,
+                                        size_t stride) {
+    rsvio_status rs = check_batch_args(t, left, right, stride);
+    if (rs != RSVIO_OK) return rs;
+    CU_TRY(t, cudaSetDevice(t->cfg.device));
+    const int slot = t->next_slot;
+    rs = upload(t, slot, left, right, stride);
+    if (rs != RSVIO_OK) return rs;
+    const uint8_t *d0 = t->d_in[slot], *d1 = t->d_in[slot] + (size_t)t->S * t->img_bytes;
+    rs = enqueue_frame(t, slot, d0, d1, (size_t)t->cfg.width, t->img_bytes);
+    if (rs != RSVIO_OK) return rs;
+    t->next_slot ^= 1;
+    t->inflight += 1;
+    return RSVIO_OK;
+}
+
+rsvio_status rsvio_tracker_submit_device(rsvio_tracker *t, const void *d_left, const void *d_right, size_t stride,
+                                         size_t pitch) {
+    if (!t) return RSVIO_ERR_INVALID_ARG;
+    if (!d_left || (t->stereo && !d_right)) return fail(t, RSVIO_ERR_INVALID_ARG, "null device image pointer");
+    if (stride < (size_t)t->cfg.width || pitch < stride * (size_t)(t->cfg.height - 1) + (size_t)t->cfg.width)
+        return fail(t, RSVIO_ERR_INVALID_ARG, "stride/pitch too small");
+    if (t->inflight >= kSlots) return fail(t, RSVIO_ERR_STATE, "two frames already in flight: call rsvio_tracker_sync");
+    CU_TRY(t, cudaSetDevice(t->cfg.device));
+    const int slot = t->next_slot;
+    t->up_valid[slot] = false;
+    rsvio_status rs = enqueue_frame(t, slot, (const uint8_t *)d_left, (const uint8_t *)d_right, stride, pitch);
+    if (rs != RSVIO_OK) return rs;
+    t->next_slot ^= 1;
+    t->inflight += 1;
+    return RSVIO_OK;
+}
+
+rsvio_status rsvio_tracker_sync(rsvio_tracker *t) {
+    if (!t) return RSVIO_ERR_INVALID_ARG;
+    if (t->inflight <= 0) return fail(t, RSVIO_ERR_STATE, "nothing in flight");
+    CU_TRY(t, cudaSetDevice(t->cfg.device));
+    const int slot = t->oldest_slot;
+    CU_TRY(t, cudaEventSynchronize(t->ev_done[slot]));
+    if (t->stage_valid[slot]) {
+        for (int k = 1; k < RSVIO_N_STAGES; ++k) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, t->ev_stage[slot][k], t->ev_stage[slot][k + 1]) == cudaSuccess)
+                t->stage_ms[k] += ms;
+        }
+        t->stage_valid[slot] = false;
+    }
+    if (t->up_valid[slot]) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, t->ev_up[slot][0], t->ev_up[slot][1]) == cudaSuccess) t->stage_ms[0] += ms;
+        t->up_valid[slot] = false;
+    }
+    cudaGetLastError();
+    t->oldest_slot ^= 1;
+    t->inflight -= 1;
+    t->result_slot = slot;
+    if (t->h_cnt[slot][t->groups] != 0)
+        return fail(t, RSVIO_ERR_CAPACITY, "track table full: raise rsvio_config.max_tracks");
+    return RSVIO_OK;
+}
+
+rsvio_status rsvio_tracker_process_batch(rsvio_tracker *t, const uint8_t *const *left, const uint8_t *const *right,
+                                         size_t stride) {
+    rsvio_status rs = rsvio_tracker_submit_batch(t, left, right, stride);
+    if (rs != RSVIO_OK) return rs;
+    return rsvio_tracker_sync(t);
+}
+
+rsvio_status rsvio_tracker_process_stereo(rsvio_tracker *t, const uint8_t *left, const uint8_t *right, size_t stride) {
+    if (!t) return RSVIO_ERR_INVALID_ARG;
+    if (t->S != 1 || !t->stereo) return fail(t, RSVIO_ERR_INVALID_ARG, "handle is not a 1-stream stereo tracker");
+    const uint8_t *l[1] = {left}, *r[1] = {right};
+    return rsvio_tracker_process_batch(t, l, r, stride);
+}
+
+rsvio_status rsvio_tracker_process_mono(rsvio_tracker *t, const uint8_t *image, size_t stride) {
+    if (!t) return RSVIO_ERR_INVALID_ARG;
+    if (t->S != 1 || t->stereo) return fail(t, RSVIO_ERR_INVALID_ARG, "handle is not a 1-stream mono tracker");
+    const uint8_t *l[1] = {image};
+    return rsvio_tracker_process_batch(t, l, nullptr, stride);
+}
+
+static rsvio_status check_group(rsvio_tracker *t, int32_t stream, int32_t cam) {
+    if (!t) return RSVIO_ERR_INVALID_ARG;
+    if (stream < 0 || stream >= t->S || cam < 0 || cam > 1) return fail(t, RSVIO_ERR_INVALID_ARG, "bad stream/cam");
+    if (t->inflight > 0) return fail(t, RSVIO_ERR_STATE, "frames in flight: call rsvio_tracker_sync first");
+    return RSVIO_OK;
+}
+
+rsvio_status rsvio_tracker_num_tracks(rsvio_tracker *t, int32_t stream, int32_t cam, int32_t *n) {
+    rsvio_status rs = check_group(t, stream, cam);
+    if (rs != RSVIO_OK) return rs;
+    if (!n) return RSVIO_ERR_INVALID_ARG;
+    *n = t->result_slot < 0 ? 0 : t->h_cnt[t->result_slot][cam * t->S + stream];
+    return RSVIO_OK;
+}
+
+rsvio_status rsvio_tracker_get_tracks(rsvio_tracker *t, int32_t stream, int32_t cam, uint64_t *ids, float *xy,
+                                      size_t cap, size_t *n) {
+    rsvio_status rs = check_group(t, stream, cam);
+    if (rs != RSVIO_OK) return rs;
+    if (!n) return RSVIO_ERR_INVALID_ARG;
+    const int g = cam * t->S + stream;
+    const int cnt = t->result_slot < 0 ? 0 : t->h_cnt[t->result_slot][g];
+    *n = (size_t)cnt;
+    if ((size_t)cnt > cap) return fail(t, RSVIO_ERR_CAPACITY, "output arrays too small");
+    if (cnt > 0 && (!ids || !xy)) return RSVIO_ERR_INVALID_ARG;
+    const OutRecord *r = t->h_out[t->result_slot] + (size_t)g * t->cap;
+    for (int k = 0; k < cnt; ++k) {
+        ids[k] = r[k].id;
+        xy[2 * k] = r[k].x;
+        xy[2 * k + 1] = r[k].y;
+    }
+    return RSVIO_OK;
+}
+
+rsvio_status rsvio_tracker_get_transforms(rsvio_tracker *t, int32_t stream, int32_t cam, uint64_t *ids, float *T6,
+                                          size_t cap, size_t *n) {
+    rsvio_status rs = check_group(t, stream, cam);
+    if (rs != RSVIO_OK) return rs;
+    if (!n) return RSVIO_ERR_INVALID_ARG;
+    CU_TRY(t, cudaSetDevice(t->cfg.device));
+    const int g = cam * t->S + stream;
+    const TableView &tv = t->tab[t->tcur];
+    int cnt = 0;
+    CU_TRY(t, cudaMemcpyAsync(&cnt, tv.counts + g, sizeof(int), cudaMemcpyDeviceToHost, t->st));
+    CU_TRY(t, cudaStreamSynchronize(t->st));
+    *n = (size_t)cnt;
+    if ((size_t)cnt > cap) return fail(t, RSVIO_ERR_CAPACITY, "output arrays too small");
+    if (cnt > 0) {
+        if (!ids || !T6) return RSVIO_ERR_INVALID_ARG;
+        CU_TRY(t, cudaMemcpyAsync(ids, tv.ids + (size_t)g * t->cap, sizeof(uint64_t) * cnt, cudaMemcpyDeviceToHost, t->st));
+        CU_TRY(t, cudaMemcpyAsync(T6, tv.T6 + (size_t)g * t->cap * 6, sizeof(float) * 6 * cnt, cudaMemcpyDeviceToHost, t->st));
+        CU_TRY(t, cudaStreamSynchronize(t->st));
+    }
+    return RSVIO_OK;
+}
+
+rsvio_status rsvio_tracker_remove_ids(rsvio_tracker *t, int32_t stream, const uint64_t *ids, size_t n) {
+    rsvio_status rs = check_group(t, stream, 0);
+    if (rs != RSVIO_OK) return rs;
+    if (n == 0) return RSVIO_OK;
+    if (!ids) return RSVIO_ERR_INVALID_ARG;
+    CU_TRY(t, cudaSetDevice(t->cfg.device));
+    if ((int)n > t->rm_cap) {
+        cudaFree(t->d_rm);
+        t->d_rm = nullptr;
+        CU_TRY(t, dmalloc(&t->d_rm, n));
+        t->rm_cap = (int)n;
+    }
+    CU_TRY(t, cudaMemcpyAsync(t->d_rm, ids, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, t->st));
+    CU_TRY(t, remove_ids(t->tab[t->tcur], t->tab[t->tcur ^ 1], t->groups, t->cap, t->S, stream, t->d_rm, (int)n, t->st));
+    t->host_launches += 1;
+    t->tcur ^= 1;
+    // refresh the host-visible result of the affected groups
+    const int slot = t->result_slot < 0 ? 0 : t->result_slot;
+    const TableView &tv = t->tab[t->tcur];
+    std::vector<int> cnt(t->groups);
+    CU_TRY(t, cudaMemcpyAsync(cnt.data(), tv.counts, sizeof(int) * t->groups, cudaMemcpyDeviceToHost, t->st));
+    CU_TRY(t, cudaStreamSynchronize(t->st));
+    for (int cam = 0; cam < 2; ++cam) {
+        const int g = cam * t->S + stream;
+        std::vector<unsigned long long> hid(cnt[g] > 0 ? cnt[g] : 1);
+        std::vector<float> hT((size_t)(cnt[g] > 0 ? cnt[g] : 1) * 6);
+        if (cnt[g] > 0) {
+            CU_TRY(t, cudaMemcpy(hid.data(), tv.ids + (size_t)g * t->cap, sizeof(uint64_t) * cnt[g], cudaMemcpyDeviceToHost));
+            CU_TRY(t, cudaMemcpy(hT.data(), tv.T6 + (size_t)g * t->cap * 6, sizeof(float) * 6 * cnt[g], cudaMemcpyDeviceToHost));
+        }
+        OutRecord *r = t->h_out[slot] + (size_t)g * t->cap;
+        for (int k = 0; k < cnt[g]; ++k) {
+            r[k].id = hid[k];
+            r[k].x = hT[(size_t)k * 6 + 2];
+            r[k].y = hT[(size_t)k * 6 + 5];
+        }
+        t->h_cnt[slot][g] = cnt[g];
+    }
+    t->result_slot = slot;
+    return RSVIO_OK;
+}
+
+rsvio_status rsvio_tracker_counters(rsvio_tracker *t, uint64_t out[6]) {
+    if (!t || !out) return RSVIO_ERR_INVALID_ARG;
+    CU_TRY(t, cudaSetDevice(t->cfg.device));
+    unsigned long long c[CNT_N];
+    CU_TRY(t, cudaMemcpyAsync(c, t->d_counters, sizeof(c), cudaMemcpyDeviceToHost, t->st));
+    CU_TRY(t, cudaStreamSynchronize(t->st));
+    out[0] = c[CNT_TRACKS];
+    out[1] = c[CNT_FRAMES];
+    out[2] = c[CNT_ITERS];
+    out[3] = c[CNT_TEMPLATES];
+    out[4] = t->host_launches;
+    out[5] = c[CNT_DETECTED];
+    return RSVIO_OK;
+}
+
+rsvio_status rsvio_tracker_set_profiling(rsvio_tracker *t, int32_t enabled) {
+    if (!t) return RSVIO_ERR_INVALID_ARG;
+    if (t->inflight > 0) return fail(t, RSVIO_ERR_STATE, "frames in flight");
+    t->profiling = enabled != 0;
+    return RSVIO_OK;
+}
+
+rsvio_status rsvio_tracker_stage_times(rsvio_tracker *t, float ms[RSVIO_N_STAGES], uint64_t launches[RSVIO_N_STAGES],
+                                       int32_t reset) {
+    if (!t) return RSVIO_ERR_INVALID_ARG;
+    for (int k = 0; k < RSVIO_N_STAGES; ++k) {
+        if (ms) ms[k] = (float)t->stage_ms[k];
+        if (launches) launches[k] = t->stage_launches[k];
+        if (reset) {
+            t->stage_ms[k] = 0.0;
+            t->stage_launches[k] = 0;
+        }
+    }
+    return RSVIO_OK;
+}
+
+// ---- stateless entry points -------------------------------------------------------------
+
+size_t rsvio_pyramid_bytes(int32_t width, int32_t height, int32_t levels) {
+    size_t o = 0;
+    for (int i = 0; i < levels; ++i) o += (size_t)(width >> i) * (size_t)(height >> i);
+    return o;
+}
+
+#define CU_TRY0(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess) {                                                                       \
+            fprintf(stderr, "rsvio: CUDA error %d (%s) at api.cu:%d: %s\n", (int)e__,                   \
+                    cudaGetErrorString(e__), __LINE__, #expr);                                          \
+            rs = RSVIO_ERR_CUDA;                                                                        \
+            goto done;                                                                                  \
+        }                                                                                               \
+    } while (0)
+
+static bool pyr_args_ok(int32_t n_images, int32_t width, int32_t height, size_t stride, size_t pitch, int32_t levels) {
+    return n_images >= 1 && width >= 1 && height >= 1 && width <= 65535 && height <= 65535 && levels >= 1 &&
+           levels <= RSVIO_MAX_LEVELS && (width >> (levels - 1)) >= 1 && (height >> (levels - 1)) >= 1 &&
+           stride >= (size_t)width && (n_images == 1 || pitch >= stride * (size_t)(height - 1) + (size_t)width);
+}
+
+rsvio_status rsvio_build_pyramid_u8_device(int32_t device, const void *d_images, int32_t n_images, int32_t width,
+                                           int32_t height, size_t stride, size_t pitch, int32_t levels, void *d_out,
+                                           int32_t repeats, float *kernel_ms) {
+    if (!d_images || !d_out || !pyr_args_ok(n_images, width, height, stride, pitch, levels) || repeats < 1)
+        return RSVIO_ERR_INVALID_ARG;
+    rsvio_status rs = RSVIO_OK;
+    PyrPlan *plan = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    CU_TRY0(cudaSetDevice(device));
+    CU_TRY0(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CU_TRY0(pyr_plan_create(width, height, levels, st, &plan));
+    CU_TRY0(cudaEventCreate(&e0));
+    CU_TRY0(cudaEventCreate(&e1));
+    CU_TRY0(cudaEventRecord(e0, st));
+    for (int r = 0; r < repeats; ++r)
+        CU_TRY0(pyr_build(plan, (const uint8_t *)d_images, (const uint8_t *)d_images, n_images, n_images, stride, pitch,
+                          (uint8_t *)d_out, st, nullptr));
+    CU_TRY0(cudaEventRecord(e1, st));
+    CU_TRY0(cudaStreamSynchronize(st));
+    if (kernel_ms) {
+        float ms = 0.0f;
+        CU_TRY0(cudaEventElapsedTime(&ms, e0, e1));
+        *kernel_ms = ms / (float)repeats;
+    }
+done:
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    pyr_plan_destroy(plan);
+    if (st) cudaStreamDestroy(st);
+    return rs;
+}
+
+// internal (aligned) pyramid size, for callers that allocate d_out of the device variant
+size_t rsvio_pyramid_device_bytes(int32_t width, int32_t height, int32_t levels) {
+    return make_pyr_desc(width, height, levels).pyr_stride;
+}
+
+rsvio_status rsvio_build_pyramid_u8(int32_t device, const uint8_t *images, int32_t n_images, int32_t width,
+                                    int32_t height, size_t stride, size_t pitch, int32_t levels, uint8_t *out) {
+    if (!images || !out || !pyr_args_ok(n_images, width, height, stride, pitch, levels)) return RSVIO_ERR_INVALID_ARG;
+    rsvio_status rs = RSVIO_OK;
+    const PyrDesc pd = make_pyr_desc(width, height, levels);
+    const size_t dense = rsvio_pyramid_bytes(width, height, levels);
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    const size_t in_bytes = (size_t)(n_images - 1) * pitch + stride * (size_t)(height - 1) + (size_t)width;
+    CU_TRY0(cudaSetDevice(device));
+    CU_TRY0(cudaMalloc((void **)&d_in, in_bytes));
+    CU_TRY0(cudaMalloc((void **)&d_out, (size_t)n_images * pd.pyr_stride));
+    CU_TRY0(cudaMemcpy(d_in, images, in_bytes, cudaMemcpyHostToDevice));
+    rs = rsvio_build_pyramid_u8_device(device, d_in, n_images, width, height, stride, pitch, levels, d_out, 1, nullptr);
+    if (rs != RSVIO_OK) goto done;
+    for (int j = 0; j < n_images; ++j) {
+        size_t o = 0;
+        for (int i = 0; i < levels; ++i) {
+            const size_t nb = (size_t)pd.lv[i].w * pd.lv[i].h;
+            CU_TRY0(cudaMemcpy(out + (size_t)j * dense + o, d_out + (size_t)j * pd.pyr_stride + pd.lv[i].off, nb,
+                               cudaMemcpyDeviceToHost));
+            o += nb;
+        }
+    }
+done:
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rs;
+}
+
+rsvio_status rsvio_track_points(int32_t device, const uint8_t *pyr_a, const uint8_t *pyr_b, int32_t width,
+                                int32_t height, int32_t levels, int32_t n, const float *in_T6, int32_t max_iterations,
+                                float convergence_threshold, float *out_T6, int32_t *status, int32_t *iters) {
+    if (!pyr_a || !pyr_b || n < 0 || !pyr_args_ok(1, width, height, (size_t)width, 0, levels) || max_iterations < 0)
+        return RSVIO_ERR_INVALID_ARG;
+    if (n == 0) return RSVIO_OK;
+    if (!in_T6 || !out_T6 || !status) return RSVIO_ERR_INVALID_ARG;
+    rsvio_status rs = RSVIO_OK;
+    const PyrDesc pd = make_pyr_desc(width, height, levels);
+    uint8_t *d_pyr = nullptr;
+    float *d_in = nullptr, *d_out = nullptr;
+    int32_t *d_status = nullptr, *d_iters = nullptr;
+    int *d_count = nullptr;
+    CU_TRY0(cudaSetDevice(device));
+    CU_TRY0(cudaMalloc((void **)&d_pyr, 2 * (size_t)pd.pyr_stride));
+    {
+        size_t o = 0;
+        for (int i = 0; i < levels; ++i) {
+            const size_t nb = (size_t)pd.lv[i].w * pd.lv[i].h;
+            CU_TRY0(cudaMemcpy(d_pyr + pd.lv[i].off, pyr_a + o, nb, cudaMemcpyHostToDevice));
+            CU_TRY0(cudaMemcpy(d_pyr + pd.pyr_stride + pd.lv[i].off, pyr_b + o, nb, cudaMemcpyHostToDevice));
+            o += nb;
+        }
+    }
+    CU_TRY0(cudaMalloc((void **)&d_in, sizeof(float) * 6 * n));
+    CU_TRY0(cudaMalloc((void **)&d_out, sizeof(float) * 6 * n));
+    CU_TRY0(cudaMalloc((void **)&d_status, sizeof(int32_t) * n));
+    CU_TRY0(cudaMalloc((void **)&d_iters, sizeof(int32_t) * 2 * n));
+    CU_TRY0(cudaMalloc((void **)&d_count, sizeof(int)));
+    CU_TRY0(cudaMemcpy(d_in, in_T6, sizeof(float) * 6 * n, cudaMemcpyHostToDevice));
+    CU_TRY0(cudaMemcpy(d_count, &n, sizeof(int), cudaMemcpyHostToDevice));
+    {
+        LkBatch b{};
+        b.pyr_a = d_pyr;
+        b.pyr_b = d_pyr + pd.pyr_stride;
+        b.counts = d_count;
+        b.in_T6 = d_in;
+        b.out_T6 = d_out;
+        b.status = d_status;
+        b.iters = d_iters;
+        b.counters = nullptr;
+        b.groups = 1;
+        b.cap = n;
+        b.max_it = max_iterations;
+        b.thr = convergence_threshold;
+        CU_TRY0(lk_track(pd, b, 0));
+    }
+    CU_TRY0(cudaDeviceSynchronize());
+    CU_TRY0(cudaMemcpy(out_T6, d_out, sizeof(float) * 6 * n, cudaMemcpyDeviceToHost));
+    CU_TRY0(cudaMemcpy(status, d_status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    if (iters) CU_TRY0(cudaMemcpy(iters, d_iters, sizeof(int32_t) * 2 * n, cudaMemcpyDeviceToHost));
+done:
+    cudaFree(d_pyr);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    cudaFree(d_status);
+    cudaFree(d_iters);
+    cudaFree(d_count);
+    return rs;
+}
+
+rsvio_status rsvio_detect_keypoints(int32_t device, const uint8_t *image, int32_t width, int32_t height, size_t stride,
+                                    uint32_t grid_size, const uint32_t *cur_xy, int32_t n_cur, uint32_t *out_xy,
+                                    float *out_score, size_t cap, size_t *n) {
+    if (!image || !n || width < 8 || height < 8 || width > 65535 || height > 65535 || stride < (size_t)width ||
+        grid_size < 7 || grid_size > 1024 || n_cur < 0 || (n_cur > 0 && !cur_xy))
+        return RSVIO_ERR_INVALID_ARG;
+    rsvio_status rs = RSVIO_OK;
+    const GridDesc gd = make_grid_desc(width, height, grid_size);
+    const int cells = gd.ncx * gd.ncy;
+    *n = 0;
+    if (cells <= 0) return RSVIO_OK;
+    uint8_t *d_img = nullptr, *d_occ = nullptr;
+    uint32_t *d_xy = nullptr, *d_cell = nullptr;
+    float *d_score = nullptr, *d_T6 = nullptr, *d_nscore = nullptr;
+    int *d_cnt = nullptr;
+    int cnt = 0;
+    std::vector<float> hT, hs;
+    CU_TRY0(cudaSetDevice(device));
+    CU_TRY0(cudaMalloc((void **)&d_img, (size_t)width * height));
+    CU_TRY0(cudaMemcpy2D(d_img, (size_t)width, image, stride, (size_t)width, (size_t)height, cudaMemcpyHostToDevice));
+    CU_TRY0(cudaMalloc((void **)&d_occ, (size_t)gd.occ_rows * gd.occ_cols));
+    CU_TRY0(cudaMemset(d_occ, 0, (size_t)gd.occ_rows * gd.occ_cols));
+    if (n_cur > 0) {
+        CU_TRY0(cudaMalloc((void **)&d_xy, sizeof(uint32_t) * 2 * n_cur));
+        CU_TRY0(cudaMemcpy(d_xy, cur_xy, sizeof(uint32_t) * 2 * n_cur, cudaMemcpyHostToDevice));
+        CU_TRY0(mark_occupancy_xy(gd, d_xy, n_cur, d_occ, 0));
+    }
+    CU_TRY0(cudaMalloc((void **)&d_cell, sizeof(uint32_t) * cells));
+    CU_TRY0(cudaMalloc((void **)&d_score, sizeof(float) * cells));
+    CU_TRY0(cudaMalloc((void **)&d_T6, sizeof(float) * 6 * cells));
+    CU_TRY0(cudaMalloc((void **)&d_nscore, sizeof(float) * cells));
+    CU_TRY0(cudaMalloc((void **)&d_cnt, sizeof(int)));
+    CU_TRY0(detect_cells(gd, d_img, (size_t)width, 0, 1, d_occ, d_cell, d_score, 0));
+    CU_TRY0(collect_new_points(gd, 1, d_cell, d_score, d_T6, d_nscore, d_cnt, cells, nullptr, 0));
+    CU_TRY0(cudaDeviceSynchronize());
+    CU_TRY0(cudaMemcpy(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost));
+    *n = (size_t)cnt;
+    if ((size_t)cnt > cap) {
+        rs = RSVIO_ERR_CAPACITY;
+        goto done;
+    }
+    if (cnt > 0) {
+        if (!out_xy) {
+            rs = RSVIO_ERR_INVALID_ARG;
+            goto done;
+        }
+        hT.resize((size_t)cnt * 6);
+        hs.resize((size_t)cnt);
+        CU_TRY0(cudaMemcpy(hT.data(), d_T6, sizeof(float) * 6 * cnt, cudaMemcpyDeviceToHost));
+        CU_TRY0(cudaMemcpy(hs.data(), d_nscore, sizeof(float) * cnt, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < cnt; ++k) {
+            out_xy[2 * k] = (uint32_t)hT[(size_t)k * 6 + 2];
+            out_xy[2 * k + 1] = (uint32_t)hT[(size_t)k * 6 + 5];
+            if (out_score) out_score[k] = hs[k];
+        }
+    }
+done:
+    cudaFree(d_img);
+    cudaFree(d_occ);
+    cudaFree(d_xy);
+    cudaFree(d_cell);
+    cudaFree(d_score);
+    cudaFree(d_T6);
+    cudaFree(d_nscore);
+    cudaFree(d_cnt);
+    return rs;
+}
+
+rsvio_status rsvio_se2_exp(int32_t device, const float *twists, int32_t n, float *out9) {
+    if (n < 0 || (n > 0 && (!twists || !out9))) return RSVIO_ERR_INVALID_ARG;
+    if (n == 0) return RSVIO_OK;
+    rsvio_status rs = RSVIO_OK;
+    float *d_in = nullptr, *d_out = nullptr;
+    CU_TRY0(cudaSetDevice(device));
+    CU_TRY0(cudaMalloc((void **)&d_in, sizeof(float) * 3 * n));
+    CU_TRY0(cudaMalloc((void **)&d_out, sizeof(float) * 9 * n));
+    CU_TRY0(cudaMemcpy(d_in, twists, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
+    CU_TRY0(se2_exp_batch(d_in, n, d_out, 0));
+    CU_TRY0(cudaDeviceSynchronize());
+    CU_TRY0(cudaMemcpy(out9, d_out, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost));
+done:
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rs;
+}
+
+}  // extern "C"

@@ -1,0 +1,173 @@
+// common.cuh -- shared host/device declarations of librsvio_b200 (sm_100a only).
+//
+// Data layout in HBM:
+//   pyramid of one image: levels back to back, level i dense row-major (stride == w >> i),
+//   each level start aligned to 256 B; `pyr_stride` bytes between the pyramids of two slots.
+//   slot = cam * n_streams + stream.
+//   track table of one (cam, stream) group: ids[cap] (u64) and T6[cap][6] (f32,
+//   [m11,m12,tx,m21,m22,ty] of the reference's Affine2), count in counts[group].
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rsvio_b200.h"
+
+namespace rsvio {
+
+constexpr int kMaxLevels = RSVIO_MAX_LEVELS;
+constexpr int kPattern = RSVIO_PATTERN_SIZE;
+constexpr int kNumSMs = 148;  // B200
+
+struct LevelDesc {
+    int w, h;
+    uint32_t off;  // byte offset of the level inside one pyramid
+};
+
+struct PyrDesc {
+    LevelDesc lv[kMaxLevels];
+    int levels;
+    uint32_t bytes;       // dense-with-alignment size of one pyramid
+    uint32_t pyr_stride;  // bytes between consecutive slots (>= bytes, multiple of 256)
+};
+
+inline PyrDesc make_pyr_desc(int w, int h, int levels) {
+    PyrDesc d{};
+    d.levels = levels;
+    uint32_t off = 0;
+    for (int i = 0; i < levels; ++i) {
+        d.lv[i].w = w >> i;
+        d.lv[i].h = h >> i;
+        d.lv[i].off = off;
+        off += (uint32_t)(d.lv[i].w * d.lv[i].h);
+        off = (off + 255u) & ~255u;
+    }
+    d.bytes = off;
+    d.pyr_stride = off;
+    return d;
+}
+
+// separable resampling taps of one (level, axis): image 0.25 `resize` weight construction
+struct TapTable {
+    const int *left;   // [n_out] first source index
+    const int *cnt;    // [n_out] number of taps
+    const float *w;    // [n_out][kmax] normalised weights
+    int n_in, n_out, kmax;
+};
+
+struct PyrTaps {
+    TapTable x[kMaxLevels], y[kMaxLevels];  // index 0 unused (level 0 is a copy)
+};
+
+// device counters (u64): see rsvio_tracker_counters
+enum { CNT_TRACKS = 0, CNT_FRAMES, CNT_ITERS, CNT_TEMPLATES, CNT_LAUNCHES, CNT_DETECTED, CNT_N };
+
+// ---- launch wrappers implemented in the .cu files -------------------------------------
+
+// pyramid.cu
+struct PyrPlan;  // owns the tap tables and tile lists of one (w, h, levels)
+cudaError_t pyr_plan_create(int w, int h, int levels, cudaStream_t st, PyrPlan **out);
+void pyr_plan_destroy(PyrPlan *p);
+const PyrDesc &pyr_plan_desc(const PyrPlan *p);
+// n_images source images: image j at src[j < split ? 0 : 1] + (j < split ? j : j - split) * pitch
+cudaError_t pyr_build(const PyrPlan *p, const uint8_t *src0, const uint8_t *src1, int split, int n_images,
+                      size_t stride, size_t pitch, uint8_t *dst, cudaStream_t st, int *n_launches);
+
+// lk.cu
+struct LkBatch {
+    const uint8_t *pyr_a;   // slot 0 of the source pyramids
+    const uint8_t *pyr_b;   // slot 0 of the target pyramids
+    const int *counts;      // [groups] points per group (device)
+    const float *in_T6;     // [groups][cap][6]
+    float *out_T6;          // [groups][cap][6]
+    int32_t *status;        // [groups][cap]
+    int32_t *iters;         // [groups][cap][2] or nullptr
+    unsigned long long *counters;  // CNT_* or nullptr
+    int groups, cap;
+    int max_it;
+    float thr;
+};
+cudaError_t lk_track(const PyrDesc &pd, const LkBatch &b, cudaStream_t st);
+cudaError_t se2_exp_batch(const float *d_twists, int n, float *d_out9, cudaStream_t st);
+
+// detect.cu
+struct GridDesc {
+    int w, h;
+    uint32_t g;
+    int ncx, ncy;          // cells visited: w / g, h / g
+    int occ_cols, occ_rows;  // w / g + 1, h / g + 1
+    uint32_t x_start, y_start;
+};
+inline GridDesc make_grid_desc(int w, int h, uint32_t g) {
+    GridDesc d{};
+    d.w = w;
+    d.h = h;
+    d.g = g;
+    d.ncx = (int)((uint32_t)w / g);
+    d.ncy = (int)((uint32_t)h / g);
+    d.occ_cols = d.ncx + 1;
+    d.occ_rows = d.ncy + 1;
+    d.x_start = ((uint32_t)w % g) / 2;
+    d.y_start = ((uint32_t)h % g) / 2;
+    return d;
+}
+// occ: [streams][occ_rows*occ_cols] bytes, cell_pt: [streams][ncx*ncy] packed (y << 16 | x) or ~0,
+// cell_score: [streams][ncx*ncy].  img of stream s = img0 + s * pitch.
+cudaError_t detect_cells(const GridDesc &gd, const uint8_t *img0, size_t stride, size_t pitch, int streams,
+                         const uint8_t *occ, uint32_t *cell_pt, float *cell_score, cudaStream_t st);
+// ordered compaction of the per-cell results into identity transforms new_T6[s][k], new_count[s]
+cudaError_t collect_new_points(const GridDesc &gd, int streams, const uint32_t *cell_pt, const float *cell_score,
+                               float *new_T6, float *new_score, int *new_count, int new_cap,
+                               unsigned long long *counters, cudaStream_t st);
+// marks cells holding one of n (x, y) rounded positions (stateless API); occ must be zeroed
+cudaError_t mark_occupancy_xy(const GridDesc &gd, const uint32_t *d_xy, int n, uint8_t *occ, cudaStream_t st);
+
+// tracks.cu
+struct TableView {
+    unsigned long long *ids;  // [groups][cap]
+    float *T6;                // [groups][cap][6]
+    int *counts;              // [groups]
+};
+// stable compaction of the surviving tracks of every group from `in` (+ lk results) into `out`;
+// groups < streams (camera 0) also rebuild the occupancy grid of their stream.
+cudaError_t compact_tracks(const TableView &in, const float *lk_T6, const int32_t *lk_status, const TableView &out,
+                           int groups, int cap, int streams, const GridDesc &gd, uint8_t *occ, int have_prev,
+                           unsigned long long *counters, cudaStream_t st);
+// packed output record written to (mapped) host memory
+struct OutRecord {
+    unsigned long long id;
+    float x, y;
+};
+// appends the new stereo pairs (status ok) to both cameras of `tab`, assigns ids, writes the packed output
+cudaError_t merge_new_points(const TableView &tab, int streams, int cap, int stereo, const float *new_T6,
+                             const float *st_T6, const int32_t *st_status, const int *new_count, int new_cap,
+                             unsigned long long *last_id, int *err_flag, OutRecord *out_rec, int *out_counts,
+                             unsigned long long *counters, cudaStream_t st);
+cudaError_t remove_ids(const TableView &in, const TableView &out, int groups, int cap, int streams, int stream,
+                       const unsigned long long *d_ids, int n, cudaStream_t st);
+
+}  // namespace rsvio
+
+// ---- device helpers ---------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace rsvio {
+
+// Rust `f32 as u32`: saturating, NaN -> 0
+__device__ __forceinline__ uint32_t sat_u32(float v) {
+    return __float2uint_rz(v);  // cvt.rzi.u32.f32 saturates and maps NaN to 0
+}
+
+// inbound -- image_utilities.rs:75-80 (round half away from zero, then u32 compare)
+__device__ __forceinline__ bool inbound(int w, int h, float x, float y, uint32_t r) {
+    const uint32_t rx = sat_u32(roundf(x)), ry = sat_u32(roundf(y));
+    return rx >= r && ry >= r && rx < (uint32_t)w - r && ry < (uint32_t)h - r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace rsvio
+#endif

@@ -1,0 +1,209 @@
+// detect.cu -- grid-based keypoint replenishment: FAST-9 per empty cell, weakest corner wins.
+//
+// Replaces detect_key_points (reference src/feature_tracker/image_utilities.rs:108-175) with
+// num_points_in_cell == 1 (add_points, src/feature_tracker/feature_tracker.rs:222-251) and the
+// imageproc 0.25 functions it calls: corners_fast9, is_corner_fast9, fast_corner_score
+// (not vendored in the reference).
+//
+// What the reference does per empty cell: copy the g x g cell, then for thresholds 40,35,..,10
+// run corners_fast9 (raster order), stable-sort ascending by score and keep the first corner
+// that is at least 19 px from the image border.  The score is a binary search for the largest
+// threshold at which the pixel is still a corner.  Restated in closed form:
+//   score(p) = max over the 16 contiguous arcs of 9 circle pixels of
+//              max(min_arc(I - c), min_arc(c - I)) - 1            (strict inequalities)
+//   p is reported at threshold t iff score(p) >= t.
+// With class(p) = min(40, 5 * floor(score / 5)) the pick is the candidate of the highest class
+// with the smallest (score, raster index): one pass, one warp per cell, integer-only.
+// Candidates are the cell pixels [3, g-3)^2 (the FAST circle must fit inside the cell copy).
+#include "common.cuh"
+
+namespace rsvio {
+
+namespace {
+
+constexpr int kEdge = 19;  // EDGE_THRESHOLD, image_utilities.rs:114
+constexpr int kWarps = 8;
+
+__device__ __forceinline__ int min9_max16(const int (&b)[16]) {
+    // max over 16 cyclic windows of 9 of the window minimum, by doubling: 2, 4, 8, then +1
+    int m2[16], m4[16], m8[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m2[k] = min(b[k], b[(k + 1) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m4[k] = min(m2[k], m2[(k + 2) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m8[k] = min(m4[k], m4[(k + 4) & 15]);
+    int best = -1000;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) best = max(best, min(m8[k], b[(k + 8) & 15]));
+    return best;
+}
+
+// largest threshold at which (x, y) is a FAST-9 corner, < 10 if it is not one at threshold 10.
+// p points at the pixel, s is the row stride.
+__device__ __forceinline__ int fast9_score(const uint8_t *__restrict__ p, int s) {
+    const int c = __ldg(p);
+    const int p0 = __ldg(p - 3 * s), p4 = __ldg(p + 3), p8 = __ldg(p + 3 * s), p12 = __ldg(p - 3);
+    // quick reject at the lowest threshold used (10): two adjacent compass points must agree
+    const int hi = c + 10, lo = c - 10;
+    const bool above = (p0 > hi && p4 > hi) || (p4 > hi && p8 > hi) || (p8 > hi && p12 > hi) || (p12 > hi && p0 > hi);
+    const bool below = (p0 < lo && p4 < lo) || (p4 < lo && p8 < lo) || (p8 < lo && p12 < lo) || (p12 < lo && p0 < lo);
+    if (!above && !below) return -1;
+    int b[16];
+    b[0] = p0;
+    b[1] = __ldg(p - 3 * s + 1);
+    b[2] = __ldg(p - 2 * s + 2);
+    b[3] = __ldg(p - s + 3);
+    b[4] = p4;
+    b[5] = __ldg(p + s + 3);
+    b[6] = __ldg(p + 2 * s + 2);
+    b[7] = __ldg(p + 3 * s + 1);
+    b[8] = p8;
+    b[9] = __ldg(p + 3 * s - 1);
+    b[10] = __ldg(p + 2 * s - 2);
+    b[11] = __ldg(p + s - 3);
+    b[12] = p12;
+    b[13] = __ldg(p - s - 3);
+    b[14] = __ldg(p - 2 * s - 2);
+    b[15] = __ldg(p - 3 * s - 1);
+    int d[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        d[k] = c - b[k];
+        b[k] = b[k] - c;
+    }
+    return max(min9_max16(b), min9_max16(d)) - 1;
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+detect_cells_kernel(GridDesc gd, const uint8_t *__restrict__ img0, size_t stride, size_t pitch, int streams,
+                    const uint8_t *__restrict__ occ, uint32_t *__restrict__ cell_pt, float *__restrict__ cell_score) {
+    const int lane = threadIdx.x & 31;
+    const int cells = gd.ncx * gd.ncy;
+    const long long total = (long long)cells * streams;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int g = (int)gd.g;
+    const int side = g - 6;  // candidates per axis
+    for (long long item = warp0; item < total; item += n_warps) {
+        const int s = (int)(item / cells), cell = (int)(item - (long long)s * cells);
+        const int cx = cell / gd.ncy, cy = cell - cx * gd.ncy;  // visiting order: x outer, y inner
+        uint32_t best = 0;
+        const bool occupied = __ldg(occ + (size_t)s * gd.occ_rows * gd.occ_cols + (size_t)cy * gd.occ_cols + cx) != 0;
+        if (!occupied && side > 0) {
+            const int x0 = (int)gd.x_start + cx * g, y0 = (int)gd.y_start + cy * g;
+            const uint8_t *__restrict__ base = img0 + (size_t)s * pitch;
+            for (int idx = lane; idx < side * side; idx += 32) {
+                const int ly = idx / side + 3, lx = idx - (idx / side) * side + 3;
+                const int gx = x0 + lx, gy = y0 + ly;
+                // point_in_bound(.., 19): inclusive upper bound (image_utilities.rs:68-73)
+                if (gx < kEdge || gy < kEdge || gx > gd.w - kEdge || gy > gd.h - kEdge) continue;
+                const int sc = fast9_score(base + (size_t)gy * stride + gx, (int)stride);
+                if (sc < 10) continue;
+                const uint32_t cls = (uint32_t)(min(sc, 40) / 5);        // 2..8
+                const uint32_t raster = (uint32_t)(ly * g + lx);        // order inside the cell copy
+                const uint32_t key = (cls << 28) | ((uint32_t)(255 - sc) << 20) | (0xFFFFFu - raster);
+                best = max(best, key);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+        if (lane == 0) {
+            uint32_t pt = 0xFFFFFFFFu;
+            float score = 0.0f;
+            if (best != 0) {
+                const int sc = 255 - (int)((best >> 20) & 0xFFu);
+                const uint32_t raster = 0xFFFFFu - (best & 0xFFFFFu);
+                const uint32_t ly = raster / (uint32_t)g, lx = raster - ly * (uint32_t)g;
+                const uint32_t gx = gd.x_start + (uint32_t)cx * gd.g + lx, gy = gd.y_start + (uint32_t)cy * gd.g + ly;
+                pt = (gy << 16) | gx;
+                score = (float)sc;
+            }
+            cell_pt[(size_t)s * cells + cell] = pt;
+            cell_score[(size_t)s * cells + cell] = score;
+        }
+    }
+}
+
+// ordered compaction of one stream's cells (visiting order) into identity transforms
+__global__ void __launch_bounds__(256)
+collect_new_kernel(GridDesc gd, const uint32_t *__restrict__ cell_pt, const float *__restrict__ cell_score,
+                   float *__restrict__ new_T6, float *__restrict__ new_score, int *__restrict__ new_count,
+                   int new_cap, unsigned long long *counters) {
+    __shared__ int warp_tot[8];
+    __shared__ int base;
+    const int s = blockIdx.x;
+    const int cells = gd.ncx * gd.ncy;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < cells; c0 += 256) {
+        const int c = c0 + threadIdx.x;
+        const uint32_t pt = c < cells ? __ldg(cell_pt + (size_t)s * cells + c) : 0xFFFFFFFFu;
+        const bool has = pt != 0xFFFFFFFFu;
+        const unsigned m = __ballot_sync(0xffffffffu, has);
+        if (lane == 0) warp_tot[wid] = __popc(m);
+        __syncthreads();
+        int off = base;
+        for (int k = 0; k < wid; ++k) off += warp_tot[k];
+        const int rank = off + __popc(m & ((1u << lane) - 1u));
+        if (has && rank < new_cap) {
+            float *T = new_T6 + ((size_t)s * new_cap + rank) * 6;
+            T[0] = 1.0f; T[1] = 0.0f; T[2] = (float)(pt & 0xFFFFu);
+            T[3] = 0.0f; T[4] = 1.0f; T[5] = (float)(pt >> 16);
+            if (new_score) new_score[(size_t)s * new_cap + rank] = __ldg(cell_score + (size_t)s * cells + c);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int k = 0; k < 8; ++k) t += warp_tot[k];
+            base += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int n = base < new_cap ? base : new_cap;
+        new_count[s] = n;
+        if (counters) atomicAdd(counters + CNT_DETECTED, (unsigned long long)n);
+    }
+}
+
+__global__ void mark_occupancy_xy_kernel(GridDesc gd, const uint32_t *__restrict__ xy, int n, uint8_t *occ) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t x = xy[2 * i], y = xy[2 * i + 1];
+    const uint32_t x_end = gd.x_start + gd.g * (uint32_t)gd.ncx + 1, y_end = gd.y_start + gd.g * (uint32_t)gd.ncy + 1;
+    if (x >= gd.x_start && y >= gd.y_start && x < x_end && y < y_end)
+        occ[(size_t)((y - gd.y_start) / gd.g) * gd.occ_cols + (x - gd.x_start) / gd.g] = 1;
+}
+
+}  // namespace
+
+cudaError_t detect_cells(const GridDesc &gd, const uint8_t *img0, size_t stride, size_t pitch, int streams,
+                         const uint8_t *occ, uint32_t *cell_pt, float *cell_score, cudaStream_t st) {
+    const long long total = (long long)gd.ncx * gd.ncy * streams;
+    if (total <= 0) return cudaSuccess;
+    long long blocks = (total + kWarps - 1) / kWarps;
+    const long long max_blocks = (long long)kNumSMs * 8;
+    if (blocks > max_blocks) blocks = max_blocks;
+    detect_cells_kernel<<<(unsigned)blocks, kWarps * 32, 0, st>>>(gd, img0, stride, pitch, streams, occ, cell_pt,
+                                                                  cell_score);
+    return cudaGetLastError();
+}
+
+cudaError_t collect_new_points(const GridDesc &gd, int streams, const uint32_t *cell_pt, const float *cell_score,
+                               float *new_T6, float *new_score, int *new_count, int new_cap,
+                               unsigned long long *counters, cudaStream_t st) {
+    if (streams <= 0) return cudaSuccess;
+    collect_new_kernel<<<streams, 256, 0, st>>>(gd, cell_pt, cell_score, new_T6, new_score, new_count, new_cap,
+                                                counters);
+    return cudaGetLastError();
+}
+
+cudaError_t mark_occupancy_xy(const GridDesc &gd, const uint32_t *d_xy, int n, uint8_t *occ, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    mark_occupancy_xy_kernel<<<(n + 255) / 256, 256, 0, st>>>(gd, d_xy, n, occ);
+    return cudaGetLastError();
+}
+
+}  // namespace rsvio

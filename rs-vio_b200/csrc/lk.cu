@@ -1,0 +1,392 @@
+// lk.cu -- 52-point-pattern inverse-compositional SE(2) Lucas-Kanade, one warp per track.
+//
+// Replaces, fused into one launch per track_points call:
+//   track_points          reference src/feature_tracker/feature_tracker.rs:252-291
+//   track_one_point       feature_tracker.rs:292-342
+//   track_point_at_level  feature_tracker.rs:344-395
+//   Pattern52::new / set_data_jac_se2 / residual      src/feature_tracker/patch.rs:75-232
+//   image_grad / inbound / se2_exp_matrix             src/feature_tracker/image_utilities.rs:5-106
+//
+// Mapping: a warp owns one (point, forward+backward) chain.  Lane l holds pattern samples l and
+// l + 32 (the second one only for l < 20): template intensities, the three rows of H^-1 J^T and
+// the bilinear gathers live in registers; sums over the 52 samples are xor-butterfly shuffles
+// (every lane ends with the same value, so the 3x3 Cholesky solve, the SE(2) exponential and all
+// accept/reject decisions are computed redundantly per lane and stay warp-uniform).
+// Per-sample arithmetic follows the reference operation by operation (f32, no FMA contraction:
+// the library is built with -fmad=false); only the order of the 52-term sums differs (tree
+// instead of sequential), which is why positions agree with the CPU oracle to ~1e-5 px rather
+// than bit for bit.  Tensor cores are not used: nothing here is a dense contraction.
+#include "common.cuh"
+
+namespace rsvio {
+
+namespace {
+
+constexpr float kEps = 1.1920929e-07f;  // f32::EPSILON
+constexpr int kWarpsPerBlock = 4;
+
+struct Img {
+    const uint8_t *__restrict__ p;
+    int w, h;
+};
+
+__device__ __forceinline__ float px(const Img &im, uint32_t x, uint32_t y) {
+    return (float)__ldg(im.p + (size_t)y * (uint32_t)im.w + x);
+}
+
+// pattern sample i -> offset in pixels (PATTERN_RAW / pattern_scale_down, patch.rs:19-72,126-131)
+__device__ __forceinline__ void pattern_offset(int i, float &ox, float &oy) {
+    const int start[9] = {0, 4, 10, 18, 26, 34, 42, 48, 52};
+    const int half_w[8] = {3, 5, 7, 7, 7, 7, 5, 3};
+    int r = 0;
+#pragma unroll
+    for (int k = 1; k < 8; ++k) r += (i >= start[k]) ? 1 : 0;
+    int s = 0, hw = 3;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (r == k) {
+            s = start[k];
+            hw = half_w[k];
+        }
+    const int x = -hw + 2 * (i - s);
+    const int y = 7 - 2 * r;
+    ox = (float)x / 2.0f;
+    oy = (float)y / 2.0f;
+}
+
+// image_grad -- image_utilities.rs:5-66 (same products and sum order)
+__device__ __forceinline__ void image_grad(const Img &im, float x, float y, float &v, float &gx, float &gy) {
+    const uint32_t ix = sat_u32(floorf(x)), iy = sat_u32(floorf(y));
+    const float dx = x - (float)ix, dy = y - (float)iy;
+    const float ddx = 1.0f - dx, ddy = 1.0f - dy;
+    const float w00 = ddx * ddy, w01 = ddx * dy, w10 = dx * ddy, w11 = dx * dy;
+    const float p00 = px(im, ix, iy), p10 = px(im, ix + 1, iy), p01 = px(im, ix, iy + 1), p11 = px(im, ix + 1, iy + 1);
+    const float pm0 = px(im, ix - 1, iy), pm1 = px(im, ix - 1, iy + 1);
+    const float p20 = px(im, ix + 2, iy), p21 = px(im, ix + 2, iy + 1);
+    const float p0m = px(im, ix, iy - 1), p1m = px(im, ix + 1, iy - 1);
+    const float p02 = px(im, ix, iy + 2), p12 = px(im, ix + 1, iy + 2);
+    v = w00 * p00 + w01 * p01 + w10 * p10 + w11 * p11;
+    const float res_mx = w00 * pm0 + w01 * pm1 + w10 * p00 + w11 * p01;
+    const float res_px = w00 * p10 + w01 * p11 + w10 * p20 + w11 * p21;
+    gx = 0.5f * (res_px - res_mx);
+    const float res_my = w00 * p0m + w01 * p00 + w10 * p1m + w11 * p10;
+    const float res_py = w00 * p01 + w01 * p02 + w10 * p11 + w11 * p12;
+    gy = 0.5f * (res_py - res_my);
+}
+
+// nalgebra Cholesky::new + solve_mut(identity) for a 3x3 -- patch.rs:143-147
+__device__ __forceinline__ bool chol3_inverse(const float H[3][3], float Hinv[3][3]) {
+    float m[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) m[i][j] = H[i][j];
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+#pragma unroll
+        for (int k = 0; k < j; ++k) {
+            const float factor = -m[j][k];
+#pragma unroll
+            for (int i = j; i < 3; ++i) m[i][j] = factor * m[i][k] + m[i][j];
+        }
+        const float diag = m[j][j];
+        ok = ok && (diag != 0.0f) && (diag >= 0.0f);
+        const float denom = sqrtf(diag);
+        m[j][j] = denom;
+#pragma unroll
+        for (int i = j + 1; i < 3; ++i) m[i][j] = m[i][j] / denom;
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float b[3] = {c == 0 ? 1.0f : 0.0f, c == 1 ? 1.0f : 0.0f, c == 2 ? 1.0f : 0.0f};
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float coeff = b[i] / m[i][i];
+            b[i] = coeff;
+#pragma unroll
+            for (int r = i + 1; r < 3; ++r) b[r] = (-coeff) * m[r][i] + b[r];
+        }
+        b[2] = (b[2] - 0.0f) / m[2][2];
+        b[1] = (b[1] - m[2][1] * b[2]) / m[1][1];
+        b[0] = (b[0] - (m[1][0] * b[1] + m[2][0] * b[2])) / m[0][0];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) Hinv[i][c] = b[i];
+    }
+    return ok;
+}
+
+// se2_exp_matrix -- image_utilities.rs:82-106
+__device__ __forceinline__ void se2_exp(const float a[3], float m[6]) {
+    const float theta = a[2];
+    float sn, cs;
+    sincosf(theta, &sn, &cs);
+    float s_by_t, omc_by_t;
+    if (fabsf(theta) < kEps) {
+        const float t2 = theta * theta;
+        s_by_t = 1.0f - 1.0f / 6.0f * t2;
+        omc_by_t = 0.5f * theta - 1.0f / 24.0f * theta * t2;
+    } else {
+        s_by_t = sn / theta;
+        omc_by_t = (1.0f - cs) / theta;
+    }
+    m[0] = cs;
+    m[1] = -sn;
+    m[3] = sn;
+    m[4] = cs;
+    m[2] = s_by_t * a[0] - omc_by_t * a[1];
+    m[5] = omc_by_t * a[0] + s_by_t * a[1];
+}
+
+__device__ __forceinline__ bool finite3(const float a[3]) {
+    return isfinite(a[0]) && isfinite(a[1]) && isfinite(a[2]);
+}
+
+// Per-lane state of the lane's two pattern samples
+struct Lane {
+    float ox[2], oy[2];
+    bool has[2];
+};
+
+// track_one_point (feature_tracker.rs:292-342): coarse-to-fine, template from pyramid A at the
+// un-rotated source position, running transform keeps its rotation across levels.
+__device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A, const uint8_t *__restrict__ B,
+                               const float T0[6], float T1[6], int max_it, float thr, const Lane &ln,
+                               unsigned &n_iters, unsigned &n_templates) {
+    T1[0] = 1.0f; T1[1] = 0.0f; T1[2] = T0[2];
+    T1[3] = 0.0f; T1[4] = 1.0f; T1[5] = T0[5];
+    for (int lev = pd.levels - 1; lev >= 0; --lev) {
+        const float s = (float)(1 << lev);
+        T1[2] = T1[2] / s;
+        T1[5] = T1[5] / s;
+        const Img ia{A + pd.lv[lev].off, pd.lv[lev].w, pd.lv[lev].h};
+        const Img ib{B + pd.lv[lev].off, pd.lv[lev].w, pd.lv[lev].h};
+        const float pxx = T0[2] / s, pyy = T0[5] / s;
+
+        // ---- Pattern52::new (patch.rs:124-162) --------------------------------------------
+        float d[2], J[2][3];
+        float sum = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
+        int n_valid = 0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            d[k] = -1.0f;
+            J[k][0] = J[k][1] = J[k][2] = 0.0f;
+            const float x = pxx + ln.ox[k], y = pyy + ln.oy[k];
+            const bool ok = ln.has[k] && inbound(ia.w, ia.h, x, y, 2);
+            if (ok) {
+                float v, gx, gy;
+                image_grad(ia, x, y, v, gx, gy);
+                d[k] = v;
+                J[k][0] = gx * 1.0f + gy * 0.0f;
+                J[k][1] = gx * 0.0f + gy * 1.0f;
+                J[k][2] = gx * (-ln.oy[k]) + gy * ln.ox[k];
+                sum += v;
+                g0 += J[k][0];
+                g1 += J[k][1];
+                g2 += J[k][2];
+            }
+            n_valid += __popc(__ballot_sync(0xffffffffu, ok));
+        }
+        ++n_templates;
+        sum = warp_sum(sum);
+        g0 = warp_sum(g0);
+        g1 = warp_sum(g1);
+        g2 = warp_sum(g2);
+        const float mean = sum / (float)n_valid;
+        const float mean_inv = (float)n_valid / sum;
+        float h00 = 0.f, h01 = 0.f, h02 = 0.f, h11 = 0.f, h12 = 0.f, h22 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (d[k] >= 0.0f) {
+                J[k][0] += -(g0 * d[k] / sum);
+                J[k][1] += -(g1 * d[k] / sum);
+                J[k][2] += -(g2 * d[k] / sum);
+                d[k] *= mean_inv;
+            } else {
+                J[k][0] = J[k][1] = J[k][2] = 0.0f;
+            }
+            J[k][0] *= mean_inv;
+            J[k][1] *= mean_inv;
+            J[k][2] *= mean_inv;
+            if (ln.has[k]) {
+                h00 += J[k][0] * J[k][0];
+                h01 += J[k][0] * J[k][1];
+                h02 += J[k][0] * J[k][2];
+                h11 += J[k][1] * J[k][1];
+                h12 += J[k][1] * J[k][2];
+                h22 += J[k][2] * J[k][2];
+            }
+        }
+        float H[3][3], Hinv[3][3];
+        H[0][0] = warp_sum(h00);
+        H[0][1] = H[1][0] = warp_sum(h01);
+        H[0][2] = H[2][0] = warp_sum(h02);
+        H[1][1] = warp_sum(h11);
+        H[1][2] = H[2][1] = warp_sum(h12);
+        H[2][2] = warp_sum(h22);
+        bool valid = chol3_inverse(H, Hinv);
+        float M[2][3];
+        bool fin = true;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                M[k][r] = Hinv[r][0] * J[k][0] + Hinv[r][1] * J[k][1] + Hinv[r][2] * J[k][2];
+                fin = fin && (!ln.has[k] || isfinite(M[k][r]));
+            }
+            fin = fin && (!ln.has[k] || isfinite(d[k]));
+        }
+        valid = valid && (mean > kEps) && __all_sync(0xffffffffu, fin);
+        if (!valid) return RSVIO_FAIL_TEMPLATE;
+
+        // ---- track_point_at_level (feature_tracker.rs:344-395) ----------------------------
+        const float wlim = (float)((uint32_t)ib.w - 2u), hlim = (float)((uint32_t)ib.h - 2u);
+        for (int it = 0; it < max_it; ++it) {
+            ++n_iters;
+            float r[2];
+            float rsum = 0.0f;
+            int nv = 0;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const float x = (T1[0] * ln.ox[k] + T1[1] * ln.oy[k]) + T1[2];
+                const float y = (T1[3] * ln.ox[k] + T1[4] * ln.oy[k]) + T1[5];
+                const bool ok = ln.has[k] && x >= 2.0f && y >= 2.0f && x < wlim && y < hlim;
+                r[k] = -1.0f;
+                if (ok) {
+                    const uint32_t ix = sat_u32(floorf(x)), iy = sat_u32(floorf(y));
+                    const float dx = x - (float)ix, dy = y - (float)iy;
+                    const float ddx = 1.0f - dx, ddy = 1.0f - dy;
+                    const float p00 = px(ib, ix, iy), p10 = px(ib, ix + 1, iy);
+                    const float p01 = px(ib, ix, iy + 1), p11 = px(ib, ix + 1, iy + 1);
+                    r[k] = ddx * ddy * p00 + ddx * dy * p01 + dx * ddy * p10 + dx * dy * p11;
+                    rsum += r[k];
+                }
+                nv += __popc(__ballot_sync(0xffffffffu, ok));
+            }
+            rsum = warp_sum(rsum);
+            if (rsum < kEps) return RSVIO_FAIL_RESIDUAL;
+            int nres = 0;
+            float i0 = 0.0f, i1 = 0.0f, i2 = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const bool both = ln.has[k] && r[k] >= 0.0f && d[k] >= 0.0f;
+                const float res = both ? (float)nv * r[k] / rsum - d[k] : 0.0f;
+                nres += __popc(__ballot_sync(0xffffffffu, both));
+                i0 += (-M[k][0]) * res;
+                i1 += (-M[k][1]) * res;
+                i2 += (-M[k][2]) * res;
+            }
+            if (nres <= kPattern / 2) return RSVIO_FAIL_RESIDUAL;
+            float inc[3];
+            inc[0] = warp_sum(i0);
+            inc[1] = warp_sum(i1);
+            inc[2] = warp_sum(i2);
+            if (!finite3(inc)) return RSVIO_FAIL_NONFINITE;
+            const float norm = sqrtf(inc[0] * inc[0] + inc[1] * inc[1] + inc[2] * inc[2]);
+            if (norm > 1e6f) return RSVIO_FAIL_DIVERGED;
+            if (norm < thr) break;  // converged: increment not applied (feature_tracker.rs:374-376)
+            float E[6], N[6];
+            se2_exp(inc, E);
+            N[0] = T1[0] * E[0] + T1[1] * E[3];
+            N[1] = T1[0] * E[1] + T1[1] * E[4];
+            N[2] = T1[0] * E[2] + T1[1] * E[5] + T1[2];
+            N[3] = T1[3] * E[0] + T1[4] * E[3];
+            N[4] = T1[3] * E[1] + T1[4] * E[4];
+            N[5] = T1[3] * E[2] + T1[4] * E[5] + T1[5];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) T1[k] = N[k];
+            if (!inbound(ib.w, ib.h, T1[2], T1[5], 2)) return RSVIO_FAIL_OOB;
+        }
+        T1[2] = T1[2] * s;
+        T1[5] = T1[5] * s;
+    }
+    // rotation block of T0 * T1 (feature_tracker.rs:335-340)
+    const float r00 = T0[0] * T1[0] + T0[1] * T1[3];
+    const float r01 = T0[0] * T1[1] + T0[1] * T1[4];
+    const float r10 = T0[3] * T1[0] + T0[4] * T1[3];
+    const float r11 = T0[3] * T1[1] + T0[4] * T1[4];
+    T1[0] = r00; T1[1] = r01; T1[3] = r10; T1[4] = r11;
+    return RSVIO_TRACK_OK;
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+lk_track_fb_kernel(PyrDesc pd, LkBatch b) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    Lane ln;
+    pattern_offset(lane, ln.ox[0], ln.oy[0]);
+    ln.has[0] = true;
+    ln.has[1] = lane + 32 < kPattern;
+    pattern_offset(ln.has[1] ? lane + 32 : 0, ln.ox[1], ln.oy[1]);
+
+    unsigned n_iters = 0, n_templates = 0, n_tracks = 0;
+    const int total = b.groups * b.cap;
+    for (int item = warp; item < total; item += n_warps) {
+        const int g = item / b.cap, k = item - g * b.cap;
+        if (k >= __ldg(b.counts + g)) continue;
+        const uint8_t *A = b.pyr_a + (size_t)g * pd.pyr_stride;
+        const uint8_t *B = b.pyr_b + (size_t)g * pd.pyr_stride;
+        float T0[6], Tf[6], Tb[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) T0[q] = __ldg(b.in_T6 + (size_t)item * 6 + q);
+        unsigned it_f = 0, it_b = 0;
+        int st = track_one_point(pd, A, B, T0, Tf, b.max_it, b.thr, ln, it_f, n_templates);
+        if (st == RSVIO_TRACK_OK) {
+            st = track_one_point(pd, B, A, Tf, Tb, b.max_it, b.thr, ln, it_b, n_templates);
+            if (st != RSVIO_TRACK_OK) {
+                st += RSVIO_FAIL_BACKWARD;
+            } else {  // forward-backward consistency (feature_tracker.rs:277-281)
+                const float dx = T0[2] - Tb[2], dy = T0[5] - Tb[5];
+                if (!(dx * dx + dy * dy < 0.4f)) st = RSVIO_FAIL_FB;
+            }
+        }
+        n_iters += it_f + it_b;
+        ++n_tracks;
+        if (lane < 6) b.out_T6[(size_t)item * 6 + lane] = Tf[lane];
+        if (lane == 0) {
+            b.status[item] = st;
+            if (b.iters) {
+                b.iters[(size_t)item * 2] = (int)it_f;
+                b.iters[(size_t)item * 2 + 1] = (int)it_b;
+            }
+        }
+    }
+    if (b.counters && lane == 0 && n_tracks) {
+        atomicAdd(b.counters + CNT_TRACKS, (unsigned long long)n_tracks);
+        atomicAdd(b.counters + CNT_ITERS, (unsigned long long)n_iters);
+        atomicAdd(b.counters + CNT_TEMPLATES, (unsigned long long)n_templates);
+    }
+}
+
+__global__ void se2_exp_kernel(const float *__restrict__ tw, int n, float *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a[3] = {tw[3 * i], tw[3 * i + 1], tw[3 * i + 2]};
+    float m[6];
+    se2_exp(a, m);
+    float *o = out + (size_t)9 * i;
+    o[0] = m[0]; o[1] = m[1]; o[2] = m[2];
+    o[3] = m[3]; o[4] = m[4]; o[5] = m[5];
+    o[6] = 0.0f; o[7] = 0.0f; o[8] = 1.0f;
+}
+
+}  // namespace
+
+cudaError_t lk_track(const PyrDesc &pd, const LkBatch &b, cudaStream_t st) {
+    const long long total = (long long)b.groups * b.cap;
+    if (total <= 0) return cudaSuccess;
+    long long blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const long long max_blocks = (long long)kNumSMs * 16;  // 64 warps per SM resident at most
+    if (blocks > max_blocks) blocks = max_blocks;
+    lk_track_fb_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(pd, b);
+    return cudaGetLastError();
+}
+
+cudaError_t se2_exp_batch(const float *d_twists, int n, float *d_out9, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    se2_exp_kernel<<<(n + 127) / 128, 128, 0, st>>>(d_twists, n, d_out9);
+    return cudaGetLastError();
+}
+
+}  // namespace rsvio

@@ -1,0 +1,216 @@
+// tracks.cu -- device-resident track tables: survivor compaction, occupancy grid, id assignment,
+// packed output.
+//
+// Replaces the HashMap bookkeeping of StereoPatchTracker::process_frame
+// (reference src/feature_tracker/feature_tracker.rs:116-187):
+//   :125-138  tracked_points_map_cam{0,1} = track_points(..)   -> compact_tracks_kernel
+//   :228-239  add_points: rounded tracked positions -> occupancy (image_utilities.rs:128-139)
+//   :143-170  tmp maps, stereo match, `last_keypoint_id += 1` -> merge_new_kernel
+//   :177-186  frame.add_left_feature / add_right_feature      -> packed (id, x, y) records
+//   :201-206  remove_id                                        -> remove_ids_kernel
+// Tables stay sorted by id: survivors keep their order, new ids are larger than all old ones and
+// are handed out in ascending detection order (the reference uses HashMap iteration order, which
+// is randomly seeded, so ids are only defined up to relabelling there).
+#include "common.cuh"
+
+namespace rsvio {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+// block-wide stable compaction helper: returns the output rank of this thread's element
+// (valid only when keep), advances *base by the number kept in this chunk.
+__device__ __forceinline__ int block_rank(bool keep, int *warp_tot, int *base) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_tot[wid] = __popc(m);
+    __syncthreads();
+    int off = *base;
+    for (int k = 0; k < wid; ++k) off += warp_tot[k];
+    const int rank = off + __popc(m & ((1u << lane) - 1u));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < kWarps; ++k) t += warp_tot[k];
+        *base += t;
+    }
+    __syncthreads();
+    return rank;
+}
+
+__global__ void __launch_bounds__(kThreads)
+compact_tracks_kernel(TableView in, const float *__restrict__ lk_T6, const int32_t *__restrict__ lk_status,
+                      TableView out, int cap, int streams, GridDesc gd, uint8_t *__restrict__ occ, int have_prev,
+                      unsigned long long *counters) {
+    __shared__ int warp_tot[kWarps];
+    __shared__ int base;
+    const int g = blockIdx.x;
+    const int n = in.counts[g];
+    const bool cam0 = g < streams;
+    uint8_t *my_occ = occ + (size_t)g * gd.occ_rows * gd.occ_cols;  // only used when cam0
+    if (threadIdx.x == 0) base = 0;
+    if (cam0)
+        for (int i = threadIdx.x; i < gd.occ_rows * gd.occ_cols; i += kThreads) my_occ[i] = 0;
+    __syncthreads();
+    const uint32_t x_end = gd.x_start + gd.g * (uint32_t)gd.ncx + 1, y_end = gd.y_start + gd.g * (uint32_t)gd.ncy + 1;
+    for (int c0 = 0; c0 < n; c0 += kThreads) {
+        const int k = c0 + threadIdx.x;
+        const size_t src = (size_t)g * cap + k;
+        bool keep = false;
+        float T[6];
+        if (k < n) {
+            // first frame after create/reset: nothing was tracked, the table is carried over as is
+            keep = have_prev ? (lk_status[src] == RSVIO_TRACK_OK) : true;
+            const float *ps = have_prev ? lk_T6 + src * 6 : in.T6 + src * 6;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) T[q] = ps[q];
+        }
+        const int rank = block_rank(keep, warp_tot, &base);
+        if (keep) {
+            const size_t dst = (size_t)g * cap + rank;
+            out.ids[dst] = in.ids[src];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) out.T6[dst * 6 + q] = T[q];
+            if (cam0) {  // add_points: Corner::new(round(x) as u32, round(y) as u32)
+                const uint32_t x = sat_u32(roundf(T[2])), y = sat_u32(roundf(T[5]));
+                if (x >= gd.x_start && y >= gd.y_start && x < x_end && y < y_end)
+                    my_occ[(size_t)((y - gd.y_start) / gd.g) * gd.occ_cols + (x - gd.x_start) / gd.g] = 1;
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        out.counts[g] = base;
+        if (counters && g == 0) atomicAdd(counters + CNT_FRAMES, (unsigned long long)streams);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+merge_new_kernel(TableView tab, int streams, int cap, int stereo, const float *__restrict__ new_T6,
+                 const float *__restrict__ st_T6, const int32_t *__restrict__ st_status,
+                 const int *__restrict__ new_count, int new_cap, unsigned long long *__restrict__ last_id,
+                 int *err_flag, OutRecord *__restrict__ out_rec, int *__restrict__ out_counts) {
+    __shared__ int warp_tot[kWarps];
+    __shared__ int base;
+    const int s = blockIdx.x;
+    const int n_new = new_count[s];
+    const int g0 = s, g1 = streams + s;
+    const int n0 = tab.counts[g0];
+    const int n1 = stereo ? tab.counts[g1] : 0;
+    const unsigned long long id0 = last_id[s];
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < n_new; c0 += kThreads) {
+        const int k = c0 + threadIdx.x;
+        const size_t src = (size_t)s * new_cap + k;
+        const bool keep = k < n_new && (!stereo || st_status[src] == RSVIO_TRACK_OK);
+        const int rank = block_rank(keep, warp_tot, &base);
+        if (keep) {
+            if (n0 + rank < cap && n1 + rank < cap) {
+                const size_t d0 = (size_t)g0 * cap + n0 + rank;
+                tab.ids[d0] = id0 + (unsigned long long)rank;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) tab.T6[d0 * 6 + q] = new_T6[src * 6 + q];
+                if (stereo) {
+                    const size_t d1 = (size_t)g1 * cap + n1 + rank;
+                    tab.ids[d1] = id0 + (unsigned long long)rank;
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) tab.T6[d1 * 6 + q] = st_T6[src * 6 + q];
+                }
+            } else {
+                atomicExch(err_flag, 1);
+            }
+        }
+    }
+    __syncthreads();
+    int add = base;
+    if (n0 + add > cap) add = cap - n0;
+    if (stereo && n1 + add > cap) add = cap - n1 < add ? cap - n1 : add;
+    if (add < 0) add = 0;
+    const int f0 = n0 + add, f1 = stereo ? n1 + add : 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tab.counts[g0] = f0;
+        if (stereo) tab.counts[g1] = f1;
+        last_id[s] = id0 + (unsigned long long)add;
+        out_counts[g0] = f0;
+        out_counts[g1] = f1;
+    }
+    // packed output (mapped host memory): get_track_points / frame population
+    for (int k = threadIdx.x; k < f0; k += kThreads) {
+        const size_t i = (size_t)g0 * cap + k;
+        OutRecord r;
+        r.id = tab.ids[i];
+        r.x = tab.T6[i * 6 + 2];
+        r.y = tab.T6[i * 6 + 5];
+        out_rec[i] = r;
+    }
+    for (int k = threadIdx.x; k < f1; k += kThreads) {
+        const size_t i = (size_t)g1 * cap + k;
+        OutRecord r;
+        r.id = tab.ids[i];
+        r.x = tab.T6[i * 6 + 2];
+        r.y = tab.T6[i * 6 + 5];
+        out_rec[i] = r;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+remove_ids_kernel(TableView in, TableView out, int cap, int streams, int stream,
+                  const unsigned long long *__restrict__ rm, int n_rm) {
+    __shared__ int warp_tot[kWarps];
+    __shared__ int base;
+    const int g = blockIdx.x;
+    const int n = in.counts[g];
+    const bool affected = (g % streams) == stream;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < n; c0 += kThreads) {
+        const int k = c0 + threadIdx.x;
+        const size_t src = (size_t)g * cap + k;
+        bool keep = k < n;
+        unsigned long long id = 0;
+        if (keep) {
+            id = in.ids[src];
+            if (affected)
+                for (int j = 0; j < n_rm; ++j) keep = keep && (rm[j] != id);
+        }
+        const int rank = block_rank(keep, warp_tot, &base);
+        if (keep) {
+            const size_t dst = (size_t)g * cap + rank;
+            out.ids[dst] = id;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) out.T6[dst * 6 + q] = in.T6[src * 6 + q];
+        }
+    }
+    if (threadIdx.x == 0) out.counts[g] = base;
+}
+
+}  // namespace
+
+cudaError_t compact_tracks(const TableView &in, const float *lk_T6, const int32_t *lk_status, const TableView &out,
+                           int groups, int cap, int streams, const GridDesc &gd, uint8_t *occ, int have_prev,
+                           unsigned long long *counters, cudaStream_t st) {
+    compact_tracks_kernel<<<groups, kThreads, 0, st>>>(in, lk_T6, lk_status, out, cap, streams, gd, occ, have_prev,
+                                                       counters);
+    return cudaGetLastError();
+}
+
+cudaError_t merge_new_points(const TableView &tab, int streams, int cap, int stereo, const float *new_T6,
+                             const float *st_T6, const int32_t *st_status, const int *new_count, int new_cap,
+                             unsigned long long *last_id, int *err_flag, OutRecord *out_rec, int *out_counts,
+                             unsigned long long *counters, cudaStream_t st) {
+    (void)counters;
+    merge_new_kernel<<<streams, kThreads, 0, st>>>(tab, streams, cap, stereo, new_T6, st_T6, st_status, new_count,
+                                                   new_cap, last_id, err_flag, out_rec, out_counts);
+    return cudaGetLastError();
+}
+
+cudaError_t remove_ids(const TableView &in, const TableView &out, int groups, int cap, int streams, int stream,
+                       const unsigned long long *d_ids, int n, cudaStream_t st) {
+    remove_ids_kernel<<<groups, kThreads, 0, st>>>(in, out, cap, streams, stream, d_ids, n);
+    return cudaGetLastError();
+}
+
+}  // namespace rsvio

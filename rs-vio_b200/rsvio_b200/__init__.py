@@ -1,0 +1,13 @@
+"""rsvio_b200 -- Python host side of the B200-native stereo patch tracker.
+
+Thin ctypes layer over the C ABI in include/rsvio_b200.h (librsvio_b200.so, CUDA sm_100a) that
+mirrors the reference's tracker API (src/feature_tracker/feature_tracker.rs): StereoPatchTracker,
+PatchTracker, Feature.  There is no CPU fallback: loading fails loudly when the library is missing
+and every call fails with RsvioError when no CUDA device is usable.
+"""
+from .binding import (  # noqa: F401
+    ABI_SYMBOLS, Feature, PatchTracker, RsvioError, StereoPatchTracker, build_library, build_pyramid,
+    detect_keypoints, device_count, library_path, load_library, pyramid_bytes, se2_exp, split_pyramid,
+    track_points,
+)
+from . import synth  # noqa: F401

@@ -1,0 +1,366 @@
+"""ctypes binding of librsvio_b200.so -- every call goes through the C ABI of include/rsvio_b200.h.
+
+Class and method names follow the reference (src/feature_tracker/feature_tracker.rs):
+  StereoPatchTracker::new / process_frame / get_track_points / remove_id   (:103, :116, :188, :201)
+  PatchTracker::process_frame / get_track_points / remove_id               (:43, :78, :84)
+  Feature::new                                                             (:25)
+"""
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)                      # rs-vio_b200/
+_LIB_PATH = os.path.join(_ROOT, "lib", "librsvio_b200.so")
+
+OK, ERR_INVALID_ARG, ERR_CUDA, ERR_CAPACITY, ERR_STATE, ERR_ALLOC = 0, -1, -2, -3, -4, -5
+TRACK_OK, FAIL_TEMPLATE, FAIL_RESIDUAL, FAIL_NONFINITE, FAIL_DIVERGED, FAIL_OOB, FAIL_FB = range(7)
+FAIL_BACKWARD = 16
+MODE_STEREO, MODE_MONO = 0, 1
+N_STAGES = 8
+STAGE_NAMES = ("upload", "pyramid", "lk_temporal", "compact", "detect", "lk_stereo", "merge", "download")
+
+# every symbol include/rsvio_b200.h declares
+ABI_SYMBOLS = (
+    "rsvio_abi_version", "rsvio_status_string", "rsvio_device_count", "rsvio_config_default",
+    "rsvio_host_alloc", "rsvio_host_free",
+    "rsvio_tracker_create", "rsvio_tracker_destroy", "rsvio_tracker_last_error", "rsvio_tracker_reset",
+    "rsvio_tracker_process_stereo", "rsvio_tracker_process_mono", "rsvio_tracker_process_batch",
+    "rsvio_tracker_submit_batch", "rsvio_tracker_sync", "rsvio_tracker_submit_device",
+    "rsvio_tracker_num_tracks", "rsvio_tracker_get_tracks", "rsvio_tracker_get_transforms",
+    "rsvio_tracker_remove_ids", "rsvio_tracker_counters", "rsvio_tracker_set_profiling",
+    "rsvio_tracker_stage_times",
+    "rsvio_pyramid_bytes", "rsvio_pyramid_device_bytes", "rsvio_build_pyramid_u8",
+    "rsvio_build_pyramid_u8_device", "rsvio_track_points", "rsvio_detect_keypoints", "rsvio_se2_exp",
+)
+
+
+class RsvioError(RuntimeError):
+    def __init__(self, status, msg=""):
+        self.status = status
+        super().__init__(f"rsvio status {status}: {msg}")
+
+
+class Config(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("levels", C.c_int32), ("grid_size", C.c_uint32),
+                ("max_iterations", C.c_int32), ("convergence_threshold", C.c_float), ("mode", C.c_int32),
+                ("n_streams", C.c_int32), ("device", C.c_int32), ("max_tracks", C.c_int32),
+                ("cuda_stream", C.c_void_p)]
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def build_library(force=False, verbose=False):
+    """Compile csrc/*.cu for sm_100a with the package Makefile (nvcc cross-compiles without a GPU)."""
+    args = ["make", "-C", _ROOT, "-j8"]
+    if force:
+        args.insert(1, "-B")
+    subprocess.run(args, check=True, stdout=None if verbose else subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+_u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+
+
+def load_library():
+    """dlopen librsvio_b200.so.  Raises (never falls back) when the CUDA extension is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RsvioError(ERR_CUDA, f"{_LIB_PATH} is missing: build it with `make -C {_ROOT}` "
+                                   "(there is no CPU fallback)")
+    L = C.CDLL(_LIB_PATH)
+    st = C.c_int32
+    H = C.c_void_p
+    L.rsvio_abi_version.restype = C.c_int32
+    L.rsvio_status_string.restype = C.c_char_p
+    L.rsvio_status_string.argtypes = [st]
+    L.rsvio_device_count.argtypes = [C.POINTER(C.c_int32)]
+    L.rsvio_config_default.restype = None
+    L.rsvio_config_default.argtypes = [C.POINTER(Config)]
+    L.rsvio_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    L.rsvio_host_free.argtypes = [C.c_void_p]
+    L.rsvio_tracker_create.argtypes = [C.POINTER(Config), C.POINTER(H)]
+    L.rsvio_tracker_destroy.restype = None
+    L.rsvio_tracker_destroy.argtypes = [H]
+    L.rsvio_tracker_last_error.restype = C.c_char_p
+    L.rsvio_tracker_last_error.argtypes = [H]
+    L.rsvio_tracker_reset.argtypes = [H]
+    L.rsvio_tracker_process_stereo.argtypes = [H, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.rsvio_tracker_process_mono.argtypes = [H, C.c_void_p, C.c_size_t]
+    L.rsvio_tracker_process_batch.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t]
+    L.rsvio_tracker_submit_batch.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_size_t]
+    L.rsvio_tracker_sync.argtypes = [H]
+    L.rsvio_tracker_submit_device.argtypes = [H, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    L.rsvio_tracker_num_tracks.argtypes = [H, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
+    L.rsvio_tracker_get_tracks.argtypes = [H, C.c_int32, C.c_int32, _u64p, _f32p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.rsvio_tracker_get_transforms.argtypes = [H, C.c_int32, C.c_int32, _u64p, _f32p, C.c_size_t,
+                                               C.POINTER(C.c_size_t)]
+    L.rsvio_tracker_remove_ids.argtypes = [H, C.c_int32, _u64p, C.c_size_t]
+    L.rsvio_tracker_counters.argtypes = [H, _u64p]
+    L.rsvio_tracker_set_profiling.argtypes = [H, C.c_int32]
+    L.rsvio_tracker_stage_times.argtypes = [H, _f32p, _u64p, C.c_int32]
+    L.rsvio_pyramid_bytes.restype = C.c_size_t
+    L.rsvio_pyramid_bytes.argtypes = [C.c_int32] * 3
+    L.rsvio_pyramid_device_bytes.restype = C.c_size_t
+    L.rsvio_pyramid_device_bytes.argtypes = [C.c_int32] * 3
+    L.rsvio_build_pyramid_u8.argtypes = [C.c_int32, _u8p, C.c_int32, C.c_int32, C.c_int32, C.c_size_t, C.c_size_t,
+                                         C.c_int32, _u8p]
+    L.rsvio_build_pyramid_u8_device.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_size_t,
+                                                C.c_size_t, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_float)]
+    L.rsvio_track_points.argtypes = [C.c_int32, _u8p, _u8p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _f32p,
+                                     C.c_int32, C.c_float, _f32p, _i32p, _i32p]
+    L.rsvio_detect_keypoints.argtypes = [C.c_int32, _u8p, C.c_int32, C.c_int32, C.c_size_t, C.c_uint32, _u32p,
+                                         C.c_int32, _u32p, _f32p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.rsvio_se2_exp.argtypes = [C.c_int32, _f32p, C.c_int32, _f32p]
+    _lib = L
+    return L
+
+
+def _check(status, handle=None):
+    if status != OK:
+        L = load_library()
+        msg = L.rsvio_status_string(status).decode()
+        if handle:
+            detail = L.rsvio_tracker_last_error(handle).decode()
+            if detail:
+                msg += ": " + detail
+        raise RsvioError(status, msg)
+
+
+def device_count():
+    n = C.c_int32(0)
+    load_library().rsvio_device_count(C.byref(n))
+    return n.value
+
+
+# ---- stateless entry points ---------------------------------------------------------------
+def pyramid_bytes(w, h, levels):
+    return load_library().rsvio_pyramid_bytes(w, h, levels)
+
+
+def split_pyramid(buf, w0, h0, levels):
+    out, off = [], 0
+    for i in range(levels):
+        w, h = w0 >> i, h0 >> i
+        out.append(buf[off:off + w * h].reshape(h, w))
+        off += w * h
+    return out
+
+
+def build_pyramid(images, levels, device=0):
+    """images: (h, w) or (n, h, w) uint8.  Returns (n, pyramid_bytes) uint8 (flat dense pyramids)."""
+    a = np.ascontiguousarray(images, np.uint8)
+    if a.ndim == 2:
+        a = a[None]
+    n, h, w = a.shape
+    out = np.empty((n, pyramid_bytes(w, h, levels)), np.uint8)
+    _check(load_library().rsvio_build_pyramid_u8(device, a, n, w, h, w, w * h, levels, out))
+    return out
+
+
+def track_points(pyr_a, pyr_b, w0, h0, levels, in_T6, max_it, thr, device=0):
+    in_T6 = np.ascontiguousarray(in_T6, np.float32).reshape(-1, 6)
+    n = in_T6.shape[0]
+    out_T = np.zeros((max(n, 1), 6), np.float32)
+    status = np.zeros(max(n, 1), np.int32)
+    iters = np.zeros((max(n, 1), 2), np.int32)
+    _check(load_library().rsvio_track_points(device, np.ascontiguousarray(pyr_a, np.uint8),
+                                             np.ascontiguousarray(pyr_b, np.uint8), w0, h0, levels, n, in_T6, max_it,
+                                             thr, out_T, status, iters))
+    return out_T[:n], status[:n], iters[:n]
+
+
+def detect_keypoints(image, grid, cur_xy=None, device=0):
+    img = np.ascontiguousarray(image, np.uint8)
+    h, w = img.shape
+    cur = np.zeros((0, 2), np.uint32) if cur_xy is None else np.ascontiguousarray(cur_xy, np.uint32).reshape(-1, 2)
+    cap = max(1, (h // grid) * (w // grid))
+    xy = np.zeros((cap, 2), np.uint32)
+    sc = np.zeros(cap, np.float32)
+    n = C.c_size_t(0)
+    cur_arg = cur if cur.shape[0] else np.zeros((1, 2), np.uint32)
+    _check(load_library().rsvio_detect_keypoints(device, img, w, h, w, grid, cur_arg, cur.shape[0], xy, sc, cap,
+                                                 C.byref(n)))
+    return xy[:n.value].copy(), sc[:n.value].copy()
+
+
+def se2_exp(twists, device=0):
+    tw = np.ascontiguousarray(twists, np.float32).reshape(-1, 3)
+    out = np.zeros((tw.shape[0], 9), np.float32)
+    _check(load_library().rsvio_se2_exp(device, tw, tw.shape[0], out))
+    return out.reshape(-1, 3, 3)
+
+
+# ---- stateful trackers ----------------------------------------------------------------------
+@dataclass
+class Feature:
+    """reference Feature (feature_tracker.rs:12-32)"""
+    feature_id: int
+    pixel_coord: tuple
+    undistorted_coord: tuple = field(default=(-1.0, -1.0))
+
+
+class _Tracker:
+    def __init__(self, width, height, levels, grid_size, max_iterations, convergence_threshold, mode,
+                 n_streams=1, device=0, max_tracks=0, cuda_stream=None):
+        L = load_library()
+        cfg = Config()
+        L.rsvio_config_default(C.byref(cfg))
+        cfg.width, cfg.height, cfg.levels = width, height, levels
+        cfg.grid_size, cfg.max_iterations = grid_size, max_iterations
+        cfg.convergence_threshold = convergence_threshold
+        cfg.mode, cfg.n_streams, cfg.device, cfg.max_tracks = mode, n_streams, device, max_tracks
+        cfg.cuda_stream = cuda_stream
+        self._h = C.c_void_p()
+        self._L = L
+        self.width, self.height, self.levels, self.n_streams, self.device = width, height, levels, n_streams, device
+        self.stereo = mode == MODE_STEREO
+        st = L.rsvio_tracker_create(C.byref(cfg), C.byref(self._h))
+        if st != OK:
+            self._h = None
+            raise RsvioError(st, L.rsvio_status_string(st).decode() + " (rsvio_tracker_create)")
+        cells = (width // grid_size) * (height // grid_size)
+        self._cap = max_tracks if max_tracks > 0 else 4 * cells + 64
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.rsvio_tracker_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+    def reset(self):
+        _check(self._L.rsvio_tracker_reset(self._h), self._h)
+
+    @staticmethod
+    def _ptrs(images, n, w, h):
+        arrs = [np.ascontiguousarray(im, np.uint8) for im in images]
+        if len(arrs) != n or any(a.shape != (h, w) for a in arrs):
+            raise ValueError("expected %d images of shape (%d, %d)" % (n, h, w))
+        return arrs, (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+
+    def process_batch(self, left, right=None):
+        la, lp = self._ptrs(left, self.n_streams, self.width, self.height)
+        if self.stereo:
+            ra, rp = self._ptrs(right, self.n_streams, self.width, self.height)
+        else:
+            ra, rp = None, None
+        _check(self._L.rsvio_tracker_process_batch(self._h, lp, rp, self.width), self._h)
+
+    def submit_batch_ptr(self, left_ptrs, right_ptrs, stride=None):
+        """left_ptrs/right_ptrs: ctypes arrays of host addresses (e.g. into pinned memory)."""
+        _check(self._L.rsvio_tracker_submit_batch(self._h, left_ptrs, right_ptrs, stride or self.width), self._h)
+
+    def submit_device(self, d_left, d_right, stride=None, pitch=None):
+        stride = stride or self.width
+        pitch = pitch or stride * self.height
+        _check(self._L.rsvio_tracker_submit_device(self._h, C.c_void_p(d_left), C.c_void_p(d_right or 0), stride,
+                                                   pitch), self._h)
+
+    def sync(self):
+        _check(self._L.rsvio_tracker_sync(self._h), self._h)
+
+    def num_tracks(self, cam=0, stream=0):
+        n = C.c_int32(0)
+        _check(self._L.rsvio_tracker_num_tracks(self._h, stream, cam, C.byref(n)), self._h)
+        return n.value
+
+    def tracks(self, cam=0, stream=0):
+        """(ids uint64[n], xy float32[n, 2]) of one camera, ids ascending."""
+        ids = np.zeros(self._cap, np.uint64)
+        xy = np.zeros((self._cap, 2), np.float32)
+        n = C.c_size_t(0)
+        _check(self._L.rsvio_tracker_get_tracks(self._h, stream, cam, ids, xy, self._cap, C.byref(n)), self._h)
+        return ids[:n.value].copy(), xy[:n.value].copy()
+
+    def transforms(self, cam=0, stream=0):
+        ids = np.zeros(self._cap, np.uint64)
+        T = np.zeros((self._cap, 6), np.float32)
+        n = C.c_size_t(0)
+        _check(self._L.rsvio_tracker_get_transforms(self._h, stream, cam, ids, T, self._cap, C.byref(n)), self._h)
+        return ids[:n.value].copy(), T[:n.value].copy()
+
+    def remove_id(self, ids, stream=0):
+        ids = np.ascontiguousarray(ids, np.uint64)
+        if ids.size:
+            _check(self._L.rsvio_tracker_remove_ids(self._h, stream, ids, ids.size), self._h)
+
+    def counters(self):
+        out = np.zeros(6, np.uint64)
+        _check(self._L.rsvio_tracker_counters(self._h, out), self._h)
+        return dict(tracks=int(out[0]), frames=int(out[1]), iterations=int(out[2]), templates=int(out[3]),
+                    launches=int(out[4]), detected=int(out[5]))
+
+    def set_profiling(self, on=True):
+        _check(self._L.rsvio_tracker_set_profiling(self._h, 1 if on else 0), self._h)
+
+    def stage_times(self, reset=True):
+        ms = np.zeros(N_STAGES, np.float32)
+        ln = np.zeros(N_STAGES, np.uint64)
+        _check(self._L.rsvio_tracker_stage_times(self._h, ms, ln, 1 if reset else 0), self._h)
+        return {k: (float(ms[i]), int(ln[i])) for i, k in enumerate(STAGE_NAMES)}
+
+
+class StereoPatchTracker(_Tracker):
+    """StereoPatchTracker<LEVELS> (feature_tracker.rs:91-207) on the GPU."""
+
+    def __init__(self, grid_size, optical_flow_max_iterations, optical_flow_convergence_threshold, *,
+                 width, height, levels=6, n_streams=1, device=0, max_tracks=0, cuda_stream=None):
+        super().__init__(width, height, levels, grid_size, optical_flow_max_iterations,
+                         float(optical_flow_convergence_threshold), MODE_STEREO, n_streams, device, max_tracks,
+                         cuda_stream)
+
+    def process_frame(self, greyscale_image0, greyscale_image1, frame=None):
+        """feature_tracker.rs:116-187.  `frame` (optional) needs add_left_feature / add_right_feature."""
+        l = np.ascontiguousarray(greyscale_image0, np.uint8)
+        r = np.ascontiguousarray(greyscale_image1, np.uint8)
+        if l.shape != (self.height, self.width) or r.shape != l.shape:
+            raise ValueError("image shape does not match the tracker")
+        _check(self._L.rsvio_tracker_process_stereo(self._h, C.c_void_p(l.ctypes.data), C.c_void_p(r.ctypes.data),
+                                                    self.width), self._h)
+        if frame is not None:
+            for cam, add in ((0, frame.add_left_feature), (1, frame.add_right_feature)):
+                ids, xy = self.tracks(cam)
+                for i, p in zip(ids.tolist(), xy.tolist()):
+                    add(Feature(i, (p[0], p[1])))
+
+    def get_track_points(self, stream=0):
+        """[ {id: (x, y)} for cam0, cam1 ]  (feature_tracker.rs:188-200)"""
+        out = []
+        for cam in (0, 1):
+            ids, xy = self.tracks(cam, stream)
+            out.append({int(i): (float(p[0]), float(p[1])) for i, p in zip(ids, xy)})
+        return out
+
+
+class PatchTracker(_Tracker):
+    """PatchTracker<LEVELS> (feature_tracker.rs:36-89); defaults 30 iterations / 0.005 / grid 30."""
+
+    def __init__(self, *, width, height, levels=6, grid_size=30, max_iterations=30, convergence_threshold=0.005,
+                 n_streams=1, device=0, max_tracks=0, cuda_stream=None):
+        super().__init__(width, height, levels, grid_size, max_iterations, convergence_threshold, MODE_MONO,
+                         n_streams, device, max_tracks, cuda_stream)
+
+    def process_frame(self, greyscale_image):
+        im = np.ascontiguousarray(greyscale_image, np.uint8)
+        if im.shape != (self.height, self.width):
+            raise ValueError("image shape does not match the tracker")
+        _check(self._L.rsvio_tracker_process_mono(self._h, C.c_void_p(im.ctypes.data), self.width), self._h)
+
+    def get_track_points(self, stream=0):
+        ids, xy = self.tracks(0, stream)
+        return {int(i): (float(p[0]), float(p[1])) for i, p in zip(ids, xy)}

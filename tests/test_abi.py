@@ -1,0 +1,63 @@
+"""CPU: the C-ABI library loads and exports every symbol include/rsvio_b200.h declares; without a
+GPU it fails loudly instead of falling back.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "rsvio_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rsvio_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported(rsvio):
+    lib = ctypes.CDLL(rsvio.library_path())
+    declared = _declared_functions()
+    assert len(declared) >= 25
+    missing = [s for s in declared if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(declared) == set(rsvio.ABI_SYMBOLS)
+    assert lib.rsvio_abi_version() == 1
+
+
+def test_product_does_not_link_or_import_the_oracle(rsvio):
+    # the product path must never route through oracle/
+    import subprocess
+    out = subprocess.run(["ldd", rsvio.library_path()], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+    pkg = os.path.join(ROOT, "rs-vio_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", ".rs")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "rsvio_oracle" not in txt, f
+
+
+def test_invalid_arguments_are_rejected_without_touching_the_gpu(rsvio):
+    L = rsvio.load_library()
+    from rsvio_b200.binding import Config
+    cfg = Config()
+    L.rsvio_config_default(ctypes.byref(cfg))
+    assert (cfg.levels, cfg.grid_size, cfg.max_iterations) == (6, 30, 30)
+    h = ctypes.c_void_p()
+    assert L.rsvio_tracker_create(None, ctypes.byref(h)) == -1
+    cfg.width, cfg.height = 4, 4
+    assert L.rsvio_tracker_create(ctypes.byref(cfg), ctypes.byref(h)) == -1
+    assert L.rsvio_tracker_sync(None) == -1
+    assert L.rsvio_status_string(-2).decode().startswith("CUDA")
+    assert L.rsvio_pyramid_bytes(752, 480, 3) == 752 * 480 + 376 * 240 + 188 * 120
+
+
+def test_no_cpu_fallback_without_gpu(rsvio):
+    if rsvio.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(rsvio.RsvioError):
+        rsvio.StereoPatchTracker(40, 20, 0.01, width=752, height=480, levels=3)
+    import numpy as np
+    with pytest.raises(rsvio.RsvioError):
+        rsvio.build_pyramid(np.zeros((64, 64), np.uint8), 3)

@@ -1,0 +1,156 @@
+"""GPU: the fused LK kernel (through rsvio_track_points) against the CPU oracle.
+
+Bar (BASELINE.json north_star): positions within 1e-3 px, identical accept/reject flags except for
+points whose decision lies within 1e-4 of a threshold.  The warp-shuffle reductions differ from the
+oracle's sequential sums in the last bits, so a point may take a different branch only when a
+decision variable is that close to its threshold; the oracle reports those margins per point.
+Tolerances used here are tighter than the allowed 1e-4 where they can be."""
+import os
+
+import numpy as np
+import pytest
+
+from util import GOLDEN_DIR, grid_points, identity_T6, scene_pair
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 1e-3        # px, north_star
+CONV_EDGE = 1e-5      # | |inc| - thr | below this: the convergence break may flip (allowed: 1e-4)
+GEOM_EDGE = 1e-4      # px distance of a sample / the patch centre to an inbound boundary
+FB_EDGE = 1e-4        # | d^2 - 0.4 |
+
+
+def oracle_unstable(oracle, pa, pb, w, h, levels, T0, max_it, thr, T_ref, st_ref):
+    """Points on which the reference algorithm itself is numerically unstable: nudging the input
+    position by one f32 ulp flips the oracle's own accept/reject flag or moves its own answer by
+    more than the tolerance (ill-conditioned Hessian on an edge / flat patch, or iterations that
+    run into max_it without converging).  No implementation can be held to 1e-3 px there."""
+    bad = np.zeros(len(st_ref), bool)
+    for sign in (1.0, -1.0):
+        Tn = T0.copy()
+        Tn[:, 2] = np.nextafter(T0[:, 2], np.float32(sign * 1e9))
+        Tn[:, 5] = np.nextafter(T0[:, 5], np.float32(sign * 1e9))
+        T2, st2, _, _ = oracle.track_points(pa, pb, w, h, levels, Tn, max_it, thr, nthreads=8)
+        bad |= (st2 == 0) != (st_ref == 0)
+        both = (st2 == 0) & (st_ref == 0)
+        move = np.abs((T2 - Tn) - (T_ref - T0))[:, [2, 5]].max(axis=1)
+        bad |= both & (move > 0.5 * POS_TOL)
+    return bad
+
+
+def compare(rsvio, oracle, a, b, levels, T0, max_it, thr, min_ok=0.0, max_excluded=1.0, tag=""):
+    """Accept/reject flags and positions (< 1e-3 px) must agree on every point except those whose
+    decision sat on a threshold edge in the oracle's run or that are unstable in the oracle itself."""
+    h, w = a.shape
+    pa, pb = oracle.build_pyramid(a, levels, nthreads=4), oracle.build_pyramid(b, levels, nthreads=4)
+    T_ref, st_ref, it_ref, mg = oracle.track_points(pa, pb, w, h, levels, T0, max_it, thr, nthreads=8)
+    T_gpu, st_gpu, it_gpu = rsvio.track_points(pa, pb, w, h, levels, T0, max_it, thr)
+    n = len(st_ref)
+    edge = (mg[:, 0] < CONV_EDGE) | (mg[:, 1] < GEOM_EDGE) | (mg[:, 2] < FB_EDGE)
+    excluded = edge | oracle_unstable(oracle, pa, pb, w, h, levels, T0, max_it, thr, T_ref, st_ref)
+    flag_diff = (st_gpu == 0) != (st_ref == 0)
+    both_ok = (st_ref == 0) & (st_gpu == 0)
+    err = np.where(both_ok, np.abs(T_gpu - T_ref)[:, [2, 5]].max(axis=1), 0.0)
+    rot = np.where(both_ok, np.abs(T_gpu - T_ref)[:, [0, 1, 3, 4]].max(axis=1), 0.0)
+    differs = flag_diff | (err >= POS_TOL) | (rot >= 1e-4)
+    bad = differs & ~excluded
+    assert not bad.any(), \
+        f"{bad.sum()} of {n} stable points differ: idx {np.flatnonzero(bad)[:8]}, status gpu {st_gpu[bad][:8]} " \
+        f"ref {st_ref[bad][:8]}, err {err[bad][:8]}, iters gpu {it_gpu[bad][:4].tolist()} ref {it_ref[bad][:4].tolist()}"
+    assert differs.sum() <= max(2, 0.01 * n), f"{differs.sum()} of {n} points took a different branch"
+    accepted = st_ref == 0
+    if accepted.any():
+        assert excluded[accepted].mean() <= max_excluded, f"{excluded[accepted].sum()} accepted points excluded"
+    ok = both_ok & ~differs
+    assert ok.mean() >= min_ok
+    same_reason = float((st_gpu == st_ref).mean())
+    same_iters = float((it_gpu[ok] == it_ref[ok]).all(axis=1).mean()) if ok.any() else 1.0
+    assert same_reason > 0.9
+    stats = dict(tag=tag, n=n, ok=int(ok.sum()), excluded=int(excluded.sum()), edge=int(edge.sum()), differs=int(differs.sum()),
+                same_reason=same_reason, same_iters=same_iters,
+                bit_identical=float((T_gpu[ok] == T_ref[ok]).all(axis=1).mean()) if ok.any() else 1.0,
+                max_err=float(err[ok].max()) if ok.any() else 0.0)
+    record(stats)
+    return stats
+
+
+def record(stats):
+    """append the parity statistics of this comparison to gpurun_out/parity_stats.jsonl (if present)"""
+    import json
+    d = os.path.join(os.path.dirname(GOLDEN_DIR), "..", "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_stats.jsonl"), "a") as f:
+            f.write(json.dumps(stats) + "\n")
+
+
+@pytest.mark.parametrize("w,h,levels,max_it,grid", [(752, 480, 3, 20, 40), (512, 512, 4, 10, 30),
+                                                    (800, 400, 6, 10, 12), (752, 480, 6, 20, 50)])
+def test_lk_matches_oracle_on_detected_corners(rsvio, oracle, w, h, levels, max_it, grid):
+    a, b = scene_pair(w, h, 1000 + levels, (1.37, -0.62))
+    xs, ys, _ = oracle.detect_key_points(a, grid, np.zeros((0, 2), np.uint32))
+    T0 = identity_T6(np.stack([xs, ys], axis=1))
+    r = compare(rsvio, oracle, a, b, levels, T0, max_it, 0.01, min_ok=0.5, tag=f"corners {w}x{h} L{levels}")
+    print(r)
+
+
+def test_lk_random_points_including_failures(rsvio, oracle):
+    w, h, levels = 640, 480, 4
+    a, b = scene_pair(w, h, 77, (-2.4, 1.9))
+    xy = grid_points(w, h, 3000, 5, margin=-4.0)   # some outside the image
+    T0 = identity_T6(xy)
+    # give some points a rotated input transform (only affects the composed rotation)
+    T0[::7, 0], T0[::7, 1], T0[::7, 3], T0[::7, 4] = 0.8, -0.6, 0.6, 0.8
+    # random positions: many sit on edges or flat areas where the reference itself is ill-conditioned
+    r = compare(rsvio, oracle, a, b, levels, T0, 15, 0.01, tag="random points 640x480 L4")
+    print(r)
+    assert r["ok"] > 500
+
+
+def test_lk_unrelated_images_reject(rsvio, oracle):
+    w, h, levels = 320, 240, 3
+    a = scene_pair(w, h, 5)[0]
+    b = scene_pair(w, h, 55555)[0]
+    T0 = identity_T6(grid_points(w, h, 500, 6))
+    compare(rsvio, oracle, a, b, levels, T0, 20, 0.01, tag="unrelated images")
+    pa, pb = oracle.build_pyramid(a, levels), oracle.build_pyramid(b, levels)
+    _, st, _ = rsvio.track_points(pa, pb, w, h, levels, T0, 20, 0.01)
+    assert (st != 0).mean() > 0.9
+
+
+def test_lk_ground_truth_shift(rsvio, oracle):
+    w, h, levels = 752, 480, 3
+    shift = (3.25, 0.4)
+    a, b = scene_pair(w, h, 88, shift)
+    xs, ys, _ = oracle.detect_key_points(a, 40, np.zeros((0, 2), np.uint32))
+    T0 = identity_T6(np.stack([xs, ys], axis=1))
+    pa, pb = oracle.build_pyramid(a, levels), oracle.build_pyramid(b, levels)
+    T1, st, _ = rsvio.track_points(pa, pb, w, h, levels, T0, 20, 0.01)
+    ok = st == 0
+    assert ok.mean() > 0.8
+    err = np.abs((T1[ok][:, [2, 5]] - T0[ok][:, [2, 5]]) - np.array(shift, np.float32))
+    assert np.median(err) < 0.05
+
+
+def test_lk_golden(rsvio, oracle):
+    g = np.load(os.path.join(GOLDEN_DIR, "golden_small.npz"))
+    a, b, lv = g["det_img_a"], g["det_img_b"], int(g["lk_levels"])
+    h, w = a.shape
+    pa, pb = oracle.build_pyramid(a, lv), oracle.build_pyramid(b, lv)
+    T1, st, it = rsvio.track_points(pa, pb, w, h, lv, g["lk_T0"], 20, 0.01)
+    edge = g["lk_margins"][:, 0] < CONV_EDGE
+    keep = ~edge
+    assert np.array_equal(st[keep], g["lk_status"][keep])
+    ok = keep & (g["lk_status"] == 0)
+    assert np.abs(T1[ok] - g["lk_T1"][ok])[:, [2, 5]].max() < POS_TOL
+
+
+def test_se2_exp_device_matches_reference_known_answers(rsvio, oracle):
+    import math
+    tw = np.array([[0, 0, 0], [0, 0, math.pi], [1.32, -1.56, 0.0], [0.3, -0.2, 0.05], [2.0, 1.0, -1.2],
+                   [0.5, -0.25, 1e-9]], np.float32)
+    m = rsvio.se2_exp(tw)
+    assert np.allclose(m[0], np.eye(3), atol=1e-6)
+    assert np.allclose(m[1], [[-1, 0, 0], [0, -1, 0], [0, 0, 1]], atol=1e-6)
+    assert np.allclose(m[2], [[1, 0, 1.32], [0, 1, -1.56], [0, 0, 1]], atol=1e-6)
+    for k in range(len(tw)):
+        assert np.allclose(m[k], oracle.se2_exp(tw[k]), atol=2e-7, rtol=2e-6)
