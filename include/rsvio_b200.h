@@ -125,6 +125,16 @@ rsvio_status rsvio_tracker_submit_device(rsvio_tracker *t, const void *d_left, c
 rsvio_status rsvio_tracker_num_tracks(rsvio_tracker *t, int32_t stream, int32_t cam, int32_t *n);
 rsvio_status rsvio_tracker_get_tracks(rsvio_tracker *t, int32_t stream, int32_t cam, uint64_t *ids,
                                       float *xy, size_t cap, size_t *n);
+/* zero-copy view of the last synced frame's result: the merge kernel writes these records
+ * straight into host-mapped pinned memory, so populating `Frame` (feature_tracker.rs:177-186)
+ * needs no further copy.  records[(cam * n_streams + stream) * capacity + k], k < counts[group].
+ * Valid until the second-next submit; readable while at most one frame is in flight. */
+typedef struct rsvio_track_record {
+    uint64_t id;
+    float x, y;
+} rsvio_track_record;
+rsvio_status rsvio_tracker_result_view(rsvio_tracker *t, const rsvio_track_record **records,
+                                       const int32_t **counts, int32_t *groups, int32_t *capacity);
 /* the full Affine2 of every track (tracked_points_map_cam{0,1}, feature_tracker.rs:93,95) */
 rsvio_status rsvio_tracker_get_transforms(rsvio_tracker *t, int32_t stream, int32_t cam, uint64_t *ids,
                                           float *T6, size_t cap, size_t *n);

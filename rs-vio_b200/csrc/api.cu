@@ -539,15 +539,18 @@ rsvio_status rsvio_tracker_process_mono(rsvio_tracker *t, const uint8_t *image, 
     return rsvio_tracker_process_batch(t, l, nullptr, stride);
 }
 
-static rsvio_status check_group(rsvio_tracker *t, int32_t stream, int32_t cam) {
+// max_inflight = 1 for readers of the host-mapped result ring (the one frame still in flight
+// writes the other slot), 0 for anything that touches the device tables.
+static rsvio_status check_group(rsvio_tracker *t, int32_t stream, int32_t cam, int max_inflight = 0) {
     if (!t) return RSVIO_ERR_INVALID_ARG;
     if (stream < 0 || stream >= t->S || cam < 0 || cam > 1) return fail(t, RSVIO_ERR_INVALID_ARG, "bad stream/cam");
-    if (t->inflight > 0) return fail(t, RSVIO_ERR_STATE, "frames in flight: call rsvio_tracker_sync first");
+    if (t->inflight > max_inflight)
+        return fail(t, RSVIO_ERR_STATE, "frames in flight: call rsvio_tracker_sync first");
     return RSVIO_OK;
 }
 
 rsvio_status rsvio_tracker_num_tracks(rsvio_tracker *t, int32_t stream, int32_t cam, int32_t *n) {
-    rsvio_status rs = check_group(t, stream, cam);
+    rsvio_status rs = check_group(t, stream, cam, 1);
     if (rs != RSVIO_OK) return rs;
     if (!n) return RSVIO_ERR_INVALID_ARG;
     *n = t->result_slot < 0 ? 0 : t->h_cnt[t->result_slot][cam * t->S + stream];
@@ -556,7 +559,7 @@ rsvio_status rsvio_tracker_num_tracks(rsvio_tracker *t, int32_t stream, int32_t 
 
 rsvio_status rsvio_tracker_get_tracks(rsvio_tracker *t, int32_t stream, int32_t cam, uint64_t *ids, float *xy,
                                       size_t cap, size_t *n) {
-    rsvio_status rs = check_group(t, stream, cam);
+    rsvio_status rs = check_group(t, stream, cam, 1);
     if (rs != RSVIO_OK) return rs;
     if (!n) return RSVIO_ERR_INVALID_ARG;
     const int g = cam * t->S + stream;
@@ -570,6 +573,19 @@ rsvio_status rsvio_tracker_get_tracks(rsvio_tracker *t, int32_t stream, int32_t 
         xy[2 * k] = r[k].x;
         xy[2 * k + 1] = r[k].y;
     }
+    return RSVIO_OK;
+}
+
+rsvio_status rsvio_tracker_result_view(rsvio_tracker *t, const rsvio_track_record **records,
+                                       const int32_t **counts, int32_t *groups, int32_t *capacity) {
+    if (!t) return RSVIO_ERR_INVALID_ARG;
+    if (t->inflight > 1) return fail(t, RSVIO_ERR_STATE, "two frames in flight: call rsvio_tracker_sync first");
+    if (t->result_slot < 0) return fail(t, RSVIO_ERR_STATE, "no frame has been processed yet");
+    static_assert(sizeof(rsvio_track_record) == sizeof(OutRecord), "record layout");
+    if (records) *records = reinterpret_cast<const rsvio_track_record *>(t->h_out[t->result_slot]);
+    if (counts) *counts = t->h_cnt[t->result_slot];
+    if (groups) *groups = t->groups;
+    if (capacity) *capacity = t->cap;
     return RSVIO_OK;
 }
 

@@ -30,7 +30,8 @@ ABI_SYMBOLS = (
     "rsvio_tracker_create", "rsvio_tracker_destroy", "rsvio_tracker_last_error", "rsvio_tracker_reset",
     "rsvio_tracker_process_stereo", "rsvio_tracker_process_mono", "rsvio_tracker_process_batch",
     "rsvio_tracker_submit_batch", "rsvio_tracker_sync", "rsvio_tracker_submit_device",
-    "rsvio_tracker_num_tracks", "rsvio_tracker_get_tracks", "rsvio_tracker_get_transforms",
+    "rsvio_tracker_num_tracks", "rsvio_tracker_get_tracks", "rsvio_tracker_result_view",
+    "rsvio_tracker_get_transforms",
     "rsvio_tracker_remove_ids", "rsvio_tracker_counters", "rsvio_tracker_set_profiling",
     "rsvio_tracker_stage_times",
     "rsvio_pyramid_bytes", "rsvio_pyramid_device_bytes", "rsvio_build_pyramid_u8",
@@ -105,6 +106,8 @@ def load_library():
     L.rsvio_tracker_submit_device.argtypes = [H, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
     L.rsvio_tracker_num_tracks.argtypes = [H, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]
     L.rsvio_tracker_get_tracks.argtypes = [H, C.c_int32, C.c_int32, _u64p, _f32p, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.rsvio_tracker_result_view.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
+                                            C.POINTER(C.c_int32)]
     L.rsvio_tracker_get_transforms.argtypes = [H, C.c_int32, C.c_int32, _u64p, _f32p, C.c_size_t,
                                                C.POINTER(C.c_size_t)]
     L.rsvio_tracker_remove_ids.argtypes = [H, C.c_int32, _u64p, C.c_size_t]
@@ -286,6 +289,20 @@ class _Tracker:
         n = C.c_size_t(0)
         _check(self._L.rsvio_tracker_get_tracks(self._h, stream, cam, ids, xy, self._cap, C.byref(n)), self._h)
         return ids[:n.value].copy(), xy[:n.value].copy()
+
+    RECORD_DTYPE = np.dtype([("id", np.uint64), ("x", np.float32), ("y", np.float32)])
+
+    def result_view(self):
+        """Zero-copy numpy views of the last synced frame: (records[groups, cap], counts[groups]) living
+        in the host-mapped pinned ring the merge kernel writes to; group = cam * n_streams + stream."""
+        rec, cnt = C.c_void_p(), C.c_void_p()
+        groups, cap = C.c_int32(0), C.c_int32(0)
+        _check(self._L.rsvio_tracker_result_view(self._h, C.byref(rec), C.byref(cnt), C.byref(groups), C.byref(cap)),
+               self._h)
+        g, c = groups.value, cap.value
+        rbuf = (C.c_char * (g * c * 16)).from_address(rec.value)
+        cbuf = (C.c_int32 * g).from_address(cnt.value)
+        return (np.frombuffer(rbuf, dtype=self.RECORD_DTYPE).reshape(g, c), np.frombuffer(cbuf, dtype=np.int32))
 
     def transforms(self, cam=0, stream=0):
         ids = np.zeros(self._cap, np.uint64)

@@ -150,10 +150,18 @@ def test_async_submit_and_device_resident_paths(rsvio):
     pipe.submit_batch_ptr(*ptrs[0])
     for t in range(1, 4):
         pipe.submit_batch_ptr(*ptrs[t])
+        with pytest.raises(rsvio.RsvioError):
+            pipe.tracks(0)          # both result slots are being written
+        with pytest.raises(rsvio.RsvioError):
+            pipe.submit_batch_ptr(*ptrs[t])   # at most two frames in flight
         pipe.sync()
-        if t < 3:
-            with pytest.raises(rsvio.RsvioError):
-                pipe.tracks(0)      # a frame is still in flight
+        # one frame still in flight: the synced frame's host-mapped result is readable ...
+        ids, xy = pipe.tracks(0)
+        assert np.array_equal(ids, want[t - 1][0][0]) and np.array_equal(xy, want[t - 1][0][1][:, [2, 5]])
+        rec, cnt = pipe.result_view()
+        assert cnt[0] == len(ids) and np.array_equal(rec["id"][0, :cnt[0]], ids)
+        with pytest.raises(rsvio.RsvioError):
+            pipe.transforms(0)      # ... but the device tables are not
     pipe.sync()
     with pytest.raises(rsvio.RsvioError):
         pipe.sync()
