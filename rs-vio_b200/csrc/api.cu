@@ -401,6 +401,7 @@ rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) 
         }
         CU_TRY(t, cudaStreamCreateWithFlags(&t->copy_st, cudaStreamNonBlocking));
         CU_TRY(t, pyr_plan_create(cfg->width, cfg->height, cfg->levels, t->st, &t->plan));
+        CU_TRY(t, pyr_plan_reserve(t->plan, 2 * t->S));
         t->pd = pyr_plan_desc(t->plan);
         const size_t G = (size_t)t->groups, cap = (size_t)t->cap, S = (size_t)t->S;
         for (int i = 0; i < kSlots; ++i) {
@@ -726,6 +727,7 @@ rsvio_status rsvio_build_pyramid_u8_device(int32_t device, const void *d_images,
     CU_TRY0(cudaSetDevice(device));
     CU_TRY0(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     CU_TRY0(pyr_plan_create(width, height, levels, st, &plan));
+    CU_TRY0(pyr_plan_reserve(plan, n_images));
     CU_TRY0(cudaEventCreate(&e0));
     CU_TRY0(cudaEventCreate(&e1));
     CU_TRY0(cudaEventRecord(e0, st));

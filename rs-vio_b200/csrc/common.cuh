@@ -69,6 +69,8 @@ struct PyrPlan;  // owns the tap tables and tile lists of one (w, h, levels)
 cudaError_t pyr_plan_create(int w, int h, int levels, cudaStream_t st, PyrPlan **out);
 void pyr_plan_destroy(PyrPlan *p);
 const PyrDesc &pyr_plan_desc(const PyrPlan *p);
+// scratch for the deep dyadic levels (>= 4) of up to n_images images per pyr_build call
+cudaError_t pyr_plan_reserve(PyrPlan *p, int n_images);
 // n_images source images: image j at src[j < split ? 0 : 1] + (j < split ? j : j - split) * pitch
 cudaError_t pyr_build(const PyrPlan *p, const uint8_t *src0, const uint8_t *src1, int split, int n_images,
                       size_t stride, size_t pitch, uint8_t *dst, cudaStream_t st, int *n_launches);

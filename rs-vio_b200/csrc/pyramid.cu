@@ -1,37 +1,52 @@
-// pyramid.cu -- u8 image pyramid, every level resampled from the base image.
+// pyramid.cu -- u8 image pyramid, every level resampled from the base image, bit-exact.
 //
-// Replaces build_image_pyramid (reference src/feature_tracker/feature_tracker.rs:209-220),
-// i.e. image 0.25 `imageops::resize(img, w0 >> i, h0 >> i, FilterType::Triangle)` per level:
-// vertical pass first into an un-rounded f32 intermediate, then the horizontal pass, clamp,
-// round half away from zero.  Weights are tent(|i - c| / ratio) normalised by their f32 sum;
-// accumulation is `t += pix * w` in tap order with separately rounded multiply and add
-// (SURVEY.md Appendix A).  Bit-exactness is the contract, so every multiply/add that can round
-// is an explicit __fmul_rn/__fadd_rn and the whole library is compiled with -fmad=false.
+// Replaces build_image_pyramid (reference src/feature_tracker/feature_tracker.rs:209-220), i.e.
+// image 0.25 `imageops::resize(img, w0 >> i, h0 >> i, FilterType::Triangle)` per level: vertical
+// pass first into an un-rounded f32 intermediate, then the horizontal pass, clamp, round half away
+// from zero.  Weights are tent(|i - c| / ratio) normalised by their f32 sum and accumulated as
+// `t += pix * w` in tap order with separately rounded multiply and add.
 //
-// pyr_generic_kernel: faithful path for any size ratio (also the non-power-of-two levels and
-// the truncated windows at the image border).  One CTA = one tile of one level of one image;
-// the vertical pass reads the base image straight from global memory (coalesced along x, each
-// row re-used from L1/L2), leaves its f32 columns in shared memory and the horizontal pass
-// finishes from there, so nothing but the u8 levels is ever written to HBM.
+// Four kernels share the work (DESIGN.md "pyramid"):
+//
+//  pyr_fast_kernel    levels 0..3 of all images in ONE pass over the base image (HBM-bound part).
+//      When w0 and h0 are divisible by 2^i the level-i filter is the dyadic tent
+//      (1,3,..,2r-1,2r-1,..,3,1)/(2r^2), r = 2^i, and for interior outputs every f32 operation
+//      of the reference is exact up to level 3 (<= 22 significant bits), so the result equals
+//      round_half_up(N / 4r^4) with N the integer 2-D tent sum.  The tents obey
+//          T_2r[n] = T_r[n] + 2 T_r[n - r] + T_r[n - 2r],   T_1 = (1, 1)
+//      so with G_r[m] = (T_r * p)(m r) ("even phase") and O_r[o] = (T_r * p)(o r - r/2) (the
+//      level output, "odd phase"):
+//          O_2r[o] = G_r[2o-1] + 2 G_r[2o] + G_r[2o+1],   G_2r[m] = G_r[2m] + 2 G_r[2m+1] + G_r[2m+2]
+//      i.e. one 3x3 binomial per level on a 4x smaller array.  Level 1 (all the full-resolution
+//      work) is 4 DP4A per output: the (1,3,3,1)x(1,3,3,1) weights fit signed bytes and the 4
+//      row dot-products chain through the DP4A accumulator.  A CTA stages a 256x64 tile (+halo)
+//      in shared memory with 16-byte loads, writes level 0 from it with 16-byte stores and keeps
+//      G_2 / G_4 in shared memory; only u8 levels (and, for deeper pyramids, the 1/64-size G_8)
+//      go to HBM: traffic == algorithmic bytes.
+//  pyr_deep_kernel    levels 4 and 5 from G_8 (exact integers).  There the reference's horizontal
+//      f32 accumulation is no longer exact (26 > 24 bits), but its error is < 2^-10 grey levels,
+//      so round(N / D) is the reference's byte unless frac(N / D) is within 2^-10 of 1/2; those
+//      rare outputs are queued and recomputed by pyr_fixup_kernel with the faithful f32 chains.
+//  pyr_generic_kernel faithful f32 chains, one CTA per tile descriptor: the outermost ring of every
+//      dyadic level (truncated windows: weights are renormalised by a non-power-of-two sum,
+//      nothing is exact) as 1-row / 1-column tiles, whole levels whose ratio is not a power of
+//      two (w0 or h0 not divisible by 2^i), levels >= 6, and everything when the fast path's
+//      alignment requirements (16-byte aligned rows, w0 % 16 == 0) do not hold.
+//
+// Every multiply/add that can round is an explicit __fmul_rn/__fadd_rn and the library is built
+// with -fmad=false.
 #include "common.cuh"
 
+#include <cstring>
 #include <vector>
 
 namespace rsvio {
 
 namespace {
 
-constexpr int kTileRows = 8;     // output rows per CTA
-constexpr int kMaxCols = 672;    // f32 intermediate columns per CTA row
-constexpr int kThreads = 256;
-
-struct TileTable {
-    int first_block[kMaxLevels + 1];  // prefix of CTAs per level
-    int tiles_x[kMaxLevels];
-    int tox[kMaxLevels];              // output columns per tile (level >= 1); rows per block (level 0)
-};
-
-// image 0.25 sample.rs weight construction, one thread per output index
+// ------------------------------------------------------------------------------------------
+// tap tables (faithful weights) -- image 0.25 sample.rs weight construction
+// ------------------------------------------------------------------------------------------
 __global__ void taps_kernel(int n_in, int n_out, int kmax, int *left, int *cnt, float *w) {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= n_out) return;
@@ -64,33 +79,42 @@ __device__ __forceinline__ const uint8_t *image_ptr(const uint8_t *src0, const u
     return j < split ? src0 + (size_t)j * pitch : src1 + (size_t)(j - split) * pitch;
 }
 
-__global__ void __launch_bounds__(kThreads)
-pyr_generic_kernel(PyrDesc pd, PyrTaps taps, TileTable tt, const uint8_t *__restrict__ src0,
+// ------------------------------------------------------------------------------------------
+// generic faithful tile kernel: one CTA per tile descriptor (whole non-dyadic levels, and the
+// border ring of the dyadic ones as 1-row / 1-column tiles)
+// ------------------------------------------------------------------------------------------
+constexpr int kGenThreads = 256;
+constexpr int kGenSmemFloats = 5376;  // f32 intermediate (ncols x noy) per CTA
+
+struct TileDesc {
+    int16_t lev, nox, noy, pad;  // lev == 0: copy rows [oy0, oy0 + noy)
+    int32_t ox0, oy0;
+};
+
+__global__ void __launch_bounds__(kGenThreads)
+pyr_generic_kernel(PyrDesc pd, PyrTaps taps, const TileDesc *__restrict__ tiles, const uint8_t *__restrict__ src0,
                    const uint8_t *__restrict__ src1, int split, size_t stride, size_t pitch,
                    uint8_t *__restrict__ dst) {
-    __shared__ float v[kTileRows][kMaxCols];
+    __shared__ __align__(16) float v[kGenSmemFloats];
     const int img = blockIdx.y;
     const uint8_t *__restrict__ src = image_ptr(src0, src1, split, img, pitch);
     uint8_t *__restrict__ out = dst + (size_t)img * pd.pyr_stride;
-    int lev = 0;
-    while (lev + 1 < pd.levels && (int)blockIdx.x >= tt.first_block[lev + 1]) ++lev;
-    const int blk = blockIdx.x - tt.first_block[lev];
-    const int w0 = pd.lv[0].w, h0 = pd.lv[0].h;
+    const TileDesc td = tiles[blockIdx.x];
+    const int lev = td.lev;
+    const int w0 = pd.lv[0].w;
 
     if (lev == 0) {  // same size: plain copy (image `resize` short-circuit)
-        const int rows = tt.tox[0];
-        const int y0 = blk * rows;
-        const int ny = min(rows, h0 - y0);
+        const int y0 = td.oy0, ny = td.noy;
         const bool vec = ((w0 & 15) == 0) && ((stride & 15) == 0) && ((((size_t)src) & 15) == 0);
         if (vec) {
             const int wv = w0 >> 4;
-            for (int idx = threadIdx.x; idx < wv * ny; idx += kThreads) {
+            for (int idx = threadIdx.x; idx < wv * ny; idx += kGenThreads) {
                 const int y = idx / wv, x = idx - y * wv;
                 const uint4 q = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)(y0 + y) * stride) + x);
                 reinterpret_cast<uint4 *>(out + (size_t)(y0 + y) * w0)[x] = q;
             }
         } else {
-            for (int idx = threadIdx.x; idx < w0 * ny; idx += kThreads) {
+            for (int idx = threadIdx.x; idx < w0 * ny; idx += kGenThreads) {
                 const int y = idx / w0, x = idx - y * w0;
                 out[(size_t)(y0 + y) * w0 + x] = __ldg(src + (size_t)(y0 + y) * stride + x);
             }
@@ -98,56 +122,653 @@ pyr_generic_kernel(PyrDesc pd, PyrTaps taps, TileTable tt, const uint8_t *__rest
         return;
     }
 
-    const int wl = pd.lv[lev].w, hl = pd.lv[lev].h;
+    const int wl = pd.lv[lev].w;
     const TapTable tx = taps.x[lev], ty = taps.y[lev];
-    const int tox = tt.tox[lev];
-    const int tile_y = blk / tt.tiles_x[lev], tile_x = blk - tile_y * tt.tiles_x[lev];
-    const int ox0 = tile_x * tox, oy0 = tile_y * kTileRows;
-    const int nox = min(tox, wl - ox0), noy = min(kTileRows, hl - oy0);
+    const int ox0 = td.ox0, oy0 = td.oy0, nox = td.nox, noy = td.noy;
     const int xl = tx.left[ox0];
     const int xr = tx.left[ox0 + nox - 1] + tx.cnt[ox0 + nox - 1];
-    const int ncols = xr - xl;
+    const int xa = xl & ~3;                    // 4-aligned first column
+    const int ngrp = (xr - xa + 3) >> 2;       // groups of 4 columns, one 32-bit load per tap
+    const int ncols = ngrp * 4;                // intermediate columns kept (>= xr - xl)
+    const bool vec4 = ((((size_t)src) | stride) & 3) == 0;
 
-    // vertical pass: f32, tap order, multiply and add rounded separately
-    for (int idx = threadIdx.x; idx < ncols * noy; idx += kThreads) {
-        const int cy = idx / ncols, cx = idx - cy * ncols;
+    // vertical pass: f32, tap order, multiply and add rounded separately; 4 columns per thread
+    for (int idx = threadIdx.x; idx < ngrp * noy; idx += kGenThreads) {
+        const int cy = idx / ngrp, g = idx - cy * ngrp;
         const int oy = oy0 + cy;
         const int top = ty.left[oy], n = ty.cnt[oy];
         const float *__restrict__ wy = ty.w + (size_t)oy * ty.kmax;
-        const uint8_t *__restrict__ p = src + (size_t)top * stride + (xl + cx);
-        float t = 0.0f;
-        for (int k = 0; k < n; ++k) t = __fadd_rn(t, __fmul_rn((float)__ldg(p + (size_t)k * stride), wy[k]));
-        v[cy][cx] = t;
+        const int x = xa + 4 * g;
+        const uint8_t *__restrict__ p = src + (size_t)top * stride + x;
+        float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
+        if (vec4 && x + 4 <= w0) {
+            for (int k = 0; k < n; ++k) {
+                const uint32_t q = __ldg(reinterpret_cast<const uint32_t *>(p + (size_t)k * stride));
+                const float wk = __ldg(wy + k);
+                t0 = __fadd_rn(t0, __fmul_rn((float)(q & 0xFFu), wk));
+                t1 = __fadd_rn(t1, __fmul_rn((float)((q >> 8) & 0xFFu), wk));
+                t2 = __fadd_rn(t2, __fmul_rn((float)((q >> 16) & 0xFFu), wk));
+                t3 = __fadd_rn(t3, __fmul_rn((float)(q >> 24), wk));
+            }
+        } else {
+            for (int k = 0; k < n; ++k) {
+                const uint8_t *__restrict__ r = p + (size_t)k * stride;
+                const float wk = __ldg(wy + k);
+                if (x + 0 < w0) t0 = __fadd_rn(t0, __fmul_rn((float)__ldg(r + 0), wk));
+                if (x + 1 < w0) t1 = __fadd_rn(t1, __fmul_rn((float)__ldg(r + 1), wk));
+                if (x + 2 < w0) t2 = __fadd_rn(t2, __fmul_rn((float)__ldg(r + 2), wk));
+                if (x + 3 < w0) t3 = __fadd_rn(t3, __fmul_rn((float)__ldg(r + 3), wk));
+            }
+        }
+        *reinterpret_cast<float4 *>(&v[cy * ncols + 4 * g]) = make_float4(t0, t1, t2, t3);
     }
     __syncthreads();
     // horizontal pass, clamp, round half away from zero
     uint8_t *__restrict__ lo = out + pd.lv[lev].off;
-    for (int idx = threadIdx.x; idx < nox * noy; idx += kThreads) {
+    for (int idx = threadIdx.x; idx < nox * noy; idx += kGenThreads) {
         const int cy = idx / nox, cx = idx - cy * nox;
         const int ox = ox0 + cx;
-        const int left = tx.left[ox] - xl, n = tx.cnt[ox];
+        const int left = tx.left[ox] - xa, n = tx.cnt[ox];
         const float *__restrict__ wx = tx.w + (size_t)ox * tx.kmax;
+        const float *__restrict__ vr = &v[cy * ncols + left];
         float t = 0.0f;
-        for (int k = 0; k < n; ++k) t = __fadd_rn(t, __fmul_rn(v[cy][left + k], wx[k]));
+        for (int k = 0; k < n; ++k) t = __fadd_rn(t, __fmul_rn(vr[k], __ldg(wx + k)));
         t = fminf(fmaxf(t, 0.0f), 255.0f);
         lo[(size_t)(oy0 + cy) * wl + ox] = (uint8_t)__float2uint_rz(roundf(t));
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// fast dyadic kernel: levels 0..NA (NA <= 3) from one shared-memory tile
+// ------------------------------------------------------------------------------------------
+constexpr int TW = 256, TH = 64;          // base-image tile owned by one CTA
+constexpr int PITCH = TW + 32;            // tile columns [X0 - 16, X0 + TW + 16), bytes per smem row
+constexpr int NCOL = TW / 8;              // stage-1 column threads: 4 level-1 columns (8 px) each = one warp
+constexpr int NSEG = 4;                   // stage-1 row segments = warps per CTA
+constexpr int NTA = NCOL * NSEG;          // 128 threads per CTA
+constexpr int G2P = TW / 2 + 8;           // G_2 columns kept in smem (u16): j in [X0/2 - 2, X0/2 + TW/2 + 6)
+constexpr int kRingTaps = 16;             // dyadic levels <= 3: at most 2r = 16 taps
+
+template <int NA>
+struct FastCfg {
+    static constexpr int et = NA == 3 ? 2 : (NA == 2 ? 1 : 0);  // extra G_2 rows above the O range
+    static constexpr int eb = NA == 3 ? 3 : 0;                  // ... and below
+    static constexpr int ytop = 2 * et + 1, ybot = 2 * eb + 2;  // tile rows [Y0 - ytop, Y0 + TH + ybot)
+    static constexpr int ROWS = TH + ytop + ybot;
+    static constexpr int NE = TH / 2 + et + eb;                 // level-1 rows emitted per tile (O and/or G)
+    static constexpr int PER_SEG = (NE + NSEG - 1) / NSEG;
+    static constexpr int G2ROWS = NA >= 2 ? NE : 1;
+    static constexpr int GX = NA == 3 ? 5 : (NA == 2 ? 2 : 0);  // G_2 columns right of the warp's 128
+    static constexpr int G4C = TW / 4 + 2, G4R = TH / 4 + 2;    // G_4[X0/4 - 1 .. X0/4 + TW/4]
+};
+
+// faithful f32 weights of the truncated border windows of a dyadic level (ratio r = 2^lev): they
+// depend on r only, so one set serves rows and columns.  Copied from the device tap tables.
+struct RingWeights {
+    float first[kRingTaps];   // output 0:       taps [0, 1.5 r)
+    float inner[kRingTaps];   // interior output: taps [o r - r/2, o r + 1.5 r)
+    float last[kRingTaps];    // output n-1:     taps [n_in - 1.5 r, n_in)
+};
+
+struct FastParams {
+    PyrDesc pd;
+    RingWeights ring[4];      // index = level (1..3)
+    const uint8_t *src0, *src1;
+    int split;
+    size_t stride, pitch;
+    uint8_t *dst;
+    uint32_t *g8;       // [img][h0/8][w0/8] exported when deeper levels follow, else nullptr
+    int tiles_x;
+};
+
+__device__ __forceinline__ uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c) {
+    return __dp4a(a, b, c);  // u8 x u8 (weights <= 9), u32 accumulate
+}
+
+// window of output o of a dyadic level along one axis (n_out outputs, ratio r)
+struct RingTap {
+    int left, cnt;
+    const float *w;
+};
+__device__ __forceinline__ RingTap ring_tap(const RingWeights &rw, int o, int n_out, int r) {
+    RingTap t;
+    if (o == 0) {
+        t.left = 0;
+        t.cnt = r + (r >> 1);
+        t.w = rw.first;
+    } else if (o == n_out - 1) {
+        t.left = n_out * r - (r + (r >> 1));
+        t.cnt = r + (r >> 1);
+        t.w = rw.last;
+    } else {
+        t.left = o * r - (r >> 1);
+        t.cnt = 2 * r;
+        t.w = rw.inner;
+    }
+    return t;
+}
+
+// One base-image row of stage 1.  A thread holds 4 level-1 columns j0..j0+3 (O, odd phase) and
+// the 4 even-phase columns j0-2..j0+1 (G); wr points at the tile word of pixels 2*j0..2*j0+3.
+// FIRST: this row is row 2t-1 of the (1,3,3,1) vertical tent of O_t (tap weights 1|3 for the
+// accumulators), else row 2t.  Flags select which accumulators are live (peeled first/last rows).
+template <bool ROW_A, bool ON, bool OO, bool GN, bool GM, bool GO>
+__device__ __forceinline__ void stage1_row(const uint32_t *__restrict__ wr, uint32_t (&aOn)[4], uint32_t (&aOo)[4],
+                                           uint32_t (&aGn)[4], uint32_t (&aGm)[4], uint32_t (&aGo)[4]) {
+    const uint32_t k1 = 0x01030301u, k3 = 0x03090903u;
+    const uint32_t wm1 = wr[-1];
+    const uint2 w01 = *reinterpret_cast<const uint2 *>(wr);
+    if (ON || OO) {
+        const uint32_t wp2 = wr[2];
+        const uint32_t v0 = __funnelshift_r(wm1, w01.x, 24), v1 = __funnelshift_r(w01.x, w01.y, 8);
+        const uint32_t v2 = __funnelshift_r(w01.x, w01.y, 24), v3 = __funnelshift_r(w01.y, wp2, 8);
+        if (ON) {  // O_t: row 2t-1 starts it with weight 1, row 2t adds weight 3
+            aOn[0] = dp4a_u(v0, ROW_A ? k1 : k3, ROW_A ? 0u : aOn[0]);
+            aOn[1] = dp4a_u(v1, ROW_A ? k1 : k3, ROW_A ? 0u : aOn[1]);
+            aOn[2] = dp4a_u(v2, ROW_A ? k1 : k3, ROW_A ? 0u : aOn[2]);
+            aOn[3] = dp4a_u(v3, ROW_A ? k1 : k3, ROW_A ? 0u : aOn[3]);
+        }
+        if (OO) {  // O_{t-1}: rows 2t-1 (weight 3) and 2t (weight 1, completes it)
+            aOo[0] = dp4a_u(v0, ROW_A ? k3 : k1, aOo[0]);
+            aOo[1] = dp4a_u(v1, ROW_A ? k3 : k1, aOo[1]);
+            aOo[2] = dp4a_u(v2, ROW_A ? k3 : k1, aOo[2]);
+            aOo[3] = dp4a_u(v3, ROW_A ? k3 : k1, aOo[3]);
+        }
+    }
+    if (GN || GM || GO) {
+        const uint32_t g1 = __funnelshift_r(wm1, w01.x, 16), g3 = __funnelshift_r(w01.x, w01.y, 16);
+        if (GN && !ROW_A) {  // G_t starts on row 2t (weight 1)
+            aGn[0] = dp4a_u(wm1, k1, 0u);
+            aGn[1] = dp4a_u(g1, k1, 0u);
+            aGn[2] = dp4a_u(w01.x, k1, 0u);
+            aGn[3] = dp4a_u(g3, k1, 0u);
+        }
+        if (GM) {  // G_{t-1}: rows 2t-1 and 2t carry weight 3
+            aGm[0] = dp4a_u(wm1, k3, aGm[0]);
+            aGm[1] = dp4a_u(g1, k3, aGm[1]);
+            aGm[2] = dp4a_u(w01.x, k3, aGm[2]);
+            aGm[3] = dp4a_u(g3, k3, aGm[3]);
+        }
+        if (GO && ROW_A) {  // G_{t-2}: row 2t-1 is its last row (weight 1)
+            aGo[0] = dp4a_u(wm1, k1, aGo[0]);
+            aGo[1] = dp4a_u(g1, k1, aGo[1]);
+            aGo[2] = dp4a_u(w01.x, k1, aGo[2]);
+            aGo[3] = dp4a_u(g3, k1, aGo[3]);
+        }
+    }
+}
+
+template <int NA>
+__global__ void __launch_bounds__(NTA) pyr_fast_kernel(const __grid_constant__ FastParams P) {
+    using C = FastCfg<NA>;
+    __shared__ __align__(16) uint8_t tile[C::ROWS][PITCH];
+    __shared__ __align__(16) uint16_t g2[C::G2ROWS][G2P];
+    __shared__ __align__(16) uint32_t g4[NA >= 3 ? C::G4R : 1][NA >= 3 ? C::G4C : 1];
+    __shared__ float vbuf[NA][PITCH];
+
+    const int img = blockIdx.y;
+    const int tile_y = blockIdx.x / P.tiles_x, tile_x = blockIdx.x - tile_y * P.tiles_x;
+    const int X0 = tile_x * TW, Y0 = tile_y * TH;
+    const int w0 = P.pd.lv[0].w, h0 = P.pd.lv[0].h;
+    const uint8_t *__restrict__ src = image_ptr(P.src0, P.src1, P.split, img, P.pitch);
+    uint8_t *__restrict__ out = P.dst + (size_t)img * P.pd.pyr_stride;
+    const int tid = threadIdx.x;
+
+    // ---- stage 0: tile -> shared memory (16-byte loads, zero fill outside the image), level 0 out.
+    // A thread owns one 16-byte column of the tile and walks down the rows (RP rows apart).
+    {
+        constexpr int VPR = PITCH / 16;    // 16-byte vectors per tile row
+        constexpr int RP = NTA / VPR;      // rows per pass
+        if (tid < VPR * RP) {
+            const int vx = tid % VPR, r0 = tid / VPR;
+            const int x = X0 - 16 + vx * 16;
+            const bool in_x = x >= 0 && x < w0;            // w0 % 16 == 0: all 16 bytes or none
+            const bool copy_x = in_x && x >= X0 && x < X0 + TW;
+            // tile rows holding image rows, and those that are also level-0 output of this tile
+            const int ry_lo = max(0, C::ytop - Y0), ry_hi = in_x ? min(C::ROWS, h0 - Y0 + C::ytop) : 0;
+            const int cy_lo = C::ytop, cy_hi = copy_x ? min(C::ytop + TH, ry_hi) : 0;
+            const uint32_t gstep = (uint32_t)RP * (uint32_t)P.stride, ostep = (uint32_t)RP * (uint32_t)w0;
+            const uint8_t *__restrict__ gp = src + (ptrdiff_t)(Y0 - C::ytop + r0) * (ptrdiff_t)P.stride + x;
+            uint8_t *__restrict__ op = out + (ptrdiff_t)(Y0 - C::ytop + r0) * w0 + x;
+            uint8_t *sp = &tile[r0][vx * 16];
+#pragma unroll 3
+            for (int ry = r0; ry < C::ROWS; ry += RP) {
+                uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                if (ry >= ry_lo && ry < ry_hi) q = __ldg(reinterpret_cast<const uint4 *>(gp));
+                *reinterpret_cast<uint4 *>(sp) = q;
+                if (ry >= cy_lo && ry < cy_hi) *reinterpret_cast<uint4 *>(op) = q;  // level 0 == input
+                gp += gstep;
+                op += ostep;
+                sp += RP * PITCH;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 1: level-1 output O_2 (global) and G_2 (smem); 4 chained DP4A per value.
+    // Warp = one row segment, lane c = level-1 columns X0/2 + 4c .. +3 (O) and X0/2 + 4c - 2 .. +1 (G).
+    const int w1 = P.pd.lv[1].w, h1 = P.pd.lv[1].h;
+    const int t_first = Y0 / 2 - C::et;    // first emitted level-1 row of the tile
+    {
+        const int c = tid & (NCOL - 1), seg = tid / NCOL;
+        const int j0 = X0 / 2 + 4 * c;
+        const int ts = t_first + seg * C::PER_SEG;
+        const int te = min(ts + C::PER_SEG, t_first + C::NE);
+        const bool live = (2 * j0 - 8) < w0 && (2 * ts - 8) < h0 && ts < te;  // partial tiles: skip dead work
+        // level-1 rows this thread stores: its segment, the tile's O range, the level's interior
+        const int o_lo = max(max(ts, Y0 / 2), 1);
+        const int o_hi = j0 < w1 ? min(min(te, Y0 / 2 + TH / 2), h1 - 1) : o_lo;
+        const bool o_edge = j0 < 1 || j0 + 3 > w1 - 2;  // group touches the first / last column
+        uint32_t aOo[4] = {0, 0, 0, 0}, aOn[4] = {0, 0, 0, 0}, aGo[4] = {0, 0, 0, 0}, aGm[4] = {0, 0, 0, 0},
+                 aGn[4] = {0, 0, 0, 0};
+        uint8_t *__restrict__ orow = out + P.pd.lv[1].off + (ptrdiff_t)(ts - 1) * w1 + j0;  // row tau - 1
+        const uint32_t *__restrict__ wr =
+            reinterpret_cast<const uint32_t *>(&tile[2 * ts - 1 - (Y0 - C::ytop)][0]) + (4 + 2 * c);  // row 2*tau-1
+        uint2 *__restrict__ grow = reinterpret_cast<uint2 *>(&g2[0][4 * c]) + (ptrdiff_t)(ts - 2 - t_first) * (G2P / 4);
+        constexpr bool G = NA >= 2;
+        auto store_o = [&](int to) {  // O_{to} complete -> level 1, round half up: (N + 32) >> 6
+            if (to >= o_lo && to < o_hi) {
+                const uint32_t b0 = (aOo[0] + 32u) >> 6, b1 = (aOo[1] + 32u) >> 6;
+                const uint32_t b2 = (aOo[2] + 32u) >> 6, b3 = (aOo[3] + 32u) >> 6;
+                if (!o_edge) {
+                    *reinterpret_cast<uint32_t *>(orow) = __byte_perm(b0 | (b1 << 8), b2 | (b3 << 8), 0x5410);
+                } else {
+                    if (j0 + 0 >= 1 && j0 + 0 <= w1 - 2) orow[0] = (uint8_t)b0;
+                    if (j0 + 1 >= 1 && j0 + 1 <= w1 - 2) orow[1] = (uint8_t)b1;
+                    if (j0 + 2 >= 1 && j0 + 2 <= w1 - 2) orow[2] = (uint8_t)b2;
+                    if (j0 + 3 >= 1 && j0 + 3 <= w1 - 2) orow[3] = (uint8_t)b3;
+                }
+            }
+        };
+        auto rotate = [&]() {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                aOo[q] = aOn[q];
+                if (G) {
+                    aGo[q] = aGm[q];
+                    aGm[q] = aGn[q];
+                }
+            }
+            wr += 2 * (PITCH / 4);
+            orow += w1;
+            grow += G2P / 4;
+        };
+        if (live) {
+            // O_t spans rows 2t-1..2t+2 (complete in iteration t+1, second row), G_t rows 2t..2t+3
+            // (complete in iteration t+2, first row).  Iterations ts and ts+1 and te, te+1 are peeled:
+            // they only feed the accumulators of rows this segment emits.
+            // tau = ts: start O_ts (row a, b) and G_ts (row b)
+            stage1_row<true, true, false, false, false, false>(wr, aOn, aOo, aGn, aGm, aGo);
+            stage1_row<false, true, false, G, false, false>(wr + PITCH / 4, aOn, aOo, aGn, aGm, aGo);
+            rotate();
+            if (ts + 1 < te) {
+                // tau = ts+1: O_{ts+1}, O_ts (done), G_{ts+1}, G_ts
+                stage1_row<true, true, true, false, G, false>(wr, aOn, aOo, aGn, aGm, aGo);
+                stage1_row<false, true, true, G, G, false>(wr + PITCH / 4, aOn, aOo, aGn, aGm, aGo);
+                store_o(ts);
+                rotate();
+                for (int tau = ts + 2; tau < te; ++tau) {
+                    stage1_row<true, true, true, false, G, G>(wr, aOn, aOo, aGn, aGm, aGo);
+                    if (G) *grow = make_uint2(aGo[0] | (aGo[1] << 16), aGo[2] | (aGo[3] << 16));  // G_{tau-2}
+                    stage1_row<false, true, true, G, G, false>(wr + PITCH / 4, aOn, aOo, aGn, aGm, aGo);
+                    store_o(tau - 1);
+                    rotate();
+                }
+                // tau = te: finish O_{te-1}, G_{te-2}; keep G_{te-1} going; nothing new starts
+                stage1_row<true, false, true, false, G, G>(wr, aOn, aOo, aGn, aGm, aGo);
+                if (G) *grow = make_uint2(aGo[0] | (aGo[1] << 16), aGo[2] | (aGo[3] << 16));
+                stage1_row<false, false, true, false, G, false>(wr + PITCH / 4, aOn, aOo, aGn, aGm, aGo);
+                store_o(te - 1);
+                rotate();
+            } else {
+                // single-row segment: tau = te = ts + 1
+                stage1_row<true, false, true, false, G, false>(wr, aOn, aOo, aGn, aGm, aGo);
+                stage1_row<false, false, true, false, G, false>(wr + PITCH / 4, aOn, aOo, aGn, aGm, aGo);
+                store_o(ts);
+                rotate();
+            }
+            if (G) {  // tau = te+1, first row only: finish G_{te-1}
+                stage1_row<true, false, false, false, false, true>(wr, aOn, aOo, aGn, aGm, aGo);
+                *grow = make_uint2(aGo[0] | (aGo[1] << 16), aGo[2] | (aGo[3] << 16));
+            }
+        }
+        // the few G_2 columns right of the warp's 128 (needed by G_4 / O_4 at the tile's right edge)
+        if (G) {
+            constexpr int GXD = C::GX > 0 ? C::GX : 1;
+            for (int idx = tid; idx < C::GX * C::NE; idx += NTA) {
+                const int gx = idx % GXD, tr = idx / GXD;        // column X0/2 + TW/2 - 2 + gx, row t_first + tr
+                const int px = TW - 4 + 2 * gx + 16;                 // tile byte column of pixel 2j
+                const int ry = 2 * (t_first + tr) - (Y0 - C::ytop);  // tile row of base row 2t
+                uint32_t acc = 0;
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const uint32_t *__restrict__ wq = reinterpret_cast<const uint32_t *>(&tile[ry + rr][0]) + (px >> 2);
+                    const uint32_t v = (px & 2) ? __funnelshift_r(wq[0], wq[1], 16) : wq[0];
+                    acc = dp4a_u(v, (rr == 0 || rr == 3) ? 0x01030301u : 0x03090903u, acc);
+                }
+                g2[tr][TW / 2 + gx] = (uint16_t)acc;
+            }
+        }
+    }
+    if (NA >= 2) {
+        __syncthreads();
+        // ---- stage 2: level-2 output O_4 (global) and G_4 (smem) from G_2: 3x3 binomials as chained
+        // 2-way dot products on the u16 pairs.  g2[t - t_first][j - (X0/2 - 2)].
+        const int w2 = P.pd.lv[2].w, h2 = P.pd.lv[2].h;
+        uint8_t *__restrict__ o2 = out + P.pd.lv[2].off;
+        constexpr int OQ = TW / 16;                       // groups of 4 outputs per O_4 row
+        constexpr int NO = OQ * (TH / 4);
+        constexpr int GQ = NA >= 3 ? (C::G4C + 1) / 2 : 1;  // pairs of G_4 columns
+        constexpr int NG = NA >= 3 ? GQ * C::G4R : 0;
+        // byte weights for dp2a_lo: bytes (b0, b1) multiply (lo16, hi16) of the word
+        const uint32_t kA[3] = {0x0100u, 0x0200u, 0x0100u};   // (0, 1) * row weight: hi half only
+        const uint32_t kB[3] = {0x0102u, 0x0204u, 0x0102u};   // (2, 1) * row weight
+        const uint32_t kC[3] = {0x0201u, 0x0402u, 0x0201u};   // (1, 2) * row weight
+        const uint32_t kD[3] = {0x0001u, 0x0002u, 0x0001u};   // (1, 0) * row weight: lo half only
+        for (int idx = tid; idx < NO + NG; idx += NTA) {
+            if (idx < NO) {
+                // 4 outputs ox = X0/4 + 4q + {0..3}, row oy = Y0/4 + ly.  Window of output k starts at g2
+                // column 8q + 2k + 1 (odd): hi(A_i) + 2 lo(A_{i+1}) + hi(A_{i+1}), A_i = word 4q + k.
+                const int q = idx % OQ, ly = idx / OQ;
+                const int tc = 2 * ly + C::et;                 // centre row in g2
+                uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+#pragma unroll
+                for (int rr = 0; rr < 3; ++rr) {
+                    const uint32_t *__restrict__ gw = reinterpret_cast<const uint32_t *>(&g2[tc - 1 + rr][0]) + 4 * q;
+                    const uint4 a = *reinterpret_cast<const uint4 *>(gw);
+                    const uint32_t a4 = gw[4];
+                    n0 = __dp2a_lo(a.y, kB[rr], __dp2a_lo(a.x, kA[rr], n0));
+                    n1 = __dp2a_lo(a.z, kB[rr], __dp2a_lo(a.y, kA[rr], n1));
+                    n2 = __dp2a_lo(a.w, kB[rr], __dp2a_lo(a.z, kA[rr], n2));
+                    n3 = __dp2a_lo(a4, kB[rr], __dp2a_lo(a.w, kA[rr], n3));
+                }
+                const int ox = X0 / 4 + 4 * q, oy = Y0 / 4 + ly;
+                if (oy >= 1 && oy <= h2 - 2 && ox < w2) {
+                    const uint32_t b0 = (n0 + 512u) >> 10, b1 = (n1 + 512u) >> 10;
+                    const uint32_t b2 = (n2 + 512u) >> 10, b3 = (n3 + 512u) >> 10;
+                    uint8_t *__restrict__ dp = o2 + (size_t)oy * w2 + ox;
+                    if (ox >= 1 && ox + 3 <= w2 - 2) {
+                        *reinterpret_cast<uint32_t *>(dp) = __byte_perm(b0 | (b1 << 8), b2 | (b3 << 8), 0x5410);
+                    } else {
+                        if (ox + 0 >= 1 && ox + 0 <= w2 - 2) dp[0] = (uint8_t)b0;
+                        if (ox + 1 >= 1 && ox + 1 <= w2 - 2) dp[1] = (uint8_t)b1;
+                        if (ox + 2 >= 1 && ox + 2 <= w2 - 2) dp[2] = (uint8_t)b2;
+                        if (ox + 3 >= 1 && ox + 3 <= w2 - 2) dp[3] = (uint8_t)b3;
+                    }
+                }
+            } else if (NA >= 3) {
+                // 2 values G_4[X0/4 - 1 + gm + {0,1}][Y0/4 - 1 + gs]: window of gm starts at g2 column 2 gm
+                // (even): lo(A_i) + 2 hi(A_i) + lo(A_{i+1}), A_i = word gm
+                const int k = idx - NO;
+                const int gq = k % GQ, gs = k / GQ;
+                const int gm = 2 * gq;
+                const int tc = 2 * gs + 1;                     // centre row = 2 (gs - 1) + et + 1 with et == 2
+                uint32_t n0 = 0, n1 = 0;
+#pragma unroll
+                for (int rr = 0; rr < 3; ++rr) {
+                    const uint32_t *__restrict__ gw = reinterpret_cast<const uint32_t *>(&g2[tc - 1 + rr][0]) + gm;
+                    const uint32_t a0 = gw[0], a1 = gw[1], a2 = gw[2];
+                    n0 = __dp2a_lo(a1, kD[rr], __dp2a_lo(a0, kC[rr], n0));
+                    n1 = __dp2a_lo(a2, kD[rr], __dp2a_lo(a1, kC[rr], n1));
+                }
+                g4[gs][gm] = n0;
+                if (gm + 1 < C::G4C) g4[gs][gm + 1] = n1;
+            }
+        }
+    }
+    if (NA >= 3) {
+        __syncthreads();
+        // ---- stage 3: level-3 output O_8 (global) and G_8 (global scratch, if deeper levels follow)
+        const int w3 = P.pd.lv[3].w, h3 = P.pd.lv[3].h;
+        uint8_t *__restrict__ o3 = out + P.pd.lv[3].off;
+        constexpr int NO = (TW / 8) * (TH / 8);
+        const int ng = P.g8 ? NO : 0;
+        const int w8 = w0 / 8, h8 = h0 / 8;
+        for (int idx = tid; idx < NO + ng; idx += NTA) {
+            const bool is_o = idx < NO;
+            const int k = is_o ? idx : idx - NO;
+            const int lx = k % (TW / 8), ly = k / (TW / 8);
+            // g4[s - (Y0/4 - 1)][m - (X0/4 - 1)]:  O window centre m = 2*ox, G window centre m = 2*ox + 1
+            const int mc = 2 * lx + 1 + (is_o ? 0 : 1), sc = 2 * ly + 1 + (is_o ? 0 : 1);
+            const uint32_t *r0 = &g4[sc - 1][mc - 1], *r1 = &g4[sc][mc - 1], *r2 = &g4[sc + 1][mc - 1];
+            const uint32_t n = r0[0] + 2u * r0[1] + r0[2] + 2u * (r1[0] + 2u * r1[1] + r1[2]) + r2[0] + 2u * r2[1] + r2[2];
+            const int ox = X0 / 8 + lx, oy = Y0 / 8 + ly;
+            if (is_o) {
+                if (ox >= 1 && ox <= w3 - 2 && oy >= 1 && oy <= h3 - 2)
+                    o3[(size_t)oy * w3 + ox] = (uint8_t)((n + 8192u) >> 14);
+            } else if (ox < w8 && oy < h8) {
+                P.g8[((size_t)img * h8 + oy) * w8 + ox] = n;
+            }
+        }
+    }
+
+    // ---- border ring of levels 1..NA owned by this tile: the reference's f32 chains (truncated
+    // windows are renormalised by a non-dyadic sum, so nothing is exact there), read from the tile.
+    const bool top = Y0 == 0, bottom = Y0 + TH >= h0 && Y0 < h0;
+    const bool left = X0 == 0, right = X0 + TW >= w0 && X0 < w0;
+    if (!(top || bottom || left || right)) return;
+    auto pix = [&](int x, int y) { return (float)tile[y - Y0 + C::ytop][x - X0 + 16]; };
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {  // border rows: oy = 0 (top tiles), oy = hl - 1 (bottom tiles)
+        if (side == 0 ? !top : !bottom) continue;
+        __syncthreads();
+        // vertical chains of all levels: one thread per (level, column)
+        for (int idx = tid; idx < NA * PITCH; idx += NTA) {
+            const int lev = 1 + idx / PITCH, x = X0 - 16 + idx % PITCH;
+            const int r = 1 << lev, hl = P.pd.lv[lev].h;
+            const int oy = side == 0 ? 0 : hl - 1;
+            if (oy * r < Y0 || oy * r >= Y0 + TH || x < max(X0 - (r >> 1), 0) || x >= min(X0 + TW + (r >> 1), w0)) continue;
+            const RingTap ty = ring_tap(P.ring[lev], oy, hl, r);
+            float v = 0.0f;
+            for (int k = 0; k < ty.cnt; ++k) v = __fadd_rn(v, __fmul_rn(pix(x, ty.left + k), ty.w[k]));
+            vbuf[lev - 1][x - X0 + 16] = v;
+        }
+        __syncthreads();
+        // horizontal chains: one thread per (level, output column)
+        for (int idx = tid; idx < NA * (TW / 2); idx += NTA) {
+            const int lev = 1 + idx / (TW / 2), lx = idx % (TW / 2);
+            const int r = 1 << lev, wl = P.pd.lv[lev].w, hl = P.pd.lv[lev].h;
+            const int oy = side == 0 ? 0 : hl - 1;
+            const int ox = X0 / r + lx;
+            if (lx >= TW / r || ox >= wl || oy * r < Y0 || oy * r >= Y0 + TH) continue;
+            const RingTap tx = ring_tap(P.ring[lev], ox, wl, r);
+            float t = 0.0f;
+            for (int k = 0; k < tx.cnt; ++k)
+                t = __fadd_rn(t, __fmul_rn(vbuf[lev - 1][tx.left + k - X0 + 16], tx.w[k]));
+            t = fminf(fmaxf(t, 0.0f), 255.0f);
+            out[P.pd.lv[lev].off + (size_t)oy * wl + ox] = (uint8_t)__float2uint_rz(roundf(t));
+        }
+    }
+    // border columns (ox = 0 for left tiles, ox = wl - 1 for right tiles) without the corner rows
+    for (int idx = tid; idx < 2 * NA * (TH / 2); idx += NTA) {
+        const int side = idx / (NA * (TH / 2)), rem = idx % (NA * (TH / 2));
+        const int lev = 1 + rem / (TH / 2), ly = rem % (TH / 2);
+        if (side == 0 ? !left : !right) continue;
+        const int r = 1 << lev, wl = P.pd.lv[lev].w, hl = P.pd.lv[lev].h;
+        const int oy = Y0 / r + ly;
+        const int ox = side == 0 ? 0 : wl - 1;
+        if (ly >= TH / r || oy < 1 || oy > hl - 2 || ox * r < X0 || ox * r >= X0 + TW) continue;
+        const RingTap tx = ring_tap(P.ring[lev], ox, wl, r), ty = ring_tap(P.ring[lev], oy, hl, r);
+        float t = 0.0f;
+        for (int kx = 0; kx < tx.cnt; ++kx) {
+            float v = 0.0f;
+            for (int ky = 0; ky < ty.cnt; ++ky) v = __fadd_rn(v, __fmul_rn(pix(tx.left + kx, ty.left + ky), ty.w[ky]));
+            t = __fadd_rn(t, __fmul_rn(v, tx.w[kx]));
+        }
+        t = fminf(fmaxf(t, 0.0f), 255.0f);
+        out[P.pd.lv[lev].off + (size_t)oy * wl + ox] = (uint8_t)__float2uint_rz(roundf(t));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// deep dyadic levels (4, 5) from the exported G_8, with an uncertainty queue
+// ------------------------------------------------------------------------------------------
+struct FixItem {
+    int img, lev, ox, oy;
+};
+
+__global__ void __launch_bounds__(256)
+pyr_deep_kernel(PyrDesc pd, const uint32_t *__restrict__ g8, int n_images, int do5, uint8_t *__restrict__ dst,
+                FixItem *__restrict__ fix, int *__restrict__ fix_count, int fix_cap) {
+    const int w8 = pd.lv[0].w / 8, h8 = pd.lv[0].h / 8;
+    const int w4 = pd.lv[4].w, h4 = pd.lv[4].h;
+    const int n4 = max(w4 - 2, 0) * max(h4 - 2, 0);
+    const int w5 = do5 ? pd.lv[5].w : 0, h5 = do5 ? pd.lv[5].h : 0;
+    const int n5 = do5 ? max(w5 - 2, 0) * max(h5 - 2, 0) : 0;
+    const long long total = (long long)(n4 + n5) * n_images;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int img = (int)(idx / (n4 + n5));
+        int k = (int)(idx - (long long)img * (n4 + n5));
+        const uint32_t *__restrict__ g = g8 + (size_t)img * w8 * h8;
+        uint8_t *__restrict__ out = dst + (size_t)img * pd.pyr_stride;
+        uint32_t n, half;
+        int shift, lev, ox, oy;
+        if (k < n4) {  // O_16[o] = sum (1,2,1)x(1,2,1) G_8[2o-1 .. 2o+1]
+            lev = 4;
+            ox = 1 + k % (w4 - 2);
+            oy = 1 + k / (w4 - 2);
+            const uint32_t *r0 = g + (size_t)(2 * oy - 1) * w8 + (2 * ox - 1), *r1 = r0 + w8, *r2 = r1 + w8;
+            n = r0[0] + 2u * r0[1] + r0[2] + 2u * (r1[0] + 2u * r1[1] + r1[2]) + r2[0] + 2u * r2[1] + r2[2];
+            shift = 18;  // D = 4 * 16^4
+        } else {       // O_32[o] = sum (1,2,3,4,3,2,1)^2 G_8[4o-2 .. 4o+4]
+            k -= n4;
+            lev = 5;
+            ox = 1 + k % (w5 - 2);
+            oy = 1 + k / (w5 - 2);
+            n = 0;
+#pragma unroll
+            for (int a = 0; a < 7; ++a) {
+                const uint32_t *r = g + (size_t)(4 * oy - 2 + a) * w8 + (4 * ox - 2);
+                const uint32_t row = r[0] + 2u * r[1] + 3u * r[2] + 4u * r[3] + 3u * r[4] + 2u * r[5] + r[6];
+                n += (uint32_t)(a < 4 ? a + 1 : 7 - a) * row;
+            }
+            shift = 22;  // D = 4 * 32^4
+        }
+        half = 1u << (shift - 1);
+        out[pd.lv[lev].off + (size_t)oy * pd.lv[lev].w + ox] = (uint8_t)((n + half) >> shift);
+        // the reference's f32 horizontal accumulation is within 2^-10 of N / D: flag ties it could flip
+        const uint32_t frac = n & ((1u << shift) - 1u);
+        const uint32_t dist = frac > half ? frac - half : half - frac;
+        if (dist <= (1u << (shift - 10))) {
+            const int slot = atomicAdd(fix_count, 1);
+            if (slot < fix_cap) fix[slot] = FixItem{img, lev, ox, oy};
+        }
+    }
+}
+
+// one warp per queued output: faithful recomputation
+__global__ void __launch_bounds__(128)
+pyr_fixup_kernel(PyrDesc pd, PyrTaps taps, const uint8_t *__restrict__ src0, const uint8_t *__restrict__ src1,
+                 int split, size_t stride, size_t pitch, uint8_t *__restrict__ dst, const FixItem *__restrict__ fix,
+                 const int *__restrict__ fix_count, int fix_cap) {
+    __shared__ float vbuf[4][2 * 64 + 8];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int n = min(*fix_count, fix_cap);
+    for (int it = blockIdx.x * 4 + wib; it < n; it += gridDim.x * 4) {
+        const FixItem f = fix[it];
+        const uint8_t *__restrict__ src = image_ptr(src0, src1, split, f.img, pitch);
+        const TapTable tx = taps.x[f.lev], ty = taps.y[f.lev];
+        const int left = tx.left[f.ox], nx = tx.cnt[f.ox];
+        const int top = ty.left[f.oy], ny = ty.cnt[f.oy];
+        const float *__restrict__ wy = ty.w + (size_t)f.oy * ty.kmax;
+        for (int kx = lane; kx < nx; kx += 32) {  // vertical chains, one column per lane
+            const uint8_t *__restrict__ p = src + (size_t)top * stride + (left + kx);
+            float v = 0.0f;
+            for (int ky = 0; ky < ny; ++ky) v = __fadd_rn(v, __fmul_rn((float)__ldg(p + (size_t)ky * stride), wy[ky]));
+            vbuf[wib][kx] = v;
+        }
+        __syncwarp();
+        if (lane == 0) {  // horizontal chain in tap order
+            const float *__restrict__ wx = tx.w + (size_t)f.ox * tx.kmax;
+            float t = 0.0f;
+            for (int kx = 0; kx < nx; ++kx) t = __fadd_rn(t, __fmul_rn(vbuf[wib][kx], wx[kx]));
+            t = fminf(fmaxf(t, 0.0f), 255.0f);
+            dst[(size_t)f.img * pd.pyr_stride + pd.lv[f.lev].off + (size_t)f.oy * pd.lv[f.lev].w + f.ox] =
+                (uint8_t)__float2uint_rz(roundf(t));
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace
 
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
 struct PyrPlan {
     PyrDesc pd;
     PyrTaps taps;
-    TileTable tt;
-    int total_blocks;
+    // tile descriptors of the generic kernel: [0, n_all) every level (fast path unusable),
+    // [n_all, n_all + n_rest) what the fast path leaves: ring of the dyadic levels + non-dyadic levels
+    TileDesc *d_tiles;
+    int n_all, n_rest;
+    // fast path
+    int n_fast;      // deepest level on the dyadic path (0: none)
+    int n_a;         // deepest level produced by pyr_fast_kernel (<= 3)
+    int do4, do5;
+    int tiles_x, tiles_y;
+    RingWeights ring[4];
     void *d_tables;
+    // scratch for deep levels (grown on demand)
+    uint32_t *d_g8;
+    size_t g8_images;
+    FixItem *d_fix;
+    int *d_fix_count;
+    int fix_cap;
 };
+
+// tiles covering the output rectangle [x0, x0 + nx) x [y0, y0 + ny) of one level
+static void add_rect_tiles(const PyrDesc &pd, int lev, int x0, int y0, int nx, int ny, std::vector<TileDesc> &out) {
+    if (nx <= 0 || ny <= 0) return;
+    const double ratio = (double)pd.lv[0].w / (double)(pd.lv[lev].w > 0 ? pd.lv[lev].w : 1);
+    // intermediate columns per tile row: (tox + 1) * ratio + 8 must fit the smem budget with noy rows
+    int tox = nx < 32 ? nx : 32;
+    while (tox > 1 && (tox + 1) * ratio + 8 > 672) tox >>= 1;
+    const int cols = (int)((tox + 1) * ratio) + 8;
+    int toy = kGenSmemFloats / cols;
+    if (toy > 8 && nx > 1) toy = 8;  // wide tiles: 8 rows; single-column ring tiles: as tall as fits
+    if (toy > 64) toy = 64;
+    if (toy < 1) toy = 1;
+    for (int y = y0; y < y0 + ny; y += toy)
+        for (int x = x0; x < x0 + nx; x += tox) {
+            TileDesc t;
+            t.lev = (int16_t)lev;
+            t.ox0 = x;
+            t.oy0 = y;
+            t.nox = (int16_t)((x0 + nx - x) < tox ? (x0 + nx - x) : tox);
+            t.noy = (int16_t)((y0 + ny - y) < toy ? (y0 + ny - y) : toy);
+            t.pad = 0;
+            out.push_back(t);
+        }
+}
+
+static void add_level0_tiles(const PyrDesc &pd, std::vector<TileDesc> &out) {
+    const int w = pd.lv[0].w, h = pd.lv[0].h;
+    int rows = 16384 / (w > 0 ? w : 1);
+    rows = rows < 1 ? 1 : rows;
+    for (int y = 0; y < h; y += rows) {
+        TileDesc t;
+        t.lev = 0;
+        t.ox0 = 0;
+        t.oy0 = y;
+        t.nox = 0;
+        t.noy = (int16_t)((h - y) < rows ? (h - y) : rows);
+        t.pad = 0;
+        out.push_back(t);
+    }
+}
 
 cudaError_t pyr_plan_create(int w, int h, int levels, cudaStream_t st, PyrPlan **out) {
     PyrPlan *p = new PyrPlan();
     p->pd = make_pyr_desc(w, h, levels);
     p->d_tables = nullptr;
+    p->d_tiles = nullptr;
+    p->d_g8 = nullptr;
+    p->g8_images = 0;
+    p->d_fix = nullptr;
+    p->d_fix_count = nullptr;
+    p->fix_cap = 0;
     // one allocation for all tap tables
     size_t bytes = 0;
     struct Sz { int n_in, n_out, kmax; size_t off_left, off_cnt, off_w; };
@@ -194,28 +815,64 @@ cudaError_t pyr_plan_create(int w, int h, int levels, cudaStream_t st, PyrPlan *
                 taps_kernel<<<(s.n_out + 127) / 128, 128, 0, st>>>(s.n_in, s.n_out, s.kmax, (int *)t.left, (int *)t.cnt,
                                                                    (float *)t.w);
         }
-    // tiles
-    int blocks = 0;
-    for (int i = 0; i < levels; ++i) {
-        p->tt.first_block[i] = blocks;
-        const int wl = w >> i, hl = h >> i;
-        if (i == 0) {
-            int rows = 16384 / (w > 0 ? w : 1);
-            rows = rows < 1 ? 1 : rows;
-            p->tt.tox[0] = rows;
-            p->tt.tiles_x[0] = 1;
-            blocks += (h + rows - 1) / rows;
-        } else {
-            const double ratio = (double)w / (double)(wl > 0 ? wl : 1);
-            int tox = 32;
-            while (tox > 1 && (tox + 1) * ratio + 3 > kMaxCols) tox >>= 1;
-            p->tt.tox[i] = tox;
-            p->tt.tiles_x[i] = (wl + tox - 1) / tox;
-            blocks += p->tt.tiles_x[i] * ((hl + kTileRows - 1) / kTileRows);
+    // dyadic fast path: level i qualifies while w and h are divisible by 2^i and the level is at
+    // least 3x3 (it needs an interior); levels >= 6 overflow the u32 tent sums
+    p->n_fast = 0;
+    if ((w % 16) == 0 && levels >= 2) {
+        for (int i = 1; i < levels && i <= 5; ++i) {
+            if ((w % (1 << i)) || (h % (1 << i)) || (w >> i) < 3 || (h >> i) < 3) break;
+            p->n_fast = i;
         }
     }
-    for (int i = levels; i <= kMaxLevels; ++i) p->tt.first_block[i] = blocks;
-    p->total_blocks = blocks;
+    p->n_a = p->n_fast < 3 ? p->n_fast : 3;
+    p->do4 = p->n_fast >= 4;
+    p->do5 = p->n_fast >= 5;
+    p->tiles_x = (w + TW - 1) / TW;
+    p->tiles_y = (h + TH - 1) / TH;
+    // faithful border weights of the dyadic levels handled by pyr_fast_kernel: they depend on the
+    // ratio only; take them from the x table (outputs 0, 1 and n-1) as computed on the device
+    memset(p->ring, 0, sizeof(p->ring));
+    for (int i = 1; i <= p->n_a; ++i) {
+        const TapTable &t = p->taps.x[i];
+        const int r = 1 << i, nb = r + r / 2;
+        e = cudaStreamSynchronize(st);
+        if (e == cudaSuccess) e = cudaMemcpy(p->ring[i].first, t.w, sizeof(float) * nb, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(p->ring[i].inner, t.w + (size_t)1 * t.kmax, sizeof(float) * 2 * r, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(p->ring[i].last, t.w + (size_t)(t.n_out - 1) * t.kmax, sizeof(float) * nb, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            pyr_plan_destroy(p);
+            return e;
+        }
+    }
+    {
+        std::vector<TileDesc> all, rest;
+        add_level0_tiles(p->pd, all);
+        for (int i = 1; i < levels; ++i) {
+            const int wl = p->pd.lv[i].w, hl = p->pd.lv[i].h;
+            add_rect_tiles(p->pd, i, 0, 0, wl, hl, all);
+            if (i > p->n_fast) {
+                add_rect_tiles(p->pd, i, 0, 0, wl, hl, rest);
+            } else if (i > p->n_a) {  // ring of the deep dyadic levels (levels <= n_a: inside pyr_fast_kernel)
+                add_rect_tiles(p->pd, i, 0, 0, wl, 1, rest);
+                add_rect_tiles(p->pd, i, 0, hl - 1, wl, 1, rest);
+                add_rect_tiles(p->pd, i, 0, 1, 1, hl - 2, rest);
+                add_rect_tiles(p->pd, i, wl - 1, 1, 1, hl - 2, rest);
+            }
+        }
+        p->n_all = (int)all.size();
+        p->n_rest = (int)rest.size();
+        all.insert(all.end(), rest.begin(), rest.end());
+        e = cudaMalloc((void **)&p->d_tiles, all.size() * sizeof(TileDesc));
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(p->d_tiles, all.data(), all.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `all` is a local
+        if (e != cudaSuccess) {
+            pyr_plan_destroy(p);
+            return e;
+        }
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) {
         pyr_plan_destroy(p);
@@ -228,18 +885,44 @@ cudaError_t pyr_plan_create(int w, int h, int levels, cudaStream_t st, PyrPlan *
 void pyr_plan_destroy(PyrPlan *p) {
     if (!p) return;
     if (p->d_tables) cudaFree(p->d_tables);
+    if (p->d_tiles) cudaFree(p->d_tiles);
+    if (p->d_g8) cudaFree(p->d_g8);
+    if (p->d_fix) cudaFree(p->d_fix);
+    if (p->d_fix_count) cudaFree(p->d_fix_count);
     delete p;
 }
 
 const PyrDesc &pyr_plan_desc(const PyrPlan *p) { return p->pd; }
 
+cudaError_t pyr_plan_reserve(PyrPlan *p, int n_images) {
+    if (!p->do4 || (size_t)n_images <= p->g8_images) return cudaSuccess;
+    if (p->d_g8) cudaFree(p->d_g8);
+    if (p->d_fix) cudaFree(p->d_fix);
+    p->d_g8 = nullptr;
+    p->d_fix = nullptr;
+    const size_t per = (size_t)(p->pd.lv[0].w / 8) * (p->pd.lv[0].h / 8);
+    cudaError_t e = cudaMalloc((void **)&p->d_g8, per * n_images * sizeof(uint32_t));
+    if (e != cudaSuccess) return e;
+    p->fix_cap = 4096 + (int)((size_t)n_images * (size_t)p->pd.lv[4].w * p->pd.lv[4].h / 64);
+    e = cudaMalloc((void **)&p->d_fix, sizeof(FixItem) * (size_t)p->fix_cap);
+    if (e != cudaSuccess) return e;
+    if (!p->d_fix_count) {
+        e = cudaMalloc((void **)&p->d_fix_count, sizeof(int));
+        if (e != cudaSuccess) return e;
+    }
+    p->g8_images = (size_t)n_images;
+    return cudaSuccess;
+}
+
 cudaError_t pyr_build(const PyrPlan *p, const uint8_t *src0, const uint8_t *src1, int split, int n_images,
                       size_t stride, size_t pitch, uint8_t *dst, cudaStream_t st, int *n_launches) {
     if (n_images <= 0) return cudaSuccess;
+    auto aligned16 = [](const void *q) { return (((size_t)q) & 15) == 0; };
+    const bool fast = p->n_fast >= 1 && aligned16(src0) && aligned16(dst) && (split >= n_images || aligned16(src1)) && (stride % 16) == 0 &&
+                      (n_images == 1 || (pitch % 16) == 0) && (!p->do4 || (size_t)n_images <= p->g8_images);
     // gridDim.y is limited to 65535 images per launch
     for (int first = 0; first < n_images; first += 65535) {
         const int n = n_images - first < 65535 ? n_images - first : 65535;
-        // images [first, first+n): shift the two sources so that local index j maps correctly
         const uint8_t *s0 = src0, *s1 = src1;
         int sp = split - first;
         if (sp < 0) {
@@ -248,10 +931,52 @@ cudaError_t pyr_build(const PyrPlan *p, const uint8_t *src0, const uint8_t *src1
         } else {
             s0 = src0 + (size_t)first * pitch;
         }
-        dim3 grid((unsigned)p->total_blocks, (unsigned)n, 1);
-        pyr_generic_kernel<<<grid, kThreads, 0, st>>>(p->pd, p->taps, p->tt, s0, s1, sp, stride, pitch,
-                                                      dst + (size_t)first * p->pd.pyr_stride);
+        uint8_t *d = dst + (size_t)first * p->pd.pyr_stride;
+        if (!fast) {
+            dim3 grid((unsigned)p->n_all, (unsigned)n, 1);
+            pyr_generic_kernel<<<grid, kGenThreads, 0, st>>>(p->pd, p->taps, p->d_tiles, s0, s1, sp, stride, pitch, d);
+            if (n_launches) ++*n_launches;
+            continue;
+        }
+        FastParams fp;
+        fp.pd = p->pd;
+        memcpy(fp.ring, p->ring, sizeof(fp.ring));
+        fp.src0 = s0;
+        fp.src1 = s1;
+        fp.split = sp;
+        fp.stride = stride;
+        fp.pitch = pitch;
+        fp.dst = d;
+        fp.g8 = p->do4 ? p->d_g8 : nullptr;
+        fp.tiles_x = p->tiles_x;
+        dim3 grid((unsigned)(p->tiles_x * p->tiles_y), (unsigned)n, 1);
+        if (p->n_a == 1)
+            pyr_fast_kernel<1><<<grid, NTA, 0, st>>>(fp);
+        else if (p->n_a == 2)
+            pyr_fast_kernel<2><<<grid, NTA, 0, st>>>(fp);
+        else
+            pyr_fast_kernel<3><<<grid, NTA, 0, st>>>(fp);
         if (n_launches) ++*n_launches;
+        if (p->do4) {
+            cudaError_t e = cudaMemsetAsync(p->d_fix_count, 0, sizeof(int), st);
+            if (e != cudaSuccess) return e;
+            const long long items = (long long)n * ((long long)p->pd.lv[4].w * p->pd.lv[4].h +
+                                                    (p->do5 ? (long long)p->pd.lv[5].w * p->pd.lv[5].h : 0));
+            long long blocks = (items + 255) / 256;
+            if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+            if (blocks < 1) blocks = 1;
+            pyr_deep_kernel<<<(unsigned)blocks, 256, 0, st>>>(p->pd, p->d_g8, n, p->do5, d, p->d_fix, p->d_fix_count,
+                                                               p->fix_cap);
+            pyr_fixup_kernel<<<kNumSMs, 128, 0, st>>>(p->pd, p->taps, s0, s1, sp, stride, pitch, d, p->d_fix,
+                                                      p->d_fix_count, p->fix_cap);
+            if (n_launches) *n_launches += 2;
+        }
+        if (p->n_rest > 0) {  // ring of the dyadic levels + whole non-dyadic levels
+            dim3 ggrid((unsigned)p->n_rest, (unsigned)n, 1);
+            pyr_generic_kernel<<<ggrid, kGenThreads, 0, st>>>(p->pd, p->taps, p->d_tiles + p->n_all, s0, s1, sp, stride,
+                                                             pitch, d);
+            if (n_launches) ++*n_launches;
+        }
     }
     return cudaGetLastError();
 }
