@@ -37,6 +37,8 @@
 // with -fmad=false.
 #include "common.cuh"
 
+#include <cuda.h>
+
 #include <cstring>
 #include <vector>
 
@@ -213,12 +215,10 @@ struct RingWeights {
 struct FastParams {
     PyrDesc pd;
     RingWeights ring[4];      // index = level (1..3)
-    const uint8_t *src0, *src1;
-    int split;
-    size_t stride, pitch;
+    int split, n_images;  // images [0, split) come through tensor map 0, the rest through map 1
     uint8_t *dst;
-    uint32_t *g8;       // [img][h0/8][w0/8] exported when deeper levels follow, else nullptr
-    int tiles_x;
+    uint32_t *g8;         // [img][h0/8][w0/8] exported when deeper levels follow, else nullptr
+    int tiles_x, tiles_y;
 };
 
 __device__ __forceinline__ uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c) {
@@ -298,56 +298,116 @@ __device__ __forceinline__ void stage1_row(const uint32_t *__restrict__ wr, uint
     }
 }
 
+// ---- TMA / mbarrier primitives (sm_100a) ---------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(mbar), "r"(parity) : "memory");
+}
+// 3-D tiled bulk tensor load global -> shared (zero fill outside the tensor), completes on mbar
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int x, int y, int z, uint32_t mbar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(z), "r"(mbar) : "memory");
+}
+
+// The tile [X0 - 16, X0 + TW + 16) x [Y0 - ytop, Y0 + TH + ybot) is wider than the 256-element TMA
+// box limit, so it is fetched as two overlapping boxes of RW columns: region A = tile columns
+// [0, RW), region B = [RB, RB + RW).  Every 16-byte window a stage-1 lane needs lies in one of them.
+constexpr int RW = 160, RB = 128;
+constexpr int kSplitCol = 144;  // tile columns below this are read from region A, the rest from B
+
 template <int NA>
-__global__ void __launch_bounds__(NTA) pyr_fast_kernel(const __grid_constant__ FastParams P) {
+struct FastSmem {
     using C = FastCfg<NA>;
-    __shared__ __align__(16) uint8_t tile[C::ROWS][PITCH];
-    __shared__ __align__(16) uint16_t g2[C::G2ROWS][G2P];
-    __shared__ __align__(16) uint32_t g4[NA >= 3 ? C::G4R : 1][NA >= 3 ? C::G4C : 1];
-    __shared__ float vbuf[NA][PITCH];
+    static constexpr int region = (C::ROWS * RW + 127) & ~127;
+    static constexpr int off_tile = 0;                                   // [2 buffers][A, B][ROWS][RW]
+    static constexpr int off_g2 = off_tile + 4 * region;
+    static constexpr int off_g4 = (off_g2 + C::G2ROWS * G2P * 2 + 15) & ~15;
+    static constexpr int off_vbuf = (off_g4 + (NA >= 3 ? C::G4R * C::G4C * 4 : 4) + 15) & ~15;
+    static constexpr int off_mbar = (off_vbuf + NA * PITCH * 4 + 15) & ~15;
+    static constexpr int bytes = off_mbar + 16 + 128;                    // + slack for the 128-B base alignment
+};
 
-    const int img = blockIdx.y;
-    const int tile_y = blockIdx.x / P.tiles_x, tile_x = blockIdx.x - tile_y * P.tiles_x;
-    const int X0 = tile_x * TW, Y0 = tile_y * TH;
-    const int w0 = P.pd.lv[0].w, h0 = P.pd.lv[0].h;
-    const uint8_t *__restrict__ src = image_ptr(P.src0, P.src1, P.split, img, P.pitch);
-    uint8_t *__restrict__ out = P.dst + (size_t)img * P.pd.pyr_stride;
+template <int NA>
+__global__ void __launch_bounds__(NTA)
+pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CUtensorMap map0,
+                const __grid_constant__ CUtensorMap map1) {
+    using C = FastCfg<NA>;
+    using S = FastSmem<NA>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint16_t(*g2)[G2P] = reinterpret_cast<uint16_t(*)[G2P]>(smem + S::off_g2);
+    uint32_t(*g4)[C::G4C] = reinterpret_cast<uint32_t(*)[C::G4C]>(smem + S::off_g4);
+    float(*vbuf)[PITCH] = reinterpret_cast<float(*)[PITCH]>(smem + S::off_vbuf);
+    const uint32_t mbar0 = smem_u32(smem + S::off_mbar);
+
     const int tid = threadIdx.x;
+    const int w0 = P.pd.lv[0].w, h0 = P.pd.lv[0].h;
+    const int w1 = P.pd.lv[1].w, h1 = P.pd.lv[1].h;
+    const int tiles_per_img = P.tiles_x * P.tiles_y;
+    const int total = tiles_per_img * P.n_images;
 
-    // ---- stage 0: tile -> shared memory (16-byte loads, zero fill outside the image), level 0 out.
-    // A thread owns one 16-byte column of the tile and walks down the rows (RP rows apart).
-    {
-        constexpr int VPR = PITCH / 16;    // 16-byte vectors per tile row
-        constexpr int RP = NTA / VPR;      // rows per pass
-        if (tid < VPR * RP) {
-            const int vx = tid % VPR, r0 = tid / VPR;
-            const int x = X0 - 16 + vx * 16;
-            const bool in_x = x >= 0 && x < w0;            // w0 % 16 == 0: all 16 bytes or none
-            const bool copy_x = in_x && x >= X0 && x < X0 + TW;
-            // tile rows holding image rows, and those that are also level-0 output of this tile
-            const int ry_lo = max(0, C::ytop - Y0), ry_hi = in_x ? min(C::ROWS, h0 - Y0 + C::ytop) : 0;
-            const int cy_lo = C::ytop, cy_hi = copy_x ? min(C::ytop + TH, ry_hi) : 0;
-            const uint32_t gstep = (uint32_t)RP * (uint32_t)P.stride, ostep = (uint32_t)RP * (uint32_t)w0;
-            const uint8_t *__restrict__ gp = src + (ptrdiff_t)(Y0 - C::ytop + r0) * (ptrdiff_t)P.stride + x;
-            uint8_t *__restrict__ op = out + (ptrdiff_t)(Y0 - C::ytop + r0) * w0 + x;
-            uint8_t *sp = &tile[r0][vx * 16];
-#pragma unroll 3
-            for (int ry = r0; ry < C::ROWS; ry += RP) {
-                uint4 q = make_uint4(0u, 0u, 0u, 0u);
-                if (ry >= ry_lo && ry < ry_hi) q = __ldg(reinterpret_cast<const uint4 *>(gp));
-                *reinterpret_cast<uint4 *>(sp) = q;
-                if (ry >= cy_lo && ry < cy_hi) *reinterpret_cast<uint4 *>(op) = q;  // level 0 == input
-                gp += gstep;
-                op += ostep;
-                sp += RP * PITCH;
-            }
-        }
+    auto issue_load = [&](int tile_id, int buf) {  // one elected thread: both boxes of one tile
+        const int img = tile_id / tiles_per_img, tl = tile_id - img * tiles_per_img;
+        const int ty = tl / P.tiles_x, tx = tl - ty * P.tiles_x;
+        const CUtensorMap *map = img < P.split ? &map0 : &map1;
+        const int z = img < P.split ? img : img - P.split;
+        const uint32_t mbar = mbar0 + 8u * buf;
+        const uint32_t dst = smem_u32(smem + S::off_tile + 2 * buf * S::region);
+        mbar_expect_tx(mbar, 2u * C::ROWS * RW);
+        tma_load_3d(dst, map, tx * TW - 16, ty * TH - C::ytop, z, mbar);
+        tma_load_3d(dst + S::region, map, tx * TW - 16 + RB, ty * TH - C::ytop, z, mbar);
+    };
+
+    if (tid == 0) {
+        mbar_init(mbar0, 1);
+        mbar_init(mbar0 + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (tid == 0 && (int)blockIdx.x < total) issue_load(blockIdx.x, 0);
+
+    int it = 0;
+    for (int tile_id = blockIdx.x; tile_id < total; tile_id += gridDim.x, ++it) {
+    const int buf = it & 1;
+    if (tid == 0 && tile_id + (int)gridDim.x < total) issue_load(tile_id + gridDim.x, buf ^ 1);  // prefetch
+    const int img = tile_id / tiles_per_img, tl = tile_id - img * tiles_per_img;
+    const int tile_y = tl / P.tiles_x, tile_x = tl - tile_y * P.tiles_x;
+    const int X0 = tile_x * TW, Y0 = tile_y * TH;
+    uint8_t *__restrict__ out = P.dst + (size_t)img * P.pd.pyr_stride;
+    const uint8_t *__restrict__ tA = smem + S::off_tile + 2 * buf * S::region;   // tile columns [0, RW)
+    const uint8_t *__restrict__ tB = tA + S::region - RB;                        // indexable by tile column >= RB
+    auto trow = [&](int ry, int col) -> const uint8_t * { return (col < kSplitCol ? tA : tB) + ry * RW + col; };
+    mbar_wait(mbar0 + 8u * buf, (it >> 1) & 1);
+
+    // ---- stage 0: level 0 == input, 16-byte copies from the staged tile
+    {
+        constexpr int VPT = TW / 16;
+        const int nrow = min(TH, h0 - Y0), nvec = min(VPT, (w0 - X0) >> 4);
+        for (int idx = tid; idx < TH * VPT; idx += NTA) {
+            const int y = idx / VPT, vx = idx - y * VPT;
+            if (y < nrow && vx < nvec)
+                *reinterpret_cast<uint4 *>(out + (size_t)(Y0 + y) * w0 + X0 + vx * 16) =
+                    *reinterpret_cast<const uint4 *>(trow(y + C::ytop, 16 + vx * 16));
+        }
+    }
 
     // ---- stage 1: level-1 output O_2 (global) and G_2 (smem); 4 chained DP4A per value.
     // Warp = one row segment, lane c = level-1 columns X0/2 + 4c .. +3 (O) and X0/2 + 4c - 2 .. +1 (G).
-    const int w1 = P.pd.lv[1].w, h1 = P.pd.lv[1].h;
     const int t_first = Y0 / 2 - C::et;    // first emitted level-1 row of the tile
     {
         const int c = tid & (NCOL - 1), seg = tid / NCOL;
@@ -362,10 +422,13 @@ __global__ void __launch_bounds__(NTA) pyr_fast_kernel(const __grid_constant__ F
         uint32_t aOo[4] = {0, 0, 0, 0}, aOn[4] = {0, 0, 0, 0}, aGo[4] = {0, 0, 0, 0}, aGm[4] = {0, 0, 0, 0},
                  aGn[4] = {0, 0, 0, 0};
         uint8_t *__restrict__ orow = out + P.pd.lv[1].off + (ptrdiff_t)(ts - 1) * w1 + j0;  // row tau - 1
+        // tile word of pixels 2*j0 .. 2*j0+3 on base row 2*tau - 1 (lanes 0..15 read region A, 16..31 region B)
         const uint32_t *__restrict__ wr =
-            reinterpret_cast<const uint32_t *>(&tile[2 * ts - 1 - (Y0 - C::ytop)][0]) + (4 + 2 * c);  // row 2*tau-1
+            reinterpret_cast<const uint32_t *>((c < 16 ? tA : tB + RB) + (2 * ts - 1 - (Y0 - C::ytop)) * RW) +
+            (c < 16 ? 4 + 2 * c : 2 * c - 28);
         uint2 *__restrict__ grow = reinterpret_cast<uint2 *>(&g2[0][4 * c]) + (ptrdiff_t)(ts - 2 - t_first) * (G2P / 4);
         constexpr bool G = NA >= 2;
+        constexpr int RWW = RW / 4;
         auto store_o = [&](int to) {  // O_{to} complete -> level 1, round half up: (N + 32) >> 6
             if (to >= o_lo && to < o_hi) {
                 const uint32_t b0 = (aOo[0] + 32u) >> 6, b1 = (aOo[1] + 32u) >> 6;
@@ -389,7 +452,7 @@ __global__ void __launch_bounds__(NTA) pyr_fast_kernel(const __grid_constant__ F
                     aGm[q] = aGn[q];
                 }
             }
-            wr += 2 * (PITCH / 4);
+            wr += 2 * RWW;
             orow += w1;
             grow += G2P / 4;
         };
@@ -397,33 +460,30 @@ __global__ void __launch_bounds__(NTA) pyr_fast_kernel(const __grid_constant__ F
             // O_t spans rows 2t-1..2t+2 (complete in iteration t+1, second row), G_t rows 2t..2t+3
             // (complete in iteration t+2, first row).  Iterations ts and ts+1 and te, te+1 are peeled:
             // they only feed the accumulators of rows this segment emits.
-            // tau = ts: start O_ts (row a, b) and G_ts (row b)
             stage1_row<true, true, false, false, false, false>(wr, aOn, aOo, aGn, aGm, aGo);
-            stage1_row<false, true, false, G, false, false>(wr + PITCH / 4, aOn, aOo, aGn, aGm, aGo);
+            stage1_row<false, true, false, G, false, false>(wr + RWW, aOn, aOo, aGn, aGm, aGo);
             rotate();
             if (ts + 1 < te) {
-                // tau = ts+1: O_{ts+1}, O_ts (done), G_{ts+1}, G_ts
                 stage1_row<true, true, true, false, G, false>(wr, aOn, aOo, aGn, aGm, aGo);
-                stage1_row<false, true, true, G, G, false>(wr + PITCH / 4, aOn, aOo, aGn, aGm, aGo);
+                stage1_row<false, true, true, G, G, false>(wr + RWW, aOn, aOo, aGn, aGm, aGo);
                 store_o(ts);
                 rotate();
                 for (int tau = ts + 2; tau < te; ++tau) {
                     stage1_row<true, true, true, false, G, G>(wr, aOn, aOo, aGn, aGm, aGo);
                     if (G) *grow = make_uint2(aGo[0] | (aGo[1] << 16), aGo[2] | (aGo[3] << 16));  // G_{tau-2}
-                    stage1_row<false, true, true, G, G, false>(wr + PITCH / 4, aOn, aOo, aGn, aGm, aGo);
+                    stage1_row<false, true, true, G, G, false>(wr + RWW, aOn, aOo, aGn, aGm, aGo);
                     store_o(tau - 1);
                     rotate();
                 }
                 // tau = te: finish O_{te-1}, G_{te-2}; keep G_{te-1} going; nothing new starts
                 stage1_row<true, false, true, false, G, G>(wr, aOn, aOo, aGn, aGm, aGo);
                 if (G) *grow = make_uint2(aGo[0] | (aGo[1] << 16), aGo[2] | (aGo[3] << 16));
-                stage1_row<false, false, true, false, G, false>(wr + PITCH / 4, aOn, aOo, aGn, aGm, aGo);
+                stage1_row<false, false, true, false, G, false>(wr + RWW, aOn, aOo, aGn, aGm, aGo);
                 store_o(te - 1);
                 rotate();
-            } else {
-                // single-row segment: tau = te = ts + 1
+            } else {  // single-row segment: tau = te = ts + 1
                 stage1_row<true, false, true, false, G, false>(wr, aOn, aOo, aGn, aGm, aGo);
-                stage1_row<false, false, true, false, G, false>(wr + PITCH / 4, aOn, aOo, aGn, aGm, aGo);
+                stage1_row<false, false, true, false, G, false>(wr + RWW, aOn, aOo, aGn, aGm, aGo);
                 store_o(ts);
                 rotate();
             }
@@ -436,13 +496,13 @@ __global__ void __launch_bounds__(NTA) pyr_fast_kernel(const __grid_constant__ F
         if (G) {
             constexpr int GXD = C::GX > 0 ? C::GX : 1;
             for (int idx = tid; idx < C::GX * C::NE; idx += NTA) {
-                const int gx = idx % GXD, tr = idx / GXD;        // column X0/2 + TW/2 - 2 + gx, row t_first + tr
-                const int px = TW - 4 + 2 * gx + 16;                 // tile byte column of pixel 2j
+                const int gx = idx % GXD, tr = idx / GXD;             // column X0/2 + TW/2 - 2 + gx, row t_first + tr
+                const int px = TW - 4 + 2 * gx + 16;                 // tile byte column of pixel 2j (region B)
                 const int ry = 2 * (t_first + tr) - (Y0 - C::ytop);  // tile row of base row 2t
                 uint32_t acc = 0;
 #pragma unroll
                 for (int rr = 0; rr < 4; ++rr) {
-                    const uint32_t *__restrict__ wq = reinterpret_cast<const uint32_t *>(&tile[ry + rr][0]) + (px >> 2);
+                    const uint32_t *__restrict__ wq = reinterpret_cast<const uint32_t *>(tB + (ry + rr) * RW) + (px >> 2);
                     const uint32_t v = (px & 2) ? __funnelshift_r(wq[0], wq[1], 16) : wq[0];
                     acc = dp4a_u(v, (rr == 0 || rr == 3) ? 0x01030301u : 0x03090903u, acc);
                 }
@@ -546,58 +606,63 @@ __global__ void __launch_bounds__(NTA) pyr_fast_kernel(const __grid_constant__ F
     // windows are renormalised by a non-dyadic sum, so nothing is exact there), read from the tile.
     const bool top = Y0 == 0, bottom = Y0 + TH >= h0 && Y0 < h0;
     const bool left = X0 == 0, right = X0 + TW >= w0 && X0 < w0;
-    if (!(top || bottom || left || right)) return;
-    auto pix = [&](int x, int y) { return (float)tile[y - Y0 + C::ytop][x - X0 + 16]; };
+    if (top || bottom || left || right) {
+        auto pix = [&](int x, int y) { return (float)*trow(y - Y0 + C::ytop, x - X0 + 16); };
 #pragma unroll 1
-    for (int side = 0; side < 2; ++side) {  // border rows: oy = 0 (top tiles), oy = hl - 1 (bottom tiles)
-        if (side == 0 ? !top : !bottom) continue;
-        __syncthreads();
-        // vertical chains of all levels: one thread per (level, column)
-        for (int idx = tid; idx < NA * PITCH; idx += NTA) {
-            const int lev = 1 + idx / PITCH, x = X0 - 16 + idx % PITCH;
-            const int r = 1 << lev, hl = P.pd.lv[lev].h;
-            const int oy = side == 0 ? 0 : hl - 1;
-            if (oy * r < Y0 || oy * r >= Y0 + TH || x < max(X0 - (r >> 1), 0) || x >= min(X0 + TW + (r >> 1), w0)) continue;
-            const RingTap ty = ring_tap(P.ring[lev], oy, hl, r);
-            float v = 0.0f;
-            for (int k = 0; k < ty.cnt; ++k) v = __fadd_rn(v, __fmul_rn(pix(x, ty.left + k), ty.w[k]));
-            vbuf[lev - 1][x - X0 + 16] = v;
+        for (int side = 0; side < 2; ++side) {  // border rows: oy = 0 (top tiles), oy = hl - 1 (bottom tiles)
+            if (side == 0 ? !top : !bottom) continue;
+            __syncthreads();
+            // vertical chains of all levels: one thread per (level, column)
+            for (int idx = tid; idx < NA * PITCH; idx += NTA) {
+                const int lev = 1 + idx / PITCH, x = X0 - 16 + idx % PITCH;
+                const int r = 1 << lev, hl = P.pd.lv[lev].h;
+                const int oy = side == 0 ? 0 : hl - 1;
+                if (oy * r < Y0 || oy * r >= Y0 + TH || x < max(X0 - (r >> 1), 0) || x >= min(X0 + TW + (r >> 1), w0))
+                    continue;
+                const RingTap ty = ring_tap(P.ring[lev], oy, hl, r);
+                float v = 0.0f;
+                for (int k = 0; k < ty.cnt; ++k) v = __fadd_rn(v, __fmul_rn(pix(x, ty.left + k), ty.w[k]));
+                vbuf[lev - 1][x - X0 + 16] = v;
+            }
+            __syncthreads();
+            // horizontal chains: one thread per (level, output column)
+            for (int idx = tid; idx < NA * (TW / 2); idx += NTA) {
+                const int lev = 1 + idx / (TW / 2), lx = idx % (TW / 2);
+                const int r = 1 << lev, wl = P.pd.lv[lev].w, hl = P.pd.lv[lev].h;
+                const int oy = side == 0 ? 0 : hl - 1;
+                const int ox = X0 / r + lx;
+                if (lx >= TW / r || ox >= wl || oy * r < Y0 || oy * r >= Y0 + TH) continue;
+                const RingTap tx = ring_tap(P.ring[lev], ox, wl, r);
+                float t = 0.0f;
+                for (int k = 0; k < tx.cnt; ++k)
+                    t = __fadd_rn(t, __fmul_rn(vbuf[lev - 1][tx.left + k - X0 + 16], tx.w[k]));
+                t = fminf(fmaxf(t, 0.0f), 255.0f);
+                out[P.pd.lv[lev].off + (size_t)oy * wl + ox] = (uint8_t)__float2uint_rz(roundf(t));
+            }
         }
-        __syncthreads();
-        // horizontal chains: one thread per (level, output column)
-        for (int idx = tid; idx < NA * (TW / 2); idx += NTA) {
-            const int lev = 1 + idx / (TW / 2), lx = idx % (TW / 2);
+        // border columns (ox = 0 for left tiles, ox = wl - 1 for right tiles) without the corner rows
+        for (int idx = tid; idx < 2 * NA * (TH / 2); idx += NTA) {
+            const int side = idx / (NA * (TH / 2)), rem = idx % (NA * (TH / 2));
+            const int lev = 1 + rem / (TH / 2), ly = rem % (TH / 2);
+            if (side == 0 ? !left : !right) continue;
             const int r = 1 << lev, wl = P.pd.lv[lev].w, hl = P.pd.lv[lev].h;
-            const int oy = side == 0 ? 0 : hl - 1;
-            const int ox = X0 / r + lx;
-            if (lx >= TW / r || ox >= wl || oy * r < Y0 || oy * r >= Y0 + TH) continue;
-            const RingTap tx = ring_tap(P.ring[lev], ox, wl, r);
+            const int oy = Y0 / r + ly;
+            const int ox = side == 0 ? 0 : wl - 1;
+            if (ly >= TH / r || oy < 1 || oy > hl - 2 || ox * r < X0 || ox * r >= X0 + TW) continue;
+            const RingTap tx = ring_tap(P.ring[lev], ox, wl, r), ty = ring_tap(P.ring[lev], oy, hl, r);
             float t = 0.0f;
-            for (int k = 0; k < tx.cnt; ++k)
-                t = __fadd_rn(t, __fmul_rn(vbuf[lev - 1][tx.left + k - X0 + 16], tx.w[k]));
+            for (int kx = 0; kx < tx.cnt; ++kx) {
+                float v = 0.0f;
+                for (int ky = 0; ky < ty.cnt; ++ky)
+                    v = __fadd_rn(v, __fmul_rn(pix(tx.left + kx, ty.left + ky), ty.w[ky]));
+                t = __fadd_rn(t, __fmul_rn(v, tx.w[kx]));
+            }
             t = fminf(fmaxf(t, 0.0f), 255.0f);
             out[P.pd.lv[lev].off + (size_t)oy * wl + ox] = (uint8_t)__float2uint_rz(roundf(t));
         }
     }
-    // border columns (ox = 0 for left tiles, ox = wl - 1 for right tiles) without the corner rows
-    for (int idx = tid; idx < 2 * NA * (TH / 2); idx += NTA) {
-        const int side = idx / (NA * (TH / 2)), rem = idx % (NA * (TH / 2));
-        const int lev = 1 + rem / (TH / 2), ly = rem % (TH / 2);
-        if (side == 0 ? !left : !right) continue;
-        const int r = 1 << lev, wl = P.pd.lv[lev].w, hl = P.pd.lv[lev].h;
-        const int oy = Y0 / r + ly;
-        const int ox = side == 0 ? 0 : wl - 1;
-        if (ly >= TH / r || oy < 1 || oy > hl - 2 || ox * r < X0 || ox * r >= X0 + TW) continue;
-        const RingTap tx = ring_tap(P.ring[lev], ox, wl, r), ty = ring_tap(P.ring[lev], oy, hl, r);
-        float t = 0.0f;
-        for (int kx = 0; kx < tx.cnt; ++kx) {
-            float v = 0.0f;
-            for (int ky = 0; ky < ty.cnt; ++ky) v = __fadd_rn(v, __fmul_rn(pix(tx.left + kx, ty.left + ky), ty.w[ky]));
-            t = __fadd_rn(t, __fmul_rn(v, tx.w[kx]));
-        }
-        t = fminf(fmaxf(t, 0.0f), 255.0f);
-        out[P.pd.lv[lev].off + (size_t)oy * wl + ox] = (uint8_t)__float2uint_rz(roundf(t));
-    }
+    __syncthreads();  // every read of this buffer, g2, g4 and vbuf is done before the next tile reuses them
+    }  // persistent tile loop
 }
 
 // ------------------------------------------------------------------------------------------
@@ -696,6 +761,55 @@ pyr_fixup_kernel(PyrDesc pd, PyrTaps taps, const uint8_t *__restrict__ src0, con
 // ------------------------------------------------------------------------------------------
 // plan
 // ------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// u8 tensor (x: w, y: h, z: images) with byte strides (1, stride, pitch); box = RW x rows x 1
+static bool make_tile_map(CUtensorMap *m, const uint8_t *base, int w, int h, int n, size_t stride, size_t pitch,
+                          int rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    if (n <= 1 || pitch == 0) pitch = stride * (size_t)h;
+    const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)(n > 0 ? n : 1)};
+    const cuuint64_t strides[2] = {(cuuint64_t)stride, (cuuint64_t)pitch};
+    const cuuint32_t box[3] = {(cuuint32_t)RW, (cuuint32_t)rows, 1u};
+    const cuuint32_t es[3] = {1u, 1u, 1u};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(base), dims, strides, box, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int NA>
+static cudaError_t fast_kernel_setup(int *grid) {
+    cudaError_t e = cudaFuncSetAttribute(pyr_fast_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         FastSmem<NA>::bytes);
+    if (e != cudaSuccess) return e;
+    int occ = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pyr_fast_kernel<NA>, NTA, FastSmem<NA>::bytes);
+    if (e != cudaSuccess) return e;
+    int dev = 0, sms = kNumSMs;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    *grid = sms * (occ > 0 ? occ : 1);
+    return cudaSuccess;
+}
+
 struct PyrPlan {
     PyrDesc pd;
     PyrTaps taps;
@@ -708,6 +822,8 @@ struct PyrPlan {
     int n_a;         // deepest level produced by pyr_fast_kernel (<= 3)
     int do4, do5;
     int tiles_x, tiles_y;
+    int fast_rows;   // tile rows fetched per CTA (TMA box height)
+    int fast_grid;   // persistent grid: SMs x resident CTAs per SM
     RingWeights ring[4];
     void *d_tables;
     // scratch for deep levels (grown on demand)
@@ -829,6 +945,21 @@ cudaError_t pyr_plan_create(int w, int h, int levels, cudaStream_t st, PyrPlan *
     p->do5 = p->n_fast >= 5;
     p->tiles_x = (w + TW - 1) / TW;
     p->tiles_y = (h + TH - 1) / TH;
+    p->fast_rows = 0;
+    p->fast_grid = kNumSMs;
+    if (p->n_fast >= 1 && !encode_tiled_fn()) p->n_fast = 0;  // no TMA descriptor encoder: generic path
+    p->n_a = p->n_fast < 3 ? p->n_fast : 3;
+    p->do4 = p->n_fast >= 4;
+    p->do5 = p->n_fast >= 5;
+    if (p->n_a >= 1) {
+        e = p->n_a == 1 ? fast_kernel_setup<1>(&p->fast_grid)
+                        : (p->n_a == 2 ? fast_kernel_setup<2>(&p->fast_grid) : fast_kernel_setup<3>(&p->fast_grid));
+        if (e != cudaSuccess) {
+            pyr_plan_destroy(p);
+            return e;
+        }
+        p->fast_rows = p->n_a == 1 ? FastCfg<1>::ROWS : (p->n_a == 2 ? FastCfg<2>::ROWS : FastCfg<3>::ROWS);
+    }
     // faithful border weights of the dyadic levels handled by pyr_fast_kernel: they depend on the
     // ratio only; take them from the x table (outputs 0, 1 and n-1) as computed on the device
     memset(p->ring, 0, sizeof(p->ring));
@@ -941,21 +1072,27 @@ cudaError_t pyr_build(const PyrPlan *p, const uint8_t *src0, const uint8_t *src1
         FastParams fp;
         fp.pd = p->pd;
         memcpy(fp.ring, p->ring, sizeof(fp.ring));
-        fp.src0 = s0;
-        fp.src1 = s1;
         fp.split = sp;
-        fp.stride = stride;
-        fp.pitch = pitch;
+        fp.n_images = n;
         fp.dst = d;
         fp.g8 = p->do4 ? p->d_g8 : nullptr;
         fp.tiles_x = p->tiles_x;
-        dim3 grid((unsigned)(p->tiles_x * p->tiles_y), (unsigned)n, 1);
+        fp.tiles_y = p->tiles_y;
+        CUtensorMap m0, m1;
+        const int n0 = sp < n ? sp : n;                 // images behind map 0
+        const uint8_t *b1 = sp < n ? s1 : s0;
+        const int n1 = sp < n ? n - sp : 1;
+        if (!make_tile_map(&m0, n0 > 0 ? s0 : b1, p->pd.lv[0].w, p->pd.lv[0].h, n0 > 0 ? n0 : 1, stride, pitch, p->fast_rows) ||
+            !make_tile_map(&m1, b1, p->pd.lv[0].w, p->pd.lv[0].h, n1, stride, pitch, p->fast_rows))
+            return cudaErrorInvalidValue;
+        const int total = p->tiles_x * p->tiles_y * n;
+        const int blocks = total < p->fast_grid ? total : p->fast_grid;
         if (p->n_a == 1)
-            pyr_fast_kernel<1><<<grid, NTA, 0, st>>>(fp);
+            pyr_fast_kernel<1><<<blocks, NTA, FastSmem<1>::bytes, st>>>(fp, m0, m1);
         else if (p->n_a == 2)
-            pyr_fast_kernel<2><<<grid, NTA, 0, st>>>(fp);
+            pyr_fast_kernel<2><<<blocks, NTA, FastSmem<2>::bytes, st>>>(fp, m0, m1);
         else
-            pyr_fast_kernel<3><<<grid, NTA, 0, st>>>(fp);
+            pyr_fast_kernel<3><<<blocks, NTA, FastSmem<3>::bytes, st>>>(fp, m0, m1);
         if (n_launches) ++*n_launches;
         if (p->do4) {
             cudaError_t e = cudaMemsetAsync(p->d_fix_count, 0, sizeof(int), st);
