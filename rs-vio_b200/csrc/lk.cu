@@ -127,8 +127,9 @@ __device__ __forceinline__ void se2_exp(const float a[3], float m[6]) {
         s_by_t = 1.0f - 1.0f / 6.0f * t2;
         omc_by_t = 0.5f * theta - 1.0f / 24.0f * theta * t2;
     } else {
-        s_by_t = sn / theta;
-        omc_by_t = (1.0f - cs) / theta;
+        const float inv_t = __frcp_rn(theta);  // one IEEE reciprocal instead of two divisions
+        s_by_t = sn * inv_t;
+        omc_by_t = (1.0f - cs) * inv_t;
     }
     m[0] = cs;
     m[1] = -sn;
@@ -142,6 +143,43 @@ __device__ __forceinline__ bool finite3(const float a[3]) {
     return isfinite(a[0]) && isfinite(a[1]) && isfinite(a[2]);
 }
 
+// Sums of several per-lane values over the warp with fewer shuffles than one butterfly per value:
+// each xor step keeps half of the values and hands the other half to the partner lane, so 4 values
+// need 2 + 1 + 3 shuffles (instead of 20) and end up on lanes 0, 8, 16, 24, from where they are
+// broadcast.  Every lane returns the same bits.
+__device__ __forceinline__ void warp_sum4(float &v0, float &v1, float &v2, float &v3, int lane) {
+    const bool up16 = lane & 16, up8 = lane & 8;
+    float a = up16 ? v2 : v0, b = up16 ? v3 : v1;
+    a += __shfl_xor_sync(0xffffffffu, up16 ? v0 : v2, 16);
+    b += __shfl_xor_sync(0xffffffffu, up16 ? v1 : v3, 16);
+    float c = (up8 ? b : a) + __shfl_xor_sync(0xffffffffu, up8 ? a : b, 8);
+    c += __shfl_xor_sync(0xffffffffu, c, 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    v0 = __shfl_sync(0xffffffffu, c, 0);
+    v1 = __shfl_sync(0xffffffffu, c, 8);
+    v2 = __shfl_sync(0xffffffffu, c, 16);
+    v3 = __shfl_sync(0xffffffffu, c, 24);
+}
+
+// 8 values: 4 + 2 + 1 + 2 shuffles, results on lanes 0, 4, .., 28
+__device__ __forceinline__ void warp_sum8(float (&v)[8], int lane) {
+    const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
+    float a[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        a[k] = (up16 ? v[4 + k] : v[k]) + __shfl_xor_sync(0xffffffffu, up16 ? v[k] : v[4 + k], 16);
+    float b[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        b[k] = (up8 ? a[2 + k] : a[k]) + __shfl_xor_sync(0xffffffffu, up8 ? a[k] : a[2 + k], 8);
+    float c = (up4 ? b[1] : b[0]) + __shfl_xor_sync(0xffffffffu, up4 ? b[0] : b[1], 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __shfl_sync(0xffffffffu, c, 4 * k);
+}
+
 // Per-lane state of the lane's two pattern samples
 struct Lane {
     float ox[2], oy[2];
@@ -151,7 +189,7 @@ struct Lane {
 // track_one_point (feature_tracker.rs:292-342): coarse-to-fine, template from pyramid A at the
 // un-rotated source position, running transform keeps its rotation across levels.
 __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A, const uint8_t *__restrict__ B,
-                               const float T0[6], float T1[6], int max_it, float thr, const Lane &ln,
+                               const float T0[6], float T1[6], int max_it, float thr, const Lane &ln, int lane,
                                unsigned &n_iters, unsigned &n_templates) {
     T1[0] = 1.0f; T1[1] = 0.0f; T1[2] = T0[2];
     T1[3] = 0.0f; T1[4] = 1.0f; T1[5] = T0[5];
@@ -188,19 +226,17 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
             n_valid += __popc(__ballot_sync(0xffffffffu, ok));
         }
         ++n_templates;
-        sum = warp_sum(sum);
-        g0 = warp_sum(g0);
-        g1 = warp_sum(g1);
-        g2 = warp_sum(g2);
+        warp_sum4(sum, g0, g1, g2, lane);
         const float mean = sum / (float)n_valid;
         const float mean_inv = (float)n_valid / sum;
+        const float inv_sum = __frcp_rn(sum);
         float h00 = 0.f, h01 = 0.f, h02 = 0.f, h11 = 0.f, h12 = 0.f, h22 = 0.f;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             if (d[k] >= 0.0f) {
-                J[k][0] += -(g0 * d[k] / sum);
-                J[k][1] += -(g1 * d[k] / sum);
-                J[k][2] += -(g2 * d[k] / sum);
+                J[k][0] += -(g0 * d[k] * inv_sum);
+                J[k][1] += -(g1 * d[k] * inv_sum);
+                J[k][2] += -(g2 * d[k] * inv_sum);
                 d[k] *= mean_inv;
             } else {
                 J[k][0] = J[k][1] = J[k][2] = 0.0f;
@@ -218,12 +254,16 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
             }
         }
         float H[3][3], Hinv[3][3];
-        H[0][0] = warp_sum(h00);
-        H[0][1] = H[1][0] = warp_sum(h01);
-        H[0][2] = H[2][0] = warp_sum(h02);
-        H[1][1] = warp_sum(h11);
-        H[1][2] = H[2][1] = warp_sum(h12);
-        H[2][2] = warp_sum(h22);
+        {
+            float hv[8] = {h00, h01, h02, h11, h12, h22, 0.0f, 0.0f};
+            warp_sum8(hv, lane);
+            H[0][0] = hv[0];
+            H[0][1] = H[1][0] = hv[1];
+            H[0][2] = H[2][0] = hv[2];
+            H[1][1] = hv[3];
+            H[1][2] = H[2][1] = hv[4];
+            H[2][2] = hv[5];
+        }
         bool valid = chol3_inverse(H, Hinv);
         float M[2][3];
         bool fin = true;
@@ -267,20 +307,22 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
             if (rsum < kEps) return RSVIO_FAIL_RESIDUAL;
             int nres = 0;
             float i0 = 0.0f, i1 = 0.0f, i2 = 0.0f;
+            const float inv_rsum = __frcp_rn(rsum);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const bool both = ln.has[k] && r[k] >= 0.0f && d[k] >= 0.0f;
-                const float res = both ? (float)nv * r[k] / rsum - d[k] : 0.0f;
+                const float res = both ? (float)nv * r[k] * inv_rsum - d[k] : 0.0f;
                 nres += __popc(__ballot_sync(0xffffffffu, both));
                 i0 += (-M[k][0]) * res;
                 i1 += (-M[k][1]) * res;
                 i2 += (-M[k][2]) * res;
             }
             if (nres <= kPattern / 2) return RSVIO_FAIL_RESIDUAL;
-            float inc[3];
-            inc[0] = warp_sum(i0);
-            inc[1] = warp_sum(i1);
-            inc[2] = warp_sum(i2);
+            float inc[3], i3 = 0.0f;
+            warp_sum4(i0, i1, i2, i3, lane);
+            inc[0] = i0;
+            inc[1] = i1;
+            inc[2] = i2;
             if (!finite3(inc)) return RSVIO_FAIL_NONFINITE;
             const float norm = sqrtf(inc[0] * inc[0] + inc[1] * inc[1] + inc[2] * inc[2]);
             if (norm > 1e6f) return RSVIO_FAIL_DIVERGED;
@@ -330,17 +372,31 @@ lk_track_fb_kernel(PyrDesc pd, LkBatch b) {
         float T0[6], Tf[6], Tb[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) T0[q] = __ldg(b.in_T6 + (size_t)item * 6 + q);
-        unsigned it_f = 0, it_b = 0;
-        int st = track_one_point(pd, A, B, T0, Tf, b.max_it, b.thr, ln, it_f, n_templates);
-        if (st == RSVIO_TRACK_OK) {
-            st = track_one_point(pd, B, A, Tf, Tb, b.max_it, b.thr, ln, it_b, n_templates);
-            if (st != RSVIO_TRACK_OK) {
+        unsigned it_d[2] = {0, 0};
+        float Tin[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) Tin[q] = T0[q];
+        int st = RSVIO_TRACK_OK;
+        // forward (A -> B) then backward (B -> A) through ONE copy of the level loop: the fused kernel
+        // stays within the instruction cache
+#pragma unroll 1
+        for (int dir = 0; dir < 2; ++dir) {
+            unsigned iters = 0;
+            st = track_one_point(pd, dir == 0 ? A : B, dir == 0 ? B : A, Tin, Tb, b.max_it, b.thr, ln, lane, iters,
+                                 n_templates);
+            it_d[dir] = iters;
+            if (dir == 0) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) Tf[q] = Tin[q] = Tb[q];
+                if (st != RSVIO_TRACK_OK) break;
+            } else if (st != RSVIO_TRACK_OK) {
                 st += RSVIO_FAIL_BACKWARD;
             } else {  // forward-backward consistency (feature_tracker.rs:277-281)
                 const float dx = T0[2] - Tb[2], dy = T0[5] - Tb[5];
                 if (!(dx * dx + dy * dy < 0.4f)) st = RSVIO_FAIL_FB;
             }
         }
+        const unsigned it_f = it_d[0], it_b = it_d[1];
         n_iters += it_f + it_b;
         ++n_tracks;
         if (lane < 6) b.out_T6[(size_t)item * 6 + lane] = Tf[lane];
