@@ -82,6 +82,7 @@ __device__ __forceinline__ bool chol3_inverse(const float H[3][3], float Hinv[3]
 #pragma unroll
         for (int j = 0; j < 3; ++j) m[i][j] = H[i][j];
     bool ok = true;
+    float inv[3];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
 #pragma unroll
@@ -94,22 +95,23 @@ __device__ __forceinline__ bool chol3_inverse(const float H[3][3], float Hinv[3]
         ok = ok && (diag != 0.0f) && (diag >= 0.0f);
         const float denom = sqrtf(diag);
         m[j][j] = denom;
+        inv[j] = __frcp_rn(denom);  // one IEEE reciprocal per pivot, multiplications below
 #pragma unroll
-        for (int i = j + 1; i < 3; ++i) m[i][j] = m[i][j] / denom;
+        for (int i = j + 1; i < 3; ++i) m[i][j] = m[i][j] * inv[j];
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         float b[3] = {c == 0 ? 1.0f : 0.0f, c == 1 ? 1.0f : 0.0f, c == 2 ? 1.0f : 0.0f};
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const float coeff = b[i] / m[i][i];
+            const float coeff = b[i] * inv[i];
             b[i] = coeff;
 #pragma unroll
             for (int r = i + 1; r < 3; ++r) b[r] = (-coeff) * m[r][i] + b[r];
         }
-        b[2] = (b[2] - 0.0f) / m[2][2];
-        b[1] = (b[1] - m[2][1] * b[2]) / m[1][1];
-        b[0] = (b[0] - (m[1][0] * b[1] + m[2][0] * b[2])) / m[0][0];
+        b[2] = (b[2] - 0.0f) * inv[2];
+        b[1] = (b[1] - m[2][1] * b[2]) * inv[1];
+        b[0] = (b[0] - (m[1][0] * b[1] + m[2][0] * b[2])) * inv[0];
 #pragma unroll
         for (int i = 0; i < 3; ++i) Hinv[i][c] = b[i];
     }
@@ -120,7 +122,23 @@ __device__ __forceinline__ bool chol3_inverse(const float H[3][3], float Hinv[3]
 __device__ __forceinline__ void se2_exp(const float a[3], float m[6]) {
     const float theta = a[2];
     float sn, cs;
-    sincosf(theta, &sn, &cs);
+    if (fabsf(theta) < 0.5f) {
+        // LK increments are small rotations: Taylor polynomials (truncation < 2e-11, i.e. below half an
+        // ulp of the result) instead of the general-range sincosf; explicitly fused, the reference's
+        // libm sinf/cosf are not reproducible bit for bit anyway
+        const float t2 = theta * theta;
+        float ps = fmaf(t2, 2.7557319e-06f, -1.9841270e-04f);
+        ps = fmaf(ps, t2, 8.3333333e-03f);
+        ps = fmaf(ps, t2, -1.6666667e-01f);
+        sn = fmaf(ps * t2, theta, theta);
+        float pc = fmaf(t2, -2.7557319e-07f, 2.4801587e-05f);
+        pc = fmaf(pc, t2, -1.3888889e-03f);
+        pc = fmaf(pc, t2, 4.1666667e-02f);
+        pc = fmaf(pc, t2, -0.5f);
+        cs = fmaf(pc, t2, 1.0f);
+    } else {
+        sincosf(theta, &sn, &cs);
+    }
     float s_by_t, omc_by_t;
     if (fabsf(theta) < kEps) {
         const float t2 = theta * theta;
@@ -352,7 +370,7 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
 }
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-lk_track_fb_kernel(PyrDesc pd, LkBatch b) {
+lk_track_fb_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ LkBatch b) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -372,7 +390,7 @@ lk_track_fb_kernel(PyrDesc pd, LkBatch b) {
         float T0[6], Tf[6], Tb[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) T0[q] = __ldg(b.in_T6 + (size_t)item * 6 + q);
-        unsigned it_d[2] = {0, 0};
+        unsigned it_f = 0, it_b = 0;
         float Tin[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) Tin[q] = T0[q];
@@ -384,7 +402,7 @@ lk_track_fb_kernel(PyrDesc pd, LkBatch b) {
             unsigned iters = 0;
             st = track_one_point(pd, dir == 0 ? A : B, dir == 0 ? B : A, Tin, Tb, b.max_it, b.thr, ln, lane, iters,
                                  n_templates);
-            it_d[dir] = iters;
+            if (dir == 0) it_f = iters; else it_b = iters;
             if (dir == 0) {
 #pragma unroll
                 for (int q = 0; q < 6; ++q) Tf[q] = Tin[q] = Tb[q];
@@ -396,7 +414,6 @@ lk_track_fb_kernel(PyrDesc pd, LkBatch b) {
                 if (!(dx * dx + dy * dy < 0.4f)) st = RSVIO_FAIL_FB;
             }
         }
-        const unsigned it_f = it_d[0], it_b = it_d[1];
         n_iters += it_f + it_b;
         ++n_tracks;
         if (lane < 6) b.out_T6[(size_t)item * 6 + lane] = Tf[lane];

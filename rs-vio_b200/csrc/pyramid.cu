@@ -94,7 +94,8 @@ struct TileDesc {
 };
 
 __global__ void __launch_bounds__(kGenThreads)
-pyr_generic_kernel(PyrDesc pd, PyrTaps taps, const TileDesc *__restrict__ tiles, const uint8_t *__restrict__ src0,
+pyr_generic_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ PyrTaps taps,
+                   const TileDesc *__restrict__ tiles, const uint8_t *__restrict__ src0,
                    const uint8_t *__restrict__ src1, int split, size_t stride, size_t pitch,
                    uint8_t *__restrict__ dst) {
     __shared__ __align__(16) float v[kGenSmemFloats];
@@ -673,7 +674,7 @@ struct FixItem {
 };
 
 __global__ void __launch_bounds__(256)
-pyr_deep_kernel(PyrDesc pd, const uint32_t *__restrict__ g8, int n_images, int do5, uint8_t *__restrict__ dst,
+pyr_deep_kernel(const __grid_constant__ PyrDesc pd, const uint32_t *__restrict__ g8, int n_images, int do5, uint8_t *__restrict__ dst,
                 FixItem *__restrict__ fix, int *__restrict__ fix_count, int fix_cap) {
     const int w8 = pd.lv[0].w / 8, h8 = pd.lv[0].h / 8;
     const int w4 = pd.lv[4].w, h4 = pd.lv[4].h;
@@ -724,7 +725,8 @@ pyr_deep_kernel(PyrDesc pd, const uint32_t *__restrict__ g8, int n_images, int d
 
 // one warp per queued output: faithful recomputation
 __global__ void __launch_bounds__(128)
-pyr_fixup_kernel(PyrDesc pd, PyrTaps taps, const uint8_t *__restrict__ src0, const uint8_t *__restrict__ src1,
+pyr_fixup_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ PyrTaps taps,
+                 const uint8_t *__restrict__ src0, const uint8_t *__restrict__ src1,
                  int split, size_t stride, size_t pitch, uint8_t *__restrict__ dst, const FixItem *__restrict__ fix,
                  const int *__restrict__ fix_count, int fix_cap) {
     __shared__ float vbuf[4][2 * 64 + 8];
