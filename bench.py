@@ -32,6 +32,7 @@ for _p in (ROOT, os.path.join(ROOT, "rs-vio_b200")):
 
 import numpy as np  # noqa: E402
 
+from rsvio_b200 import sharding  # noqa: E402
 from rsvio_b200.synth import CONFIGS, StereoSequence  # noqa: E402
 
 RING = 8
@@ -183,9 +184,10 @@ def run_reference(args, rank):
 
 def workload_config(args, S, n_gpus):
     p = CONFIGS[args.config]
+    total = args.total_streams if getattr(args, "total_streams", None) else S * n_gpus
     return {"workload": f"{args.config}: {S} independent EuRoC-shape {p['w']}x{p['h']} stereo streams per GPU, "
                         f"{p['levels']}-level pyramid, grid {p['grid']}, LK {p['max_it']} it / {p['thr']}",
-            "streams_per_gpu": S, "total_streams": S * n_gpus, "frame_ring": RING,
+            "streams_per_gpu": S, "total_streams": total, "frame_ring": RING,
             "l2": "per step the kernels touch previous+current pyramids and the input ring slot "
                   "(> 230 MB at 64 streams), larger than the 126 MB L2; no explicit flush",
             "parallelism": f"{n_gpus} x independent replicas (streams sharded, no collective)"}
@@ -199,7 +201,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C5", choices=list(CONFIGS))
-    ap.add_argument("--streams-per-gpu", type=int, default=None)
+    ap.add_argument("--streams-per-gpu", type=int, default=None,
+                    help="weak scaling (default): every GPU runs this many streams (C5: 64)")
+    ap.add_argument("--total-streams", type=int, default=None,
+                    help="strong scaling: this many streams block-partitioned over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pyramid-roofline", action="store_true")
     args = ap.parse_args()
@@ -207,22 +212,28 @@ def main():
         args.warmup = 3
     if args.streams_per_gpu is None:
         args.streams_per_gpu = CONFIGS[args.config].get("streams", 1)
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank, local_rank, world = sharding.rank_info()
 
     if args.impl == "reference":
         run_reference(args, rank)
         return
 
-    S = args.streams_per_gpu
+    if args.total_streams:   # strong scaling: fixed job, block partition (rsvio_b200.sharding)
+        stream_ids = sharding.partition_streams(args.total_streams, world, rank)
+        scaling = "strong"
+    else:                    # weak scaling: fixed work per GPU
+        stream_ids = sharding.weak_streams(args.streams_per_gpu, rank)
+        scaling = "weak"
+    S = len(stream_ids)
+    if S < 1:
+        raise SystemExit("bench.py: this rank has no streams")
+    args.streams_per_gpu = S
     p = CONFIGS[args.config]
     w, h = p["w"], p["h"]
     cores = os.cpu_count() or 1
     # synthetic frames first (fork pool, before CUDA is initialised); distinct seeds per rank and stream
     t_gen = time.perf_counter()
-    frames_np = generate_frames(args.config, [rank * S + s for s in range(S)], RING,
-                                max(1, min(16, cores // max(world, 1))))
+    frames_np = generate_frames(args.config, stream_ids, RING, max(1, min(16, cores // max(world, 1))))
     t_gen = time.perf_counter() - t_gen
 
     import torch
@@ -299,10 +310,10 @@ def main():
         e1.synchronize()
         sampler.active = False
         barrier()
-        ms_dev = reduce_max(e0.elapsed_time(e1))
         c1 = tr.counters()
-        tracks_dev = reduce_sum(c1["tracks"] - c0["tracks"])
-        iters_dev = reduce_sum(c1["iterations"] - c0["iterations"])
+        tracks_dev, frames_dev, iters_dev, ms_dev = sharding.aggregate(
+            dist, dev, c1["tracks"] - c0["tracks"], S * args.steps, c1["iterations"] - c0["iterations"],
+            e0.elapsed_time(e1))
         templ_dev = reduce_sum(c1["templates"] - c0["templates"])
         launches = c1["launches"] - c0["launches"]
         n_tracks_alive = int(tr.result_view()[1].sum())
@@ -352,7 +363,7 @@ def main():
         ms_e2e_dev = reduce_max(e2.elapsed_time(e3))
         ms_e2e = max(ms_e2e_dev, reduce_max(wall_e2e * 1e3))   # host reads are part of the step
         c3 = tr.counters()
-        tracks_e2e = reduce_sum(c3["tracks"] - c2["tracks"])
+        tracks_e2e, frames_e2e, _, _ = sharding.aggregate(dist, dev, c3["tracks"] - c2["tracks"], S * args.steps, 0, 0.0)
         d2h_per_step = (recs * 16 + 2 * S * 4) / args.steps
 
         # ---- per-stage device times (CUDA events inside the library, same stream) ----------------
@@ -366,13 +377,15 @@ def main():
         tr.set_profiling(False)
 
     total_stage_ms = sum(v[0] for k, v in stages.items() if k != "upload")
-    pyr_ms = stages["pyramid"][0] / max(1, stages["pyramid"][1])
+    pyr_launches = max(1, stages["pyramid"][1] // prof_steps)     # kernels per pyramid build
+    pyr_ms = stages["pyramid"][0] / prof_steps                    # all of them: the whole pyramid of a step
     alg_bytes_launch = 2 * S * (w * h + rsvio_b200.pyramid_bytes(w, h, p["levels"]))
     peak, peak_src = measured_peaks()
     achieved = alg_bytes_launch / (pyr_ms * 1e-3) / 1e9 if pyr_ms > 0 else 0.0
-    roofline = {"kernel": "pyr_generic_kernel (pyramid stage of the step)", "bound": "hbm", "achieved": achieved,
+    roofline = {"kernel": "pyr_fast_kernel (pyramid build of one step: %d launch(es), both cameras, all streams)" % pyr_launches,
+                "bound": "hbm", "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "alg_bytes_per_launch": alg_bytes_launch, "ms_per_launch": pyr_ms,
+                "alg_bytes_per_launch": alg_bytes_launch, "ms_per_launch": pyr_ms, "launches_per_step": pyr_launches,
                 "share_of_step": stages["pyramid"][0] / total_stage_ms if total_stage_ms else None}
     stage_share = {k: (v[0] / prof_steps, v[0] / total_stage_ms if (total_stage_ms and k != "upload") else None)
                    for k, v in stages.items()}
@@ -406,7 +419,8 @@ def main():
     # ---- CPU baseline (oracle port) on a bounded sample, rank 0 at N = 1 only -------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ns, nf = min(S, 2 * cores if cores < 32 else 64), 6
+        ns = min(S, 2 * cores if cores < 32 else 64)
+        nf = 40 if cores >= 8 else 12      # about 10-30 s of CPU work on the box's cores
         tracks, nframes, dt = cpu_run(args.config, frames_np, ns, nf, 2, cores)
         cpu_baseline = {"value": tracks / dt, "unit": "tracks/s", "cores": min(cores, ns), "kind": "port",
                         "stereo_frames_per_sec": nframes / dt,
@@ -418,15 +432,15 @@ def main():
         line = {
             "metric": "feature_tracks_per_sec", "value": value, "unit": "tracks/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (u8 pyramid)",
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32 (u8 pyramid)",
             "data": "synthetic",
             "config": workload_config(args, S, world),
-            "stereo_frames_per_sec": world * S * args.steps / (ms_dev * 1e-3),
+            "stereo_frames_per_sec": frames_dev / (ms_dev * 1e-3),
             "lk_iterations_per_sec": iters_dev / (ms_dev * 1e-3),
             "lk_gflops": (6.3e3 * templ_dev + 1.8e3 * iters_dev) / (ms_dev * 1e-3) / 1e9,
             "tracks_alive_per_gpu": n_tracks_alive,
             "e2e": {"value": tracks_e2e / (ms_e2e * 1e-3), "unit": "tracks/s",
-                    "stereo_frames_per_sec": world * S * args.steps / (ms_e2e * 1e-3),
+                    "stereo_frames_per_sec": frames_e2e / (ms_e2e * 1e-3),
                     "ms_per_step": ms_e2e / args.steps, "ms_per_step_device_events": ms_e2e_dev / args.steps,
                     "h2d_bytes_per_step": 2 * S * img_bytes, "d2h_bytes_per_step": d2h_per_step},
             "gpu_launches": int(launches),

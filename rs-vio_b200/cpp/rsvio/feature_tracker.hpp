@@ -1,0 +1,168 @@
+// feature_tracker.hpp -- C++ host mirror of RS-VIO's tracker API over the C ABI (include/rsvio_b200.h).
+//
+// The reference is Rust (no toolchain in this image), so the host side above the C ABI is written in
+// C++ with the reference's names, argument meaning and error behaviour:
+//   rsvio::Feature                      src/feature_tracker/feature_tracker.rs:12-32
+//   rsvio::StereoPatchTracker<LEVELS>   :91-207  (new :103, process_frame :116, get_track_points :188, remove_id :201)
+//   rsvio::PatchTracker<LEVELS>         :36-89   (process_frame :43, get_track_points :78, remove_id :84)
+// `Frame` is any type with add_left_feature(Feature) / add_right_feature(Feature)
+// (src/estimator/frame.rs:107-134).  Infallible signatures like the reference: errors of the GPU
+// layer surface as rsvio::Error exceptions at construction, and as std::runtime_error from the
+// per-frame calls (a reference user never sees per-point failures either: points just disappear).
+#pragma once
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "../../../include/rsvio_b200.h"
+
+namespace rsvio {
+
+struct Error : std::runtime_error {
+    rsvio_status status;
+    Error(rsvio_status s, const std::string &what) : std::runtime_error(what), status(s) {}
+};
+
+struct Feature {
+    std::size_t feature_id;
+    float pixel_coord[2];
+    float undistorted_coord[2];  // [-1, -1] == invalid, filled by Frame::add_*_feature
+    Feature(std::size_t id, float x, float y) : feature_id(id), pixel_coord{x, y}, undistorted_coord{-1.0f, -1.0f} {}
+};
+
+// GrayImage: row-major 8-bit luma, stride == width (image::GrayImage)
+struct GrayImageView {
+    const std::uint8_t *data;
+    std::uint32_t width, height;
+};
+
+namespace detail {
+inline void check(rsvio_status s, rsvio_tracker *t, const char *what) {
+    if (s != RSVIO_OK)
+        throw Error(s, std::string(what) + ": " + rsvio_status_string(s) + (t ? std::string(" / ") + rsvio_tracker_last_error(t) : ""));
+}
+
+class Handle {
+  public:
+    Handle() = default;
+    Handle(const Handle &) = delete;
+    Handle &operator=(const Handle &) = delete;
+    Handle(Handle &&o) noexcept : t_(o.t_), w_(o.w_), h_(o.h_) { o.t_ = nullptr; }
+    ~Handle() {
+        if (t_) rsvio_tracker_destroy(t_);
+    }
+    // the reference learns the image size from the first frame; the handle is created lazily the same way
+    void ensure(const rsvio_config &base, std::uint32_t w, std::uint32_t h) {
+        if (t_ && w == w_ && h == h_) return;
+        if (t_) rsvio_tracker_destroy(t_);
+        t_ = nullptr;
+        rsvio_config cfg = base;
+        cfg.width = (std::int32_t)w;
+        cfg.height = (std::int32_t)h;
+        check(rsvio_tracker_create(&cfg, &t_), nullptr, "rsvio_tracker_create");
+        w_ = w;
+        h_ = h;
+    }
+    rsvio_tracker *get() const { return t_; }
+    std::unordered_map<std::size_t, std::pair<float, float>> tracks(int cam) const {
+        std::unordered_map<std::size_t, std::pair<float, float>> out;
+        if (!t_) return out;
+        const rsvio_track_record *rec = nullptr;
+        const std::int32_t *counts = nullptr;
+        std::int32_t groups = 0, cap = 0;
+        if (rsvio_tracker_result_view(t_, &rec, &counts, &groups, &cap) != RSVIO_OK) return out;  // no frame yet
+        const int g = cam * (groups / 2);
+        out.reserve((std::size_t)counts[g]);
+        for (std::int32_t k = 0; k < counts[g]; ++k) {
+            const rsvio_track_record &r = rec[(std::size_t)g * cap + k];
+            out.emplace((std::size_t)r.id, std::make_pair(r.x, r.y));
+        }
+        return out;
+    }
+    void remove(const std::vector<std::size_t> &ids) {
+        if (!t_ || ids.empty()) return;
+        std::vector<std::uint64_t> v(ids.begin(), ids.end());
+        check(rsvio_tracker_remove_ids(t_, 0, v.data(), v.size()), t_, "rsvio_tracker_remove_ids");
+    }
+
+  private:
+    rsvio_tracker *t_ = nullptr;
+    std::uint32_t w_ = 0, h_ = 0;
+};
+}  // namespace detail
+
+template <std::uint32_t LEVELS>
+class StereoPatchTracker {
+  public:
+    // StereoPatchTracker::new(grid_size, optical_flow_max_iterations, optical_flow_convergence_threshold)
+    StereoPatchTracker(std::uint32_t grid_size, std::uint32_t optical_flow_max_iterations,
+                       double optical_flow_convergence_threshold, int device = 0) {
+        rsvio_config_default(&cfg_);
+        cfg_.levels = (std::int32_t)LEVELS;
+        cfg_.grid_size = grid_size;
+        cfg_.max_iterations = (std::int32_t)optical_flow_max_iterations;
+        cfg_.convergence_threshold = (float)optical_flow_convergence_threshold;
+        cfg_.mode = RSVIO_MODE_STEREO;
+        cfg_.device = device;
+    }
+
+    // process_frame(&mut self, greyscale_image0, greyscale_image1, frame)
+    template <typename Frame>
+    void process_frame(const GrayImageView &image0, const GrayImageView &image1, Frame &frame) {
+        process(image0, image1);
+        const rsvio_track_record *rec = nullptr;
+        const std::int32_t *counts = nullptr;
+        std::int32_t groups = 0, cap = 0;
+        detail::check(rsvio_tracker_result_view(h_.get(), &rec, &counts, &groups, &cap), h_.get(), "result_view");
+        for (int cam = 0; cam < 2; ++cam)
+            for (std::int32_t k = 0; k < counts[cam]; ++k) {
+                const rsvio_track_record &r = rec[(std::size_t)cam * cap + k];
+                Feature f((std::size_t)r.id, r.x, r.y);
+                if (cam == 0) frame.add_left_feature(f); else frame.add_right_feature(f);
+            }
+    }
+    void process(const GrayImageView &image0, const GrayImageView &image1) {
+        if (image0.width != image1.width || image0.height != image1.height) throw Error(RSVIO_ERR_INVALID_ARG, "stereo images differ in size");
+        h_.ensure(cfg_, image0.width, image0.height);
+        detail::check(rsvio_tracker_process_stereo(h_.get(), image0.data, image1.data, image0.width), h_.get(),
+                      "rsvio_tracker_process_stereo");
+    }
+    // get_track_points(&self) -> [HashMap<usize, (f32, f32)>; 2]
+    std::pair<std::unordered_map<std::size_t, std::pair<float, float>>, std::unordered_map<std::size_t, std::pair<float, float>>>
+    get_track_points() const {
+        return {h_.tracks(0), h_.tracks(1)};
+    }
+    // remove_id(&mut self, ids)
+    void remove_id(const std::vector<std::size_t> &ids) { h_.remove(ids); }
+
+  private:
+    rsvio_config cfg_{};
+    detail::Handle h_;
+};
+
+template <std::uint32_t LEVELS>
+class PatchTracker {
+  public:
+    explicit PatchTracker(int device = 0) {  // Default: 30 iterations, 0.005, grid 30 (feature_tracker.rs:51-52,65)
+        rsvio_config_default(&cfg_);
+        cfg_.levels = (std::int32_t)LEVELS;
+        cfg_.mode = RSVIO_MODE_MONO;
+        cfg_.device = device;
+    }
+    void process_frame(const GrayImageView &image) {
+        h_.ensure(cfg_, image.width, image.height);
+        detail::check(rsvio_tracker_process_mono(h_.get(), image.data, image.width), h_.get(), "rsvio_tracker_process_mono");
+    }
+    std::unordered_map<std::size_t, std::pair<float, float>> get_track_points() const { return h_.tracks(0); }
+    void remove_id(const std::vector<std::size_t> &ids) { h_.remove(ids); }
+
+  private:
+    rsvio_config cfg_{};
+    detail::Handle h_;
+};
+
+}  // namespace rsvio

@@ -10,4 +10,4 @@ from .binding import (  # noqa: F401
     detect_keypoints, device_count, library_path, load_library, pyramid_bytes, se2_exp, split_pyramid,
     track_points,
 )
-from . import synth  # noqa: F401
+from . import sharding, synth  # noqa: F401

@@ -1,0 +1,190 @@
+//! GPU drop-in for `rs_vio::feature_tracker` (reference src/feature_tracker/feature_tracker.rs).
+//!
+//! Same public items and signatures as the reference module so that `src/estimator/estimator.rs:27,85-89,190`
+//! compiles unchanged after replacing `use crate::feature_tracker::...` by this crate:
+//!   Feature::new                                  feature_tracker.rs:25
+//!   StereoPatchTracker::<N>::new / process_frame / get_track_points / remove_id   :103 / :116 / :188 / :201
+//!   PatchTracker::<N>::process_frame / get_track_points / remove_id               :43 / :78 / :84
+//! The tracker owns an opaque handle of librsvio_b200.so; all kernels run on the B200.  There is no
+//! CPU fallback: construction panics with the library's error text when no CUDA device is usable
+//! (the reference's signatures are infallible, so there is no Result to put it in).
+//!
+//! NOT COMPILED IN THIS REPOSITORY (no Rust toolchain in the image) -- INTEGRATION.md.
+pub mod ffi;
+
+use image::GrayImage;
+use std::collections::HashMap;
+use std::ffi::CStr;
+
+#[derive(Debug, Clone)]
+pub struct Feature {
+    pub feature_id: usize,
+    pub pixel_coord: [f32; 2],
+    /// `[-1, -1]` means invalid; filled by `Frame::add_left_feature` / `add_right_feature`.
+    pub undistorted_coord: [f32; 2],
+}
+
+impl Feature {
+    pub fn new(feature_id: usize, pixel_coord: [f32; 2]) -> Self {
+        Self { feature_id, pixel_coord, undistorted_coord: [-1.0, -1.0] }
+    }
+}
+
+/// What `process_frame` needs from `crate::estimator::Frame` (src/estimator/frame.rs:107-134).
+pub trait FeatureSink {
+    fn add_left_feature(&mut self, f: Feature);
+    fn add_right_feature(&mut self, f: Feature);
+}
+
+struct Handle {
+    ptr: *mut ffi::rsvio_tracker,
+    dims: (u32, u32),
+    cfg: ffi::rsvio_config,
+}
+// one handle == one CUDA stream; `&mut self` on every call gives the exclusivity the C ABI asks for
+unsafe impl Send for Handle {}
+
+impl Handle {
+    fn new(levels: u32, grid: u32, max_it: u32, thr: f32, mode: i32) -> Self {
+        let mut cfg = unsafe { std::mem::zeroed::<ffi::rsvio_config>() };
+        unsafe { ffi::rsvio_config_default(&mut cfg) };
+        cfg.levels = levels as i32;
+        cfg.grid_size = grid;
+        cfg.max_iterations = max_it as i32;
+        cfg.convergence_threshold = thr;
+        cfg.mode = mode;
+        Self { ptr: std::ptr::null_mut(), dims: (0, 0), cfg }
+    }
+    /// The reference learns the image size from the first frame; so does the handle.
+    fn ensure(&mut self, w: u32, h: u32) {
+        if !self.ptr.is_null() && self.dims == (w, h) {
+            return;
+        }
+        self.release();
+        let mut cfg = self.cfg;
+        cfg.width = w as i32;
+        cfg.height = h as i32;
+        let st = unsafe { ffi::rsvio_tracker_create(&cfg, &mut self.ptr) };
+        assert!(st == ffi::RSVIO_OK, "rsvio_tracker_create: {}", status_text(st));
+        self.dims = (w, h);
+    }
+    fn check(&self, st: ffi::rsvio_status, what: &str) {
+        if st != ffi::RSVIO_OK {
+            let detail = unsafe { CStr::from_ptr(ffi::rsvio_tracker_last_error(self.ptr)) }.to_string_lossy().into_owned();
+            panic!("{what}: {} ({detail})", status_text(st));
+        }
+    }
+    /// zero-copy view of the host-mapped result the merge kernel wrote
+    fn for_each(&self, cam: usize, mut f: impl FnMut(usize, f32, f32)) {
+        if self.ptr.is_null() {
+            return;
+        }
+        let (mut rec, mut cnt) = (std::ptr::null(), std::ptr::null());
+        let (mut groups, mut cap) = (0i32, 0i32);
+        let st = unsafe { ffi::rsvio_tracker_result_view(self.ptr, &mut rec, &mut cnt, &mut groups, &mut cap) };
+        if st != ffi::RSVIO_OK {
+            return; // no frame processed yet
+        }
+        let g = cam * (groups as usize / 2);
+        let n = unsafe { *cnt.add(g) } as usize;
+        let base = unsafe { rec.add(g * cap as usize) };
+        for k in 0..n {
+            let r = unsafe { *base.add(k) };
+            f(r.id as usize, r.x, r.y);
+        }
+    }
+    fn remove(&mut self, ids: &[usize]) {
+        if self.ptr.is_null() || ids.is_empty() {
+            return;
+        }
+        let v: Vec<u64> = ids.iter().map(|&i| i as u64).collect();
+        let st = unsafe { ffi::rsvio_tracker_remove_ids(self.ptr, 0, v.as_ptr(), v.len()) };
+        self.check(st, "rsvio_tracker_remove_ids");
+    }
+    fn release(&mut self) {
+        if !self.ptr.is_null() {
+            unsafe { ffi::rsvio_tracker_destroy(self.ptr) };
+            self.ptr = std::ptr::null_mut();
+        }
+    }
+}
+
+impl Drop for Handle {
+    fn drop(&mut self) {
+        self.release();
+    }
+}
+
+fn status_text(st: ffi::rsvio_status) -> String {
+    unsafe { CStr::from_ptr(ffi::rsvio_status_string(st)) }.to_string_lossy().into_owned()
+}
+
+pub struct StereoPatchTracker<const N: u32> {
+    h: Handle,
+}
+
+impl<const LEVELS: u32> StereoPatchTracker<LEVELS> {
+    pub fn new(grid_size: u32, optical_flow_max_iterations: u32, optical_flow_convergence_threshold: f64) -> Self {
+        Self {
+            h: Handle::new(LEVELS, grid_size, optical_flow_max_iterations, optical_flow_convergence_threshold as f32,
+                           ffi::RSVIO_MODE_STEREO),
+        }
+    }
+
+    pub fn process_frame<F: FeatureSink>(&mut self, greyscale_image0: &GrayImage, greyscale_image1: &GrayImage, frame: &mut F) {
+        let (w, h) = greyscale_image0.dimensions();
+        assert_eq!((w, h), greyscale_image1.dimensions(), "stereo images differ in size");
+        self.h.ensure(w, h);
+        let st = unsafe {
+            ffi::rsvio_tracker_process_stereo(self.h.ptr, greyscale_image0.as_raw().as_ptr(), greyscale_image1.as_raw().as_ptr(),
+                                              w as usize)
+        };
+        self.h.check(st, "rsvio_tracker_process_stereo");
+        self.h.for_each(0, |id, x, y| frame.add_left_feature(Feature::new(id, [x, y])));
+        self.h.for_each(1, |id, x, y| frame.add_right_feature(Feature::new(id, [x, y])));
+    }
+
+    pub fn get_track_points(&self) -> [HashMap<usize, (f32, f32)>; 2] {
+        let mut out = [HashMap::new(), HashMap::new()];
+        for cam in 0..2 {
+            self.h.for_each(cam, |id, x, y| {
+                out[cam].insert(id, (x, y));
+            });
+        }
+        out
+    }
+
+    pub fn remove_id(&mut self, ids: &[usize]) {
+        self.h.remove(ids);
+    }
+}
+
+pub struct PatchTracker<const N: u32> {
+    h: Handle,
+}
+
+impl<const LEVELS: u32> Default for PatchTracker<LEVELS> {
+    fn default() -> Self {
+        // DEFAULT_GRID_SIZE 30, 30 iterations, 0.005 (feature_tracker.rs:51-52,65)
+        Self { h: Handle::new(LEVELS, 30, 30, 0.005, ffi::RSVIO_MODE_MONO) }
+    }
+}
+
+impl<const LEVELS: u32> PatchTracker<LEVELS> {
+    pub fn process_frame(&mut self, greyscale_image: &GrayImage) {
+        let (w, h) = greyscale_image.dimensions();
+        self.h.ensure(w, h);
+        let st = unsafe { ffi::rsvio_tracker_process_mono(self.h.ptr, greyscale_image.as_raw().as_ptr(), w as usize) };
+        self.h.check(st, "rsvio_tracker_process_mono");
+    }
+    pub fn get_track_points(&self) -> HashMap<usize, (f32, f32)> {
+        let mut out = HashMap::new();
+        self.h.for_each(0, |id, x, y| {
+            out.insert(id, (x, y));
+        });
+        out
+    }
+    pub fn remove_id(&mut self, ids: &[usize]) {
+        self.h.remove(ids);
+    }
+}
