@@ -392,7 +392,7 @@ def main():
 
     # ---- pyramid kernel alone on a batch far larger than L2 (C4 shape, >= 512 MB per launch) --------
     extra_roofline = None
-    if not args.no_pyramid_roofline and rank == 0:
+    if not args.no_pyramid_roofline and rank == 0 and world == 1:
         try:
             cw, ch, cl, n_img = 1920, 1200, 5, 64
             src = torch.randint(0, 256, (n_img, ch, cw), dtype=torch.uint8, device=dev)
