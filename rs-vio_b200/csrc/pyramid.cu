@@ -419,34 +419,36 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
     }
 
     // ---- stage 1: level-1 output O_2 (global) and G_2 (smem); 4 chained DP4A per value.
-    // Warp = one row segment, lane c = level-1 columns X0/2 + 4c .. +3 (O) and X0/2 + 4c - 2 .. +1 (G).
+    // Warp = one row segment, lane c = level-1 columns j0 .. j0+3, j0 = X0/2 - 2 + 4c, both phases (the tile
+    // owns level-1 columns [X0/2 - 2, X0/2 + 126)).  The lane's pixels 2 j0 - 4 .. 2 j0 + 11 are 16 bytes at
+    // tile byte 8c + 8: two aligned 8-byte loads, conflict free.
     const int t_first = Y0 / 2 - C::et;    // first emitted level-1 row of the tile
     {
         const int c = tid & (NCOL - 1), seg = tid / NCOL;
-        const int j0 = X0 / 2 + 4 * c;
+        const int j0 = X0 / 2 - 2 + 4 * c;
         const int ts = t_first + seg * C::PER_SEG;
         const int te = min(ts + C::PER_SEG, t_first + C::NE);
         const bool live = (2 * j0 - 8) < w0 && (2 * ts - 8) < h0 && ts < te;  // partial tiles: skip dead work
         // level-1 rows this thread stores: its segment, the tile's O range, the level's interior
         const int o_lo = max(max(ts, Y0 / 2), 1);
-        const int o_hi = j0 < w1 ? min(min(te, Y0 / 2 + TH / 2), h1 - 1) : o_lo;
+        const int o_hi = (j0 < w1 && j0 + 3 >= 1) ? min(min(te, Y0 / 2 + TH / 2), h1 - 1) : o_lo;
         const bool o_edge = j0 < 1 || j0 + 3 > w1 - 2;  // group touches the first / last column
         uint32_t aOo[4] = {0, 0, 0, 0}, aOn[4] = {0, 0, 0, 0}, aGo[4] = {0, 0, 0, 0}, aGm[4] = {0, 0, 0, 0},
                  aGn[4] = {0, 0, 0, 0};
         uint8_t *__restrict__ orow = out + P.pd.lv[1].off + (ptrdiff_t)(ts - 1) * w1 + j0;  // row tau - 1
-        // tile word of pixels 2*j0 .. 2*j0+3 on base row 2*tau - 1 (lanes 0..15 read region A, 16..31 region B)
-        const uint32_t *__restrict__ wr =
-            reinterpret_cast<const uint32_t *>((c < 16 ? tA : tB + RB) + (2 * ts - 1 - (Y0 - C::ytop)) * RW) +
-            (c < 16 ? 4 + 2 * c : 2 * c - 28);
+        // the lane's 16 bytes on base row 2*tau - 1 (lanes 0..15 read region A, 16..31 region B)
+        const uint2 *__restrict__ wr = reinterpret_cast<const uint2 *>(
+            (c < 16 ? tA : tB + RB) + (2 * ts - 1 - (Y0 - C::ytop)) * RW + 8 * (c & 15) + 8);
         uint2 *__restrict__ grow = reinterpret_cast<uint2 *>(&g2[0][4 * c]) + (ptrdiff_t)(ts - 2 - t_first) * (G2P / 4);
         constexpr bool G = NA >= 2;
-        constexpr int RWW = RW / 4;
+        constexpr int RWW = RW / 8;  // row pitch in 8-byte units
         auto store_o = [&](int to) {  // O_{to} complete -> level 1, round half up: (N + 32) >> 6
             if (to >= o_lo && to < o_hi) {
                 const uint32_t b0 = (aOo[0] + 32u) >> 6, b1 = (aOo[1] + 32u) >> 6;
                 const uint32_t b2 = (aOo[2] + 32u) >> 6, b3 = (aOo[3] + 32u) >> 6;
-                if (!o_edge) {
-                    *reinterpret_cast<uint32_t *>(orow) = __byte_perm(b0 | (b1 << 8), b2 | (b3 << 8), 0x5410);
+                if (!o_edge) {  // j0 = 2 (mod 4): two aligned 16-bit stores
+                    reinterpret_cast<uint16_t *>(orow)[0] = (uint16_t)(b0 | (b1 << 8));
+                    reinterpret_cast<uint16_t *>(orow)[1] = (uint16_t)(b2 | (b3 << 8));
                 } else {
                     if (j0 + 0 >= 1 && j0 + 0 <= w1 - 2) orow[0] = (uint8_t)b0;
                     if (j0 + 1 >= 1 && j0 + 1 <= w1 - 2) orow[1] = (uint8_t)b1;
@@ -472,36 +474,55 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
             // O_t spans rows 2t-1..2t+2 (complete in iteration t+1, second row), G_t rows 2t..2t+3
             // (complete in iteration t+2, first row).  Iterations ts and ts+1 and te, te+1 are peeled:
             // they only feed the accumulators of rows this segment emits.
-            stage1_row<true, true, false, false, false, false>(wr, aOn, aOo, aGn, aGm, aGo);
-            stage1_row<false, true, false, G, false, false>(wr + RWW, aOn, aOo, aGn, aGm, aGo);
+            { const uint2 q0 = (wr)[0], q1 = (wr)[1]; stage1_words<true, true, false, false, false, false, true>(q0.x, make_uint2(q0.y, q1.x), q1.y, aOn, aOo, aGn, aGm, aGo); }
+            { const uint2 q0 = (wr + RWW)[0], q1 = (wr + RWW)[1]; stage1_words<false, true, false, G, false, false, true>(q0.x, make_uint2(q0.y, q1.x), q1.y, aOn, aOo, aGn, aGm, aGo); }
             rotate();
             if (ts + 1 < te) {
-                stage1_row<true, true, true, false, G, false>(wr, aOn, aOo, aGn, aGm, aGo);
-                stage1_row<false, true, true, G, G, false>(wr + RWW, aOn, aOo, aGn, aGm, aGo);
+                { const uint2 q0 = (wr)[0], q1 = (wr)[1]; stage1_words<true, true, true, false, G, false, true>(q0.x, make_uint2(q0.y, q1.x), q1.y, aOn, aOo, aGn, aGm, aGo); }
+                { const uint2 q0 = (wr + RWW)[0], q1 = (wr + RWW)[1]; stage1_words<false, true, true, G, G, false, true>(q0.x, make_uint2(q0.y, q1.x), q1.y, aOn, aOo, aGn, aGm, aGo); }
                 store_o(ts);
                 rotate();
                 for (int tau = ts + 2; tau < te; ++tau) {
-                    stage1_row<true, true, true, false, G, G>(wr, aOn, aOo, aGn, aGm, aGo);
+                    { const uint2 q0 = (wr)[0], q1 = (wr)[1]; stage1_words<true, true, true, false, G, G, true>(q0.x, make_uint2(q0.y, q1.x), q1.y, aOn, aOo, aGn, aGm, aGo); }
                     if (G) *grow = make_uint2(aGo[0] | (aGo[1] << 16), aGo[2] | (aGo[3] << 16));  // G_{tau-2}
-                    stage1_row<false, true, true, G, G, false>(wr + RWW, aOn, aOo, aGn, aGm, aGo);
+                    { const uint2 q0 = (wr + RWW)[0], q1 = (wr + RWW)[1]; stage1_words<false, true, true, G, G, false, true>(q0.x, make_uint2(q0.y, q1.x), q1.y, aOn, aOo, aGn, aGm, aGo); }
                     store_o(tau - 1);
                     rotate();
                 }
                 // tau = te: finish O_{te-1}, G_{te-2}; keep G_{te-1} going; nothing new starts
-                stage1_row<true, false, true, false, G, G>(wr, aOn, aOo, aGn, aGm, aGo);
+                { const uint2 q0 = (wr)[0], q1 = (wr)[1]; stage1_words<true, false, true, false, G, G, true>(q0.x, make_uint2(q0.y, q1.x), q1.y, aOn, aOo, aGn, aGm, aGo); }
                 if (G) *grow = make_uint2(aGo[0] | (aGo[1] << 16), aGo[2] | (aGo[3] << 16));
-                stage1_row<false, false, true, false, G, false>(wr + RWW, aOn, aOo, aGn, aGm, aGo);
+                { const uint2 q0 = (wr + RWW)[0], q1 = (wr + RWW)[1]; stage1_words<false, false, true, false, G, false, true>(q0.x, make_uint2(q0.y, q1.x), q1.y, aOn, aOo, aGn, aGm, aGo); }
                 store_o(te - 1);
                 rotate();
             } else {  // single-row segment: tau = te = ts + 1
-                stage1_row<true, false, true, false, G, false>(wr, aOn, aOo, aGn, aGm, aGo);
-                stage1_row<false, false, true, false, G, false>(wr + RWW, aOn, aOo, aGn, aGm, aGo);
+                { const uint2 q0 = (wr)[0], q1 = (wr)[1]; stage1_words<true, false, true, false, G, false, true>(q0.x, make_uint2(q0.y, q1.x), q1.y, aOn, aOo, aGn, aGm, aGo); }
+                { const uint2 q0 = (wr + RWW)[0], q1 = (wr + RWW)[1]; stage1_words<false, false, true, false, G, false, true>(q0.x, make_uint2(q0.y, q1.x), q1.y, aOn, aOo, aGn, aGm, aGo); }
                 store_o(ts);
                 rotate();
             }
             if (G) {  // tau = te+1, first row only: finish G_{te-1}
-                stage1_row<true, false, false, false, false, true>(wr, aOn, aOo, aGn, aGm, aGo);
+                { const uint2 q0 = (wr)[0], q1 = (wr)[1]; stage1_words<true, false, false, false, false, true, true>(q0.x, make_uint2(q0.y, q1.x), q1.y, aOn, aOo, aGn, aGm, aGo); }
                 *grow = make_uint2(aGo[0] | (aGo[1] << 16), aGo[2] | (aGo[3] << 16));
+            }
+        }
+        // last tile column: level-1 column X0/2 + 126 would be lane 0 of a further tile that does not exist
+        // (the image ends there): 4 chained DP4A per output straight from the tile
+        if (tile_x == P.tiles_x - 1) {
+            const int j = X0 / 2 + 126;
+            if (j >= 1 && j <= w1 - 2) {
+                for (int idx = tid; idx < TH / 2; idx += NTA) {
+                    const int t = Y0 / 2 + idx;
+                    if (t < 1 || t > h1 - 2) continue;
+                    const int ry = 2 * t - 1 - (Y0 - C::ytop);
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {  // pixels 2j-1 .. 2j+2 = tile bytes 267 .. 270 (region B)
+                        const uint32_t *__restrict__ wq = reinterpret_cast<const uint32_t *>(tB + (ry + rr) * RW) + 66;
+                        acc = dp4a_u(__funnelshift_r(wq[0], wq[1], 24), (rr == 0 || rr == 3) ? 0x01030301u : 0x03090903u, acc);
+                    }
+                    out[P.pd.lv[1].off + (size_t)t * w1 + j] = (uint8_t)((acc + 32u) >> 6);
+                }
             }
         }
         // the few G_2 columns right of the warp's 128 (needed by G_4 / O_4 at the tile's right edge)
@@ -1317,7 +1338,7 @@ cudaError_t pyr_plan_create(int w, int h, int levels, cudaStream_t st, PyrPlan *
     p->n_a = p->n_fast < 3 ? p->n_fast : 3;
     p->do4 = p->n_fast >= 4;
     p->do5 = p->n_fast >= 5;
-    p->tiles_x = (w + TW - 1) / TW;
+    p->tiles_x = (w + TW - 1) / TW;  // a tile's lanes own level-1 columns [128 k - 2, 128 k + 126); the last tile adds + 126
     p->tiles_y = (h + TH - 1) / TH;
     p->fast_rows = 0;
     p->fast_grid = kNumSMs;
