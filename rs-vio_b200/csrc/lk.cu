@@ -30,10 +30,6 @@ struct Img {
     int w, h;
 };
 
-__device__ __forceinline__ float px(const Img &im, uint32_t x, uint32_t y) {
-    return (float)__ldg(im.p + (size_t)y * (uint32_t)im.w + x);
-}
-
 // pattern sample i -> offset in pixels (PATTERN_RAW / pattern_scale_down, patch.rs:19-72,126-131)
 __device__ __forceinline__ void pattern_offset(int i, float &ox, float &oy) {
     const int start[9] = {0, 4, 10, 18, 26, 34, 42, 48, 52};
@@ -54,17 +50,26 @@ __device__ __forceinline__ void pattern_offset(int i, float &ox, float &oy) {
     oy = (float)y / 2.0f;
 }
 
-// image_grad -- image_utilities.rs:5-66 (same products and sum order)
-__device__ __forceinline__ void image_grad(const Img &im, float x, float y, float &v, float &gx, float &gy) {
-    const uint32_t ix = sat_u32(floorf(x)), iy = sat_u32(floorf(y));
+// image_grad -- image_utilities.rs:5-66 (same products and sum order).  `ok` == the sample passed the
+// inbound test; otherwise the 12 gathers are redirected to clamped in-image addresses (results unused),
+// which keeps the warp free of divergent branches.
+__device__ __forceinline__ void image_grad(const Img &im, float x, float y, bool ok, float &v, float &gx, float &gy) {
+    const uint32_t ix = ok ? __float2uint_rd(x) : 1u, iy = ok ? __float2uint_rd(y) : 1u;  // floor, x >= 1.5 when ok
     const float dx = x - (float)ix, dy = y - (float)iy;
     const float ddx = 1.0f - dx, ddy = 1.0f - dy;
     const float w00 = ddx * ddy, w01 = ddx * dy, w10 = dx * ddy, w11 = dx * dy;
-    const float p00 = px(im, ix, iy), p10 = px(im, ix + 1, iy), p01 = px(im, ix, iy + 1), p11 = px(im, ix + 1, iy + 1);
-    const float pm0 = px(im, ix - 1, iy), pm1 = px(im, ix - 1, iy + 1);
-    const float p20 = px(im, ix + 2, iy), p21 = px(im, ix + 2, iy + 1);
-    const float p0m = px(im, ix, iy - 1), p1m = px(im, ix + 1, iy - 1);
-    const float p02 = px(im, ix, iy + 2), p12 = px(im, ix + 1, iy + 2);
+    const uint32_t W = (uint32_t)im.w, Hh = (uint32_t)im.h;
+    // columns ix-1 .. ix+2 and rows iy-1 .. iy+2, clamped (a no-op for samples that passed inbound(.., 2))
+    const uint32_t x0 = min(ix, W - 1u), xm = min(ix - 1u, W - 1u), x1 = min(ix + 1u, W - 1u), x2 = min(ix + 2u, W - 1u);
+    const uint8_t *__restrict__ rm = im.p + (size_t)min(iy - 1u, Hh - 1u) * W;
+    const uint8_t *__restrict__ r0 = im.p + (size_t)min(iy, Hh - 1u) * W;
+    const uint8_t *__restrict__ r1 = im.p + (size_t)min(iy + 1u, Hh - 1u) * W;
+    const uint8_t *__restrict__ r2 = im.p + (size_t)min(iy + 2u, Hh - 1u) * W;
+    const float p00 = (float)__ldg(r0 + x0), p10 = (float)__ldg(r0 + x1), p01 = (float)__ldg(r1 + x0), p11 = (float)__ldg(r1 + x1);
+    const float pm0 = (float)__ldg(r0 + xm), pm1 = (float)__ldg(r1 + xm);
+    const float p20 = (float)__ldg(r0 + x2), p21 = (float)__ldg(r1 + x2);
+    const float p0m = (float)__ldg(rm + x0), p1m = (float)__ldg(rm + x1);
+    const float p02 = (float)__ldg(r2 + x0), p12 = (float)__ldg(r2 + x1);
     v = w00 * p00 + w01 * p01 + w10 * p10 + w11 * p11;
     const float res_mx = w00 * pm0 + w01 * pm1 + w10 * p00 + w11 * p01;
     const float res_px = w00 * p10 + w01 * p11 + w10 * p20 + w11 * p21;
@@ -223,15 +228,16 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
         float d[2], J[2][3];
         float sum = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
         int n_valid = 0;
+        unsigned tmask[2];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             d[k] = -1.0f;
             J[k][0] = J[k][1] = J[k][2] = 0.0f;
             const float x = pxx + ln.ox[k], y = pyy + ln.oy[k];
             const bool ok = ln.has[k] && inbound(ia.w, ia.h, x, y, 2);
+            float v, gx, gy;
+            image_grad(ia, x, y, ok, v, gx, gy);
             if (ok) {
-                float v, gx, gy;
-                image_grad(ia, x, y, v, gx, gy);
                 d[k] = v;
                 J[k][0] = gx * 1.0f + gy * 0.0f;
                 J[k][1] = gx * 0.0f + gy * 1.0f;
@@ -241,7 +247,8 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
                 g1 += J[k][1];
                 g2 += J[k][2];
             }
-            n_valid += __popc(__ballot_sync(0xffffffffu, ok));
+            tmask[k] = __ballot_sync(0xffffffffu, ok);  // samples valid in the template (data >= 0)
+            n_valid += __popc(tmask[k]);
         }
         ++n_templates;
         warp_sum4(sum, g0, g1, g2, lane);
@@ -304,33 +311,37 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
             float r[2];
             float rsum = 0.0f;
             int nv = 0;
+            unsigned cmask[2];
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const float x = (T1[0] * ln.ox[k] + T1[1] * ln.oy[k]) + T1[2];
                 const float y = (T1[3] * ln.ox[k] + T1[4] * ln.oy[k]) + T1[5];
                 const bool ok = ln.has[k] && x >= 2.0f && y >= 2.0f && x < wlim && y < hlim;
-                r[k] = -1.0f;
-                if (ok) {
-                    const uint32_t ix = sat_u32(floorf(x)), iy = sat_u32(floorf(y));
-                    const float dx = x - (float)ix, dy = y - (float)iy;
-                    const float ddx = 1.0f - dx, ddy = 1.0f - dy;
-                    const float p00 = px(ib, ix, iy), p10 = px(ib, ix + 1, iy);
-                    const float p01 = px(ib, ix, iy + 1), p11 = px(ib, ix + 1, iy + 1);
-                    r[k] = ddx * ddy * p00 + ddx * dy * p01 + dx * ddy * p10 + dx * dy * p11;
-                    rsum += r[k];
-                }
-                nv += __popc(__ballot_sync(0xffffffffu, ok));
+                // branch-free gather: rejected samples read pixel (0,0)..(1,1) clamped into the image, unused
+                const uint32_t ix = ok ? __float2uint_rd(x) : 0u, iy = ok ? __float2uint_rd(y) : 0u;
+                const float dx = x - (float)ix, dy = y - (float)iy;
+                const float ddx = 1.0f - dx, ddy = 1.0f - dy;
+                const uint32_t x1 = min(ix + 1u, (uint32_t)ib.w - 1u);
+                const uint8_t *__restrict__ q0 = ib.p + (size_t)iy * (uint32_t)ib.w;
+                const uint8_t *__restrict__ q1 = ib.p + (size_t)min(iy + 1u, (uint32_t)ib.h - 1u) * (uint32_t)ib.w;
+                const float p00 = (float)__ldg(q0 + ix), p10 = (float)__ldg(q0 + x1);
+                const float p01 = (float)__ldg(q1 + ix), p11 = (float)__ldg(q1 + x1);
+                const float val = ddx * ddy * p00 + ddx * dy * p01 + dx * ddy * p10 + dx * dy * p11;
+                r[k] = ok ? val : -1.0f;
+                rsum += ok ? val : 0.0f;
+                cmask[k] = __ballot_sync(0xffffffffu, ok);
+                nv += __popc(cmask[k]);
             }
             rsum = warp_sum(rsum);
             if (rsum < kEps) return RSVIO_FAIL_RESIDUAL;
-            int nres = 0;
+            // residuals exist where the sample is valid in the template and in the current image
+            const int nres = __popc(cmask[0] & tmask[0]) + __popc(cmask[1] & tmask[1]);
             float i0 = 0.0f, i1 = 0.0f, i2 = 0.0f;
             const float inv_rsum = __frcp_rn(rsum);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const bool both = ln.has[k] && r[k] >= 0.0f && d[k] >= 0.0f;
+                const bool both = r[k] >= 0.0f && d[k] >= 0.0f;
                 const float res = both ? (float)nv * r[k] * inv_rsum - d[k] : 0.0f;
-                nres += __popc(__ballot_sync(0xffffffffu, both));
                 i0 += (-M[k][0]) * res;
                 i1 += (-M[k][1]) * res;
                 i2 += (-M[k][2]) * res;
