@@ -56,6 +56,7 @@ struct rsvio_tracker {
     unsigned long long *d_last_id = nullptr, *d_counters = nullptr, *d_rm = nullptr;
     int rm_cap = 0;
     int *d_err = nullptr;
+    unsigned *d_work = nullptr;
     // host-mapped output ring: records [groups][cap] and counts [groups] (+1 error flag)
     OutRecord *h_out[kSlots] = {nullptr, nullptr}, *d_out[kSlots] = {nullptr, nullptr};
     int *h_cnt[kSlots] = {nullptr, nullptr}, *d_cnt[kSlots] = {nullptr, nullptr};
@@ -140,6 +141,7 @@ void free_all(rsvio_tracker *t) {
     cudaFree(t->d_counters);
     cudaFree(t->d_rm);
     cudaFree(t->d_err);
+    cudaFree(t->d_work);
     if (t->copy_st) cudaStreamDestroy(t->copy_st);
     if (t->own_stream && t->st) cudaStreamDestroy(t->st);
     cudaGetLastError();
@@ -197,6 +199,7 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
         b.status = t->d_lk_status;
         b.iters = nullptr;
         b.counters = t->d_counters;
+        b.work_counter = t->d_work;
         b.groups = t->stereo ? t->groups : t->S;
         b.cap = t->cap;
         b.max_it = t->cfg.max_iterations;
@@ -225,6 +228,7 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
         b.status = t->d_st_status;
         b.iters = nullptr;
         b.counters = t->d_counters;
+        b.work_counter = t->d_work + 1;
         b.groups = t->S;
         b.cap = t->new_cap;
         b.max_it = t->cfg.max_iterations;
@@ -434,6 +438,7 @@ rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) 
         CU_TRY(t, dmalloc(&t->d_last_id, S));
         CU_TRY(t, dmalloc(&t->d_counters, (size_t)CNT_N));
         CU_TRY(t, dmalloc(&t->d_err, (size_t)1));
+        CU_TRY(t, dmalloc(&t->d_work, (size_t)4));
         return clear_state(t);
     };
     rs = body();
@@ -824,6 +829,7 @@ rsvio_status rsvio_track_points(int32_t device, const uint8_t *pyr_a, const uint
         b.status = d_status;
         b.iters = d_iters;
         b.counters = nullptr;
+        b.work_counter = nullptr;  // one group: static striding is already balanced
         b.groups = 1;
         b.cap = n;
         b.max_it = max_iterations;

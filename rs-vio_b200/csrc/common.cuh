@@ -85,6 +85,7 @@ struct LkBatch {
     int32_t *status;        // [groups][cap]
     int32_t *iters;         // [groups][cap][2] or nullptr
     unsigned long long *counters;  // CNT_* or nullptr
+    unsigned *work_counter;        // device scratch for dynamic point scheduling (zeroed per launch) or nullptr
     int groups, cap;
     int max_it;
     float thr;

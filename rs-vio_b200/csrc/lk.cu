@@ -24,6 +24,7 @@ namespace {
 
 constexpr float kEps = 1.1920929e-07f;  // f32::EPSILON
 constexpr int kWarpsPerBlock = 4;
+constexpr int kMaxGroupsSmem = 2048;  // groups whose live-point prefix fits the shared-memory table
 
 struct Img {
     const uint8_t *__restrict__ p;
@@ -380,7 +381,7 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
     return RSVIO_TRACK_OK;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 6)
 lk_track_fb_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ LkBatch b) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -391,11 +392,59 @@ lk_track_fb_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ L
     ln.has[1] = lane + 32 < kPattern;
     pattern_offset(ln.has[1] ? lane + 32 : 0, ln.ox[1], ln.oy[1]);
 
+    // Work distribution: the live points of all groups form one compacted list (exclusive prefix of the
+    // per-group counts in shared memory); warps fetch the next point from a global counter, so a warp that
+    // drew long tracks (many iterations) does not hold up the launch while others idle.
+    __shared__ int prefix[kMaxGroupsSmem + 1];
+    __shared__ int warp_tot[kWarpsPerBlock];
+    const bool dynamic = b.work_counter != nullptr && b.groups <= kMaxGroupsSmem;
+    if (dynamic) {
+        int base = 0;
+        for (int g0 = 0; g0 < b.groups; g0 += blockDim.x) {
+            const int g = g0 + threadIdx.x;
+            const int c = g < b.groups ? min(__ldg(b.counts + g), b.cap) : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) warp_tot[threadIdx.x >> 5] = incl;
+            __syncthreads();
+            int off = base;
+            for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) off += warp_tot[w];
+            if (g < b.groups) prefix[g] = off + incl - c;
+            int tot = 0;
+            for (int w = 0; w < kWarpsPerBlock; ++w) tot += warp_tot[w];
+            base += tot;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) prefix[b.groups] = base;
+        __syncthreads();
+    }
     unsigned n_iters = 0, n_templates = 0, n_tracks = 0;
-    const int total = b.groups * b.cap;
-    for (int item = warp; item < total; item += n_warps) {
-        const int g = item / b.cap, k = item - g * b.cap;
-        if (k >= __ldg(b.counts + g)) continue;
+    const int total = dynamic ? prefix[b.groups] : b.groups * b.cap;
+    for (int it0 = warp;; it0 += n_warps) {
+        int g, k, item;
+        if (dynamic) {
+            int w = 0;
+            if (lane == 0) w = (int)atomicAdd(b.work_counter, 1u);
+            w = __shfl_sync(0xffffffffu, w, 0);
+            if (w >= total) break;
+            int lo = 0, hi = b.groups;  // largest g with prefix[g] <= w
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (prefix[mid] <= w) lo = mid; else hi = mid;
+            }
+            g = lo;
+            k = w - prefix[g];
+        } else {
+            if (it0 >= total) break;
+            g = it0 / b.cap;
+            k = it0 - g * b.cap;
+            if (k >= __ldg(b.counts + g)) continue;
+        }
+        item = g * b.cap + k;
         const uint8_t *A = b.pyr_a + (size_t)g * pd.pyr_stride;
         const uint8_t *B = b.pyr_b + (size_t)g * pd.pyr_stride;
         float T0[6], Tf[6], Tb[6];
@@ -461,8 +510,14 @@ cudaError_t lk_track(const PyrDesc &pd, const LkBatch &b, cudaStream_t st) {
     const long long total = (long long)b.groups * b.cap;
     if (total <= 0) return cudaSuccess;
     long long blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const long long max_blocks = (long long)kNumSMs * 16;  // 64 warps per SM resident at most
+    const bool dynamic = b.work_counter != nullptr && b.groups <= kMaxGroupsSmem;
+    // dynamic scheduling: one resident wave (80 registers -> 6 CTAs per SM); static striding: up to 16 per SM
+    const long long max_blocks = (long long)kNumSMs * (dynamic ? 6 : 16);
     if (blocks > max_blocks) blocks = max_blocks;
+    if (dynamic) {
+        cudaError_t e = cudaMemsetAsync(b.work_counter, 0, sizeof(unsigned), st);
+        if (e != cudaSuccess) return e;
+    }
     lk_track_fb_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(pd, b);
     return cudaGetLastError();
 }
