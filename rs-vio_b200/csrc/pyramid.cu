@@ -221,6 +221,8 @@ struct FastParams {
     uint8_t *dst;
     uint32_t *g8;         // [img][h0/8][w0/8] exported when deeper levels follow, else nullptr
     int tiles_x, tiles_y;
+    int nbuf;             // tile buffers per CTA: 2 = next tile prefetched during compute, 1 = more CTAs per SM
+    unsigned *tile_counter;  // single-buffer mode: tiles are handed out dynamically (zeroed before the launch)
 };
 
 __device__ __forceinline__ uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c) {
@@ -362,10 +364,12 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
     using S = FastSmem<NA>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-    uint16_t(*g2)[G2P] = reinterpret_cast<uint16_t(*)[G2P]>(smem + S::off_g2);
-    uint32_t(*g4)[C::G4C] = reinterpret_cast<uint32_t(*)[C::G4C]>(smem + S::off_g4);
-    float(*vbuf)[PITCH] = reinterpret_cast<float(*)[PITCH]>(smem + S::off_vbuf);
-    const uint32_t mbar0 = smem_u32(smem + S::off_mbar);
+    // layout: [nbuf x (region A, region B)] [g2] [g4] [vbuf] [mbarriers]
+    const int shrink = (2 - P.nbuf) * 2 * S::region;
+    uint16_t(*g2)[G2P] = reinterpret_cast<uint16_t(*)[G2P]>(smem + S::off_g2 - shrink);
+    uint32_t(*g4)[C::G4C] = reinterpret_cast<uint32_t(*)[C::G4C]>(smem + S::off_g4 - shrink);
+    float(*vbuf)[PITCH] = reinterpret_cast<float(*)[PITCH]>(smem + S::off_vbuf - shrink);
+    const uint32_t mbar0 = smem_u32(smem + S::off_mbar - shrink);
 
     const int tid = threadIdx.x;
     const int w0 = P.pd.lv[0].w, h0 = P.pd.lv[0].h;
@@ -391,12 +395,25 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0 && (int)blockIdx.x < total) issue_load(blockIdx.x, 0);
+    const bool dbl = P.nbuf == 2;
+    if (dbl && tid == 0 && (int)blockIdx.x < total) issue_load(blockIdx.x, 0);
 
+    __shared__ int next_tile;
     int it = 0;
-    for (int tile_id = blockIdx.x; tile_id < total; tile_id += gridDim.x, ++it) {
-    const int buf = it & 1;
-    if (tid == 0 && tile_id + (int)gridDim.x < total) issue_load(tile_id + gridDim.x, buf ^ 1);  // prefetch
+    for (int tile_id = blockIdx.x;; ++it) {
+    if (!dbl) {  // dynamic hand-out: border tiles (extra ring work) no longer decide the makespan
+        if (tid == 0) next_tile = (int)atomicAdd(P.tile_counter, 1u);
+        __syncthreads();
+        tile_id = next_tile;
+    } else if (it > 0) {
+        tile_id += gridDim.x;
+    }
+    if (tile_id >= total) break;
+    const int buf = dbl ? (it & 1) : 0;
+    if (tid == 0) {
+        if (!dbl) issue_load(tile_id, 0);  // single buffer: the previous tile's last reader passed the barrier below
+        else if (tile_id + (int)gridDim.x < total) issue_load(tile_id + gridDim.x, buf ^ 1);  // prefetch
+    }
     const int img = tile_id / tiles_per_img, tl = tile_id - img * tiles_per_img;
     const int tile_y = tl / P.tiles_x, tile_x = tl - tile_y * P.tiles_x;
     const int X0 = tile_x * TW, Y0 = tile_y * TH;
@@ -404,7 +421,7 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
     const uint8_t *__restrict__ tA = smem + S::off_tile + 2 * buf * S::region;   // tile columns [0, RW)
     const uint8_t *__restrict__ tB = tA + S::region - RB;                        // indexable by tile column >= RB
     auto trow = [&](int ry, int col) -> const uint8_t * { return (col < kSplitCol ? tA : tB) + ry * RW + col; };
-    mbar_wait(mbar0 + 8u * buf, (it >> 1) & 1);
+    mbar_wait(mbar0 + 8u * buf, (dbl ? (it >> 1) : it) & 1);
 
     // ---- stage 0: level 0 == input, 16-byte copies from the staged tile
     {
@@ -1179,12 +1196,14 @@ static bool make_tile_map(CUtensorMap *m, const uint8_t *base, int w, int h, int
 }
 
 template <int NA>
-static cudaError_t fast_kernel_setup(int *grid) {
+static cudaError_t fast_kernel_setup(int *grid, int nbuf, int *smem_bytes) {
+    const int bytes = FastSmem<NA>::bytes - (2 - nbuf) * 2 * FastSmem<NA>::region;
+    *smem_bytes = bytes;
     cudaError_t e = cudaFuncSetAttribute(pyr_fast_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          FastSmem<NA>::bytes);
     if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pyr_fast_kernel<NA>, NTA, FastSmem<NA>::bytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pyr_fast_kernel<NA>, NTA, bytes);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = kNumSMs;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1217,6 +1236,8 @@ struct PyrPlan {
     int tiles_x, tiles_y;
     int fast_rows;   // tile rows fetched per CTA (TMA box height)
     int fast_grid;   // persistent grid: SMs x resident CTAs per SM
+    int fast_nbuf, fast_smem;  // tile buffers per CTA and the resulting dynamic shared memory
+    unsigned *d_tile_counter;
     int use_stream;  // streaming warp-per-strip kernel instead of the CTA-tile kernel
     int stream_grid; // resident warps (1-warp CTAs) on the device
     RingWeights ring[4];
@@ -1274,6 +1295,7 @@ cudaError_t pyr_plan_create(int w, int h, int levels, cudaStream_t st, PyrPlan *
     PyrPlan *p = new PyrPlan();
     p->pd = make_pyr_desc(w, h, levels);
     p->d_tables = nullptr;
+    p->d_tile_counter = nullptr;
     p->d_tiles = nullptr;
     p->d_g8 = nullptr;
     p->g8_images = 0;
@@ -1349,8 +1371,16 @@ cudaError_t pyr_plan_create(int w, int h, int levels, cudaStream_t st, PyrPlan *
     p->do4 = p->n_fast >= 4;
     p->do5 = p->n_fast >= 5;
     if (p->n_a >= 1) {
-        e = p->n_a == 1 ? fast_kernel_setup<1>(&p->fast_grid)
-                        : (p->n_a == 2 ? fast_kernel_setup<2>(&p->fast_grid) : fast_kernel_setup<3>(&p->fast_grid));
+        e = cudaMalloc((void **)&p->d_tile_counter, sizeof(unsigned));
+        if (e != cudaSuccess) {
+            pyr_plan_destroy(p);
+            return e;
+        }
+        const char *nb = getenv("RSVIO_PYR_NBUF");
+        p->fast_nbuf = (nb && atoi(nb) == 2) ? 2 : 1;
+        e = p->n_a == 1 ? fast_kernel_setup<1>(&p->fast_grid, p->fast_nbuf, &p->fast_smem)
+                        : (p->n_a == 2 ? fast_kernel_setup<2>(&p->fast_grid, p->fast_nbuf, &p->fast_smem)
+                                       : fast_kernel_setup<3>(&p->fast_grid, p->fast_nbuf, &p->fast_smem));
         if (e != cudaSuccess) {
             pyr_plan_destroy(p);
             return e;
@@ -1424,6 +1454,7 @@ cudaError_t pyr_plan_create(int w, int h, int levels, cudaStream_t st, PyrPlan *
 void pyr_plan_destroy(PyrPlan *p) {
     if (!p) return;
     if (p->d_tables) cudaFree(p->d_tables);
+    if (p->d_tile_counter) cudaFree(p->d_tile_counter);
     if (p->d_tiles) cudaFree(p->d_tiles);
     if (p->d_g8) cudaFree(p->d_g8);
     if (p->d_fix) cudaFree(p->d_fix);
@@ -1543,6 +1574,12 @@ cudaError_t pyr_build(const PyrPlan *p, const uint8_t *src0, const uint8_t *src1
         fp.g8 = p->do4 ? p->d_g8 : nullptr;
         fp.tiles_x = p->tiles_x;
         fp.tiles_y = p->tiles_y;
+        fp.nbuf = p->fast_nbuf;
+        fp.tile_counter = p->d_tile_counter;
+        if (p->fast_nbuf == 1) {
+            cudaError_t em = cudaMemsetAsync(p->d_tile_counter, 0, sizeof(unsigned), st);
+            if (em != cudaSuccess) return em;
+        }
         CUtensorMap m0, m1;
         const int n0 = sps < n ? sps : n;               // images behind map 0
         const uint8_t *b1 = sps < n ? s1 : s0;
@@ -1553,11 +1590,11 @@ cudaError_t pyr_build(const PyrPlan *p, const uint8_t *src0, const uint8_t *src1
         const int total = p->tiles_x * p->tiles_y * n;
         const int blocks = total < p->fast_grid ? total : p->fast_grid;
         if (p->n_a == 1)
-            pyr_fast_kernel<1><<<blocks, NTA, FastSmem<1>::bytes, st>>>(fp, m0, m1);
+            pyr_fast_kernel<1><<<blocks, NTA, p->fast_smem, st>>>(fp, m0, m1);
         else if (p->n_a == 2)
-            pyr_fast_kernel<2><<<blocks, NTA, FastSmem<2>::bytes, st>>>(fp, m0, m1);
+            pyr_fast_kernel<2><<<blocks, NTA, p->fast_smem, st>>>(fp, m0, m1);
         else
-            pyr_fast_kernel<3><<<blocks, NTA, FastSmem<3>::bytes, st>>>(fp, m0, m1);
+            pyr_fast_kernel<3><<<blocks, NTA, p->fast_smem, st>>>(fp, m0, m1);
         if (n_launches) ++*n_launches;
         }
         if (p->do4) {
