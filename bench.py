@@ -420,7 +420,9 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ns = min(S, 2 * cores if cores < 32 else 64)
-        nf = 40 if cores >= 8 else 12      # about 10-30 s of CPU work on the box's cores
+        # calibrate on a few frames, then size the sample for roughly 12 s of CPU work on this box
+        _, _, dt0 = cpu_run(args.config, frames_np, ns, 8, 2, cores)
+        nf = int(max(20, min(4000, 8 * 12.0 / max(dt0, 1e-3))))
         tracks, nframes, dt = cpu_run(args.config, frames_np, ns, nf, 2, cores)
         cpu_baseline = {"value": tracks / dt, "unit": "tracks/s", "cores": min(cores, ns), "kind": "port",
                         "stereo_frames_per_sec": nframes / dt,
