@@ -51,3 +51,27 @@ def test_pyramid_constant_and_batch_independence(rsvio):
     batch = rsvio.build_pyramid(rnd, levels)
     for j in range(4):
         assert np.array_equal(batch[j], rsvio.build_pyramid(rnd[j], levels)[0])
+
+
+def test_streaming_kernel_variant_is_bit_exact_too():
+    """RSVIO_PYR_KERNEL=stream selects the experimental warp-per-strip kernel (read once per process):
+    run the same oracle comparison in a child process."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import rsvio_b200\n"
+        "from oracle import oracle as orc\n"
+        "from util import random_image, scene_pair\n"
+        "for (w, h, lv) in ((752, 480, 3), (512, 512, 4), (1920, 1200, 5), (752, 480, 6)):\n"
+        "    imgs = np.stack([random_image(w, h, 5), scene_pair(w, h, 6)[0]])\n"
+        "    got = rsvio_b200.build_pyramid(imgs, lv)\n"
+        "    for j in range(2):\n"
+        "        assert np.array_equal(got[j], orc.build_pyramid(imgs[j], lv, nthreads=4)), (w, h, lv, j)\n"
+        "print('stream ok')\n"
+    ) % (os.path.join(os.path.dirname(GOLDEN_DIR), ".."), os.path.join(os.path.dirname(GOLDEN_DIR), "..", "rs-vio_b200"),
+         os.path.dirname(GOLDEN_DIR))
+    env = dict(os.environ, RSVIO_PYR_KERNEL="stream")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "stream ok" in out.stdout, out.stdout + out.stderr
