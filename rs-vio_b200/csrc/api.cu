@@ -76,6 +76,7 @@ struct rsvio_tracker {
 namespace {
 
 rsvio_status fail_cuda(rsvio_tracker *t, cudaError_t e, const char *what, int line) {
+    cudaGetLastError();  // the error has been reported: do not leave it pending for an unrelated later call
     if (t) {
         char buf[512];
         snprintf(buf, sizeof(buf), "CUDA error %d (%s) at api.cu:%d: %s", (int)e, cudaGetErrorString(e), line, what);
@@ -709,6 +710,7 @@ size_t rsvio_pyramid_bytes(int32_t width, int32_t height, int32_t levels) {
         if (e__ != cudaSuccess) {                                                                       \
             fprintf(stderr, "rsvio: CUDA error %d (%s) at api.cu:%d: %s\n", (int)e__,                   \
                     cudaGetErrorString(e__), __LINE__, #expr);                                          \
+            cudaGetLastError(); /* reported: clear the pending error */                                 \
             rs = RSVIO_ERR_CUDA;                                                                        \
             goto done;                                                                                  \
         }                                                                                               \
