@@ -413,6 +413,28 @@ def main():
         except Exception as ex:  # the headline number does not depend on this microbenchmark
             extra_roofline = {"error": str(ex)}
 
+    # ---- latency of ONE stream through the synchronous reference-facing call (the drop-in use case) ----
+    single = None
+    if rank == 0:
+        try:
+            tr1 = rsvio_b200.StereoPatchTracker(p["grid"], p["max_it"], p["thr"], width=w, height=h, levels=p["levels"],
+                                                device=local_rank)
+            lat = []
+            for i in range(60):
+                k = ring_index(i)
+                lp, rp = host[k, 0, 0], host[k, 1, 0]
+                t0 = time.perf_counter()
+                rsvio_b200.binding._check(tr1._L.rsvio_tracker_process_stereo(tr1._h, C.c_void_p(lp.data_ptr()),
+                                                                                C.c_void_p(rp.data_ptr()), w), tr1._h)
+                lat.append(time.perf_counter() - t0)
+            lat = np.array(lat[10:]) * 1e3
+            single = {"ms_per_frame_median": float(np.median(lat)), "ms_per_frame_p95": float(np.percentile(lat, 95)),
+                      "stereo_frames_per_sec": float(1e3 / np.median(lat)), "tracks_alive": tr1.num_tracks(0) + tr1.num_tracks(1),
+                      "what": "1 stream, rsvio_tracker_process_stereo per frame (upload + 7 kernels + result), host wall clock"}
+            tr1.close()
+        except Exception as ex:
+            single = {"error": str(ex)}
+
     sampler.stop_flag = True
     clocks = sampler.summary()
 
@@ -451,6 +473,7 @@ def main():
             "stage_ms_per_step": {k: v[0] for k, v in stage_share.items()},
             "stage_share": {k: v[1] for k, v in stage_share.items()},
             "cpu_baseline": cpu_baseline,
+            "single_stream_latency": single,
             "clocks": clocks,
             "datagen_s": t_gen,
         }

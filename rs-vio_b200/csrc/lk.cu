@@ -381,7 +381,7 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
     return RSVIO_TRACK_OK;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 6)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 8)
 lk_track_fb_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ LkBatch b) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -512,7 +512,7 @@ cudaError_t lk_track(const PyrDesc &pd, const LkBatch &b, cudaStream_t st) {
     long long blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const bool dynamic = b.work_counter != nullptr && b.groups <= kMaxGroupsSmem;
     // dynamic scheduling: one resident wave (80 registers -> 6 CTAs per SM); static striding: up to 16 per SM
-    const long long max_blocks = (long long)kNumSMs * (dynamic ? 6 : 16);
+    const long long max_blocks = (long long)kNumSMs * (dynamic ? 8 : 16);
     if (blocks > max_blocks) blocks = max_blocks;
     if (dynamic) {
         cudaError_t e = cudaMemsetAsync(b.work_counter, 0, sizeof(unsigned), st);
