@@ -200,7 +200,6 @@ struct FastCfg {
     static constexpr int ytop = 2 * et + 1, ybot = 2 * eb + 2;  // tile rows [Y0 - ytop, Y0 + TH + ybot)
     static constexpr int ROWS = TH + ytop + ybot;
     static constexpr int NE = TH / 2 + et + eb;                 // level-1 rows emitted per tile (O and/or G)
-    static constexpr int PER_SEG = (NE + NSEG - 1) / NSEG;
     static constexpr int G2ROWS = NA >= 2 ? NE : 1;
     static constexpr int GX = NA == 3 ? 5 : (NA == 2 ? 2 : 0);  // G_2 columns right of the warp's 128
     static constexpr int G4C = TW / 4 + 2, G4R = TH / 4 + 2;    // G_4[X0/4 - 1 .. X0/4 + TW/4]
@@ -443,8 +442,10 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
     {
         const int c = tid & (NCOL - 1), seg = tid / NCOL;
         const int j0 = X0 / 2 - 2 + 4 * c;
-        const int ts = t_first + seg * C::PER_SEG;
-        const int te = min(ts + C::PER_SEG, t_first + C::NE);
+        // balanced row segments: NE = 33 -> 9, 8, 8, 8 (the slowest warp decides when the CTA reaches the barrier)
+        constexpr int SEG_BASE = C::NE / NSEG, SEG_EXTRA = C::NE % NSEG;
+        const int ts = t_first + seg * SEG_BASE + min(seg, SEG_EXTRA);
+        const int te = ts + SEG_BASE + (seg < SEG_EXTRA ? 1 : 0);
         const bool live = (2 * j0 - 8) < w0 && (2 * ts - 8) < h0 && ts < te;  // partial tiles: skip dead work
         // level-1 rows this thread stores: its segment, the tile's O range, the level's interior
         const int o_lo = max(max(ts, Y0 / 2), 1);
@@ -1110,10 +1111,12 @@ pyr_deep_kernel(const __grid_constant__ PyrDesc pd, const uint32_t *__restrict__
         }
         half = 1u << (shift - 1);
         out[pd.lv[lev].off + (size_t)oy * pd.lv[lev].w + ox] = (uint8_t)((n + half) >> shift);
-        // the reference's f32 horizontal accumulation is within 2^-10 of N / D: flag ties it could flip
+        // The reference's f32 horizontal accumulation differs from N / D by at most 31 * 2^-17 = 2.4e-4 grey
+        // levels at level 4 (products exact, 31 rounded adds below 256) and 63 * 2^-17 + 64 * 2^-22 = 5.0e-4
+        // at level 5: flag the outputs within 2^-11 resp. 2^-10 of a tie, they could round the other way.
         const uint32_t frac = n & ((1u << shift) - 1u);
         const uint32_t dist = frac > half ? frac - half : half - frac;
-        if (dist <= (1u << (shift - 10))) {
+        if (dist <= (1u << (shift - (lev == 4 ? 11 : 10)))) {
             const int slot = atomicAdd(fix_count, 1);
             if (slot < fix_cap) fix[slot] = FixItem{img, lev, ox, oy};
         }
