@@ -205,8 +205,10 @@ __device__ __forceinline__ void warp_sum8(float (&v)[8], int lane) {
 }
 
 // Per-lane state of the lane's two pattern samples
+// The lane's two pattern offsets live in a shared-memory table (float2 per sample): the compiler
+// otherwise rematerialises them from the lane id inside the iteration loop (~20 instructions per sample).
 struct Lane {
-    float ox[2], oy[2];
+    const float2 *pat;  // &table[lane]; sample k is pat[32 * k]
     bool has[2];
 };
 
@@ -234,7 +236,8 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
         for (int k = 0; k < 2; ++k) {
             d[k] = -1.0f;
             J[k][0] = J[k][1] = J[k][2] = 0.0f;
-            const float x = pxx + ln.ox[k], y = pyy + ln.oy[k];
+            const float2 o = ln.pat[32 * k];
+            const float x = pxx + o.x, y = pyy + o.y;
             const bool ok = ln.has[k] && inbound(ia.w, ia.h, x, y, 2);
             float v, gx, gy;
             image_grad(ia, x, y, ok, v, gx, gy);
@@ -242,7 +245,7 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
                 d[k] = v;
                 J[k][0] = gx * 1.0f + gy * 0.0f;
                 J[k][1] = gx * 0.0f + gy * 1.0f;
-                J[k][2] = gx * (-ln.oy[k]) + gy * ln.ox[k];
+                J[k][2] = gx * (-o.y) + gy * o.x;
                 sum += v;
                 g0 += J[k][0];
                 g1 += J[k][1];
@@ -315,8 +318,9 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
             unsigned cmask[2];
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const float x = (T1[0] * ln.ox[k] + T1[1] * ln.oy[k]) + T1[2];
-                const float y = (T1[3] * ln.ox[k] + T1[4] * ln.oy[k]) + T1[5];
+                const float2 o = ln.pat[32 * k];
+                const float x = (T1[0] * o.x + T1[1] * o.y) + T1[2];
+                const float y = (T1[3] * o.x + T1[4] * o.y) + T1[5];
                 const bool ok = ln.has[k] && x >= 2.0f && y >= 2.0f && x < wlim && y < hlim;
                 // branch-free gather: rejected samples read pixel (0,0)..(1,1) clamped into the image, unused
                 const uint32_t ix = ok ? __float2uint_rd(x) : 0u, iy = ok ? __float2uint_rd(y) : 0u;
@@ -386,11 +390,17 @@ lk_track_fb_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ L
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    __shared__ float2 s_pat[64];
+    if (threadIdx.x < 64) {
+        float ox, oy;
+        pattern_offset(threadIdx.x < kPattern ? (int)threadIdx.x : 0, ox, oy);
+        s_pat[threadIdx.x] = make_float2(ox, oy);
+    }
+    __syncthreads();
     Lane ln;
-    pattern_offset(lane, ln.ox[0], ln.oy[0]);
+    ln.pat = s_pat + lane;
     ln.has[0] = true;
     ln.has[1] = lane + 32 < kPattern;
-    pattern_offset(ln.has[1] ? lane + 32 : 0, ln.ox[1], ln.oy[1]);
 
     // Work distribution: the live points of all groups form one compacted list (exclusive prefix of the
     // per-group counts in shared memory); warps fetch the next point from a global counter, so a warp that
