@@ -50,6 +50,8 @@ struct rsvio_tracker {
     uint8_t *d_occ = nullptr;
     uint32_t *d_cell_pt = nullptr;
     float *d_cell_score = nullptr;
+    uint32_t *d_cell_list = nullptr;
+    int *d_cell_list_n = nullptr;
     float *d_new_T6 = nullptr, *d_st_T6 = nullptr;
     int *d_new_count = nullptr;
     int32_t *d_st_status = nullptr;
@@ -134,6 +136,8 @@ void free_all(rsvio_tracker *t) {
     cudaFree(t->d_occ);
     cudaFree(t->d_cell_pt);
     cudaFree(t->d_cell_score);
+    cudaFree(t->d_cell_list);
+    cudaFree(t->d_cell_list_n);
     cudaFree(t->d_new_T6);
     cudaFree(t->d_st_T6);
     cudaFree(t->d_new_count);
@@ -214,10 +218,10 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
     count(3, 1);
     mark(++stage);  // 4: detection (level 0 of the current left pyramid is the input image)
     CU_TRY(t, detect_cells(t->gd, cur + t->pd.lv[0].off, (size_t)t->pd.lv[0].w, (size_t)t->pd.pyr_stride, t->S,
-                           t->d_occ, t->d_cell_pt, t->d_cell_score, st));
+                           t->d_occ, t->d_cell_pt, t->d_cell_score, t->d_cell_list, t->d_cell_list_n, st));
     CU_TRY(t, collect_new_points(t->gd, t->S, t->d_cell_pt, t->d_cell_score, t->d_new_T6, nullptr, t->d_new_count,
                                  t->new_cap, t->d_counters, st));
-    count(4, 2);
+    count(4, 4);
     mark(++stage);  // 5: stereo LK (left -> right of the current frame)
     if (t->stereo) {
         LkBatch b{};
@@ -432,6 +436,8 @@ rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) 
         CU_TRY(t, dmalloc(&t->d_occ, S * (size_t)t->gd.occ_rows * t->gd.occ_cols));
         CU_TRY(t, dmalloc(&t->d_cell_pt, S * (size_t)t->new_cap));
         CU_TRY(t, dmalloc(&t->d_cell_score, S * (size_t)t->new_cap));
+        CU_TRY(t, dmalloc(&t->d_cell_list, S * (size_t)t->new_cap));
+        CU_TRY(t, dmalloc(&t->d_cell_list_n, (size_t)1));
         CU_TRY(t, dmalloc(&t->d_new_T6, S * (size_t)t->new_cap * 6));
         CU_TRY(t, dmalloc(&t->d_st_T6, S * (size_t)t->new_cap * 6));
         CU_TRY(t, dmalloc(&t->d_new_count, S));
@@ -866,7 +872,8 @@ rsvio_status rsvio_detect_keypoints(int32_t device, const uint8_t *image, int32_
     uint8_t *d_img = nullptr, *d_occ = nullptr;
     uint32_t *d_xy = nullptr, *d_cell = nullptr;
     float *d_score = nullptr, *d_T6 = nullptr, *d_nscore = nullptr;
-    int *d_cnt = nullptr;
+    int *d_cnt = nullptr, *d_list_n = nullptr;
+    uint32_t *d_list = nullptr;
     int cnt = 0;
     std::vector<float> hT, hs;
     CU_TRY0(cudaSetDevice(device));
@@ -884,7 +891,9 @@ rsvio_status rsvio_detect_keypoints(int32_t device, const uint8_t *image, int32_
     CU_TRY0(cudaMalloc((void **)&d_T6, sizeof(float) * 6 * cells));
     CU_TRY0(cudaMalloc((void **)&d_nscore, sizeof(float) * cells));
     CU_TRY0(cudaMalloc((void **)&d_cnt, sizeof(int)));
-    CU_TRY0(detect_cells(gd, d_img, (size_t)width, 0, 1, d_occ, d_cell, d_score, 0));
+    CU_TRY0(cudaMalloc((void **)&d_list, sizeof(uint32_t) * cells));
+    CU_TRY0(cudaMalloc((void **)&d_list_n, sizeof(int)));
+    CU_TRY0(detect_cells(gd, d_img, (size_t)width, 0, 1, d_occ, d_cell, d_score, d_list, d_list_n, 0));
     CU_TRY0(collect_new_points(gd, 1, d_cell, d_score, d_T6, d_nscore, d_cnt, cells, nullptr, 0));
     CU_TRY0(cudaDeviceSynchronize());
     CU_TRY0(cudaMemcpy(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost));
@@ -917,6 +926,8 @@ done:
     cudaFree(d_T6);
     cudaFree(d_nscore);
     cudaFree(d_cnt);
+    cudaFree(d_list);
+    cudaFree(d_list_n);
     return rs;
 }
 

@@ -116,8 +116,10 @@ inline GridDesc make_grid_desc(int w, int h, uint32_t g) {
 }
 // occ: [streams][occ_rows*occ_cols] bytes, cell_pt: [streams][ncx*ncy] packed (y << 16 | x) or ~0,
 // cell_score: [streams][ncx*ncy].  img of stream s = img0 + s * pitch.
+// list / list_count: scratch for the work list of empty cells ([streams * cells] and one int).  3 launches.
 cudaError_t detect_cells(const GridDesc &gd, const uint8_t *img0, size_t stride, size_t pitch, int streams,
-                         const uint8_t *occ, uint32_t *cell_pt, float *cell_score, cudaStream_t st);
+                         const uint8_t *occ, uint32_t *cell_pt, float *cell_score, uint32_t *list, int *list_count,
+                         cudaStream_t st);
 // ordered compaction of the per-cell results into identity transforms new_T6[s][k], new_count[s]
 cudaError_t collect_new_points(const GridDesc &gd, int streams, const uint32_t *cell_pt, const float *cell_score,
                                float *new_T6, float *new_score, int *new_count, int new_cap,

@@ -22,7 +22,6 @@ namespace rsvio {
 namespace {
 
 constexpr int kEdge = 19;  // EDGE_THRESHOLD, image_utilities.rs:114
-constexpr int kWarps = 8;
 
 __device__ __forceinline__ int min9_max16(const int (&b)[16]) {
     // max over 16 cyclic windows of 9 of the window minimum, by doubling: 2, 4, 8, then +1
@@ -75,53 +74,75 @@ __device__ __forceinline__ int fast9_score(const uint8_t *__restrict__ p, int s)
     return max(min9_max16(b), min9_max16(d)) - 1;
 }
 
-__global__ void __launch_bounds__(kWarps * 32)
-detect_cells_kernel(GridDesc gd, const uint8_t *__restrict__ img0, size_t stride, size_t pitch, int streams,
-                    const uint8_t *__restrict__ occ, uint32_t *__restrict__ cell_pt, float *__restrict__ cell_score) {
-    const int lane = threadIdx.x & 31;
+// Occupied cells get "no point"; empty cells are appended (any order) to a global work list.
+__global__ void __launch_bounds__(256)
+list_empty_cells_kernel(GridDesc gd, int streams, const uint8_t *__restrict__ occ, uint32_t *__restrict__ cell_pt,
+                        float *__restrict__ cell_score, uint32_t *__restrict__ list, int *__restrict__ list_count) {
     const int cells = gd.ncx * gd.ncy;
     const long long total = (long long)cells * streams;
-    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const int g = (int)gd.g;
-    const int side = g - 6;  // candidates per axis
-    for (long long item = warp0; item < total; item += n_warps) {
+    const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool empty = false;
+    if (item < total) {
         const int s = (int)(item / cells), cell = (int)(item - (long long)s * cells);
         const int cx = cell / gd.ncy, cy = cell - cx * gd.ncy;  // visiting order: x outer, y inner
+        empty = __ldg(occ + (size_t)s * gd.occ_rows * gd.occ_cols + (size_t)cy * gd.occ_cols + cx) == 0;
+        cell_pt[item] = 0xFFFFFFFFu;
+        cell_score[item] = 0.0f;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, empty);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(list_count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (empty) list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)item;
+}
+
+// One CTA per empty cell: the (g-6)^2 candidates are spread over 128 threads, block-wide packed-key max.
+constexpr int kDetThreads = 128;
+__global__ void __launch_bounds__(kDetThreads)
+detect_list_kernel(GridDesc gd, const uint8_t *__restrict__ img0, size_t stride, size_t pitch,
+                   const uint32_t *__restrict__ list, const int *__restrict__ list_count,
+                   uint32_t *__restrict__ cell_pt, float *__restrict__ cell_score) {
+    __shared__ uint32_t wbest[kDetThreads / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int cells = gd.ncx * gd.ncy;
+    const int g = (int)gd.g;
+    const int side = g - 6;  // candidates per axis
+    const int n = *list_count;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint32_t item = __ldg(list + i);
+        const int s = (int)(item / (uint32_t)cells), cell = (int)(item - (uint32_t)s * (uint32_t)cells);
+        const int cx = cell / gd.ncy, cy = cell - cx * gd.ncy;
+        const int x0 = (int)gd.x_start + cx * g, y0 = (int)gd.y_start + cy * g;
+        const uint8_t *__restrict__ base = img0 + (size_t)s * pitch;
         uint32_t best = 0;
-        const bool occupied = __ldg(occ + (size_t)s * gd.occ_rows * gd.occ_cols + (size_t)cy * gd.occ_cols + cx) != 0;
-        if (!occupied && side > 0) {
-            const int x0 = (int)gd.x_start + cx * g, y0 = (int)gd.y_start + cy * g;
-            const uint8_t *__restrict__ base = img0 + (size_t)s * pitch;
-            for (int idx = lane; idx < side * side; idx += 32) {
-                const int ly = idx / side + 3, lx = idx - (idx / side) * side + 3;
-                const int gx = x0 + lx, gy = y0 + ly;
-                // point_in_bound(.., 19): inclusive upper bound (image_utilities.rs:68-73)
-                if (gx < kEdge || gy < kEdge || gx > gd.w - kEdge || gy > gd.h - kEdge) continue;
-                const int sc = fast9_score(base + (size_t)gy * stride + gx, (int)stride);
-                if (sc < 10) continue;
-                const uint32_t cls = (uint32_t)(min(sc, 40) / 5);        // 2..8
-                const uint32_t raster = (uint32_t)(ly * g + lx);        // order inside the cell copy
-                const uint32_t key = (cls << 28) | ((uint32_t)(255 - sc) << 20) | (0xFFFFFu - raster);
-                best = max(best, key);
-            }
+        for (int idx = threadIdx.x; idx < side * side; idx += kDetThreads) {
+            const int ly = idx / side + 3, lx = idx - (idx / side) * side + 3;
+            const int gx = x0 + lx, gy = y0 + ly;
+            // point_in_bound(.., 19): inclusive upper bound (image_utilities.rs:68-73)
+            if (gx < kEdge || gy < kEdge || gx > gd.w - kEdge || gy > gd.h - kEdge) continue;
+            const int sc = fast9_score(base + (size_t)gy * stride + gx, (int)stride);
+            if (sc < 10) continue;
+            const uint32_t cls = (uint32_t)(min(sc, 40) / 5);        // 2..8
+            const uint32_t raster = (uint32_t)(ly * g + lx);        // order inside the cell copy
+            best = max(best, (cls << 28) | ((uint32_t)(255 - sc) << 20) | (0xFFFFFu - raster));
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-        if (lane == 0) {
-            uint32_t pt = 0xFFFFFFFFu;
-            float score = 0.0f;
+        if (lane == 0) wbest[wid] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int k = 1; k < kDetThreads / 32; ++k) best = max(best, wbest[k]);
             if (best != 0) {
                 const int sc = 255 - (int)((best >> 20) & 0xFFu);
                 const uint32_t raster = 0xFFFFFu - (best & 0xFFFFFu);
                 const uint32_t ly = raster / (uint32_t)g, lx = raster - ly * (uint32_t)g;
                 const uint32_t gx = gd.x_start + (uint32_t)cx * gd.g + lx, gy = gd.y_start + (uint32_t)cy * gd.g + ly;
-                pt = (gy << 16) | gx;
-                score = (float)sc;
+                cell_pt[item] = (gy << 16) | gx;
+                cell_score[item] = (float)sc;
             }
-            cell_pt[(size_t)s * cells + cell] = pt;
-            cell_score[(size_t)s * cells + cell] = score;
         }
+        __syncthreads();
     }
 }
 
@@ -168,6 +189,8 @@ collect_new_kernel(GridDesc gd, const uint32_t *__restrict__ cell_pt, const floa
     }
 }
 
+__global__ void zero_int_kernel(int *p) { *p = 0; }
+
 __global__ void mark_occupancy_xy_kernel(GridDesc gd, const uint32_t *__restrict__ xy, int n, uint8_t *occ) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -180,14 +203,16 @@ __global__ void mark_occupancy_xy_kernel(GridDesc gd, const uint32_t *__restrict
 }  // namespace
 
 cudaError_t detect_cells(const GridDesc &gd, const uint8_t *img0, size_t stride, size_t pitch, int streams,
-                         const uint8_t *occ, uint32_t *cell_pt, float *cell_score, cudaStream_t st) {
+                         const uint8_t *occ, uint32_t *cell_pt, float *cell_score, uint32_t *list, int *list_count,
+                         cudaStream_t st) {
     const long long total = (long long)gd.ncx * gd.ncy * streams;
     if (total <= 0) return cudaSuccess;
-    long long blocks = (total + kWarps - 1) / kWarps;
-    const long long max_blocks = (long long)kNumSMs * 8;
-    if (blocks > max_blocks) blocks = max_blocks;
-    detect_cells_kernel<<<(unsigned)blocks, kWarps * 32, 0, st>>>(gd, img0, stride, pitch, streams, occ, cell_pt,
-                                                                  cell_score);
+    zero_int_kernel<<<1, 1, 0, st>>>(list_count);
+    list_empty_cells_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gd, streams, occ, cell_pt, cell_score, list,
+                                                                             list_count);
+    long long blocks = total < (long long)kNumSMs * 8 ? total : (long long)kNumSMs * 8;
+    detect_list_kernel<<<(unsigned)blocks, kDetThreads, 0, st>>>(gd, img0, stride, pitch, list, list_count, cell_pt,
+                                                                 cell_score);
     return cudaGetLastError();
 }
 
