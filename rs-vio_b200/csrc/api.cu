@@ -58,7 +58,8 @@ struct rsvio_tracker {
     unsigned long long *d_last_id = nullptr, *d_counters = nullptr, *d_rm = nullptr;
     int rm_cap = 0;
     int *d_err = nullptr;
-    unsigned *d_work = nullptr;
+    unsigned *d_work = nullptr;  // [0,1] temporal LK counters, [2,3] stereo LK counters
+    int lk_par[2] = {0, 0}, det_par = 0;
     // host-mapped output ring: records [groups][cap] and counts [groups] (+1 error flag)
     OutRecord *h_out[kSlots] = {nullptr, nullptr}, *d_out[kSlots] = {nullptr, nullptr};
     int *h_cnt[kSlots] = {nullptr, nullptr}, *d_cnt[kSlots] = {nullptr, nullptr};
@@ -159,6 +160,9 @@ rsvio_status clear_state(rsvio_tracker *t) {
     CU_TRY(t, cudaMemsetAsync(t->d_counters, 0, sizeof(unsigned long long) * CNT_N, t->st));
     CU_TRY(t, cudaMemsetAsync(t->d_err, 0, sizeof(int), t->st));
     CU_TRY(t, cudaMemsetAsync(t->d_new_count, 0, sizeof(int) * t->S, t->st));
+    CU_TRY(t, cudaMemsetAsync(t->d_work, 0, sizeof(unsigned) * 4, t->st));
+    CU_TRY(t, cudaMemsetAsync(t->d_cell_list_n, 0, sizeof(int) * 2, t->st));
+    t->lk_par[0] = t->lk_par[1] = t->det_par = 0;
     CU_TRY(t, cudaStreamSynchronize(t->st));
     for (int i = 0; i < kSlots; ++i) memset(t->h_cnt[i], 0, sizeof(int) * (t->groups + 1));
     t->have_prev = false;
@@ -205,6 +209,8 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
         b.iters = nullptr;
         b.counters = t->d_counters;
         b.work_counter = t->d_work;
+        b.work_parity = t->lk_par[0];
+        t->lk_par[0] ^= 1;
         b.groups = t->stereo ? t->groups : t->S;
         b.cap = t->cap;
         b.max_it = t->cfg.max_iterations;
@@ -218,10 +224,11 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
     count(3, 1);
     mark(++stage);  // 4: detection (level 0 of the current left pyramid is the input image)
     CU_TRY(t, detect_cells(t->gd, cur + t->pd.lv[0].off, (size_t)t->pd.lv[0].w, (size_t)t->pd.pyr_stride, t->S,
-                           t->d_occ, t->d_cell_pt, t->d_cell_score, t->d_cell_list, t->d_cell_list_n, st));
+                           t->d_occ, t->d_cell_pt, t->d_cell_score, t->d_cell_list, t->d_cell_list_n, t->det_par, st));
+    t->det_par ^= 1;
     CU_TRY(t, collect_new_points(t->gd, t->S, t->d_cell_pt, t->d_cell_score, t->d_new_T6, nullptr, t->d_new_count,
                                  t->new_cap, t->d_counters, st));
-    count(4, 4);
+    count(4, 3);
     mark(++stage);  // 5: stereo LK (left -> right of the current frame)
     if (t->stereo) {
         LkBatch b{};
@@ -233,7 +240,9 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
         b.status = t->d_st_status;
         b.iters = nullptr;
         b.counters = t->d_counters;
-        b.work_counter = t->d_work + 1;
+        b.work_counter = t->d_work + 2;
+        b.work_parity = t->lk_par[1];
+        t->lk_par[1] ^= 1;
         b.groups = t->S;
         b.cap = t->new_cap;
         b.max_it = t->cfg.max_iterations;
@@ -437,7 +446,7 @@ rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) 
         CU_TRY(t, dmalloc(&t->d_cell_pt, S * (size_t)t->new_cap));
         CU_TRY(t, dmalloc(&t->d_cell_score, S * (size_t)t->new_cap));
         CU_TRY(t, dmalloc(&t->d_cell_list, S * (size_t)t->new_cap));
-        CU_TRY(t, dmalloc(&t->d_cell_list_n, (size_t)1));
+        CU_TRY(t, dmalloc(&t->d_cell_list_n, (size_t)2));
         CU_TRY(t, dmalloc(&t->d_new_T6, S * (size_t)t->new_cap * 6));
         CU_TRY(t, dmalloc(&t->d_st_T6, S * (size_t)t->new_cap * 6));
         CU_TRY(t, dmalloc(&t->d_new_count, S));
@@ -892,8 +901,9 @@ rsvio_status rsvio_detect_keypoints(int32_t device, const uint8_t *image, int32_
     CU_TRY0(cudaMalloc((void **)&d_nscore, sizeof(float) * cells));
     CU_TRY0(cudaMalloc((void **)&d_cnt, sizeof(int)));
     CU_TRY0(cudaMalloc((void **)&d_list, sizeof(uint32_t) * cells));
-    CU_TRY0(cudaMalloc((void **)&d_list_n, sizeof(int)));
-    CU_TRY0(detect_cells(gd, d_img, (size_t)width, 0, 1, d_occ, d_cell, d_score, d_list, d_list_n, 0));
+    CU_TRY0(cudaMalloc((void **)&d_list_n, 2 * sizeof(int)));
+    CU_TRY0(cudaMemset(d_list_n, 0, 2 * sizeof(int)));
+    CU_TRY0(detect_cells(gd, d_img, (size_t)width, 0, 1, d_occ, d_cell, d_score, d_list, d_list_n, 0, 0));
     CU_TRY0(collect_new_points(gd, 1, d_cell, d_score, d_T6, d_nscore, d_cnt, cells, nullptr, 0));
     CU_TRY0(cudaDeviceSynchronize());
     CU_TRY0(cudaMemcpy(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost));

@@ -85,7 +85,8 @@ struct LkBatch {
     int32_t *status;        // [groups][cap]
     int32_t *iters;         // [groups][cap][2] or nullptr
     unsigned long long *counters;  // CNT_* or nullptr
-    unsigned *work_counter;        // device scratch for dynamic point scheduling (zeroed per launch) or nullptr
+    unsigned *work_counter;        // 2 device counters for dynamic point scheduling (zero at first use) or nullptr
+    int work_parity;               // which of the two this launch uses; it clears the other for the next launch
     int groups, cap;
     int max_it;
     float thr;
@@ -119,7 +120,7 @@ inline GridDesc make_grid_desc(int w, int h, uint32_t g) {
 // list / list_count: scratch for the work list of empty cells ([streams * cells] and one int).  3 launches.
 cudaError_t detect_cells(const GridDesc &gd, const uint8_t *img0, size_t stride, size_t pitch, int streams,
                          const uint8_t *occ, uint32_t *cell_pt, float *cell_score, uint32_t *list, int *list_count,
-                         cudaStream_t st);
+                         int parity, cudaStream_t st);  // list_count: 2 ints used alternately (parity), zero at first use
 // ordered compaction of the per-cell results into identity transforms new_T6[s][k], new_count[s]
 cudaError_t collect_new_points(const GridDesc &gd, int streams, const uint32_t *cell_pt, const float *cell_score,
                                float *new_T6, float *new_score, int *new_count, int new_cap,

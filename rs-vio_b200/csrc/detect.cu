@@ -77,7 +77,9 @@ __device__ __forceinline__ int fast9_score(const uint8_t *__restrict__ p, int s)
 // Occupied cells get "no point"; empty cells are appended (any order) to a global work list.
 __global__ void __launch_bounds__(256)
 list_empty_cells_kernel(GridDesc gd, int streams, const uint8_t *__restrict__ occ, uint32_t *__restrict__ cell_pt,
-                        float *__restrict__ cell_score, uint32_t *__restrict__ list, int *__restrict__ list_count) {
+                        float *__restrict__ cell_score, uint32_t *__restrict__ list, int *__restrict__ list_count,
+                        int *__restrict__ next_count) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;  // the other counter, for the next frame
     const int cells = gd.ncx * gd.ncy;
     const long long total = (long long)cells * streams;
     const long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -189,8 +191,6 @@ collect_new_kernel(GridDesc gd, const uint32_t *__restrict__ cell_pt, const floa
     }
 }
 
-__global__ void zero_int_kernel(int *p) { *p = 0; }
-
 __global__ void mark_occupancy_xy_kernel(GridDesc gd, const uint32_t *__restrict__ xy, int n, uint8_t *occ) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -204,14 +204,14 @@ __global__ void mark_occupancy_xy_kernel(GridDesc gd, const uint32_t *__restrict
 
 cudaError_t detect_cells(const GridDesc &gd, const uint8_t *img0, size_t stride, size_t pitch, int streams,
                          const uint8_t *occ, uint32_t *cell_pt, float *cell_score, uint32_t *list, int *list_count,
-                         cudaStream_t st) {
+                         int parity, cudaStream_t st) {
     const long long total = (long long)gd.ncx * gd.ncy * streams;
     if (total <= 0) return cudaSuccess;
-    zero_int_kernel<<<1, 1, 0, st>>>(list_count);
+    int *cnt = list_count + (parity & 1), *other = list_count + ((parity & 1) ^ 1);
     list_empty_cells_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gd, streams, occ, cell_pt, cell_score, list,
-                                                                             list_count);
+                                                                             cnt, other);
     long long blocks = total < (long long)kNumSMs * 8 ? total : (long long)kNumSMs * 8;
-    detect_list_kernel<<<(unsigned)blocks, kDetThreads, 0, st>>>(gd, img0, stride, pitch, list, list_count, cell_pt,
+    detect_list_kernel<<<(unsigned)blocks, kDetThreads, 0, st>>>(gd, img0, stride, pitch, list, cnt, cell_pt,
                                                                  cell_score);
     return cudaGetLastError();
 }

@@ -408,6 +408,9 @@ lk_track_fb_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ L
     __shared__ int prefix[kMaxGroupsSmem + 1];
     __shared__ int warp_tot[kWarpsPerBlock];
     const bool dynamic = b.work_counter != nullptr && b.groups <= kMaxGroupsSmem;
+    // two counters used alternately: this launch draws from [work_parity] and clears the other one for the next
+    unsigned *const wc = dynamic ? b.work_counter + b.work_parity : nullptr;
+    if (dynamic && blockIdx.x == 0 && threadIdx.x == 0) b.work_counter[b.work_parity ^ 1] = 0u;
     if (dynamic) {
         int base = 0;
         for (int g0 = 0; g0 < b.groups; g0 += blockDim.x) {
@@ -438,7 +441,7 @@ lk_track_fb_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ L
         int g, k, item;
         if (dynamic) {
             int w = 0;
-            if (lane == 0) w = (int)atomicAdd(b.work_counter, 1u);
+            if (lane == 0) w = (int)atomicAdd(wc, 1u);
             w = __shfl_sync(0xffffffffu, w, 0);
             if (w >= total) break;
             int lo = 0, hi = b.groups;  // largest g with prefix[g] <= w
@@ -524,10 +527,6 @@ cudaError_t lk_track(const PyrDesc &pd, const LkBatch &b, cudaStream_t st) {
     // dynamic scheduling: one resident wave (80 registers -> 6 CTAs per SM); static striding: up to 16 per SM
     const long long max_blocks = (long long)kNumSMs * (dynamic ? 8 : 16);
     if (blocks > max_blocks) blocks = max_blocks;
-    if (dynamic) {
-        cudaError_t e = cudaMemsetAsync(b.work_counter, 0, sizeof(unsigned), st);
-        if (e != cudaSuccess) return e;
-    }
     lk_track_fb_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(pd, b);
     return cudaGetLastError();
 }

@@ -220,9 +220,20 @@ struct FastParams {
     uint8_t *dst;
     uint32_t *g8;         // [img][h0/8][w0/8] exported when deeper levels follow, else nullptr
     int tiles_x, tiles_y;
+    unsigned magic_tpi, magic_tx;  // ceil(2^32 / d) for d = tiles per image, tiles_x (0: plain division)
     int nbuf;             // tile buffers per CTA: 2 = next tile prefetched during compute, 1 = more CTAs per SM
-    unsigned *tile_counter;  // single-buffer mode: tiles are handed out dynamically (zeroed before the launch)
+    unsigned *tile_counter;  // single-buffer mode: tiles are handed out dynamically from this counter ...
+    unsigned *tile_counter_next;  // ... and the other one of the pair is cleared for the next launch
 };
+
+// n / d with the host-made multiplier m = ceil(2^32 / d); exact while n * d < 2^32 (the host checks)
+__device__ __forceinline__ int magic_div(int n, int d, unsigned m) {
+    return m ? (int)__umulhi((unsigned)n, m) : n / d;
+}
+inline unsigned magic_for(unsigned d, uint64_t n_max) {
+    if (d < 2 || n_max * d >= (1ull << 32)) return 0u;
+    return (unsigned)(((1ull << 32) + d - 1) / d);
+}
 
 __device__ __forceinline__ uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c) {
     return __dp4a(a, b, c);  // u8 x u8 (weights <= 9), u32 accumulate
@@ -343,6 +354,92 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
 constexpr int RW = 160, RB = 128;
 constexpr int kSplitCol = 144;  // tile columns below this are read from region A, the rest from B
 
+// ---- border ring helpers of the tile kernel -------------------------------------------------
+// A tile in shared memory: tile column c of row ry is byte a[(c >= kSplitCol ? delta : 0) + ry * RW + c].
+struct RingTile {
+    const uint8_t *a;
+    int delta, X0, Y0, ytop;
+    __device__ __forceinline__ const uint8_t *at(int ry, int col) const {
+        return a + (col >= kSplitCol ? delta : 0) + ry * RW + col;
+    }
+};
+__device__ __forceinline__ uint8_t ring_round(float t) {
+    t = fminf(fmaxf(t, 0.0f), 255.0f);
+    return (uint8_t)__float2uint_rz(roundf(t));
+}
+
+// vertical chains of border row `side` (0: oy = 0, 1: oy = hl - 1) of level LEV, one thread per tile column
+template <int LEV>
+__device__ __forceinline__ void ring_rows_vertical(const FastParams &P, const RingTile &rt, float *__restrict__ vrow,
+                                                   int side, int tid) {
+    constexpr int r = 1 << LEV, CNT = r + (r >> 1);
+    const int hl = P.pd.lv[LEV].h, w0 = P.pd.lv[0].w;
+    const int oy = side == 0 ? 0 : hl - 1;
+    if (oy * r < rt.Y0 || oy * r >= rt.Y0 + TH) return;
+    float wv[CNT];
+#pragma unroll
+    for (int k = 0; k < CNT; ++k) wv[k] = side == 0 ? P.ring[LEV].first[k] : P.ring[LEV].last[k];
+    const int row0 = (side == 0 ? 0 : hl * r - CNT) - rt.Y0 + rt.ytop;
+    const int clo = max(rt.X0 - (r >> 1), 0) - rt.X0 + 16, chi = min(rt.X0 + TW + (r >> 1), w0) - rt.X0 + 16;
+    for (int c = clo + tid; c < chi; c += NTA) {
+        const uint8_t *__restrict__ s = rt.at(row0, c);
+        float v = 0.0f;
+#pragma unroll
+        for (int k = 0; k < CNT; ++k) v = __fadd_rn(v, __fmul_rn((float)s[k * RW], wv[k]));
+        vrow[c] = v;
+    }
+}
+
+// horizontal chains of that row: one thread per output column of the tile
+template <int LEV>
+__device__ __forceinline__ void ring_rows_horizontal(const FastParams &P, const RingTile &rt,
+                                                     const float *__restrict__ vrow, uint8_t *__restrict__ out, int side,
+                                                     int t) {
+    constexpr int r = 1 << LEV, CIN = 2 * r;
+    const int wl = P.pd.lv[LEV].w, hl = P.pd.lv[LEV].h;
+    const int oy = side == 0 ? 0 : hl - 1;
+    if (oy * r < rt.Y0 || oy * r >= rt.Y0 + TH) return;
+    if (t >= TW / r) return;
+    const int ox = rt.X0 / r + t;
+    if (ox >= wl) return;
+    float acc = 0.0f;
+    if (ox > 0 && ox < wl - 1) {
+        const float *__restrict__ v = vrow + (ox * r - (r >> 1) - rt.X0 + 16);
+#pragma unroll
+        for (int k = 0; k < CIN; ++k) acc = __fadd_rn(acc, __fmul_rn(v[k], P.ring[LEV].inner[k]));
+    } else {
+        const RingTap tx = ring_tap(P.ring[LEV], ox, wl, r);
+        for (int k = 0; k < tx.cnt; ++k) acc = __fadd_rn(acc, __fmul_rn(vrow[tx.left + k - rt.X0 + 16], tx.w[k]));
+    }
+    out[P.pd.lv[LEV].off + (size_t)oy * wl + ox] = ring_round(acc);
+}
+
+// border columns of level LEV: item = side * (TH / r) + row of the tile; interior rows only
+template <int LEV>
+__device__ __forceinline__ void ring_cols(const FastParams &P, const RingTile &rt, uint8_t *__restrict__ out, bool left,
+                                          bool right, int item) {
+    constexpr int r = 1 << LEV, CX = r + (r >> 1), CY = 2 * r, ROWS = TH / r;
+    const int side = item / ROWS, ly = item % ROWS;
+    if (side == 0 ? !left : !right) return;
+    const int wl = P.pd.lv[LEV].w, hl = P.pd.lv[LEV].h, w0 = P.pd.lv[0].w;
+    const int oy = rt.Y0 / r + ly, ox = side == 0 ? 0 : wl - 1;
+    if (oy < 1 || oy > hl - 2 || ox * r < rt.X0 || ox * r >= rt.X0 + TW) return;
+    float wy[CY];
+#pragma unroll
+    for (int k = 0; k < CY; ++k) wy[k] = P.ring[LEV].inner[k];
+    const int c0 = (side == 0 ? 0 : w0 - CX) - rt.X0 + 16, row0 = oy * r - (r >> 1) - rt.Y0 + rt.ytop;
+    float t = 0.0f;
+#pragma unroll(LEV < 3 ? CX : 1)
+    for (int kx = 0; kx < CX; ++kx) {
+        const uint8_t *__restrict__ s = rt.at(row0, c0 + kx);
+        float v = 0.0f;
+#pragma unroll
+        for (int ky = 0; ky < CY; ++ky) v = __fadd_rn(v, __fmul_rn((float)s[ky * RW], wy[ky]));
+        t = __fadd_rn(t, __fmul_rn(v, side == 0 ? P.ring[LEV].first[kx] : P.ring[LEV].last[kx]));
+    }
+    out[P.pd.lv[LEV].off + (size_t)oy * wl + ox] = ring_round(t);
+}
+
 template <int NA>
 struct FastSmem {
     using C = FastCfg<NA>;
@@ -362,7 +459,9 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
     using C = FastCfg<NA>;
     using S = FastSmem<NA>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    // 128-byte alignment for the TMA destinations; offset arithmetic on the array keeps the pointer in the
+    // shared address space (LDS/STS with 32-bit addresses instead of generic loads)
+    uint8_t *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     // layout: [nbuf x (region A, region B)] [g2] [g4] [vbuf] [mbarriers]
     const int shrink = (2 - P.nbuf) * 2 * S::region;
     uint16_t(*g2)[G2P] = reinterpret_cast<uint16_t(*)[G2P]>(smem + S::off_g2 - shrink);
@@ -377,8 +476,8 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
     const int total = tiles_per_img * P.n_images;
 
     auto issue_load = [&](int tile_id, int buf) {  // one elected thread: both boxes of one tile
-        const int img = tile_id / tiles_per_img, tl = tile_id - img * tiles_per_img;
-        const int ty = tl / P.tiles_x, tx = tl - ty * P.tiles_x;
+        const int img = magic_div(tile_id, tiles_per_img, P.magic_tpi), tl = tile_id - img * tiles_per_img;
+        const int ty = magic_div(tl, P.tiles_x, P.magic_tx), tx = tl - ty * P.tiles_x;
         const CUtensorMap *map = img < P.split ? &map0 : &map1;
         const int z = img < P.split ? img : img - P.split;
         const uint32_t mbar = mbar0 + 8u * buf;
@@ -397,24 +496,34 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
     const bool dbl = P.nbuf == 2;
     if (dbl && tid == 0 && (int)blockIdx.x < total) issue_load(blockIdx.x, 0);
 
+    // single-buffer mode: tiles are handed out dynamically (border tiles carry extra ring work, so a
+    // static assignment would let them decide the makespan).  Thread 0 draws the index of the next tile
+    // at the top of a tile and issues its load as soon as the last reader of the buffer is done.
     __shared__ int next_tile;
+    int my_next = 0;
+    auto hand_out = [&](int t) {
+        next_tile = t;
+        if (t < total) issue_load(t, 0);
+    };
+    if (!dbl) {
+        if (tid == 0) {
+            if (blockIdx.x == 0) *P.tile_counter_next = 0u;
+            hand_out((int)atomicAdd(P.tile_counter, 1u));
+        }
+        __syncthreads();
+    }
     int it = 0;
     for (int tile_id = blockIdx.x;; ++it) {
-    if (!dbl) {  // dynamic hand-out: border tiles (extra ring work) no longer decide the makespan
-        if (tid == 0) next_tile = (int)atomicAdd(P.tile_counter, 1u);
-        __syncthreads();
-        tile_id = next_tile;
-    } else if (it > 0) {
-        tile_id += gridDim.x;
-    }
+    if (!dbl) tile_id = next_tile;
+    else if (it > 0) tile_id += gridDim.x;
     if (tile_id >= total) break;
     const int buf = dbl ? (it & 1) : 0;
     if (tid == 0) {
-        if (!dbl) issue_load(tile_id, 0);  // single buffer: the previous tile's last reader passed the barrier below
+        if (!dbl) my_next = (int)atomicAdd(P.tile_counter, 1u);  // used after stage 1: latency hidden
         else if (tile_id + (int)gridDim.x < total) issue_load(tile_id + gridDim.x, buf ^ 1);  // prefetch
     }
-    const int img = tile_id / tiles_per_img, tl = tile_id - img * tiles_per_img;
-    const int tile_y = tl / P.tiles_x, tile_x = tl - tile_y * P.tiles_x;
+    const int img = magic_div(tile_id, tiles_per_img, P.magic_tpi), tl = tile_id - img * tiles_per_img;
+    const int tile_y = magic_div(tl, P.tiles_x, P.magic_tx), tile_x = tl - tile_y * P.tiles_x;
     const int X0 = tile_x * TW, Y0 = tile_y * TH;
     uint8_t *__restrict__ out = P.dst + (size_t)img * P.pd.pyr_stride;
     const uint8_t *__restrict__ tA = smem + S::off_tile + 2 * buf * S::region;   // tile columns [0, RW)
@@ -422,15 +531,20 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
     auto trow = [&](int ry, int col) -> const uint8_t * { return (col < kSplitCol ? tA : tB) + ry * RW + col; };
     mbar_wait(mbar0 + 8u * buf, (dbl ? (it >> 1) : it) & 1);
 
-    // ---- stage 0: level 0 == input, 16-byte copies from the staged tile
+    // ---- stage 0: level 0 == input, 16-byte copies from the staged tile.  A thread owns one 16-byte
+    // column and every (NTA/16)-th row: one pointer pair, constant strides.
     {
-        constexpr int VPT = TW / 16;
+        constexpr int VPT = TW / 16, RPP = NTA / VPT;  // vectors per row, rows per pass
         const int nrow = min(TH, h0 - Y0), nvec = min(VPT, (w0 - X0) >> 4);
-        for (int idx = tid; idx < TH * VPT; idx += NTA) {
-            const int y = idx / VPT, vx = idx - y * VPT;
-            if (y < nrow && vx < nvec)
-                *reinterpret_cast<uint4 *>(out + (size_t)(Y0 + y) * w0 + X0 + vx * 16) =
-                    *reinterpret_cast<const uint4 *>(trow(y + C::ytop, 16 + vx * 16));
+        const int vx = tid % VPT, y0 = tid / VPT;
+        if (vx < nvec) {
+            const uint8_t *__restrict__ s0 = trow(y0 + C::ytop, 16 + vx * 16);
+            uint8_t *__restrict__ d0 = out + (size_t)(Y0 + y0) * w0 + X0 + vx * 16;
+            const size_t dstep = (size_t)RPP * w0;
+#pragma unroll
+            for (int k = 0; k < TH / RPP; ++k)
+                if (y0 + k * RPP < nrow)
+                    *reinterpret_cast<uint4 *>(d0 + k * dstep) = *reinterpret_cast<const uint4 *>(s0 + k * RPP * RW);
         }
     }
 
@@ -561,8 +675,37 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
             }
         }
     }
+    // ---- border ring of levels 1..NA owned by this tile: the reference's f32 chains (truncated
+    // windows are renormalised by a non-dyadic sum, so nothing is exact there), read from the tile.
+    const bool top = Y0 == 0, bottom = Y0 + TH >= h0 && Y0 < h0;
+    const bool left = X0 == 0, right = X0 + TW >= w0 && X0 < w0;
+    if (top || bottom || left || right) {
+        const RingTile rt{tA, S::region - RB, X0, Y0, C::ytop};
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {  // border rows: oy = 0 (top tiles), oy = hl - 1 (bottom tiles)
+            if (side == 0 ? !top : !bottom) continue;
+            __syncthreads();
+            ring_rows_vertical<1>(P, rt, vbuf[0], side, tid);
+            if (NA >= 2) ring_rows_vertical<2>(P, rt, vbuf[NA >= 2 ? 1 : 0], side, tid);
+            if (NA >= 3) ring_rows_vertical<3>(P, rt, vbuf[NA >= 3 ? 2 : 0], side, tid);
+            __syncthreads();
+            ring_rows_horizontal<1>(P, rt, vbuf[0], out, side, tid);
+            if (NA >= 2) ring_rows_horizontal<2>(P, rt, vbuf[NA >= 2 ? 1 : 0], out, side, (tid + 64) % NTA);
+            if (NA >= 3) ring_rows_horizontal<3>(P, rt, vbuf[NA >= 3 ? 2 : 0], out, side, (tid + 32) % NTA);
+        }
+        // border columns (ox = 0 for left tiles, ox = wl - 1 for right tiles) without the corner rows:
+        // one thread per (level, side, row); a warp holds one level
+        static_assert(NTA == 128 && TH == 64, "ring column items are mapped to thread ranges");
+        if (left || right) {
+            if (tid < 64) ring_cols<1>(P, rt, out, left, right, tid);
+            else if (tid < 96) { if (NA >= 2) ring_cols<2>(P, rt, out, left, right, tid - 64); }
+            else if (tid < 112) { if (NA >= 3) ring_cols<3>(P, rt, out, left, right, tid - 96); }
+        }
+    }
     if (NA >= 2) {
         __syncthreads();
+        // the tile buffer is dead from here on: fetch the next tile while stages 2 and 3 run
+        if (!dbl && tid == 0) hand_out(my_next);
         // ---- stage 2: level-2 output O_4 (global) and G_4 (smem) from G_2: 3x3 binomials as chained
         // 2-way dot products on the u16 pairs.  g2[t - t_first][j - (X0/2 - 2)].
         const int w2 = P.pd.lv[2].w, h2 = P.pd.lv[2].h;
@@ -653,66 +796,11 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
         }
     }
 
-    // ---- border ring of levels 1..NA owned by this tile: the reference's f32 chains (truncated
-    // windows are renormalised by a non-dyadic sum, so nothing is exact there), read from the tile.
-    const bool top = Y0 == 0, bottom = Y0 + TH >= h0 && Y0 < h0;
-    const bool left = X0 == 0, right = X0 + TW >= w0 && X0 < w0;
-    if (top || bottom || left || right) {
-        auto pix = [&](int x, int y) { return (float)*trow(y - Y0 + C::ytop, x - X0 + 16); };
-#pragma unroll 1
-        for (int side = 0; side < 2; ++side) {  // border rows: oy = 0 (top tiles), oy = hl - 1 (bottom tiles)
-            if (side == 0 ? !top : !bottom) continue;
-            __syncthreads();
-            // vertical chains of all levels: one thread per (level, column)
-            for (int idx = tid; idx < NA * PITCH; idx += NTA) {
-                const int lev = 1 + idx / PITCH, x = X0 - 16 + idx % PITCH;
-                const int r = 1 << lev, hl = P.pd.lv[lev].h;
-                const int oy = side == 0 ? 0 : hl - 1;
-                if (oy * r < Y0 || oy * r >= Y0 + TH || x < max(X0 - (r >> 1), 0) || x >= min(X0 + TW + (r >> 1), w0))
-                    continue;
-                const RingTap ty = ring_tap(P.ring[lev], oy, hl, r);
-                float v = 0.0f;
-                for (int k = 0; k < ty.cnt; ++k) v = __fadd_rn(v, __fmul_rn(pix(x, ty.left + k), ty.w[k]));
-                vbuf[lev - 1][x - X0 + 16] = v;
-            }
-            __syncthreads();
-            // horizontal chains: one thread per (level, output column)
-            for (int idx = tid; idx < NA * (TW / 2); idx += NTA) {
-                const int lev = 1 + idx / (TW / 2), lx = idx % (TW / 2);
-                const int r = 1 << lev, wl = P.pd.lv[lev].w, hl = P.pd.lv[lev].h;
-                const int oy = side == 0 ? 0 : hl - 1;
-                const int ox = X0 / r + lx;
-                if (lx >= TW / r || ox >= wl || oy * r < Y0 || oy * r >= Y0 + TH) continue;
-                const RingTap tx = ring_tap(P.ring[lev], ox, wl, r);
-                float t = 0.0f;
-                for (int k = 0; k < tx.cnt; ++k)
-                    t = __fadd_rn(t, __fmul_rn(vbuf[lev - 1][tx.left + k - X0 + 16], tx.w[k]));
-                t = fminf(fmaxf(t, 0.0f), 255.0f);
-                out[P.pd.lv[lev].off + (size_t)oy * wl + ox] = (uint8_t)__float2uint_rz(roundf(t));
-            }
-        }
-        // border columns (ox = 0 for left tiles, ox = wl - 1 for right tiles) without the corner rows
-        for (int idx = tid; idx < 2 * NA * (TH / 2); idx += NTA) {
-            const int side = idx / (NA * (TH / 2)), rem = idx % (NA * (TH / 2));
-            const int lev = 1 + rem / (TH / 2), ly = rem % (TH / 2);
-            if (side == 0 ? !left : !right) continue;
-            const int r = 1 << lev, wl = P.pd.lv[lev].w, hl = P.pd.lv[lev].h;
-            const int oy = Y0 / r + ly;
-            const int ox = side == 0 ? 0 : wl - 1;
-            if (ly >= TH / r || oy < 1 || oy > hl - 2 || ox * r < X0 || ox * r >= X0 + TW) continue;
-            const RingTap tx = ring_tap(P.ring[lev], ox, wl, r), ty = ring_tap(P.ring[lev], oy, hl, r);
-            float t = 0.0f;
-            for (int kx = 0; kx < tx.cnt; ++kx) {
-                float v = 0.0f;
-                for (int ky = 0; ky < ty.cnt; ++ky)
-                    v = __fadd_rn(v, __fmul_rn(pix(tx.left + kx, ty.left + ky), ty.w[ky]));
-                t = __fadd_rn(t, __fmul_rn(v, tx.w[kx]));
-            }
-            t = fminf(fmaxf(t, 0.0f), 255.0f);
-            out[P.pd.lv[lev].off + (size_t)oy * wl + ox] = (uint8_t)__float2uint_rz(roundf(t));
-        }
-    }
     __syncthreads();  // every read of this buffer, g2, g4 and vbuf is done before the next tile reuses them
+    if (NA < 2 && !dbl) {
+        if (tid == 0) hand_out(my_next);
+        __syncthreads();
+    }
     }  // persistent tile loop
 }
 
@@ -1240,7 +1328,8 @@ struct PyrPlan {
     int fast_rows;   // tile rows fetched per CTA (TMA box height)
     int fast_grid;   // persistent grid: SMs x resident CTAs per SM
     int fast_nbuf, fast_smem;  // tile buffers per CTA and the resulting dynamic shared memory
-    unsigned *d_tile_counter;
+    unsigned *d_tile_counter;  // two counters used alternately
+    int tile_parity;
     int use_stream;  // streaming warp-per-strip kernel instead of the CTA-tile kernel
     int stream_grid; // resident warps (1-warp CTAs) on the device
     RingWeights ring[4];
@@ -1374,7 +1463,9 @@ cudaError_t pyr_plan_create(int w, int h, int levels, cudaStream_t st, PyrPlan *
     p->do4 = p->n_fast >= 4;
     p->do5 = p->n_fast >= 5;
     if (p->n_a >= 1) {
-        e = cudaMalloc((void **)&p->d_tile_counter, sizeof(unsigned));
+        e = cudaMalloc((void **)&p->d_tile_counter, 2 * sizeof(unsigned));
+        if (e == cudaSuccess) e = cudaMemsetAsync(p->d_tile_counter, 0, 2 * sizeof(unsigned), st);
+        p->tile_parity = 0;
         if (e != cudaSuccess) {
             pyr_plan_destroy(p);
             return e;
@@ -1577,11 +1668,17 @@ cudaError_t pyr_build(const PyrPlan *p, const uint8_t *src0, const uint8_t *src1
         fp.g8 = p->do4 ? p->d_g8 : nullptr;
         fp.tiles_x = p->tiles_x;
         fp.tiles_y = p->tiles_y;
+        {
+            const unsigned tpi = (unsigned)(p->tiles_x * p->tiles_y);
+            fp.magic_tpi = magic_for(tpi, (uint64_t)tpi * (uint64_t)n);
+            fp.magic_tx = magic_for((unsigned)p->tiles_x, tpi);
+        }
         fp.nbuf = p->fast_nbuf;
-        fp.tile_counter = p->d_tile_counter;
-        if (p->fast_nbuf == 1) {
-            cudaError_t em = cudaMemsetAsync(p->d_tile_counter, 0, sizeof(unsigned), st);
-            if (em != cudaSuccess) return em;
+        {
+            PyrPlan *mp = const_cast<PyrPlan *>(p);  // launches of one plan are stream ordered
+            fp.tile_counter = p->d_tile_counter + mp->tile_parity;
+            fp.tile_counter_next = p->d_tile_counter + (mp->tile_parity ^ 1);
+            mp->tile_parity ^= 1;
         }
         CUtensorMap m0, m1;
         const int n0 = sps < n ? sps : n;               // images behind map 0
