@@ -55,22 +55,23 @@ __device__ __forceinline__ void pattern_offset(int i, float &ox, float &oy) {
 // inbound test; otherwise the 12 gathers are redirected to clamped in-image addresses (results unused),
 // which keeps the warp free of divergent branches.
 __device__ __forceinline__ void image_grad(const Img &im, float x, float y, bool ok, float &v, float &gx, float &gy) {
-    const uint32_t ix = ok ? __float2uint_rd(x) : 1u, iy = ok ? __float2uint_rd(y) : 1u;  // floor, x >= 1.5 when ok
+    // floor; a sample that passed inbound(.., 2) has 1 <= ix <= w - 3 and 1 <= iy <= h - 3, so the 4x4
+    // neighbourhood needs no clamping; rejected samples read the neighbourhood of (1, 1) (the caller
+    // guarantees w, h >= 5)
+    const uint32_t ix = ok ? __float2uint_rd(x) : 1u, iy = ok ? __float2uint_rd(y) : 1u;
     const float dx = x - (float)ix, dy = y - (float)iy;
     const float ddx = 1.0f - dx, ddy = 1.0f - dy;
     const float w00 = ddx * ddy, w01 = ddx * dy, w10 = dx * ddy, w11 = dx * dy;
-    const uint32_t W = (uint32_t)im.w, Hh = (uint32_t)im.h;
-    // columns ix-1 .. ix+2 and rows iy-1 .. iy+2, clamped (a no-op for samples that passed inbound(.., 2))
-    const uint32_t x0 = min(ix, W - 1u), xm = min(ix - 1u, W - 1u), x1 = min(ix + 1u, W - 1u), x2 = min(ix + 2u, W - 1u);
-    const uint8_t *__restrict__ rm = im.p + (size_t)min(iy - 1u, Hh - 1u) * W;
-    const uint8_t *__restrict__ r0 = im.p + (size_t)min(iy, Hh - 1u) * W;
-    const uint8_t *__restrict__ r1 = im.p + (size_t)min(iy + 1u, Hh - 1u) * W;
-    const uint8_t *__restrict__ r2 = im.p + (size_t)min(iy + 2u, Hh - 1u) * W;
-    const float p00 = (float)__ldg(r0 + x0), p10 = (float)__ldg(r0 + x1), p01 = (float)__ldg(r1 + x0), p11 = (float)__ldg(r1 + x1);
-    const float pm0 = (float)__ldg(r0 + xm), pm1 = (float)__ldg(r1 + xm);
-    const float p20 = (float)__ldg(r0 + x2), p21 = (float)__ldg(r1 + x2);
-    const float p0m = (float)__ldg(rm + x0), p1m = (float)__ldg(rm + x1);
-    const float p02 = (float)__ldg(r2 + x0), p12 = (float)__ldg(r2 + x1);
+    const uint32_t W = (uint32_t)im.w;
+    const uint8_t *__restrict__ r0 = im.p + (iy * W + ix);  // 32-bit offset inside one level
+    const uint8_t *__restrict__ rm = r0 - W;
+    const uint8_t *__restrict__ r1 = r0 + W;
+    const uint8_t *__restrict__ r2 = r1 + W;
+    const float p00 = (float)__ldg(r0), p10 = (float)__ldg(r0 + 1), p01 = (float)__ldg(r1), p11 = (float)__ldg(r1 + 1);
+    const float pm0 = (float)__ldg(r0 - 1), pm1 = (float)__ldg(r1 - 1);
+    const float p20 = (float)__ldg(r0 + 2), p21 = (float)__ldg(r1 + 2);
+    const float p0m = (float)__ldg(rm), p1m = (float)__ldg(rm + 1);
+    const float p02 = (float)__ldg(r2), p12 = (float)__ldg(r2 + 1);
     v = w00 * p00 + w01 * p01 + w10 * p10 + w11 * p11;
     const float res_mx = w00 * pm0 + w01 * pm1 + w10 * p00 + w11 * p01;
     const float res_px = w00 * p10 + w01 * p11 + w10 * p20 + w11 * p21;
@@ -208,8 +209,14 @@ __device__ __forceinline__ void warp_sum8(float (&v)[8], int lane) {
 // The lane's two pattern offsets live in a shared-memory table (float2 per sample): the compiler
 // otherwise rematerialises them from the lane id inside the iteration loop (~20 instructions per sample).
 struct Lane {
-    const float2 *pat;  // &table[lane]; sample k is pat[32 * k]
+    uint32_t pat;  // shared-window address of table[lane]; sample k is 256 k bytes further
     bool has[2];
+    // reloaded at every use (volatile): one live register instead of four, and no address rematerialisation
+    __device__ __forceinline__ float2 offset(int k) const {
+        float2 v;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(pat + 256u * (uint32_t)k));
+        return v;
+    }
 };
 
 // track_one_point (feature_tracker.rs:292-342): coarse-to-fine, template from pyramid A at the
@@ -226,6 +233,12 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
         const Img ia{A + pd.lv[lev].off, pd.lv[lev].w, pd.lv[lev].h};
         const Img ib{B + pd.lv[lev].off, pd.lv[lev].w, pd.lv[lev].h};
         const float pxx = T0[2] / s, pyy = T0[5] / s;
+        // a level smaller than 5x5 has no sample that passes inbound(.., 2): the template is invalid
+        // (patch.rs:95,146: n = 0, mean = NaN), and the unclamped gathers below need w, h >= 5
+        if (ia.w < 5 || ia.h < 5) {
+            ++n_templates;
+            return RSVIO_FAIL_TEMPLATE;
+        }
 
         // ---- Pattern52::new (patch.rs:124-162) --------------------------------------------
         float d[2], J[2][3];
@@ -236,7 +249,7 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
         for (int k = 0; k < 2; ++k) {
             d[k] = -1.0f;
             J[k][0] = J[k][1] = J[k][2] = 0.0f;
-            const float2 o = ln.pat[32 * k];
+            const float2 o = ln.offset(k);
             const float x = pxx + o.x, y = pyy + o.y;
             const bool ok = ln.has[k] && inbound(ia.w, ia.h, x, y, 2);
             float v, gx, gy;
@@ -318,19 +331,19 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
             unsigned cmask[2];
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const float2 o = ln.pat[32 * k];
+                const float2 o = ln.offset(k);
                 const float x = (T1[0] * o.x + T1[1] * o.y) + T1[2];
                 const float y = (T1[3] * o.x + T1[4] * o.y) + T1[5];
                 const bool ok = ln.has[k] && x >= 2.0f && y >= 2.0f && x < wlim && y < hlim;
-                // branch-free gather: rejected samples read pixel (0,0)..(1,1) clamped into the image, unused
+                // branch-free gather: rejected samples read pixels (0,0)..(1,1), unused; accepted ones have
+                // ix + 1 <= w - 2 and iy + 1 <= h - 2, so nothing needs clamping
                 const uint32_t ix = ok ? __float2uint_rd(x) : 0u, iy = ok ? __float2uint_rd(y) : 0u;
                 const float dx = x - (float)ix, dy = y - (float)iy;
                 const float ddx = 1.0f - dx, ddy = 1.0f - dy;
-                const uint32_t x1 = min(ix + 1u, (uint32_t)ib.w - 1u);
-                const uint8_t *__restrict__ q0 = ib.p + (size_t)iy * (uint32_t)ib.w;
-                const uint8_t *__restrict__ q1 = ib.p + (size_t)min(iy + 1u, (uint32_t)ib.h - 1u) * (uint32_t)ib.w;
-                const float p00 = (float)__ldg(q0 + ix), p10 = (float)__ldg(q0 + x1);
-                const float p01 = (float)__ldg(q1 + ix), p11 = (float)__ldg(q1 + x1);
+                const uint8_t *__restrict__ q0 = ib.p + (iy * (uint32_t)ib.w + ix);
+                const uint8_t *__restrict__ q1 = q0 + (uint32_t)ib.w;
+                const float p00 = (float)__ldg(q0), p10 = (float)__ldg(q0 + 1);
+                const float p01 = (float)__ldg(q1), p11 = (float)__ldg(q1 + 1);
                 const float val = ddx * ddy * p00 + ddx * dy * p01 + dx * ddy * p10 + dx * dy * p11;
                 r[k] = ok ? val : -1.0f;
                 rsum += ok ? val : 0.0f;
@@ -398,7 +411,7 @@ lk_track_fb_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ L
     }
     __syncthreads();
     Lane ln;
-    ln.pat = s_pat + lane;
+    ln.pat = (uint32_t)__cvta_generic_to_shared(s_pat + lane);
     ln.has[0] = true;
     ln.has[1] = lane + 32 < kPattern;
 
