@@ -323,6 +323,11 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
 
         // ---- track_point_at_level (feature_tracker.rs:344-395) ----------------------------
         const float wlim = (float)((uint32_t)ib.w - 2u), hlim = (float)((uint32_t)ib.h - 2u);
+        // the level base and row pitch stay in registers across the iterations (opaque to rematerialisation)
+        const uint8_t *ibp = ib.p;
+        uint32_t ibw = (uint32_t)ib.w;
+        asm volatile("mov.u64 %0, %0;" : "+l"(ibp));
+        asm volatile("mov.u32 %0, %0;" : "+r"(ibw));
         for (int it = 0; it < max_it; ++it) {
             ++n_iters;
             float r[2];
@@ -340,8 +345,8 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
                 const uint32_t ix = ok ? __float2uint_rd(x) : 0u, iy = ok ? __float2uint_rd(y) : 0u;
                 const float dx = x - (float)ix, dy = y - (float)iy;
                 const float ddx = 1.0f - dx, ddy = 1.0f - dy;
-                const uint8_t *__restrict__ q0 = ib.p + (iy * (uint32_t)ib.w + ix);
-                const uint8_t *__restrict__ q1 = q0 + (uint32_t)ib.w;
+                const uint8_t *__restrict__ q0 = ibp + (iy * ibw + ix);
+                const uint8_t *__restrict__ q1 = q0 + ibw;
                 const float p00 = (float)__ldg(q0), p10 = (float)__ldg(q0 + 1);
                 const float p01 = (float)__ldg(q1), p11 = (float)__ldg(q1 + 1);
                 const float val = ddx * ddy * p00 + ddx * dy * p01 + dx * ddy * p10 + dx * dy * p11;
@@ -412,6 +417,7 @@ lk_track_fb_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ L
     __syncthreads();
     Lane ln;
     ln.pat = (uint32_t)__cvta_generic_to_shared(s_pat + lane);
+    asm volatile("mov.u32 %0, %0;" : "+r"(ln.pat));  // opaque: kept in a register, not rematerialised from the thread id
     ln.has[0] = true;
     ln.has[1] = lane + 32 < kPattern;
 
