@@ -447,8 +447,10 @@ struct FastSmem {
     static constexpr int off_tile = 0;                                   // [2 buffers][A, B][ROWS][RW]
     static constexpr int off_g2 = off_tile + 4 * region;
     static constexpr int off_g4 = (off_g2 + C::G2ROWS * G2P * 2 + 15) & ~15;
-    static constexpr int off_vbuf = (off_g4 + (NA >= 3 ? C::G4R * C::G4C * 4 : 4) + 15) & ~15;
-    static constexpr int off_mbar = (off_vbuf + NA * PITCH * 4 + 15) & ~15;
+    static constexpr int off_vbuf = off_g2;  // ring scratch, dead before stage 1 writes g2
+    static constexpr int end_g = (off_g4 + (NA >= 3 ? C::G4R * C::G4C * 4 : 4) + 15) & ~15;
+    static constexpr int end_v = (off_vbuf + NA * PITCH * 4 + 15) & ~15;
+    static constexpr int off_mbar = end_g > end_v ? end_g : end_v;
     static constexpr int bytes = off_mbar + 16 + 128;                    // + slack for the 128-B base alignment
 };
 
@@ -462,7 +464,7 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
     // 128-byte alignment for the TMA destinations; offset arithmetic on the array keeps the pointer in the
     // shared address space (LDS/STS with 32-bit addresses instead of generic loads)
     uint8_t *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
-    // layout: [nbuf x (region A, region B)] [g2] [g4] [vbuf] [mbarriers]
+    // layout: [nbuf x (region A, region B)] [g2 | vbuf] [g4] [mbarriers]
     const int shrink = (2 - P.nbuf) * 2 * S::region;
     uint16_t(*g2)[G2P] = reinterpret_cast<uint16_t(*)[G2P]>(smem + S::off_g2 - shrink);
     uint32_t(*g4)[C::G4C] = reinterpret_cast<uint32_t(*)[C::G4C]>(smem + S::off_g4 - shrink);
@@ -488,6 +490,8 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
     };
 
     if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map0)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map1)) : "memory");
         mbar_init(mbar0, 1);
         mbar_init(mbar0 + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -501,14 +505,17 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
     // at the top of a tile and issues its load as soon as the last reader of the buffer is done.
     __shared__ int next_tile;
     int my_next = 0;
+    const bool boss = tid == NTA - 32;  // lane 0 of the warp with the shortest stage-1 segment
     auto hand_out = [&](int t) {
         next_tile = t;
         if (t < total) issue_load(t, 0);
     };
+    // the first tile of a CTA is its block index (no round trip to the counter before the first load);
+    // the counter hands out tiles gridDim.x, gridDim.x + 1, ...
     if (!dbl) {
-        if (tid == 0) {
+        if (boss) {
             if (blockIdx.x == 0) *P.tile_counter_next = 0u;
-            hand_out((int)atomicAdd(P.tile_counter, 1u));
+            hand_out((int)blockIdx.x);
         }
         __syncthreads();
     }
@@ -518,9 +525,10 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
     else if (it > 0) tile_id += gridDim.x;
     if (tile_id >= total) break;
     const int buf = dbl ? (it & 1) : 0;
-    if (tid == 0) {
-        if (!dbl) my_next = (int)atomicAdd(P.tile_counter, 1u);  // used after stage 1: latency hidden
-        else if (tile_id + (int)gridDim.x < total) issue_load(tile_id + gridDim.x, buf ^ 1);  // prefetch
+    if (!dbl) {
+        if (boss) my_next = (int)(gridDim.x + atomicAdd(P.tile_counter, 1u));  // used after stage 0: latency hidden
+    } else if (tid == 0 && tile_id + (int)gridDim.x < total) {
+        issue_load(tile_id + gridDim.x, buf ^ 1);  // prefetch
     }
     const int img = magic_div(tile_id, tiles_per_img, P.magic_tpi), tl = tile_id - img * tiles_per_img;
     const int tile_y = magic_div(tl, P.tiles_x, P.magic_tx), tile_x = tl - tile_y * P.tiles_x;
@@ -546,6 +554,36 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
                 if (y0 + k * RPP < nrow)
                     *reinterpret_cast<uint4 *>(d0 + k * dstep) = *reinterpret_cast<const uint4 *>(s0 + k * RPP * RW);
         }
+    }
+
+    // ---- border ring of levels 1..NA owned by this tile (before stage 1: its scratch row vbuf lives in the
+    // bytes of g2): the reference's f32 chains (truncated
+    // windows are renormalised by a non-dyadic sum, so nothing is exact there), read from the tile.
+    const bool top = Y0 == 0, bottom = Y0 + TH >= h0 && Y0 < h0;
+    const bool left = X0 == 0, right = X0 + TW >= w0 && X0 < w0;
+    if (top || bottom || left || right) {
+        const RingTile rt{tA, S::region - RB, X0, Y0, C::ytop};
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {  // border rows: oy = 0 (top tiles), oy = hl - 1 (bottom tiles)
+            if (side == 0 ? !top : !bottom) continue;
+            __syncthreads();
+            ring_rows_vertical<1>(P, rt, vbuf[0], side, tid);
+            if (NA >= 2) ring_rows_vertical<2>(P, rt, vbuf[NA >= 2 ? 1 : 0], side, tid);
+            if (NA >= 3) ring_rows_vertical<3>(P, rt, vbuf[NA >= 3 ? 2 : 0], side, tid);
+            __syncthreads();
+            ring_rows_horizontal<1>(P, rt, vbuf[0], out, side, tid);
+            if (NA >= 2) ring_rows_horizontal<2>(P, rt, vbuf[NA >= 2 ? 1 : 0], out, side, (tid + 64) % NTA);
+            if (NA >= 3) ring_rows_horizontal<3>(P, rt, vbuf[NA >= 3 ? 2 : 0], out, side, (tid + 32) % NTA);
+        }
+        // border columns (ox = 0 for left tiles, ox = wl - 1 for right tiles) without the corner rows:
+        // one thread per (level, side, row); a warp holds one level
+        static_assert(NTA == 128 && TH == 64, "ring column items are mapped to thread ranges");
+        if (left || right) {
+            if (tid < 64) ring_cols<1>(P, rt, out, left, right, tid);
+            else if (tid < 96) { if (NA >= 2) ring_cols<2>(P, rt, out, left, right, tid - 64); }
+            else if (tid < 112) { if (NA >= 3) ring_cols<3>(P, rt, out, left, right, tid - 96); }
+        }
+            __syncthreads();  // vbuf shares its bytes with g2, which stage 1 writes next
     }
 
     // ---- stage 1: level-1 output O_2 (global) and G_2 (smem); 4 chained DP4A per value.
@@ -675,37 +713,10 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
             }
         }
     }
-    // ---- border ring of levels 1..NA owned by this tile: the reference's f32 chains (truncated
-    // windows are renormalised by a non-dyadic sum, so nothing is exact there), read from the tile.
-    const bool top = Y0 == 0, bottom = Y0 + TH >= h0 && Y0 < h0;
-    const bool left = X0 == 0, right = X0 + TW >= w0 && X0 < w0;
-    if (top || bottom || left || right) {
-        const RingTile rt{tA, S::region - RB, X0, Y0, C::ytop};
-#pragma unroll 1
-        for (int side = 0; side < 2; ++side) {  // border rows: oy = 0 (top tiles), oy = hl - 1 (bottom tiles)
-            if (side == 0 ? !top : !bottom) continue;
-            __syncthreads();
-            ring_rows_vertical<1>(P, rt, vbuf[0], side, tid);
-            if (NA >= 2) ring_rows_vertical<2>(P, rt, vbuf[NA >= 2 ? 1 : 0], side, tid);
-            if (NA >= 3) ring_rows_vertical<3>(P, rt, vbuf[NA >= 3 ? 2 : 0], side, tid);
-            __syncthreads();
-            ring_rows_horizontal<1>(P, rt, vbuf[0], out, side, tid);
-            if (NA >= 2) ring_rows_horizontal<2>(P, rt, vbuf[NA >= 2 ? 1 : 0], out, side, (tid + 64) % NTA);
-            if (NA >= 3) ring_rows_horizontal<3>(P, rt, vbuf[NA >= 3 ? 2 : 0], out, side, (tid + 32) % NTA);
-        }
-        // border columns (ox = 0 for left tiles, ox = wl - 1 for right tiles) without the corner rows:
-        // one thread per (level, side, row); a warp holds one level
-        static_assert(NTA == 128 && TH == 64, "ring column items are mapped to thread ranges");
-        if (left || right) {
-            if (tid < 64) ring_cols<1>(P, rt, out, left, right, tid);
-            else if (tid < 96) { if (NA >= 2) ring_cols<2>(P, rt, out, left, right, tid - 64); }
-            else if (tid < 112) { if (NA >= 3) ring_cols<3>(P, rt, out, left, right, tid - 96); }
-        }
-    }
     if (NA >= 2) {
         __syncthreads();
         // the tile buffer is dead from here on: fetch the next tile while stages 2 and 3 run
-        if (!dbl && tid == 0) hand_out(my_next);
+        if (!dbl && boss) hand_out(my_next);
         // ---- stage 2: level-2 output O_4 (global) and G_4 (smem) from G_2: 3x3 binomials as chained
         // 2-way dot products on the u16 pairs.  g2[t - t_first][j - (X0/2 - 2)].
         const int w2 = P.pd.lv[2].w, h2 = P.pd.lv[2].h;
@@ -798,7 +809,7 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
 
     __syncthreads();  // every read of this buffer, g2, g4 and vbuf is done before the next tile reuses them
     if (NA < 2 && !dbl) {
-        if (tid == 0) hand_out(my_next);
+        if (boss) hand_out(my_next);
         __syncthreads();
     }
     }  // persistent tile loop
