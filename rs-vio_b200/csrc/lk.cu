@@ -227,12 +227,14 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
     T1[0] = 1.0f; T1[1] = 0.0f; T1[2] = T0[2];
     T1[3] = 0.0f; T1[4] = 1.0f; T1[5] = T0[5];
     for (int lev = pd.levels - 1; lev >= 0; --lev) {
-        const float s = (float)(1 << lev);
-        T1[2] = T1[2] / s;
-        T1[5] = T1[5] / s;
+        // the reference divides by 2^lev (feature_tracker.rs:305-313): a power of two, so multiplying by its
+        // exact reciprocal gives the same bits without four IEEE division sequences per level
+        const float s = (float)(1 << lev), inv_s = __int_as_float((127 - lev) << 23);
+        T1[2] = T1[2] * inv_s;
+        T1[5] = T1[5] * inv_s;
         const Img ia{A + pd.lv[lev].off, pd.lv[lev].w, pd.lv[lev].h};
         const Img ib{B + pd.lv[lev].off, pd.lv[lev].w, pd.lv[lev].h};
-        const float pxx = T0[2] / s, pyy = T0[5] / s;
+        const float pxx = T0[2] * inv_s, pyy = T0[5] * inv_s;
         // a level smaller than 5x5 has no sample that passes inbound(.., 2): the template is invalid
         // (patch.rs:95,146: n = 0, mean = NaN), and the unclamped gathers below need w, h >= 5
         if (ia.w < 5 || ia.h < 5) {
