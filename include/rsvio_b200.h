@@ -138,7 +138,8 @@ rsvio_status rsvio_tracker_result_view(rsvio_tracker *t, const rsvio_track_recor
 /* the full Affine2 of every track (tracked_points_map_cam{0,1}, feature_tracker.rs:93,95) */
 rsvio_status rsvio_tracker_get_transforms(rsvio_tracker *t, int32_t stream, int32_t cam, uint64_t *ids,
                                           float *T6, size_t cap, size_t *n);
-/* remove_id (feature_tracker.rs:201-206): removes from both cameras */
+/* remove_id (feature_tracker.rs:201-206): removes from both cameras.  RSVIO_ERR_STATE while a submitted
+ * frame has not been synced. */
 rsvio_status rsvio_tracker_remove_ids(rsvio_tracker *t, int32_t stream, const uint64_t *ids, size_t n);
 
 /* counters since create/reset, summed over streams:

@@ -34,6 +34,8 @@ struct rsvio_tracker {
     int S = 1, groups = 2, cap = 0, new_cap = 0, stereo = 1;
     size_t img_bytes = 0;
     cudaStream_t st = nullptr, copy_st = nullptr;
+    cudaStream_t exp_st = nullptr;  // record export + error flag: beside the next frame on big batches, else == st
+    bool own_exp = false;
     bool own_stream = false;
     PyrPlan *plan = nullptr;
     PyrDesc pd{};
@@ -63,7 +65,7 @@ struct rsvio_tracker {
     // host-mapped output ring: records [groups][cap] and counts [groups] (+1 error flag)
     OutRecord *h_out[kSlots] = {nullptr, nullptr}, *d_out[kSlots] = {nullptr, nullptr};
     int *h_cnt[kSlots] = {nullptr, nullptr}, *d_cnt[kSlots] = {nullptr, nullptr};
-    cudaEvent_t ev_h2d[kSlots]{}, ev_in_free[kSlots]{}, ev_done[kSlots]{};
+    cudaEvent_t ev_h2d[kSlots]{}, ev_in_free[kSlots]{}, ev_done[kSlots]{}, ev_merged[kSlots]{};
     int next_slot = 0, oldest_slot = 0, inflight = 0, result_slot = -1;
     uint64_t host_launches = 0;
     // profiling
@@ -112,6 +114,7 @@ void free_all(rsvio_tracker *t) {
     cudaSetDevice(t->cfg.device);
     if (t->st) cudaStreamSynchronize(t->st);
     if (t->copy_st) cudaStreamSynchronize(t->copy_st);
+    if (t->own_exp && t->exp_st) cudaStreamSynchronize(t->exp_st);
     pyr_plan_destroy(t->plan);
     for (int i = 0; i < kSlots; ++i) {
         cudaFree(t->d_in[i]);
@@ -121,6 +124,7 @@ void free_all(rsvio_tracker *t) {
         if (t->ev_h2d[i]) cudaEventDestroy(t->ev_h2d[i]);
         if (t->ev_in_free[i]) cudaEventDestroy(t->ev_in_free[i]);
         if (t->ev_done[i]) cudaEventDestroy(t->ev_done[i]);
+        if (t->ev_merged[i]) cudaEventDestroy(t->ev_merged[i]);
         for (int k = 0; k <= RSVIO_N_STAGES; ++k)
             if (t->ev_stage[i][k]) cudaEventDestroy(t->ev_stage[i][k]);
         for (int k = 0; k < 2; ++k)
@@ -149,6 +153,7 @@ void free_all(rsvio_tracker *t) {
     cudaFree(t->d_err);
     cudaFree(t->d_work);
     if (t->copy_st) cudaStreamDestroy(t->copy_st);
+    if (t->own_exp && t->exp_st) cudaStreamDestroy(t->exp_st);
     if (t->own_stream && t->st) cudaStreamDestroy(t->st);
     cudaGetLastError();
     delete t;
@@ -163,6 +168,7 @@ rsvio_status clear_state(rsvio_tracker *t) {
     CU_TRY(t, cudaMemsetAsync(t->d_work, 0, sizeof(unsigned) * 4, t->st));
     CU_TRY(t, cudaMemsetAsync(t->d_cell_list_n, 0, sizeof(int) * 2, t->st));
     t->lk_par[0] = t->lk_par[1] = t->det_par = 0;
+    if (t->own_exp) CU_TRY(t, cudaStreamSynchronize(t->exp_st));
     CU_TRY(t, cudaStreamSynchronize(t->st));
     for (int i = 0; i < kSlots; ++i) memset(t->h_cnt[i], 0, sizeof(int) * (t->groups + 1));
     t->have_prev = false;
@@ -250,17 +256,27 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
         CU_TRY(t, lk_track(t->pd, b, st));
         count(5, 1);
     }
-    mark(++stage);  // 6: merge + packed output
+    mark(++stage);  // 6: merge (ids, table append)
     CU_TRY(t, merge_new_points(tout, t->S, t->cap, t->stereo, t->d_new_T6, t->d_st_T6, t->d_st_status,
-                               t->d_new_count, t->new_cap, t->d_last_id, t->d_err, t->d_out[slot], t->d_cnt[slot],
-                               t->d_counters, st));
+                               t->d_new_count, t->new_cap, t->d_last_id, t->d_err, st));
     count(6, 1);
-    mark(++stage);  // 7: download (error flag; the records were written to mapped host memory above)
-    CU_TRY(t, cudaMemcpyAsync(t->h_cnt[slot] + t->groups, t->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
-    t->stage_launches[7] += 1;  // a copy, not a kernel: not added to host_launches
-    mark(++stage);  // end
+    // 7: download -- packed records into mapped host memory + the error flag.  With many streams this runs on
+    // its own CUDA stream beside the next frame (the table it reads is not written again before the frame after
+    // next, which cannot be submitted until this one has been synced).
+    cudaStream_t xs = t->exp_st;
+    if (xs != st) {
+        CU_TRY(t, cudaEventRecord(t->ev_merged[slot], st));
+        CU_TRY(t, cudaStreamWaitEvent(xs, t->ev_merged[slot], 0));
+    }
+    ++stage;
+    if (prof) cudaEventRecord(t->ev_stage[slot][stage], xs);
+    CU_TRY(t, export_records(tout, t->groups, t->cap, t->d_out[slot], t->d_cnt[slot], xs));
+    count(7, 1);
+    CU_TRY(t, cudaMemcpyAsync(t->h_cnt[slot] + t->groups, t->d_err, sizeof(int), cudaMemcpyDeviceToHost, xs));
+    ++stage;
+    if (prof) cudaEventRecord(t->ev_stage[slot][stage], xs);  // end
     t->stage_valid[slot] = prof;
-    CU_TRY(t, cudaEventRecord(t->ev_done[slot], st));
+    CU_TRY(t, cudaEventRecord(t->ev_done[slot], xs));
     t->tcur ^= 1;
     t->pcur ^= 1;
     t->have_prev = true;
@@ -418,6 +434,12 @@ rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) 
             t->own_stream = true;
         }
         CU_TRY(t, cudaStreamCreateWithFlags(&t->copy_st, cudaStreamNonBlocking));
+        if (t->S >= 8) {  // small batches: the cross-stream hand-off would cost more latency than the export
+            CU_TRY(t, cudaStreamCreateWithFlags(&t->exp_st, cudaStreamNonBlocking));
+            t->own_exp = true;
+        } else {
+            t->exp_st = t->st;
+        }
         CU_TRY(t, pyr_plan_create(cfg->width, cfg->height, cfg->levels, t->st, &t->plan));
         CU_TRY(t, pyr_plan_reserve(t->plan, 2 * t->S));
         t->pd = pyr_plan_desc(t->plan);
@@ -431,6 +453,7 @@ rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) 
             CU_TRY(t, cudaEventCreateWithFlags(&t->ev_h2d[i], cudaEventDisableTiming));
             CU_TRY(t, cudaEventCreateWithFlags(&t->ev_in_free[i], cudaEventDisableTiming));
             CU_TRY(t, cudaEventCreateWithFlags(&t->ev_done[i], cudaEventDisableTiming));
+            CU_TRY(t, cudaEventCreateWithFlags(&t->ev_merged[i], cudaEventDisableTiming));
             for (int k = 0; k <= RSVIO_N_STAGES; ++k) CU_TRY(t, cudaEventCreate(&t->ev_stage[i][k]));
             for (int k = 0; k < 2; ++k) CU_TRY(t, cudaEventCreate(&t->ev_up[i][k]));
         }
@@ -638,6 +661,7 @@ rsvio_status rsvio_tracker_remove_ids(rsvio_tracker *t, int32_t stream, const ui
     if (rs != RSVIO_OK) return rs;
     if (n == 0) return RSVIO_OK;
     if (!ids) return RSVIO_ERR_INVALID_ARG;
+    if (t->inflight > 0) return fail(t, RSVIO_ERR_STATE, "frames in flight: call rsvio_tracker_sync before remove_ids");
     CU_TRY(t, cudaSetDevice(t->cfg.device));
     if ((int)n > t->rm_cap) {
         cudaFree(t->d_rm);

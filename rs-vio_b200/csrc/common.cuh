@@ -144,11 +144,13 @@ struct OutRecord {
     unsigned long long id;
     float x, y;
 };
-// appends the new stereo pairs (status ok) to both cameras of `tab`, assigns ids, writes the packed output
+// appends the new stereo pairs (status ok) to both cameras of `tab` and assigns their ids
 cudaError_t merge_new_points(const TableView &tab, int streams, int cap, int stereo, const float *new_T6,
                              const float *st_T6, const int32_t *st_status, const int *new_count, int new_cap,
-                             unsigned long long *last_id, int *err_flag, OutRecord *out_rec, int *out_counts,
-                             unsigned long long *counters, cudaStream_t st);
+                             unsigned long long *last_id, int *err_flag, cudaStream_t st);
+// packed (id, x, y) records and counts of every group -> out_rec / out_counts (mapped host memory)
+cudaError_t export_records(const TableView &tab, int groups, int cap, OutRecord *out_rec, int *out_counts,
+                           cudaStream_t st);
 cudaError_t remove_ids(const TableView &in, const TableView &out, int groups, int cap, int streams, int stream,
                        const unsigned long long *d_ids, int n, cudaStream_t st);
 

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kThreads)
 merge_new_kernel(TableView tab, int streams, int cap, int stereo, const float *__restrict__ new_T6,
                  const float *__restrict__ st_T6, const int32_t *__restrict__ st_status,
                  const int *__restrict__ new_count, int new_cap, unsigned long long *__restrict__ last_id,
-                 int *err_flag, OutRecord *__restrict__ out_rec, int *__restrict__ out_counts) {
+                 int *err_flag) {
     __shared__ int warp_tot[kWarps];
     __shared__ int base;
     const int s = blockIdx.x;
@@ -134,20 +134,19 @@ merge_new_kernel(TableView tab, int streams, int cap, int stereo, const float *_
         tab.counts[g0] = f0;
         if (stereo) tab.counts[g1] = f1;
         last_id[s] = id0 + (unsigned long long)add;
-        out_counts[g0] = f0;
-        out_counts[g1] = f1;
     }
-    // packed output (mapped host memory): get_track_points / frame population
-    for (int k = threadIdx.x; k < f0; k += kThreads) {
-        const size_t i = (size_t)g0 * cap + k;
-        OutRecord r;
-        r.id = tab.ids[i];
-        r.x = tab.T6[i * 6 + 2];
-        r.y = tab.T6[i * 6 + 5];
-        out_rec[i] = r;
-    }
-    for (int k = threadIdx.x; k < f1; k += kThreads) {
-        const size_t i = (size_t)g1 * cap + k;
+}
+
+// packed output (mapped host memory): get_track_points / frame population (feature_tracker.rs:177-200).
+// Own kernel so that it can run beside the next frame: only live records cross PCIe.
+constexpr int kExportChunks = 4;
+__global__ void __launch_bounds__(kThreads)
+export_records_kernel(TableView tab, int cap, OutRecord *__restrict__ out_rec, int *__restrict__ out_counts) {
+    const int g = blockIdx.x;
+    const int n = tab.counts[g];
+    if (blockIdx.y == 0 && threadIdx.x == 0) out_counts[g] = n;
+    for (int k = blockIdx.y * kThreads + threadIdx.x; k < n; k += kExportChunks * kThreads) {
+        const size_t i = (size_t)g * cap + k;
         OutRecord r;
         r.id = tab.ids[i];
         r.x = tab.T6[i * 6 + 2];
@@ -199,11 +198,15 @@ cudaError_t compact_tracks(const TableView &in, const float *lk_T6, const int32_
 
 cudaError_t merge_new_points(const TableView &tab, int streams, int cap, int stereo, const float *new_T6,
                              const float *st_T6, const int32_t *st_status, const int *new_count, int new_cap,
-                             unsigned long long *last_id, int *err_flag, OutRecord *out_rec, int *out_counts,
-                             unsigned long long *counters, cudaStream_t st) {
-    (void)counters;
+                             unsigned long long *last_id, int *err_flag, cudaStream_t st) {
     merge_new_kernel<<<streams, kThreads, 0, st>>>(tab, streams, cap, stereo, new_T6, st_T6, st_status, new_count,
-                                                   new_cap, last_id, err_flag, out_rec, out_counts);
+                                                   new_cap, last_id, err_flag);
+    return cudaGetLastError();
+}
+
+cudaError_t export_records(const TableView &tab, int groups, int cap, OutRecord *out_rec, int *out_counts,
+                           cudaStream_t st) {
+    export_records_kernel<<<dim3((unsigned)groups, kExportChunks, 1), kThreads, 0, st>>>(tab, cap, out_rec, out_counts);
     return cudaGetLastError();
 }
 
