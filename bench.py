@@ -432,7 +432,7 @@ def main():
             lat = np.array(lat[10:]) * 1e3
             single = {"ms_per_frame_median": float(np.median(lat)), "ms_per_frame_p95": float(np.percentile(lat, 95)),
                       "stereo_frames_per_sec": float(1e3 / np.median(lat)), "tracks_alive": tr1.num_tracks(0) + tr1.num_tracks(1),
-                      "what": "1 stream, rsvio_tracker_process_stereo per frame (upload + 7 kernels + result), host wall clock"}
+                      "what": "1 stream, rsvio_tracker_process_stereo per frame (upload + 9 kernels + result), host wall clock"}
             tr1.close()
         except Exception as ex:
             single = {"error": str(ex)}

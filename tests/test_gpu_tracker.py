@@ -133,6 +133,48 @@ def test_batched_streams_equal_single_streams(rsvio):
                 assert np.array_equal(batch.tracks(cam, s)[1], T1[:, [2, 5]])
 
 
+def test_pipelined_batch_with_side_stream_export(rsvio):
+    """>= 8 streams: the record export runs on its own CUDA stream beside the next frame; the mapped
+    result of every synced frame must equal what independent 1-stream handles report."""
+    import ctypes as C
+    from rsvio_b200.synth import StereoSequence
+    S, frames, w, h = 9, 4, 256, 160
+    seqs = [StereoSequence("C5", stream_id=s, w=w, h=h) for s in range(S)]
+    data = [[q.frame(t) for q in seqs] for t in range(frames)]
+    singles = [rsvio.StereoPatchTracker(40, 20, 0.01, width=w, height=h, levels=3) for _ in range(S)]
+    want = []
+    for t in range(frames):
+        per = []
+        for s in range(S):
+            singles[s].process_frame(*data[t][s])
+            per.append([singles[s].tracks(c) for c in (0, 1)])
+        want.append(per)
+    batch = rsvio.StereoPatchTracker(40, 20, 0.01, width=w, height=h, levels=3, n_streams=S)
+    ptrs = [((C.c_void_p * S)(*[f[0].ctypes.data for f in data[t]]), (C.c_void_p * S)(*[f[1].ctypes.data for f in data[t]]))
+            for t in range(frames)]
+
+    def check(t):
+        rec, cnt = batch.result_view()
+        for s in range(S):
+            for cam in (0, 1):
+                g = cam * S + s
+                ids, xy = want[t][s][cam]
+                assert cnt[g] == len(ids)
+                assert np.array_equal(rec["id"][g, :cnt[g]], ids)
+                assert np.array_equal(np.stack([rec["x"][g, :cnt[g]], rec["y"][g, :cnt[g]]], 1), xy)
+
+    batch.submit_batch_ptr(*ptrs[0])
+    for t in range(1, frames):
+        batch.submit_batch_ptr(*ptrs[t])
+        with pytest.raises(rsvio.RsvioError):
+            batch.remove_id([1], stream=0)     # a submitted frame has not been synced
+        batch.sync()
+        check(t - 1)
+    batch.sync()
+    check(frames - 1)
+    assert want[-1][0][0][0].size > 5
+
+
 def test_async_submit_and_device_resident_paths(rsvio):
     import ctypes as C
     from rsvio_b200.synth import StereoSequence

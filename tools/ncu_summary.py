@@ -24,14 +24,20 @@ def launches(src, dst):
     rows = list(csv.reader(open(src)))
     hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     H, data = rows[hdr], rows[hdr + 1:]
-    ki, vi = H.index("Kernel Name"), H.index("Metric Value")
+    ki, vi, gi = H.index("Kernel Name"), H.index("Metric Value"), H.index("Grid Size")
     agg = collections.defaultdict(list)
+    prev = ""
     for r in data:
         if len(r) > vi:
-            agg[r[ki]].append(float(r[vi].replace(",", "")))
+            name = r[ki].replace("unnamed>::", "").replace("void ", "").replace("rsvio::<", "").split("(")[0]
+            if "lk_track_fb" in name:  # two launches per frame: after the pyramid (temporal), after collect (stereo)
+                name += " [temporal]" if "pyr_" in prev else " [stereo, new points]"
+            agg[f"{name} grid={r[gi]}"].append(float(r[vi].replace(",", "")))
+            prev = r[ki]
     tot = sum(sum(v) for v in agg.values())
     with open(dst, "w") as f:
-        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare shares)\n")
+        f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare shares);\n"
+                "# rows are (kernel, grid): the bench's 64-stream handle and its 1-stream latency probe launch the same kernels\n")
         f.write(f"{'kernel':70s} {'n':>5s} {'avg_us':>10s} {'share':>7s}\n")
         for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
             f.write(f"{k[:70]:70s} {len(v):5d} {sum(v) / len(v) / 1e3:10.1f} {sum(v) / tot:7.3f}\n")
