@@ -146,13 +146,21 @@ pyr_generic_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ P
         const uint8_t *__restrict__ p = src + (size_t)top * stride + x;
         float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
         if (vec4 && x + 4 <= w0) {
+            // u8 -> f32 without the quarter-rate I2F: one PRMT drops byte j into the mantissa of 2^23
+            // (0x4B0000bb == 8388608 + b), one exact FADD removes the 2^23.  This loop is conversion-bound otherwise.
+            constexpr float kTwo23 = 8388608.0f;
+#pragma unroll 8  // the loads do not depend on the f32 chains: 8 in flight per thread
             for (int k = 0; k < n; ++k) {
                 const uint32_t q = __ldg(reinterpret_cast<const uint32_t *>(p + (size_t)k * stride));
                 const float wk = __ldg(wy + k);
-                t0 = __fadd_rn(t0, __fmul_rn((float)(q & 0xFFu), wk));
-                t1 = __fadd_rn(t1, __fmul_rn((float)((q >> 8) & 0xFFu), wk));
-                t2 = __fadd_rn(t2, __fmul_rn((float)((q >> 16) & 0xFFu), wk));
-                t3 = __fadd_rn(t3, __fmul_rn((float)(q >> 24), wk));
+                const float p0 = __fadd_rn(__uint_as_float(__byte_perm(q, 0x4B000000u, 0x7440)), -kTwo23);
+                const float p1 = __fadd_rn(__uint_as_float(__byte_perm(q, 0x4B000000u, 0x7441)), -kTwo23);
+                const float p2 = __fadd_rn(__uint_as_float(__byte_perm(q, 0x4B000000u, 0x7442)), -kTwo23);
+                const float p3 = __fadd_rn(__uint_as_float(__byte_perm(q, 0x4B000000u, 0x7443)), -kTwo23);
+                t0 = __fadd_rn(t0, __fmul_rn(p0, wk));
+                t1 = __fadd_rn(t1, __fmul_rn(p1, wk));
+                t2 = __fadd_rn(t2, __fmul_rn(p2, wk));
+                t3 = __fadd_rn(t3, __fmul_rn(p3, wk));
             }
         } else {
             for (int k = 0; k < n; ++k) {
@@ -1360,11 +1368,15 @@ static void add_rect_tiles(const PyrDesc &pd, int lev, int x0, int y0, int nx, i
     // intermediate columns per tile row: (tox + 1) * ratio + 8 must fit the smem budget with noy rows
     int tox = nx < 32 ? nx : 32;
     while (tox > 1 && (tox + 1) * ratio + 8 > 672) tox >>= 1;
+    tox = (nx + (nx + tox - 1) / tox - 1) / ((nx + tox - 1) / tox);  // equal tiles: 23 -> 8, 8, 7 instead of 11, 11, 1
     const int cols = (int)((tox + 1) * ratio) + 8;
-    int toy = kGenSmemFloats / cols;
-    if (toy > 8 && nx > 1) toy = 8;  // wide tiles: 8 rows; single-column ring tiles: as tall as fits
+    // rows per tile: one round of the vertical pass (a thread = 4 columns x 1 output row) fills the CTA once, so
+    // that tiles are short and numerous (no wave quantisation; rows share no work, only columns do)
+    int toy = kGenThreads / ((cols + 3) / 4);
+    if (toy > kGenSmemFloats / cols) toy = kGenSmemFloats / cols;
     if (toy > 64) toy = 64;
     if (toy < 1) toy = 1;
+    toy = (ny + (ny + toy - 1) / toy - 1) / ((ny + toy - 1) / toy);
     for (int y = y0; y < y0 + ny; y += toy)
         for (int x = x0; x < x0 + nx; x += tox) {
             TileDesc t;
