@@ -75,3 +75,36 @@ def test_streaming_kernel_variant_is_bit_exact_too():
     env = dict(os.environ, RSVIO_PYR_KERNEL="stream")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "stream ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_pyramid_random_shapes_fuzz(rsvio, oracle):
+    """random sizes (tile-aligned, 16-aligned, arbitrary), level counts, batch sizes and tie-heavy content:
+    every byte equals the oracle's (the tile hand-out, the border ring and the generic tiling all depend on shape)"""
+    rng = np.random.default_rng(2024)
+    for c in range(36):
+        kind = c % 4
+        if kind == 0:
+            m = int(rng.choice([16, 32, 64]))
+            w, h = m * int(rng.integers(2, 30)), m * int(rng.integers(1, 16))
+        elif kind == 1:
+            w, h = 16 * int(rng.integers(2, 50)), int(rng.integers(20, 500))
+        elif kind == 2:
+            w, h = int(rng.integers(20, 900)), int(rng.integers(20, 600))
+        else:
+            w = 256 * int(rng.integers(1, 4)) + 16 * int(rng.integers(0, 3))
+            h = 64 * int(rng.integers(1, 6)) + int(rng.choice([0, 16, 32]))
+        levels = int(rng.integers(1, 8))
+        while levels > 1 and ((w >> (levels - 1)) < 1 or (h >> (levels - 1)) < 1):
+            levels -= 1
+        n = int(rng.integers(1, 4))
+        if c % 3 == 0:
+            img = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+        elif c % 3 == 1:   # few grey values: many exact x.5 ties
+            img = (rng.integers(0, 4, (n, h, w)) * 64 + rng.integers(0, 2, (n, h, w))).astype(np.uint8)
+        else:
+            img = np.full((n, h, w), int(rng.integers(0, 256)), np.uint8)
+            img[:, ::7, ::5] = 255
+        got = rsvio.build_pyramid(img, levels)
+        for j in range(n):
+            want = oracle.build_pyramid(img[j], levels, nthreads=4)
+            assert np.array_equal(got[j], want), f"{w}x{h} L{levels} n={n} case {c} image {j}"
