@@ -26,7 +26,7 @@
 //  pyr_deep_kernel    levels 4 and 5 from G_8 (exact integers).  There the reference's horizontal
 //      f32 accumulation is no longer exact (26 > 24 bits), but its error is < 2^-10 grey levels,
 //      so round(N / D) is the reference's byte unless frac(N / D) is within 2^-10 of 1/2; those
-//      rare outputs are queued and recomputed by pyr_fixup_kernel with the faithful f32 chains.
+//      rare outputs are recomputed on the spot, warp-cooperatively, with the faithful f32 chains.
 //  pyr_generic_kernel faithful f32 chains, one CTA per tile descriptor: the outermost ring of every
 //      dyadic level (truncated windows: weights are renormalised by a non-power-of-two sum,
 //      nothing is exact) as 1-row / 1-column tiles, whole levels whose ratio is not a power of
@@ -1172,27 +1172,30 @@ pyr_stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------
-// deep dyadic levels (4, 5) from the exported G_8, with an uncertainty queue
+// deep dyadic levels (4, 5) from the exported G_8; near ties fall back to the faithful chains
 // ------------------------------------------------------------------------------------------
-struct FixItem {
-    int img, lev, ox, oy;
-};
+constexpr int kDeepThreads = 256;
 
-__global__ void __launch_bounds__(256)
-pyr_deep_kernel(const __grid_constant__ PyrDesc pd, const uint32_t *__restrict__ g8, int n_images, int do5, uint8_t *__restrict__ dst,
-                FixItem *__restrict__ fix, int *__restrict__ fix_count, int fix_cap) {
+__global__ void __launch_bounds__(kDeepThreads)
+pyr_deep_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ PyrTaps taps,
+                const uint32_t *__restrict__ g8, int n_images, int do5, const uint8_t *__restrict__ src0,
+                const uint8_t *__restrict__ src1, int split, size_t stride, size_t pitch, uint8_t *__restrict__ dst) {
+    __shared__ float vbuf[kDeepThreads / 32][2 * 64 + 8];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int w8 = pd.lv[0].w / 8, h8 = pd.lv[0].h / 8;
     const int w4 = pd.lv[4].w, h4 = pd.lv[4].h;
     const int n4 = max(w4 - 2, 0) * max(h4 - 2, 0);
     const int w5 = do5 ? pd.lv[5].w : 0, h5 = do5 ? pd.lv[5].h : 0;
     const int n5 = do5 ? max(w5 - 2, 0) * max(h5 - 2, 0) : 0;
     const long long total = (long long)(n4 + n5) * n_images;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
+    // warp-uniform trip count: the tie fix-up below is a warp-cooperative step
+    for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < total;
+         base += (long long)gridDim.x * blockDim.x) {
+        const bool act = base + lane < total;
+        const long long idx = act ? base + lane : total - 1;
         const int img = (int)(idx / (n4 + n5));
         int k = (int)(idx - (long long)img * (n4 + n5));
         const uint32_t *__restrict__ g = g8 + (size_t)img * w8 * h8;
-        uint8_t *__restrict__ out = dst + (size_t)img * pd.pyr_stride;
         uint32_t n, half;
         int shift, lev, ox, oy;
         if (k < n4) {  // O_16[o] = sum (1,2,1)x(1,2,1) G_8[2o-1 .. 2o+1]
@@ -1217,51 +1220,45 @@ pyr_deep_kernel(const __grid_constant__ PyrDesc pd, const uint32_t *__restrict__
             shift = 22;  // D = 4 * 32^4
         }
         half = 1u << (shift - 1);
-        out[pd.lv[lev].off + (size_t)oy * pd.lv[lev].w + ox] = (uint8_t)((n + half) >> shift);
         // The reference's f32 horizontal accumulation differs from N / D by at most 31 * 2^-17 = 2.4e-4 grey
         // levels at level 4 (products exact, 31 rounded adds below 256) and 63 * 2^-17 + 64 * 2^-22 = 5.0e-4
-        // at level 5: flag the outputs within 2^-11 resp. 2^-10 of a tie, they could round the other way.
+        // at level 5: the outputs within 2^-11 resp. 2^-10 of a tie could round the other way (~0.2 % of them).
         const uint32_t frac = n & ((1u << shift) - 1u);
         const uint32_t dist = frac > half ? frac - half : half - frac;
-        if (dist <= (1u << (shift - (lev == 4 ? 11 : 10)))) {
-            const int slot = atomicAdd(fix_count, 1);
-            if (slot < fix_cap) fix[slot] = FixItem{img, lev, ox, oy};
+        const bool tie = act && dist <= (1u << (shift - (lev == 4 ? 11 : 10)));
+        if (act && !tie)
+            dst[(size_t)img * pd.pyr_stride + pd.lv[lev].off + (size_t)oy * pd.lv[lev].w + ox] = (uint8_t)((n + half) >> shift);
+        // near ties: the warp recomputes them one by one with the reference's f32 chains from the base image
+        // (a lane per window column, then the horizontal chain in tap order)
+        unsigned todo = __ballot_sync(0xffffffffu, tie);
+        while (todo) {
+            const int from = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int f_img = __shfl_sync(0xffffffffu, img, from), f_lev = __shfl_sync(0xffffffffu, lev, from);
+            const int f_ox = __shfl_sync(0xffffffffu, ox, from), f_oy = __shfl_sync(0xffffffffu, oy, from);
+            const uint8_t *__restrict__ src = image_ptr(src0, src1, split, f_img, pitch);
+            const TapTable tx = taps.x[f_lev], ty = taps.y[f_lev];
+            const int left = tx.left[f_ox], nx = tx.cnt[f_ox];
+            const int top = ty.left[f_oy], ny = ty.cnt[f_oy];
+            const float *__restrict__ wy = ty.w + (size_t)f_oy * ty.kmax;
+            for (int kx = lane; kx < nx; kx += 32) {
+                const uint8_t *__restrict__ p = src + (size_t)top * stride + (left + kx);
+                float v = 0.0f;
+#pragma unroll 8  // independent loads: keep 8 in flight
+                for (int ky = 0; ky < ny; ++ky) v = __fadd_rn(v, __fmul_rn((float)__ldg(p + (size_t)ky * stride), wy[ky]));
+                vbuf[wib][kx] = v;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                const float *__restrict__ wx = tx.w + (size_t)f_ox * tx.kmax;
+                float t = 0.0f;
+                for (int kx = 0; kx < nx; ++kx) t = __fadd_rn(t, __fmul_rn(vbuf[wib][kx], wx[kx]));
+                t = fminf(fmaxf(t, 0.0f), 255.0f);
+                dst[(size_t)f_img * pd.pyr_stride + pd.lv[f_lev].off + (size_t)f_oy * pd.lv[f_lev].w + f_ox] =
+                    (uint8_t)__float2uint_rz(roundf(t));
+            }
+            __syncwarp();
         }
-    }
-}
-
-// one warp per queued output: faithful recomputation
-__global__ void __launch_bounds__(128)
-pyr_fixup_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ PyrTaps taps,
-                 const uint8_t *__restrict__ src0, const uint8_t *__restrict__ src1,
-                 int split, size_t stride, size_t pitch, uint8_t *__restrict__ dst, const FixItem *__restrict__ fix,
-                 const int *__restrict__ fix_count, int fix_cap) {
-    __shared__ float vbuf[4][2 * 64 + 8];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int n = min(*fix_count, fix_cap);
-    for (int it = blockIdx.x * 4 + wib; it < n; it += gridDim.x * 4) {
-        const FixItem f = fix[it];
-        const uint8_t *__restrict__ src = image_ptr(src0, src1, split, f.img, pitch);
-        const TapTable tx = taps.x[f.lev], ty = taps.y[f.lev];
-        const int left = tx.left[f.ox], nx = tx.cnt[f.ox];
-        const int top = ty.left[f.oy], ny = ty.cnt[f.oy];
-        const float *__restrict__ wy = ty.w + (size_t)f.oy * ty.kmax;
-        for (int kx = lane; kx < nx; kx += 32) {  // vertical chains, one column per lane
-            const uint8_t *__restrict__ p = src + (size_t)top * stride + (left + kx);
-            float v = 0.0f;
-            for (int ky = 0; ky < ny; ++ky) v = __fadd_rn(v, __fmul_rn((float)__ldg(p + (size_t)ky * stride), wy[ky]));
-            vbuf[wib][kx] = v;
-        }
-        __syncwarp();
-        if (lane == 0) {  // horizontal chain in tap order
-            const float *__restrict__ wx = tx.w + (size_t)f.ox * tx.kmax;
-            float t = 0.0f;
-            for (int kx = 0; kx < nx; ++kx) t = __fadd_rn(t, __fmul_rn(vbuf[wib][kx], wx[kx]));
-            t = fminf(fmaxf(t, 0.0f), 255.0f);
-            dst[(size_t)f.img * pd.pyr_stride + pd.lv[f.lev].off + (size_t)f.oy * pd.lv[f.lev].w + f.ox] =
-                (uint8_t)__float2uint_rz(roundf(t));
-        }
-        __syncwarp();
     }
 }
 
@@ -1356,9 +1353,6 @@ struct PyrPlan {
     // scratch for deep levels (grown on demand)
     uint32_t *d_g8;
     size_t g8_images;
-    FixItem *d_fix;
-    int *d_fix_count;
-    int fix_cap;
 };
 
 // tiles covering the output rectangle [x0, x0 + nx) x [y0, y0 + ny) of one level
@@ -1414,9 +1408,6 @@ cudaError_t pyr_plan_create(int w, int h, int levels, cudaStream_t st, PyrPlan *
     p->d_tiles = nullptr;
     p->d_g8 = nullptr;
     p->g8_images = 0;
-    p->d_fix = nullptr;
-    p->d_fix_count = nullptr;
-    p->fix_cap = 0;
     // one allocation for all tap tables
     size_t bytes = 0;
     struct Sz { int n_in, n_out, kmax; size_t off_left, off_cnt, off_w; };
@@ -1574,8 +1565,6 @@ void pyr_plan_destroy(PyrPlan *p) {
     if (p->d_tile_counter) cudaFree(p->d_tile_counter);
     if (p->d_tiles) cudaFree(p->d_tiles);
     if (p->d_g8) cudaFree(p->d_g8);
-    if (p->d_fix) cudaFree(p->d_fix);
-    if (p->d_fix_count) cudaFree(p->d_fix_count);
     delete p;
 }
 
@@ -1584,19 +1573,10 @@ const PyrDesc &pyr_plan_desc(const PyrPlan *p) { return p->pd; }
 cudaError_t pyr_plan_reserve(PyrPlan *p, int n_images) {
     if (!p->do4 || (size_t)n_images <= p->g8_images) return cudaSuccess;
     if (p->d_g8) cudaFree(p->d_g8);
-    if (p->d_fix) cudaFree(p->d_fix);
     p->d_g8 = nullptr;
-    p->d_fix = nullptr;
     const size_t per = (size_t)(p->pd.lv[0].w / 8) * (p->pd.lv[0].h / 8);
     cudaError_t e = cudaMalloc((void **)&p->d_g8, per * n_images * sizeof(uint32_t));
     if (e != cudaSuccess) return e;
-    p->fix_cap = 4096 + (int)((size_t)n_images * (size_t)p->pd.lv[4].w * p->pd.lv[4].h / 64);
-    e = cudaMalloc((void **)&p->d_fix, sizeof(FixItem) * (size_t)p->fix_cap);
-    if (e != cudaSuccess) return e;
-    if (!p->d_fix_count) {
-        e = cudaMalloc((void **)&p->d_fix_count, sizeof(int));
-        if (e != cudaSuccess) return e;
-    }
     p->g8_images = (size_t)n_images;
     return cudaSuccess;
 }
@@ -1721,18 +1701,14 @@ cudaError_t pyr_build(const PyrPlan *p, const uint8_t *src0, const uint8_t *src1
         if (n_launches) ++*n_launches;
         }
         if (p->do4) {
-            cudaError_t e = cudaMemsetAsync(p->d_fix_count, 0, sizeof(int), st);
-            if (e != cudaSuccess) return e;
             const long long items = (long long)n * ((long long)p->pd.lv[4].w * p->pd.lv[4].h +
                                                     (p->do5 ? (long long)p->pd.lv[5].w * p->pd.lv[5].h : 0));
-            long long blocks = (items + 255) / 256;
+            long long blocks = (items + kDeepThreads - 1) / kDeepThreads;
             if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
             if (blocks < 1) blocks = 1;
-            pyr_deep_kernel<<<(unsigned)blocks, 256, 0, st>>>(p->pd, p->d_g8, n, p->do5, d, p->d_fix, p->d_fix_count,
-                                                               p->fix_cap);
-            pyr_fixup_kernel<<<kNumSMs, 128, 0, st>>>(p->pd, p->taps, s0, s1, sps, stride, pitch, d, p->d_fix,
-                                                      p->d_fix_count, p->fix_cap);
-            if (n_launches) *n_launches += 2;
+            pyr_deep_kernel<<<(unsigned)blocks, kDeepThreads, 0, st>>>(p->pd, p->taps, p->d_g8, n, p->do5, s0, s1, sps,
+                                                                        stride, pitch, d);
+            if (n_launches) ++*n_launches;
         }
         if (p->n_rest > 0) {  // ring of the dyadic levels + whole non-dyadic levels
             dim3 ggrid((unsigned)p->n_rest, (unsigned)n, 1);
