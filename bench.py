@@ -194,6 +194,28 @@ def workload_config(args, S, n_gpus):
 
 
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-GPU runs: keep this rank's threads -- and with them the first-touch pages of the pinned frame ring --
+    on the CPUs NVML reports as local to its GPU, so that the uploads do not cross the socket interconnect.
+    Returns the number of CPUs bound to, or None when NVML has no answer."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
+        hdl = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(hdl, words)
+        cpus = {64 * i + b for i, wd in enumerate(mask) for b in range(64) if (wd >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -230,6 +252,7 @@ def main():
     args.streams_per_gpu = S
     p = CONFIGS[args.config]
     w, h = p["w"], p["h"]
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     cores = os.cpu_count() or 1
     # synthetic frames first (fork pool, before CUDA is initialised); distinct seeds per rank and stream
     t_gen = time.perf_counter()
@@ -478,6 +501,7 @@ def main():
             "single_stream_latency": single,
             "clocks": clocks,
             "datagen_s": t_gen,
+            "numa_bound_cpus": numa,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
