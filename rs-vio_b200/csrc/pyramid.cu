@@ -193,7 +193,7 @@ pyr_generic_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ P
 // ------------------------------------------------------------------------------------------
 // fast dyadic kernel: levels 0..NA (NA <= 3) from one shared-memory tile
 // ------------------------------------------------------------------------------------------
-constexpr int TW = 256, TH = 64;          // base-image tile owned by one CTA
+constexpr int TW = 256, TH = 64;          // base-image tile owned by one CTA (TH = 32 with NSEG = 2 measured the same on C1, slower with NA = 3)
 constexpr int PITCH = TW + 32;            // tile columns [X0 - 16, X0 + TW + 16), bytes per smem row
 constexpr int NCOL = TW / 8;              // stage-1 column threads: 4 level-1 columns (8 px) each = one warp
 constexpr int NSEG = 4;                   // stage-1 row segments = warps per CTA
@@ -407,19 +407,20 @@ __device__ __forceinline__ void ring_rows_horizontal(const FastParams &P, const 
     const int wl = P.pd.lv[LEV].w, hl = P.pd.lv[LEV].h;
     const int oy = side == 0 ? 0 : hl - 1;
     if (oy * r < rt.Y0 || oy * r >= rt.Y0 + TH) return;
-    if (t >= TW / r) return;
-    const int ox = rt.X0 / r + t;
-    if (ox >= wl) return;
-    float acc = 0.0f;
-    if (ox > 0 && ox < wl - 1) {
-        const float *__restrict__ v = vrow + (ox * r - (r >> 1) - rt.X0 + 16);
+    for (; t < TW / r; t += NTA) {
+        const int ox = rt.X0 / r + t;
+        if (ox >= wl) return;
+        float acc = 0.0f;
+        if (ox > 0 && ox < wl - 1) {
+            const float *__restrict__ v = vrow + (ox * r - (r >> 1) - rt.X0 + 16);
 #pragma unroll
-        for (int k = 0; k < CIN; ++k) acc = __fadd_rn(acc, __fmul_rn(v[k], P.ring[LEV].inner[k]));
-    } else {
-        const RingTap tx = ring_tap(P.ring[LEV], ox, wl, r);
-        for (int k = 0; k < tx.cnt; ++k) acc = __fadd_rn(acc, __fmul_rn(vrow[tx.left + k - rt.X0 + 16], tx.w[k]));
+            for (int k = 0; k < CIN; ++k) acc = __fadd_rn(acc, __fmul_rn(v[k], P.ring[LEV].inner[k]));
+        } else {
+            const RingTap tx = ring_tap(P.ring[LEV], ox, wl, r);
+            for (int k = 0; k < tx.cnt; ++k) acc = __fadd_rn(acc, __fmul_rn(vrow[tx.left + k - rt.X0 + 16], tx.w[k]));
+        }
+        out[P.pd.lv[LEV].off + (size_t)oy * wl + ox] = ring_round(acc);
     }
-    out[P.pd.lv[LEV].off + (size_t)oy * wl + ox] = ring_round(acc);
 }
 
 // border columns of level LEV: item = side * (TH / r) + row of the tile; interior rows only
@@ -585,11 +586,11 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
         }
         // border columns (ox = 0 for left tiles, ox = wl - 1 for right tiles) without the corner rows:
         // one thread per (level, side, row); a warp holds one level
-        static_assert(NTA == 128 && TH == 64, "ring column items are mapped to thread ranges");
+        static_assert(4 * NTA >= 7 * TH, "ring column items (TH + TH/2 + TH/4) are mapped to thread ranges");
         if (left || right) {
-            if (tid < 64) ring_cols<1>(P, rt, out, left, right, tid);
-            else if (tid < 96) { if (NA >= 2) ring_cols<2>(P, rt, out, left, right, tid - 64); }
-            else if (tid < 112) { if (NA >= 3) ring_cols<3>(P, rt, out, left, right, tid - 96); }
+            if (tid < TH) ring_cols<1>(P, rt, out, left, right, tid);
+            else if (tid < TH + TH / 2) { if (NA >= 2) ring_cols<2>(P, rt, out, left, right, tid - TH); }
+            else if (tid < TH + TH / 2 + TH / 4) { if (NA >= 3) ring_cols<3>(P, rt, out, left, right, tid - TH - TH / 2); }
         }
             __syncthreads();  // vbuf shares its bytes with g2, which stage 1 writes next
     }
