@@ -18,6 +18,7 @@
  *    T = [m11, m12, m13(tx), m21, m22, m23(ty)]; the third row is (0, 0, 1).
  *  - one handle == one CUDA device + one CUDA stream; a handle is not re-entrant, distinct
  *    handles may be driven from distinct threads (mirrors `&mut self`, feature_tracker.rs:116).
+ *    Every call runs on the handle's device and restores the calling thread's current device.
  *  - there is no CPU fallback: without a usable CUDA device every entry point fails with
  *    RSVIO_ERR_CUDA.
  */

@@ -21,6 +21,23 @@ namespace {
 
 constexpr int kSlots = 2;
 
+// Every entry point runs on the handle's (or the requested) device and leaves the caller's current device as
+// it found it.
+struct DeviceScope {
+    int prev = -1, cur = -1;
+    cudaError_t enter(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            cudaGetLastError();
+            prev = -1;
+        }
+        cur = dev;
+        return prev == dev ? cudaSuccess : cudaSetDevice(dev);
+    }
+    ~DeviceScope() {
+        if (prev >= 0 && prev != cur) cudaSetDevice(prev);
+    }
+};
+
 #define CU_TRY(t, expr)                                                                        \
     do {                                                                                       \
         cudaError_t e__ = (expr);                                                              \
@@ -111,7 +128,8 @@ cudaError_t dmalloc(T **p, size_t n) {
 
 void free_all(rsvio_tracker *t) {
     if (!t) return;
-    cudaSetDevice(t->cfg.device);
+    DeviceScope dev_scope;
+    dev_scope.enter(t->cfg.device);
     if (t->st) cudaStreamSynchronize(t->st);
     if (t->copy_st) cudaStreamSynchronize(t->copy_st);
     if (t->own_exp && t->exp_st) cudaStreamSynchronize(t->exp_st);
@@ -413,7 +431,8 @@ rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) 
         cudaGetLastError();
         return RSVIO_ERR_CUDA;
     }
-    if (cudaSetDevice(cfg->device) != cudaSuccess) return RSVIO_ERR_CUDA;
+    DeviceScope dev_scope;
+    if (dev_scope.enter(cfg->device) != cudaSuccess) return RSVIO_ERR_CUDA;
     rsvio_tracker *t = new (std::nothrow) rsvio_tracker();
     if (!t) return RSVIO_ERR_ALLOC;
     t->cfg = *cfg;
@@ -496,7 +515,8 @@ const char *rsvio_tracker_last_error(const rsvio_tracker *t) { return t ? t->err
 
 rsvio_status rsvio_tracker_reset(rsvio_tracker *t) {
     if (!t) return RSVIO_ERR_INVALID_ARG;
-    CU_TRY(t, cudaSetDevice(t->cfg.device));
+    DeviceScope dev_scope;
+    CU_TRY(t, dev_scope.enter(t->cfg.device));
     CU_TRY(t, cudaStreamSynchronize(t->copy_st));
     CU_TRY(t, cudaStreamSynchronize(t->st));
     return clear_state(t);
@@ -506,7 +526,8 @@ rsvio_status rsvio_tracker_submit_batch(rsvio_tracker *t, const uint8_t *const *
                                         size_t stride) {
     rsvio_status rs = check_batch_args(t, left, right, stride);
     if (rs != RSVIO_OK) return rs;
-    CU_TRY(t, cudaSetDevice(t->cfg.device));
+    DeviceScope dev_scope;
+    CU_TRY(t, dev_scope.enter(t->cfg.device));
     const int slot = t->next_slot;
     rs = upload(t, slot, left, right, stride);
     if (rs != RSVIO_OK) return rs;
@@ -525,7 +546,8 @@ rsvio_status rsvio_tracker_submit_device(rsvio_tracker *t, const void *d_left, c
     if (stride < (size_t)t->cfg.width || pitch < stride * (size_t)(t->cfg.height - 1) + (size_t)t->cfg.width)
         return fail(t, RSVIO_ERR_INVALID_ARG, "stride/pitch too small");
     if (t->inflight >= kSlots) return fail(t, RSVIO_ERR_STATE, "two frames already in flight: call rsvio_tracker_sync");
-    CU_TRY(t, cudaSetDevice(t->cfg.device));
+    DeviceScope dev_scope;
+    CU_TRY(t, dev_scope.enter(t->cfg.device));
     const int slot = t->next_slot;
     t->up_valid[slot] = false;
     rsvio_status rs = enqueue_frame(t, slot, (const uint8_t *)d_left, (const uint8_t *)d_right, stride, pitch);
@@ -538,7 +560,8 @@ rsvio_status rsvio_tracker_submit_device(rsvio_tracker *t, const void *d_left, c
 rsvio_status rsvio_tracker_sync(rsvio_tracker *t) {
     if (!t) return RSVIO_ERR_INVALID_ARG;
     if (t->inflight <= 0) return fail(t, RSVIO_ERR_STATE, "nothing in flight");
-    CU_TRY(t, cudaSetDevice(t->cfg.device));
+    DeviceScope dev_scope;
+    CU_TRY(t, dev_scope.enter(t->cfg.device));
     const int slot = t->oldest_slot;
     CU_TRY(t, cudaEventSynchronize(t->ev_done[slot]));
     if (t->stage_valid[slot]) {
@@ -639,7 +662,8 @@ rsvio_status rsvio_tracker_get_transforms(rsvio_tracker *t, int32_t stream, int3
     rsvio_status rs = check_group(t, stream, cam);
     if (rs != RSVIO_OK) return rs;
     if (!n) return RSVIO_ERR_INVALID_ARG;
-    CU_TRY(t, cudaSetDevice(t->cfg.device));
+    DeviceScope dev_scope;
+    CU_TRY(t, dev_scope.enter(t->cfg.device));
     const int g = cam * t->S + stream;
     const TableView &tv = t->tab[t->tcur];
     int cnt = 0;
@@ -662,7 +686,8 @@ rsvio_status rsvio_tracker_remove_ids(rsvio_tracker *t, int32_t stream, const ui
     if (n == 0) return RSVIO_OK;
     if (!ids) return RSVIO_ERR_INVALID_ARG;
     if (t->inflight > 0) return fail(t, RSVIO_ERR_STATE, "frames in flight: call rsvio_tracker_sync before remove_ids");
-    CU_TRY(t, cudaSetDevice(t->cfg.device));
+    DeviceScope dev_scope;
+    CU_TRY(t, dev_scope.enter(t->cfg.device));
     if ((int)n > t->rm_cap) {
         cudaFree(t->d_rm);
         t->d_rm = nullptr;
@@ -701,7 +726,8 @@ rsvio_status rsvio_tracker_remove_ids(rsvio_tracker *t, int32_t stream, const ui
 
 rsvio_status rsvio_tracker_counters(rsvio_tracker *t, uint64_t out[6]) {
     if (!t || !out) return RSVIO_ERR_INVALID_ARG;
-    CU_TRY(t, cudaSetDevice(t->cfg.device));
+    DeviceScope dev_scope;
+    CU_TRY(t, dev_scope.enter(t->cfg.device));
     unsigned long long c[CNT_N];
     CU_TRY(t, cudaMemcpyAsync(c, t->d_counters, sizeof(c), cudaMemcpyDeviceToHost, t->st));
     CU_TRY(t, cudaStreamSynchronize(t->st));
@@ -767,10 +793,11 @@ rsvio_status rsvio_build_pyramid_u8_device(int32_t device, const void *d_images,
     if (!d_images || !d_out || !pyr_args_ok(n_images, width, height, stride, pitch, levels) || repeats < 1)
         return RSVIO_ERR_INVALID_ARG;
     rsvio_status rs = RSVIO_OK;
+    DeviceScope dev_scope;
     PyrPlan *plan = nullptr;
     cudaStream_t st = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    CU_TRY0(cudaSetDevice(device));
+    CU_TRY0(dev_scope.enter(device));
     CU_TRY0(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     CU_TRY0(pyr_plan_create(width, height, levels, st, &plan));
     CU_TRY0(pyr_plan_reserve(plan, n_images));
@@ -804,11 +831,12 @@ rsvio_status rsvio_build_pyramid_u8(int32_t device, const uint8_t *images, int32
                                     int32_t height, size_t stride, size_t pitch, int32_t levels, uint8_t *out) {
     if (!images || !out || !pyr_args_ok(n_images, width, height, stride, pitch, levels)) return RSVIO_ERR_INVALID_ARG;
     rsvio_status rs = RSVIO_OK;
+    DeviceScope dev_scope;
     const PyrDesc pd = make_pyr_desc(width, height, levels);
     const size_t dense = rsvio_pyramid_bytes(width, height, levels);
     uint8_t *d_in = nullptr, *d_out = nullptr;
     const size_t in_bytes = (size_t)(n_images - 1) * pitch + stride * (size_t)(height - 1) + (size_t)width;
-    CU_TRY0(cudaSetDevice(device));
+    CU_TRY0(dev_scope.enter(device));
     CU_TRY0(cudaMalloc((void **)&d_in, in_bytes));
     CU_TRY0(cudaMalloc((void **)&d_out, (size_t)n_images * pd.pyr_stride));
     CU_TRY0(cudaMemcpy(d_in, images, in_bytes, cudaMemcpyHostToDevice));
@@ -837,12 +865,13 @@ rsvio_status rsvio_track_points(int32_t device, const uint8_t *pyr_a, const uint
     if (n == 0) return RSVIO_OK;
     if (!in_T6 || !out_T6 || !status) return RSVIO_ERR_INVALID_ARG;
     rsvio_status rs = RSVIO_OK;
+    DeviceScope dev_scope;
     const PyrDesc pd = make_pyr_desc(width, height, levels);
     uint8_t *d_pyr = nullptr;
     float *d_in = nullptr, *d_out = nullptr;
     int32_t *d_status = nullptr, *d_iters = nullptr;
     int *d_count = nullptr;
-    CU_TRY0(cudaSetDevice(device));
+    CU_TRY0(dev_scope.enter(device));
     CU_TRY0(cudaMalloc((void **)&d_pyr, 2 * (size_t)pd.pyr_stride));
     {
         size_t o = 0;
@@ -898,6 +927,7 @@ rsvio_status rsvio_detect_keypoints(int32_t device, const uint8_t *image, int32_
         grid_size < 7 || grid_size > 1024 || n_cur < 0 || (n_cur > 0 && !cur_xy))
         return RSVIO_ERR_INVALID_ARG;
     rsvio_status rs = RSVIO_OK;
+    DeviceScope dev_scope;
     const GridDesc gd = make_grid_desc(width, height, grid_size);
     const int cells = gd.ncx * gd.ncy;
     *n = 0;
@@ -909,7 +939,7 @@ rsvio_status rsvio_detect_keypoints(int32_t device, const uint8_t *image, int32_
     uint32_t *d_list = nullptr;
     int cnt = 0;
     std::vector<float> hT, hs;
-    CU_TRY0(cudaSetDevice(device));
+    CU_TRY0(dev_scope.enter(device));
     CU_TRY0(cudaMalloc((void **)&d_img, (size_t)width * height));
     CU_TRY0(cudaMemcpy2D(d_img, (size_t)width, image, stride, (size_t)width, (size_t)height, cudaMemcpyHostToDevice));
     CU_TRY0(cudaMalloc((void **)&d_occ, (size_t)gd.occ_rows * gd.occ_cols));
@@ -969,8 +999,9 @@ rsvio_status rsvio_se2_exp(int32_t device, const float *twists, int32_t n, float
     if (n < 0 || (n > 0 && (!twists || !out9))) return RSVIO_ERR_INVALID_ARG;
     if (n == 0) return RSVIO_OK;
     rsvio_status rs = RSVIO_OK;
+    DeviceScope dev_scope;
     float *d_in = nullptr, *d_out = nullptr;
-    CU_TRY0(cudaSetDevice(device));
+    CU_TRY0(dev_scope.enter(device));
     CU_TRY0(cudaMalloc((void **)&d_in, sizeof(float) * 3 * n));
     CU_TRY0(cudaMalloc((void **)&d_out, sizeof(float) * 9 * n));
     CU_TRY0(cudaMemcpy(d_in, twists, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));

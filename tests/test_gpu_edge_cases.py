@@ -140,3 +140,22 @@ def test_many_small_streams_in_one_batch(rsvio):
     ib, Tb = batch.transforms(0, 4)
     i1, T1 = single.transforms(0)
     assert np.array_equal(ib, i1) and np.array_equal(Tb, T1)
+
+
+def test_calls_leave_the_current_device_alone(rsvio):
+    """a handle on device 0 driven from a thread whose current device is another one (needs >= 2 GPUs;
+    on a 1-GPU box this only checks that the guard is a no-op)"""
+    import torch
+    from rsvio_b200.synth import StereoSequence
+    n = torch.cuda.device_count()
+    other = 1 if n > 1 else 0
+    seq = StereoSequence("C1", w=256, h=160)
+    tr = rsvio.StereoPatchTracker(40, 20, 0.01, width=256, height=160, levels=3, device=0)
+    torch.cuda.set_device(other)
+    for t in range(2):
+        tr.process_frame(*seq.frame(t))
+        assert torch.cuda.current_device() == other
+    assert tr.num_tracks(0) > 0
+    pyr = rsvio.build_pyramid(seq.frame(0)[0], 3, device=0)
+    assert pyr.shape[0] == 1 and torch.cuda.current_device() == other
+    torch.cuda.set_device(0)
