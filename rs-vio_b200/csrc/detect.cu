@@ -38,30 +38,35 @@ __device__ __forceinline__ int min9_max16(const int (&b)[16]) {
     return best;
 }
 
-// largest threshold at which (x, y) is a FAST-9 corner, < 10 if it is not one at threshold 10.
+// quick reject at the lowest threshold used (10): a 9-arc always holds two adjacent compass points, so a
+// corner needs two adjacent compass points both brighter than c + 10 or both darker than c - 10.
 // p points at the pixel, s is the row stride.
-__device__ __forceinline__ int fast9_score(const uint8_t *__restrict__ p, int s) {
+__device__ __forceinline__ bool fast9_compass(const uint8_t *__restrict__ p, int s) {
     const int c = __ldg(p);
     const int p0 = __ldg(p - 3 * s), p4 = __ldg(p + 3), p8 = __ldg(p + 3 * s), p12 = __ldg(p - 3);
-    // quick reject at the lowest threshold used (10): two adjacent compass points must agree
     const int hi = c + 10, lo = c - 10;
     const bool above = (p0 > hi && p4 > hi) || (p4 > hi && p8 > hi) || (p8 > hi && p12 > hi) || (p12 > hi && p0 > hi);
     const bool below = (p0 < lo && p4 < lo) || (p4 < lo && p8 < lo) || (p8 < lo && p12 < lo) || (p12 < lo && p0 < lo);
-    if (!above && !below) return -1;
+    return above || below;
+}
+
+// largest threshold at which (x, y) is a FAST-9 corner, < 10 if it is not one at threshold 10
+__device__ __forceinline__ int fast9_score_full(const uint8_t *__restrict__ p, int s) {
+    const int c = __ldg(p);
     int b[16];
-    b[0] = p0;
+    b[0] = __ldg(p - 3 * s);
     b[1] = __ldg(p - 3 * s + 1);
     b[2] = __ldg(p - 2 * s + 2);
     b[3] = __ldg(p - s + 3);
-    b[4] = p4;
+    b[4] = __ldg(p + 3);
     b[5] = __ldg(p + s + 3);
     b[6] = __ldg(p + 2 * s + 2);
     b[7] = __ldg(p + 3 * s + 1);
-    b[8] = p8;
+    b[8] = __ldg(p + 3 * s);
     b[9] = __ldg(p + 3 * s - 1);
     b[10] = __ldg(p + 2 * s - 2);
     b[11] = __ldg(p + s - 3);
-    b[12] = p12;
+    b[12] = __ldg(p - 3);
     b[13] = __ldg(p - s - 3);
     b[14] = __ldg(p - 2 * s - 2);
     b[15] = __ldg(p - 3 * s - 1);
@@ -101,11 +106,14 @@ list_empty_cells_kernel(GridDesc gd, int streams, const uint8_t *__restrict__ oc
 
 // One CTA per empty cell: the (g-6)^2 candidates are spread over 128 threads, block-wide packed-key max.
 constexpr int kDetThreads = 128;
+constexpr int kDetChunk = 2048;  // candidates per compaction pass (a 40-px cell has 1156)
 __global__ void __launch_bounds__(kDetThreads)
 detect_list_kernel(GridDesc gd, const uint8_t *__restrict__ img0, size_t stride, size_t pitch,
                    const uint32_t *__restrict__ list, const int *__restrict__ list_count,
                    uint32_t *__restrict__ cell_pt, float *__restrict__ cell_score) {
     __shared__ uint32_t wbest[kDetThreads / 32];
+    __shared__ uint32_t surv[kDetChunk];
+    __shared__ int n_surv;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int cells = gd.ncx * gd.ncy;
     const int g = (int)gd.g;
@@ -118,16 +126,47 @@ detect_list_kernel(GridDesc gd, const uint8_t *__restrict__ img0, size_t stride,
         const int x0 = (int)gd.x_start + cx * g, y0 = (int)gd.y_start + cy * g;
         const uint8_t *__restrict__ base = img0 + (size_t)s * pitch;
         uint32_t best = 0;
-        for (int idx = threadIdx.x; idx < side * side; idx += kDetThreads) {
-            const int ly = idx / side + 3, lx = idx - (idx / side) * side + 3;
-            const int gx = x0 + lx, gy = y0 + ly;
-            // point_in_bound(.., 19): inclusive upper bound (image_utilities.rs:68-73)
-            if (gx < kEdge || gy < kEdge || gx > gd.w - kEdge || gy > gd.h - kEdge) continue;
-            const int sc = fast9_score(base + (size_t)gy * stride + gx, (int)stride);
-            if (sc < 10) continue;
-            const uint32_t cls = (uint32_t)(min(sc, 40) / 5);        // 2..8
-            const uint32_t raster = (uint32_t)(ly * g + lx);        // order inside the cell copy
-            best = max(best, (cls << 28) | ((uint32_t)(255 - sc) << 20) | (0xFFFFFu - raster));
+        // two passes per chunk of candidates: the cheap compass test compacts the survivors into a list, then the
+        // 16-pixel score runs on full warps of survivors (a third of the pixels pass; testing and scoring in one
+        // loop made every warp pay the full score in every round)
+        for (int c0 = 0; c0 < side * side; c0 += kDetChunk) {
+            if (threadIdx.x == 0) n_surv = 0;
+            __syncthreads();
+            const int c1 = min(c0 + kDetChunk, side * side);
+            // tests first (independent loads of several candidates in flight), compaction afterwards
+            uint32_t passbits = 0;
+            static_assert(kDetChunk / kDetThreads <= 32, "one pass bit per candidate of a thread");
+#pragma unroll 4
+            for (int j = 0; j < kDetChunk / kDetThreads; ++j) {
+                const int idx = c0 + j * kDetThreads + (int)threadIdx.x;
+                if (idx < c1) {
+                    const int ly = idx / side + 3, lx = idx - (idx / side) * side + 3;
+                    const int gx = x0 + lx, gy = y0 + ly;
+                    // point_in_bound(.., 19): inclusive upper bound (image_utilities.rs:68-73)
+                    if (!(gx < kEdge || gy < kEdge || gx > gd.w - kEdge || gy > gd.h - kEdge) &&
+                        fast9_compass(base + (size_t)gy * stride + gx, (int)stride))
+                        passbits |= 1u << j;
+                }
+            }
+            for (int j = 0; c0 + j * kDetThreads < c1; ++j) {
+                const bool pass = (passbits >> j) & 1u;
+                const unsigned m = __ballot_sync(0xffffffffu, pass);
+                int at = 0;
+                if (lane == 0 && m) at = atomicAdd(&n_surv, __popc(m));
+                at = __shfl_sync(0xffffffffu, at, 0);
+                if (pass) surv[at + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(c0 + j * kDetThreads + (int)threadIdx.x);
+            }
+            __syncthreads();
+            for (int k = threadIdx.x; k < n_surv; k += kDetThreads) {
+                const int idx = (int)surv[k];
+                const int ly = idx / side + 3, lx = idx - (idx / side) * side + 3;
+                const int sc = fast9_score_full(base + (size_t)(y0 + ly) * stride + (x0 + lx), (int)stride);
+                if (sc < 10) continue;
+                const uint32_t cls = (uint32_t)(min(sc, 40) / 5);        // 2..8
+                const uint32_t raster = (uint32_t)(ly * g + lx);        // order inside the cell copy
+                best = max(best, (cls << 28) | ((uint32_t)(255 - sc) << 20) | (0xFFFFFu - raster));
+            }
+            __syncthreads();
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
@@ -210,7 +249,9 @@ cudaError_t detect_cells(const GridDesc &gd, const uint8_t *img0, size_t stride,
     int *cnt = list_count + (parity & 1), *other = list_count + ((parity & 1) ^ 1);
     list_empty_cells_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gd, streams, occ, cell_pt, cell_score, list,
                                                                              cnt, other);
-    long long blocks = total < (long long)kNumSMs * 8 ? total : (long long)kNumSMs * 8;
+    // one CTA per cell that could be empty (the hardware scheduler balances them; CTAs beyond the list length
+    // exit at once), capped for very large grids, where CTAs loop
+    long long blocks = total < (long long)kNumSMs * 128 ? total : (long long)kNumSMs * 128;
     detect_list_kernel<<<(unsigned)blocks, kDetThreads, 0, st>>>(gd, img0, stride, pitch, list, cnt, cell_pt,
                                                                  cell_score);
     return cudaGetLastError();
