@@ -51,4 +51,45 @@ extern "C" {
     pub fn rsvio_tracker_result_view(t: *mut rsvio_tracker, records: *mut *const rsvio_track_record, counts: *mut *const i32,
                                      groups: *mut i32, capacity: *mut i32) -> rsvio_status;
     pub fn rsvio_tracker_remove_ids(t: *mut rsvio_tracker, stream: i32, ids: *const u64, n: usize) -> rsvio_status;
+
+    // ---- batched / asynchronous forms (n_streams > 1; at most two frames in flight) ----
+    pub fn rsvio_device_count(n: *mut i32) -> rsvio_status;
+    pub fn rsvio_tracker_process_batch(t: *mut rsvio_tracker, left: *const *const u8, right: *const *const u8,
+                                       stride: usize) -> rsvio_status;
+    pub fn rsvio_tracker_submit_batch(t: *mut rsvio_tracker, left: *const *const u8, right: *const *const u8,
+                                      stride: usize) -> rsvio_status;
+    pub fn rsvio_tracker_submit_device(t: *mut rsvio_tracker, d_left: *const c_void, d_right: *const c_void,
+                                       stride: usize, pitch: usize) -> rsvio_status;
+    pub fn rsvio_tracker_sync(t: *mut rsvio_tracker) -> rsvio_status;
+
+    // ---- copies of the track tables ----
+    pub fn rsvio_tracker_num_tracks(t: *mut rsvio_tracker, stream: i32, cam: i32, n: *mut i32) -> rsvio_status;
+    pub fn rsvio_tracker_get_tracks(t: *mut rsvio_tracker, stream: i32, cam: i32, ids: *mut u64, xy: *mut f32,
+                                    cap: usize, n: *mut usize) -> rsvio_status;
+    pub fn rsvio_tracker_get_transforms(t: *mut rsvio_tracker, stream: i32, cam: i32, ids: *mut u64, t6: *mut f32,
+                                        cap: usize, n: *mut usize) -> rsvio_status;
+
+    // ---- counters and per-stage device times ----
+    pub fn rsvio_tracker_counters(t: *mut rsvio_tracker, out: *mut u64) -> rsvio_status; // out[6]
+    pub fn rsvio_tracker_set_profiling(t: *mut rsvio_tracker, enabled: i32) -> rsvio_status;
+    pub fn rsvio_tracker_stage_times(t: *mut rsvio_tracker, ms: *mut f32, launches: *mut u64, reset: i32)
+        -> rsvio_status; // ms[RSVIO_N_STAGES], launches[RSVIO_N_STAGES]
+
+    // ---- stateless entry points (parity tests, kernel benchmarks) ----
+    pub fn rsvio_pyramid_bytes(width: i32, height: i32, levels: i32) -> usize;
+    pub fn rsvio_pyramid_device_bytes(width: i32, height: i32, levels: i32) -> usize;
+    pub fn rsvio_build_pyramid_u8(device: i32, images: *const u8, n_images: i32, width: i32, height: i32,
+                                  stride: usize, pitch: usize, levels: i32, out: *mut u8) -> rsvio_status;
+    pub fn rsvio_build_pyramid_u8_device(device: i32, d_images: *const c_void, n_images: i32, width: i32, height: i32,
+                                         stride: usize, pitch: usize, levels: i32, d_out: *mut c_void, repeats: i32,
+                                         kernel_ms: *mut f32) -> rsvio_status;
+    pub fn rsvio_track_points(device: i32, pyr_a: *const u8, pyr_b: *const u8, width: i32, height: i32, levels: i32,
+                              n: i32, in_t6: *const f32, max_iterations: i32, convergence_threshold: f32,
+                              out_t6: *mut f32, status: *mut i32, iters: *mut i32) -> rsvio_status;
+    pub fn rsvio_detect_keypoints(device: i32, image: *const u8, width: i32, height: i32, stride: usize,
+                                  grid_size: u32, cur_xy: *const u32, n_cur: i32, out_xy: *mut u32,
+                                  out_score: *mut f32, cap: usize, n: *mut usize) -> rsvio_status;
+    pub fn rsvio_se2_exp(device: i32, twists: *const f32, n: i32, out9: *mut f32) -> rsvio_status;
 }
+
+pub const RSVIO_N_STAGES: usize = 8;
