@@ -61,3 +61,15 @@ def test_no_cpu_fallback_without_gpu(rsvio):
     import numpy as np
     with pytest.raises(rsvio.RsvioError):
         rsvio.build_pyramid(np.zeros((64, 64), np.uint8), 3)
+
+
+def test_rust_ffi_declares_every_header_symbol():
+    """the Rust crate cannot be compiled here (no cargo); at least its raw bindings must name every entry point
+    of include/rsvio_b200.h and nothing else"""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "rsvio_b200.h")).read()
+    ffi = open(os.path.join(root, "rs-vio_b200", "rust", "feature_tracker", "src", "ffi.rs")).read()
+    in_header = set(_declared_functions())
+    in_ffi = set(re.findall(r"pub fn (rsvio_[a-z0-9_]+)", ffi))
+    assert in_header == in_ffi, (sorted(in_header - in_ffi), sorted(in_ffi - in_header))
