@@ -159,3 +159,42 @@ def test_calls_leave_the_current_device_alone(rsvio):
     pyr = rsvio.build_pyramid(seq.frame(0)[0], 3, device=0)
     assert pyr.shape[0] == 1 and torch.cuda.current_device() == other
     torch.cuda.set_device(0)
+
+
+def test_two_handles_driven_from_two_threads(rsvio):
+    """distinct handles are independent (own stream, own tables, no global mutable state): two threads that
+    drive one handle each get the results of a single-threaded run (ctypes releases the GIL during the calls)"""
+    import threading
+    from rsvio_b200.synth import StereoSequence
+    w, h, frames = 256, 160, 5
+    seqs = [StereoSequence("C5", stream_id=s, w=w, h=h) for s in range(2)]
+    data = [[q.frame(t) for t in range(frames)] for q in seqs]
+    want = []
+    for s in range(2):
+        tr = rsvio.StereoPatchTracker(40, 20, 0.01, width=w, height=h, levels=3)
+        for l, r in data[s]:
+            tr.process_frame(l, r)
+        want.append([tr.transforms(c) for c in (0, 1)])
+    got, errors = [None, None], []
+
+    def work(s):
+        try:
+            tr = rsvio.StereoPatchTracker(40, 20, 0.01, width=w, height=h, levels=3)
+            for _ in range(3):                       # several passes: more chances to interleave
+                tr.reset()
+                for l, r in data[s]:
+                    tr.process_frame(l, r)
+            got[s] = [tr.transforms(c) for c in (0, 1)]
+        except Exception as e:                       # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(s,)) for s in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for s in range(2):
+        for cam in (0, 1):
+            assert np.array_equal(got[s][cam][0], want[s][cam][0])
+            assert np.array_equal(got[s][cam][1], want[s][cam][1])
