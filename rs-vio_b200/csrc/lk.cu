@@ -325,6 +325,7 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
 
         // ---- track_point_at_level (feature_tracker.rs:344-395) ----------------------------
         const float wlim = (float)((uint32_t)ib.w - 2u), hlim = (float)((uint32_t)ib.h - 2u);
+        const float thr2 = thr * thr;
         // the level base and row pitch stay in registers across the iterations (opaque to rematerialisation)
         const uint8_t *ibp = ib.p;
         uint32_t ibw = (uint32_t)ib.w;
@@ -378,9 +379,11 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
             inc[1] = i1;
             inc[2] = i2;
             if (!finite3(inc)) return RSVIO_FAIL_NONFINITE;
-            const float norm = sqrtf(inc[0] * inc[0] + inc[1] * inc[1] + inc[2] * inc[2]);
-            if (norm > 1e6f) return RSVIO_FAIL_DIVERGED;
-            if (norm < thr) break;  // converged: increment not applied (feature_tracker.rs:374-376)
+            // |inc| > 1e6 and |inc| < thr (feature_tracker.rs:369-376) on the squared norm: no square root on the
+            // per-iteration path; the two forms can only disagree within an ulp of the threshold itself
+            const float norm2 = inc[0] * inc[0] + inc[1] * inc[1] + inc[2] * inc[2];
+            if (norm2 > 1e12f) return RSVIO_FAIL_DIVERGED;
+            if (norm2 < thr2) break;  // converged: increment not applied (feature_tracker.rs:374-376)
             float E[6], N[6];
             se2_exp(inc, E);
             N[0] = T1[0] * E[0] + T1[1] * E[3];
