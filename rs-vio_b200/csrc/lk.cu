@@ -258,8 +258,10 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
             image_grad(ia, x, y, ok, v, gx, gy);
             if (ok) {
                 d[k] = v;
-                J[k][0] = gx * 1.0f + gy * 0.0f;
-                J[k][1] = gx * 0.0f + gy * 1.0f;
+                // grad^T [[1, 0, -o_y], [0, 1, o_x]] (patch.rs:100-101); the products with 1 and 0 of the first two
+                // columns are exact for finite gradients and are not spelled out
+                J[k][0] = gx;
+                J[k][1] = gy;
                 J[k][2] = gx * (-o.y) + gy * o.x;
                 sum += v;
                 g0 += J[k][0];
@@ -324,7 +326,9 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
         if (!valid) return RSVIO_FAIL_TEMPLATE;
 
         // ---- track_point_at_level (feature_tracker.rs:344-395) ----------------------------
-        const float wlim = (float)((uint32_t)ib.w - 2u), hlim = (float)((uint32_t)ib.h - 2u);
+        float wlim = (float)((uint32_t)ib.w - 2u), hlim = (float)((uint32_t)ib.h - 2u);
+        asm volatile("mov.b32 %0, %0;" : "+f"(wlim));  // kept in registers across the iterations, as the base and pitch below
+        asm volatile("mov.b32 %0, %0;" : "+f"(hlim));
         const float thr2 = thr * thr;
         // the level base and row pitch stay in registers across the iterations (opaque to rematerialisation)
         const uint8_t *ibp = ib.p;
