@@ -273,12 +273,12 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
         }
         ++n_templates;
         warp_sum4(sum, g0, g1, g2, lane);
-        const float mean = sum / (float)n_valid;
         const float mean_inv = (float)n_valid / sum;
         const float inv_sum = __frcp_rn(sum);
         float h00 = 0.f, h01 = 0.f, h02 = 0.f, h11 = 0.f, h12 = 0.f, h22 = 0.f;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
+            const bool first = k == 0;  // every lane holds sample 0: its products start the sums (no 0 + x)
             if (d[k] >= 0.0f) {
                 J[k][0] += -(g0 * d[k] * inv_sum);
                 J[k][1] += -(g1 * d[k] * inv_sum);
@@ -290,7 +290,14 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
             J[k][0] *= mean_inv;
             J[k][1] *= mean_inv;
             J[k][2] *= mean_inv;
-            if (ln.has[k]) {
+            if (first) {
+                h00 = J[k][0] * J[k][0];
+                h01 = J[k][0] * J[k][1];
+                h02 = J[k][0] * J[k][2];
+                h11 = J[k][1] * J[k][1];
+                h12 = J[k][1] * J[k][2];
+                h22 = J[k][2] * J[k][2];
+            } else if (ln.has[k]) {
                 h00 += J[k][0] * J[k][0];
                 h01 += J[k][0] * J[k][1];
                 h02 += J[k][0] * J[k][2];
@@ -322,7 +329,9 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
             }
             fin = fin && (!ln.has[k] || isfinite(d[k]));
         }
-        valid = valid && (mean > kEps) && __all_sync(0xffffffffu, fin);
+        // mean = sum / n > EPSILON (patch.rs:146,156) without the division: n = 0 gives 0 > 0, invalid as the
+        // reference's NaN > EPSILON; the two forms differ only for a patch mean within an ulp of 1.2e-7 grey levels
+        valid = valid && (sum > kEps * (float)n_valid) && __all_sync(0xffffffffu, fin);
         if (!valid) return RSVIO_FAIL_TEMPLATE;
 
         // ---- track_point_at_level (feature_tracker.rs:344-395) ----------------------------
@@ -358,7 +367,7 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
                 const float p01 = (float)__ldg(q1), p11 = (float)__ldg(q1 + 1);
                 const float val = ddx * ddy * p00 + ddx * dy * p01 + dx * ddy * p10 + dx * dy * p11;
                 r[k] = ok ? val : -1.0f;
-                rsum += ok ? val : 0.0f;
+                rsum = k == 0 ? (ok ? val : 0.0f) : rsum + (ok ? val : 0.0f);
                 cmask[k] = __ballot_sync(0xffffffffu, ok);
                 nv += __popc(cmask[k]);
             }
@@ -372,9 +381,9 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
             for (int k = 0; k < 2; ++k) {
                 const bool both = r[k] >= 0.0f && d[k] >= 0.0f;
                 const float res = both ? (float)nv * r[k] * inv_rsum - d[k] : 0.0f;
-                i0 += (-M[k][0]) * res;
-                i1 += (-M[k][1]) * res;
-                i2 += (-M[k][2]) * res;
+                i0 = k == 0 ? (-M[k][0]) * res : i0 + (-M[k][0]) * res;
+                i1 = k == 0 ? (-M[k][1]) * res : i1 + (-M[k][1]) * res;
+                i2 = k == 0 ? (-M[k][2]) * res : i2 + (-M[k][2]) * res;
             }
             if (nres <= kPattern / 2) return RSVIO_FAIL_RESIDUAL;
             float inc[3], i3 = 0.0f;
