@@ -118,7 +118,9 @@ rsvio_status rsvio_tracker_submit_batch(rsvio_tracker *t, const uint8_t *const *
                                         const uint8_t *const *right, size_t stride);
 rsvio_status rsvio_tracker_sync(rsvio_tracker *t);
 /* inputs already resident in HBM: n_streams images back to back, `pitch` bytes apart,
- * `stride` bytes between rows.  Asynchronous on the handle's stream; rsvio_tracker_sync waits. */
+ * `stride` bytes between rows.  Asynchronous; rsvio_tracker_sync waits.  The images must be complete
+ * in device memory when the call is made and stay untouched until the frame has been synced: on
+ * batched handles the pyramid is built on an internal stream, beside the tail of the previous frame. */
 rsvio_status rsvio_tracker_submit_device(rsvio_tracker *t, const void *d_left, const void *d_right,
                                          size_t stride, size_t pitch);
 

@@ -53,6 +53,9 @@ struct rsvio_tracker {
     cudaStream_t st = nullptr, copy_st = nullptr;
     cudaStream_t exp_st = nullptr;  // record export + error flag: beside the next frame on big batches, else == st
     bool own_exp = false;
+    cudaStream_t pyr_st = nullptr;  // pyramid of frame t+1 beside detection / stereo LK / merge of frame t (big batches), else == st
+    bool own_pyr = false;
+    cudaEvent_t ev_lk_done = nullptr, ev_pyr[kSlots]{};
     bool own_stream = false;
     PyrPlan *plan = nullptr;
     PyrDesc pd{};
@@ -133,6 +136,7 @@ void free_all(rsvio_tracker *t) {
     if (t->st) cudaStreamSynchronize(t->st);
     if (t->copy_st) cudaStreamSynchronize(t->copy_st);
     if (t->own_exp && t->exp_st) cudaStreamSynchronize(t->exp_st);
+    if (t->own_pyr && t->pyr_st) cudaStreamSynchronize(t->pyr_st);
     pyr_plan_destroy(t->plan);
     for (int i = 0; i < kSlots; ++i) {
         cudaFree(t->d_in[i]);
@@ -143,6 +147,7 @@ void free_all(rsvio_tracker *t) {
         if (t->ev_in_free[i]) cudaEventDestroy(t->ev_in_free[i]);
         if (t->ev_done[i]) cudaEventDestroy(t->ev_done[i]);
         if (t->ev_merged[i]) cudaEventDestroy(t->ev_merged[i]);
+        if (t->ev_pyr[i]) cudaEventDestroy(t->ev_pyr[i]);
         for (int k = 0; k <= RSVIO_N_STAGES; ++k)
             if (t->ev_stage[i][k]) cudaEventDestroy(t->ev_stage[i][k]);
         for (int k = 0; k < 2; ++k)
@@ -172,6 +177,8 @@ void free_all(rsvio_tracker *t) {
     cudaFree(t->d_work);
     if (t->copy_st) cudaStreamDestroy(t->copy_st);
     if (t->own_exp && t->exp_st) cudaStreamDestroy(t->exp_st);
+    if (t->own_pyr && t->pyr_st) cudaStreamDestroy(t->pyr_st);
+    if (t->ev_lk_done) cudaEventDestroy(t->ev_lk_done);
     if (t->own_stream && t->st) cudaStreamDestroy(t->st);
     cudaGetLastError();
     delete t;
@@ -187,6 +194,7 @@ rsvio_status clear_state(rsvio_tracker *t) {
     CU_TRY(t, cudaMemsetAsync(t->d_cell_list_n, 0, sizeof(int) * 2, t->st));
     t->lk_par[0] = t->lk_par[1] = t->det_par = 0;
     if (t->own_exp) CU_TRY(t, cudaStreamSynchronize(t->exp_st));
+    if (t->own_pyr) CU_TRY(t, cudaStreamSynchronize(t->pyr_st));
     CU_TRY(t, cudaStreamSynchronize(t->st));
     for (int i = 0; i < kSlots; ++i) memset(t->h_cnt[i], 0, sizeof(int) * (t->groups + 1));
     t->have_prev = false;
@@ -216,11 +224,21 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
     const int n_img = t->stereo ? 2 * t->S : t->S;
     const TableView &tin = t->tab[t->tcur], &tout = t->tab[t->tcur ^ 1];
 
-    mark(stage);  // 1: pyramid
+    // 1: pyramid.  On batched handles it runs on its own stream, so that the pyramid of this frame overlaps
+    // the low-occupancy tail (compaction, detection, stereo LK, merge) of the previous one.  It overwrites the
+    // set that was the previous frame's `prev`, last read by that frame's temporal LK.  Profiling keeps
+    // everything on one stream (stage times would overlap otherwise).
+    cudaStream_t ps = prof ? st : t->pyr_st;
+    if (ps != st) CU_TRY(t, cudaStreamWaitEvent(ps, t->ev_lk_done, 0));
+    mark(stage);
     int nl = 0;
-    CU_TRY(t, pyr_build(t->plan, src0, src1, t->S, n_img, stride, pitch, cur, st, &nl));
+    CU_TRY(t, pyr_build(t->plan, src0, src1, t->S, n_img, stride, pitch, cur, ps, &nl));
     count(1, nl);
-    CU_TRY(t, cudaEventRecord(t->ev_in_free[slot], st));
+    CU_TRY(t, cudaEventRecord(t->ev_in_free[slot], ps));
+    if (ps != st) {
+        CU_TRY(t, cudaEventRecord(t->ev_pyr[slot], ps));
+        CU_TRY(t, cudaStreamWaitEvent(st, t->ev_pyr[slot], 0));
+    }
     mark(++stage);  // 2: temporal LK
     if (t->have_prev) {
         LkBatch b{};
@@ -242,6 +260,7 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
         CU_TRY(t, lk_track(t->pd, b, st));
         count(2, 1);
     }
+    CU_TRY(t, cudaEventRecord(t->ev_lk_done, st));  // `prev` may be overwritten from here on
     mark(++stage);  // 3: compaction + occupancy
     CU_TRY(t, compact_tracks(tin, t->d_lk_T6, t->d_lk_status, tout, t->groups, t->cap, t->S, t->gd, t->d_occ,
                              t->have_prev ? 1 : 0, t->d_counters, st));
@@ -343,6 +362,7 @@ rsvio_status upload(rsvio_tracker *t, int slot, const uint8_t *const *left, cons
     t->up_valid[slot] = t->profiling;
     CU_TRY(t, cudaEventRecord(t->ev_h2d[slot], t->copy_st));
     CU_TRY(t, cudaStreamWaitEvent(t->st, t->ev_h2d[slot], 0));
+    if (t->pyr_st != t->st) CU_TRY(t, cudaStreamWaitEvent(t->pyr_st, t->ev_h2d[slot], 0));
     return RSVIO_OK;
 }
 
@@ -453,12 +473,20 @@ rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) 
             t->own_stream = true;
         }
         CU_TRY(t, cudaStreamCreateWithFlags(&t->copy_st, cudaStreamNonBlocking));
-        if (t->S >= 8) {  // small batches: the cross-stream hand-off would cost more latency than the export
+        if (t->S >= 8) {  // small batches: the cross-stream hand-offs would cost more latency than they hide
             CU_TRY(t, cudaStreamCreateWithFlags(&t->exp_st, cudaStreamNonBlocking));
             t->own_exp = true;
+            {   // lowest priority: the pyramid fills what the latency-bound tail of the previous frame leaves idle
+                int lo = 0, hi = 0;
+                CU_TRY(t, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                CU_TRY(t, cudaStreamCreateWithPriority(&t->pyr_st, cudaStreamNonBlocking, lo));
+            }
+            t->own_pyr = true;
         } else {
             t->exp_st = t->st;
+            t->pyr_st = t->st;
         }
+        CU_TRY(t, cudaEventCreateWithFlags(&t->ev_lk_done, cudaEventDisableTiming));
         CU_TRY(t, pyr_plan_create(cfg->width, cfg->height, cfg->levels, t->st, &t->plan));
         CU_TRY(t, pyr_plan_reserve(t->plan, 2 * t->S));
         t->pd = pyr_plan_desc(t->plan);
@@ -473,6 +501,7 @@ rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) 
             CU_TRY(t, cudaEventCreateWithFlags(&t->ev_in_free[i], cudaEventDisableTiming));
             CU_TRY(t, cudaEventCreateWithFlags(&t->ev_done[i], cudaEventDisableTiming));
             CU_TRY(t, cudaEventCreateWithFlags(&t->ev_merged[i], cudaEventDisableTiming));
+            CU_TRY(t, cudaEventCreateWithFlags(&t->ev_pyr[i], cudaEventDisableTiming));
             for (int k = 0; k <= RSVIO_N_STAGES; ++k) CU_TRY(t, cudaEventCreate(&t->ev_stage[i][k]));
             for (int k = 0; k < 2; ++k) CU_TRY(t, cudaEventCreate(&t->ev_up[i][k]));
         }

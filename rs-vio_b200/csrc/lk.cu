@@ -442,7 +442,8 @@ lk_track_fb_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ L
     // Work distribution: the live points of all groups form one compacted list (exclusive prefix of the
     // per-group counts in shared memory); warps fetch the next point from a global counter, so a warp that
     // drew long tracks (many iterations) does not hold up the launch while others idle.
-    __shared__ int prefix[kMaxGroupsSmem + 1];
+    extern __shared__ int prefix[];  // groups + 1 entries when the launch schedules dynamically (sized at launch:
+                                     // a small table leaves the shared memory to kernels running beside this one)
     __shared__ int warp_tot[kWarpsPerBlock];
     const bool dynamic = b.work_counter != nullptr && b.groups <= kMaxGroupsSmem;
     // two counters used alternately: this launch draws from [work_parity] and clears the other one for the next
@@ -561,10 +562,11 @@ cudaError_t lk_track(const PyrDesc &pd, const LkBatch &b, cudaStream_t st) {
     if (total <= 0) return cudaSuccess;
     long long blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const bool dynamic = b.work_counter != nullptr && b.groups <= kMaxGroupsSmem;
-    // dynamic scheduling: one resident wave (80 registers -> 6 CTAs per SM); static striding: up to 16 per SM
+    // dynamic scheduling: one resident wave (64 registers -> 8 CTAs per SM); static striding: up to 16 per SM
     const long long max_blocks = (long long)kNumSMs * (dynamic ? 8 : 16);
     if (blocks > max_blocks) blocks = max_blocks;
-    lk_track_fb_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, 0, st>>>(pd, b);
+    const size_t smem = dynamic ? sizeof(int) * (size_t)(b.groups + 1) : 0;
+    lk_track_fb_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(pd, b);
     return cudaGetLastError();
 }
 
