@@ -145,6 +145,30 @@ rsvio_status rsvio_tracker_get_transforms(rsvio_tracker *t, int32_t stream, int3
  * frame has not been synced. */
 rsvio_status rsvio_tracker_remove_ids(rsvio_tracker *t, int32_t stream, const uint64_t *ids, size_t n);
 
+/* ---- next step of every feature: unprojection -------------------------------
+ * Frame::add_left_feature / add_right_feature (estimator/frame.rs:107-134) fill
+ * Feature::undistorted_coord with camera.unproject_one(pixel)[0..2]; the estimator consumes it as the
+ * normalised image coordinate (x/z, y/z) (optimization/factors.rs:13-25).  With a camera model set,
+ * the export kernel writes that coordinate for every live record next to the (id, x, y) records.
+ * The arithmetic of the reference lives in the un-vendored crate camera-intrinsic-model 0.7.2:
+ * PARITY UNPINNED (model equations restated from the literature, inverse solved to f64 convergence;
+ * tools/reference_vectors dumps the crate's own answers for comparison).
+ *   RSVIO_CAMERA_PINHOLE_RADTAN: params = fx fy cx cy k1 k2 p1 p2 k3   (datasets/mod.rs:115-127)
+ *   RSVIO_CAMERA_EUCM:           params = fx fy cx cy alpha beta        (datasets/mod.rs:100-108)
+ * Pixels outside the model's domain give NaN. */
+enum { RSVIO_CAMERA_NONE = 0, RSVIO_CAMERA_PINHOLE_RADTAN = 1, RSVIO_CAMERA_EUCM = 2 };
+typedef struct rsvio_camera_model {
+    int32_t model;
+    int32_t reserved;
+    double params[9];
+} rsvio_camera_model;
+/* cam: 0 = left, 1 = right; model RSVIO_CAMERA_NONE switches the output off again.  RSVIO_ERR_STATE while a
+ * submitted frame has not been synced.  Takes effect from the next frame. */
+rsvio_status rsvio_tracker_set_camera(rsvio_tracker *t, int32_t cam, const rsvio_camera_model *model);
+/* uxy[(group * capacity + k) * 2 + {0, 1}] for the records of rsvio_tracker_result_view (same groups, same
+ * capacity, same validity); NULL in *uxy when no camera model has been set. */
+rsvio_status rsvio_tracker_undistorted_view(rsvio_tracker *t, const float **uxy, int32_t *groups, int32_t *capacity);
+
 /* counters since create/reset, summed over streams:
  * [0] tracks attempted (track_points elements)  [1] frames (per stream)
  * [2] LK iterations evaluated                   [3] Pattern52 templates built
@@ -197,6 +221,10 @@ rsvio_status rsvio_detect_keypoints(int32_t device, const uint8_t *image, int32_
 /* se2_exp_matrix (image_utilities.rs:82-106) evaluated by the device code: n twists
  * [vx, vy, theta] -> n row-major 3x3 matrices */
 rsvio_status rsvio_se2_exp(int32_t device, const float *twists, int32_t n, float *out9);
+
+/* unproject_one for n pixels (host pointers): xy = n x (u, v) float, out_xy = n x (x/z, y/z) float */
+rsvio_status rsvio_unproject_points(int32_t device, const rsvio_camera_model *model, const float *xy, int32_t n,
+                                    float *out_xy);
 
 #ifdef __cplusplus
 }

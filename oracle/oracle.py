@@ -117,6 +117,36 @@ def se2_exp(a):
     return out.reshape(3, 3)
 
 
+CAMERA_PINHOLE_RADTAN, CAMERA_EUCM = 1, 2
+
+
+def unproject(model, params, uv):
+    """camera.unproject_one for an (n, 2) array of pixels -> (n, 2) float64 normalised coordinates (NaN outside)."""
+    P = (C.c_double * 9)(*(list(params) + [0.0] * 9)[:9])
+    uv = np.asarray(uv, np.float64).reshape(-1, 2)
+    out = np.full(uv.shape, np.nan)
+    o = (C.c_double * 2)()
+    f = lib().orc_unproject
+    f.restype = C.c_int
+    for i, (u, v) in enumerate(uv):
+        if f(C.c_int(model), P, C.c_double(u), C.c_double(v), o):
+            out[i] = (o[0], o[1])
+    return out
+
+
+def project(model, params, xy):
+    P = (C.c_double * 9)(*(list(params) + [0.0] * 9)[:9])
+    xy = np.asarray(xy, np.float64).reshape(-1, 2)
+    out = np.full(xy.shape, np.nan)
+    o = (C.c_double * 2)()
+    f = lib().orc_project
+    f.restype = C.c_int
+    for i, (x, y) in enumerate(xy):
+        if f(C.c_int(model), P, C.c_double(x), C.c_double(y), o):
+            out[i] = (o[0], o[1])
+    return out
+
+
 def image_grad(img, x, y):
     img = np.ascontiguousarray(img, np.uint8)
     out = np.empty(3, np.float32)

@@ -730,6 +730,66 @@ void orc_se2_exp(const float a[3], float out[9]) {
     out[8] = 1.0f;
 }
 
+int orc_project(int model, const double p[9], double x, double y, double out_uv[2]) {
+    double xd, yd;
+    if (model == 1) {
+        const double k1 = p[4], k2 = p[5], p1 = p[6], p2 = p[7], k3 = p[8];
+        const double r2 = x * x + y * y;
+        const double rad = 1.0 + k1 * r2 + k2 * r2 * r2 + k3 * r2 * r2 * r2;
+        xd = x * rad + 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x);
+        yd = y * rad + p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y;
+    } else if (model == 2) {  // EUCM: pi(X) = (x, y) / (alpha d + (1 - alpha) z), d = sqrt(beta (x^2 + y^2) + z^2), z = 1
+        const double alpha = p[4], beta = p[5];
+        const double d = std::sqrt(beta * (x * x + y * y) + 1.0);
+        const double den = alpha * d + (1.0 - alpha);
+        if (!(den > 0.0)) return 0;
+        xd = x / den;
+        yd = y / den;
+    } else {
+        return 0;
+    }
+    out_uv[0] = p[0] * xd + p[2];
+    out_uv[1] = p[1] * yd + p[3];
+    return 1;
+}
+
+int orc_unproject(int model, const double p[9], double u, double v, double out_xy[2]) {
+    const double xd = (u - p[2]) / p[0], yd = (v - p[3]) / p[1];
+    out_xy[0] = out_xy[1] = std::nan("");
+    if (model == 1) {
+        const double k1 = p[4], k2 = p[5], p1 = p[6], p2 = p[7], k3 = p[8];
+        double x = xd, y = yd;
+        for (int it = 0; it < 2000; ++it) {
+            const double r2 = x * x + y * y;
+            const double rad = 1.0 + k1 * r2 + k2 * r2 * r2 + k3 * r2 * r2 * r2;
+            const double dx = 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x);
+            const double dy = p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y;
+            const double nx = (xd - dx) / rad, ny = (yd - dy) / rad;
+            const double step = std::fabs(nx - x) + std::fabs(ny - y);
+            x = nx;
+            y = ny;
+            if (step <= 1e-14 * (1.0 + std::fabs(x) + std::fabs(y))) {  // a few ulps: the iteration may oscillate in the last bit
+                out_xy[0] = x;
+                out_xy[1] = y;
+                return 1;
+            }
+        }
+        return 0;
+    }
+    if (model == 2) {
+        const double alpha = p[4], beta = p[5];
+        const double r2 = xd * xd + yd * yd;
+        const double disc = 1.0 - (2.0 * alpha - 1.0) * beta * r2;
+        if (disc < 0.0) return 0;
+        const double mz = (1.0 - beta * alpha * alpha * r2) / (alpha * std::sqrt(disc) + (1.0 - alpha));
+        if (!(mz > 0.0)) return 0;
+        out_xy[0] = xd / mz;
+        out_xy[1] = yd / mz;
+        return 1;
+    }
+    return 0;
+}
+
 void orc_image_grad(const uint8_t *img, int w, int h, float x, float y, float out[3]) {
     Level l{img, w, h};
     image_grad(l, x, y, out);

@@ -56,8 +56,9 @@ class Handle {
         if (t_) rsvio_tracker_destroy(t_);
     }
     // the reference learns the image size from the first frame; the handle is created lazily the same way
-    void ensure(const rsvio_config &base, std::uint32_t w, std::uint32_t h) {
-        if (t_ && w == w_ && h == h_) return;
+    // returns true when a handle was (re)created
+    bool ensure(const rsvio_config &base, std::uint32_t w, std::uint32_t h) {
+        if (t_ && w == w_ && h == h_) return false;
         if (t_) rsvio_tracker_destroy(t_);
         t_ = nullptr;
         rsvio_config cfg = base;
@@ -66,6 +67,7 @@ class Handle {
         check(rsvio_tracker_create(&cfg, &t_), nullptr, "rsvio_tracker_create");
         w_ = w;
         h_ = h;
+        return true;
     }
     rsvio_tracker *get() const { return t_; }
     std::unordered_map<std::size_t, std::pair<float, float>> tracks(int cam) const {
@@ -118,16 +120,35 @@ class StereoPatchTracker {
         const std::int32_t *counts = nullptr;
         std::int32_t groups = 0, cap = 0;
         detail::check(rsvio_tracker_result_view(h_.get(), &rec, &counts, &groups, &cap), h_.get(), "result_view");
+        const float *uxy = nullptr;  // unprojected coordinates, when set_camera() was called
+        detail::check(rsvio_tracker_undistorted_view(h_.get(), &uxy, nullptr, nullptr), h_.get(), "undistorted_view");
         for (int cam = 0; cam < 2; ++cam)
             for (std::int32_t k = 0; k < counts[cam]; ++k) {
-                const rsvio_track_record &r = rec[(std::size_t)cam * cap + k];
+                const std::size_t i = (std::size_t)cam * cap + k;
+                const rsvio_track_record &r = rec[i];
                 Feature f((std::size_t)r.id, r.x, r.y);
+                if (uxy) {
+                    f.undistorted_coord[0] = uxy[2 * i];
+                    f.undistorted_coord[1] = uxy[2 * i + 1];
+                }
                 if (cam == 0) frame.add_left_feature(f); else frame.add_right_feature(f);
             }
     }
+    // Optional: the camera model of cam 0 (left) / 1 (right) (src/datasets/mod.rs:93-163).  Features then carry
+    // undistorted_coord and Frame::add_*_feature can skip unproject_one (src/estimator/frame.rs:118,131).
+    // Call it after the first frame has created the handle, or before: it is re-applied on creation.
+    void set_camera(int cam, const rsvio_camera_model &model) {
+        cams_[cam] = model;
+        have_cam_[cam] = true;
+        if (h_.get()) detail::check(rsvio_tracker_set_camera(h_.get(), cam, &model), h_.get(), "rsvio_tracker_set_camera");
+    }
     void process(const GrayImageView &image0, const GrayImageView &image1) {
         if (image0.width != image1.width || image0.height != image1.height) throw Error(RSVIO_ERR_INVALID_ARG, "stereo images differ in size");
-        h_.ensure(cfg_, image0.width, image0.height);
+        const bool created = h_.ensure(cfg_, image0.width, image0.height);
+        if (created)
+            for (int cam = 0; cam < 2; ++cam)
+                if (have_cam_[cam])
+                    detail::check(rsvio_tracker_set_camera(h_.get(), cam, &cams_[cam]), h_.get(), "rsvio_tracker_set_camera");
         detail::check(rsvio_tracker_process_stereo(h_.get(), image0.data, image1.data, image0.width), h_.get(),
                       "rsvio_tracker_process_stereo");
     }
@@ -142,6 +163,8 @@ class StereoPatchTracker {
   private:
     rsvio_config cfg_{};
     detail::Handle h_;
+    rsvio_camera_model cams_[2]{};
+    bool have_cam_[2] = {false, false};
 };
 
 template <std::uint32_t LEVELS>

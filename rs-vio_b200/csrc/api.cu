@@ -85,6 +85,9 @@ struct rsvio_tracker {
     // host-mapped output ring: records [groups][cap] and counts [groups] (+1 error flag)
     OutRecord *h_out[kSlots] = {nullptr, nullptr}, *d_out[kSlots] = {nullptr, nullptr};
     int *h_cnt[kSlots] = {nullptr, nullptr}, *d_cnt[kSlots] = {nullptr, nullptr};
+    // unprojection (row f-1): camera models and the host-mapped coordinate ring, allocated when a model is set
+    CameraModelDev cam_model[2]{};
+    float *h_uxy[kSlots] = {nullptr, nullptr}, *d_uxy[kSlots] = {nullptr, nullptr};
     cudaEvent_t ev_h2d[kSlots]{}, ev_in_free[kSlots]{}, ev_done[kSlots]{}, ev_merged[kSlots]{};
     int next_slot = 0, oldest_slot = 0, inflight = 0, result_slot = -1;
     uint64_t host_launches = 0;
@@ -143,6 +146,7 @@ void free_all(rsvio_tracker *t) {
         if (t->h_stage[i]) cudaFreeHost(t->h_stage[i]);
         if (t->h_out[i]) cudaFreeHost(t->h_out[i]);
         if (t->h_cnt[i]) cudaFreeHost(t->h_cnt[i]);
+        if (t->h_uxy[i]) cudaFreeHost(t->h_uxy[i]);
         if (t->ev_h2d[i]) cudaEventDestroy(t->ev_h2d[i]);
         if (t->ev_in_free[i]) cudaEventDestroy(t->ev_in_free[i]);
         if (t->ev_done[i]) cudaEventDestroy(t->ev_done[i]);
@@ -307,7 +311,8 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
     }
     ++stage;
     if (prof) cudaEventRecord(t->ev_stage[slot][stage], xs);
-    CU_TRY(t, export_records(tout, t->groups, t->cap, t->d_out[slot], t->d_cnt[slot], xs));
+    CU_TRY(t, export_records(tout, t->groups, t->cap, t->S, t->d_out[slot], t->d_cnt[slot], t->cam_model[0], t->cam_model[1],
+                             t->d_uxy[slot], xs));
     count(7, 1);
     CU_TRY(t, cudaMemcpyAsync(t->h_cnt[slot] + t->groups, t->d_err, sizeof(int), cudaMemcpyDeviceToHost, xs));
     ++stage;
@@ -686,6 +691,40 @@ rsvio_status rsvio_tracker_result_view(rsvio_tracker *t, const rsvio_track_recor
     return RSVIO_OK;
 }
 
+rsvio_status rsvio_tracker_set_camera(rsvio_tracker *t, int32_t cam, const rsvio_camera_model *model) {
+    if (!t || !model || cam < 0 || cam > 1) return RSVIO_ERR_INVALID_ARG;
+    if (model->model != RSVIO_CAMERA_NONE && model->model != RSVIO_CAMERA_PINHOLE_RADTAN &&
+        model->model != RSVIO_CAMERA_EUCM)
+        return fail(t, RSVIO_ERR_INVALID_ARG, "unknown camera model");
+    if (model->model != RSVIO_CAMERA_NONE && !(model->params[0] != 0.0 && model->params[1] != 0.0))
+        return fail(t, RSVIO_ERR_INVALID_ARG, "focal lengths must be non-zero");
+    if (t->inflight > 0) return fail(t, RSVIO_ERR_STATE, "frames in flight: call rsvio_tracker_sync before set_camera");
+    DeviceScope dev_scope;
+    CU_TRY(t, dev_scope.enter(t->cfg.device));
+    if (model->model != RSVIO_CAMERA_NONE && !t->h_uxy[0]) {
+        const size_t bytes = (size_t)t->groups * t->cap * 2 * sizeof(float);
+        for (int i = 0; i < kSlots; ++i) {
+            CU_TRY(t, cudaHostAlloc((void **)&t->h_uxy[i], bytes, cudaHostAllocMapped));
+            CU_TRY(t, cudaHostGetDevicePointer((void **)&t->d_uxy[i], t->h_uxy[i], 0));
+            memset(t->h_uxy[i], 0, bytes);
+        }
+    }
+    t->cam_model[cam].model = model->model;
+    for (int k = 0; k < 9; ++k) t->cam_model[cam].p[k] = model->params[k];
+    return RSVIO_OK;
+}
+
+rsvio_status rsvio_tracker_undistorted_view(rsvio_tracker *t, const float **uxy, int32_t *groups, int32_t *capacity) {
+    if (!t || !uxy) return RSVIO_ERR_INVALID_ARG;
+    if (t->inflight > 1) return fail(t, RSVIO_ERR_STATE, "two frames in flight: call rsvio_tracker_sync first");
+    if (t->result_slot < 0) return fail(t, RSVIO_ERR_STATE, "no frame has been processed yet");
+    const bool on = t->cam_model[0].model != RSVIO_CAMERA_NONE || t->cam_model[1].model != RSVIO_CAMERA_NONE;
+    *uxy = on ? t->h_uxy[t->result_slot] : nullptr;
+    if (groups) *groups = t->groups;
+    if (capacity) *capacity = t->cap;
+    return RSVIO_OK;
+}
+
 rsvio_status rsvio_tracker_get_transforms(rsvio_tracker *t, int32_t stream, int32_t cam, uint64_t *ids, float *T6,
                                           size_t cap, size_t *n) {
     rsvio_status rs = check_group(t, stream, cam);
@@ -746,6 +785,13 @@ rsvio_status rsvio_tracker_remove_ids(rsvio_tracker *t, int32_t stream, const ui
             r[k].id = hid[k];
             r[k].x = hT[(size_t)k * 6 + 2];
             r[k].y = hT[(size_t)k * 6 + 5];
+            if (t->h_uxy[slot] && t->cam_model[cam].model != RSVIO_CAMERA_NONE) {
+                double ux, uy;
+                unproject_pixel(t->cam_model[cam], (double)r[k].x, (double)r[k].y, ux, uy);
+                float *u = t->h_uxy[slot] + ((size_t)g * t->cap + k) * 2;
+                u[0] = (float)ux;
+                u[1] = (float)uy;
+            }
         }
         t->h_cnt[slot][g] = cnt[g];
     }
@@ -1037,6 +1083,29 @@ rsvio_status rsvio_se2_exp(int32_t device, const float *twists, int32_t n, float
     CU_TRY0(se2_exp_batch(d_in, n, d_out, 0));
     CU_TRY0(cudaDeviceSynchronize());
     CU_TRY0(cudaMemcpy(out9, d_out, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost));
+done:
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rs;
+}
+
+rsvio_status rsvio_unproject_points(int32_t device, const rsvio_camera_model *model, const float *xy, int32_t n,
+                                    float *out_xy) {
+    if (!model || !xy || !out_xy || n < 0) return RSVIO_ERR_INVALID_ARG;
+    if (model->model != RSVIO_CAMERA_PINHOLE_RADTAN && model->model != RSVIO_CAMERA_EUCM) return RSVIO_ERR_INVALID_ARG;
+    if (n == 0) return RSVIO_OK;
+    rsvio_status rs = RSVIO_OK;
+    DeviceScope dev_scope;
+    float *d_in = nullptr, *d_out = nullptr;
+    CameraModelDev cm{};
+    cm.model = model->model;
+    for (int k = 0; k < 9; ++k) cm.p[k] = model->params[k];
+    CU_TRY0(dev_scope.enter(device));
+    CU_TRY0(cudaMalloc((void **)&d_in, sizeof(float) * 2 * (size_t)n));
+    CU_TRY0(cudaMalloc((void **)&d_out, sizeof(float) * 2 * (size_t)n));
+    CU_TRY0(cudaMemcpy(d_in, xy, sizeof(float) * 2 * (size_t)n, cudaMemcpyHostToDevice));
+    CU_TRY0(unproject_points(cm, d_in, n, d_out, 0));
+    CU_TRY0(cudaMemcpy(out_xy, d_out, sizeof(float) * 2 * (size_t)n, cudaMemcpyDeviceToHost));
 done:
     cudaFree(d_in);
     cudaFree(d_out);

@@ -12,6 +12,7 @@
 #include <stdint.h>
 
 #include "../../include/rsvio_b200.h"
+#include "camera.cuh"
 
 namespace rsvio {
 
@@ -148,9 +149,11 @@ struct OutRecord {
 cudaError_t merge_new_points(const TableView &tab, int streams, int cap, int stereo, const float *new_T6,
                              const float *st_T6, const int32_t *st_status, const int *new_count, int new_cap,
                              unsigned long long *last_id, int *err_flag, cudaStream_t st);
-// packed (id, x, y) records and counts of every group -> out_rec / out_counts (mapped host memory)
-cudaError_t export_records(const TableView &tab, int groups, int cap, OutRecord *out_rec, int *out_counts,
-                           cudaStream_t st);
+// packed (id, x, y) records and counts of every group -> out_rec / out_counts (mapped host memory); with a camera
+// model (groups < streams: cam0, else cam1) also the unprojected coordinate of every record -> out_uxy
+cudaError_t export_records(const TableView &tab, int groups, int cap, int streams, OutRecord *out_rec, int *out_counts,
+                           const CameraModelDev &cam0, const CameraModelDev &cam1, float *out_uxy, cudaStream_t st);
+cudaError_t unproject_points(const CameraModelDev &cm, const float *d_xy, int n, float *d_out, cudaStream_t st);
 cudaError_t remove_ids(const TableView &in, const TableView &out, int groups, int cap, int streams, int stream,
                        const unsigned long long *d_ids, int n, cudaStream_t st);
 

@@ -141,10 +141,14 @@ merge_new_kernel(TableView tab, int streams, int cap, int stereo, const float *_
 // Own kernel so that it can run beside the next frame: only live records cross PCIe.
 constexpr int kExportChunks = 4;
 __global__ void __launch_bounds__(kThreads)
-export_records_kernel(TableView tab, int cap, OutRecord *__restrict__ out_rec, int *__restrict__ out_counts) {
+export_records_kernel(TableView tab, int cap, int streams, OutRecord *__restrict__ out_rec, int *__restrict__ out_counts,
+                      const __grid_constant__ CameraModelDev cam0, const __grid_constant__ CameraModelDev cam1,
+                      float2 *__restrict__ out_uxy) {
     const int g = blockIdx.x;
     const int n = tab.counts[g];
     if (blockIdx.y == 0 && threadIdx.x == 0) out_counts[g] = n;
+    const CameraModelDev &cm = g < streams ? cam0 : cam1;
+    const bool unproject = out_uxy != nullptr && cm.model != RSVIO_CAMERA_NONE;
     for (int k = blockIdx.y * kThreads + threadIdx.x; k < n; k += kExportChunks * kThreads) {
         const size_t i = (size_t)g * cap + k;
         OutRecord r;
@@ -152,7 +156,21 @@ export_records_kernel(TableView tab, int cap, OutRecord *__restrict__ out_rec, i
         r.x = tab.T6[i * 6 + 2];
         r.y = tab.T6[i * 6 + 5];
         out_rec[i] = r;
+        if (unproject) {  // Frame::add_left_feature / add_right_feature (estimator/frame.rs:118-119,131-132)
+            double ux, uy;
+            unproject_pixel(cm, (double)r.x, (double)r.y, ux, uy);
+            out_uxy[i] = make_float2((float)ux, (float)uy);
+        }
     }
+}
+
+__global__ void unproject_points_kernel(const __grid_constant__ CameraModelDev cm, const float2 *__restrict__ xy, int n,
+                                        float2 *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double ux, uy;
+    unproject_pixel(cm, (double)xy[i].x, (double)xy[i].y, ux, uy);
+    out[i] = make_float2((float)ux, (float)uy);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -204,9 +222,17 @@ cudaError_t merge_new_points(const TableView &tab, int streams, int cap, int ste
     return cudaGetLastError();
 }
 
-cudaError_t export_records(const TableView &tab, int groups, int cap, OutRecord *out_rec, int *out_counts,
-                           cudaStream_t st) {
-    export_records_kernel<<<dim3((unsigned)groups, kExportChunks, 1), kThreads, 0, st>>>(tab, cap, out_rec, out_counts);
+cudaError_t export_records(const TableView &tab, int groups, int cap, int streams, OutRecord *out_rec, int *out_counts,
+                           const CameraModelDev &cam0, const CameraModelDev &cam1, float *out_uxy, cudaStream_t st) {
+    export_records_kernel<<<dim3((unsigned)groups, kExportChunks, 1), kThreads, 0, st>>>(
+        tab, cap, streams, out_rec, out_counts, cam0, cam1, reinterpret_cast<float2 *>(out_uxy));
+    return cudaGetLastError();
+}
+
+cudaError_t unproject_points(const CameraModelDev &cm, const float *d_xy, int n, float *d_out, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    unproject_points_kernel<<<(n + 255) / 256, 256, 0, st>>>(cm, reinterpret_cast<const float2 *>(d_xy), n,
+                                                             reinterpret_cast<float2 *>(d_out));
     return cudaGetLastError();
 }
 

@@ -36,7 +36,10 @@ ABI_SYMBOLS = (
     "rsvio_tracker_stage_times",
     "rsvio_pyramid_bytes", "rsvio_pyramid_device_bytes", "rsvio_build_pyramid_u8",
     "rsvio_build_pyramid_u8_device", "rsvio_track_points", "rsvio_detect_keypoints", "rsvio_se2_exp",
+    "rsvio_tracker_set_camera", "rsvio_tracker_undistorted_view", "rsvio_unproject_points",
 )
+
+CAMERA_NONE, CAMERA_PINHOLE_RADTAN, CAMERA_EUCM = 0, 1, 2
 
 
 class RsvioError(RuntimeError):
@@ -71,6 +74,21 @@ _f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
 _u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
 _u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+
+
+class CameraModel(C.Structure):
+    """rsvio_camera_model: pinhole-radtan = fx fy cx cy k1 k2 p1 p2 k3, EUCM = fx fy cx cy alpha beta
+    (the parameter vectors of the reference's create_camera_models_from_config, datasets/mod.rs:93-163)."""
+    _fields_ = [("model", C.c_int32), ("reserved", C.c_int32), ("params", C.c_double * 9)]
+
+    @classmethod
+    def pinhole_radtan(cls, intrinsics, distortion):
+        d = (list(distortion) + [0.0] * 5)[:5]            # k1 k2 p1 p2 k3, missing ones 0 (mod.rs:121-125)
+        return cls(CAMERA_PINHOLE_RADTAN, 0, (C.c_double * 9)(*(list(intrinsics)[:4] + d)))
+
+    @classmethod
+    def eucm(cls, intrinsics, distortion):
+        return cls(CAMERA_EUCM, 0, (C.c_double * 9)(*(list(intrinsics)[:4] + list(distortion)[:2] + [0.0] * 3)))
 
 
 def load_library():
@@ -127,6 +145,9 @@ def load_library():
     L.rsvio_detect_keypoints.argtypes = [C.c_int32, _u8p, C.c_int32, C.c_int32, C.c_size_t, C.c_uint32, _u32p,
                                          C.c_int32, _u32p, _f32p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.rsvio_se2_exp.argtypes = [C.c_int32, _f32p, C.c_int32, _f32p]
+    L.rsvio_tracker_set_camera.argtypes = [H, C.c_int32, C.POINTER(CameraModel)]
+    L.rsvio_tracker_undistorted_view.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.rsvio_unproject_points.argtypes = [C.c_int32, C.POINTER(CameraModel), _f32p, C.c_int32, _f32p]
     _lib = L
     return L
 
@@ -197,6 +218,14 @@ def detect_keypoints(image, grid, cur_xy=None, device=0):
     _check(load_library().rsvio_detect_keypoints(device, img, w, h, w, grid, cur_arg, cur.shape[0], xy, sc, cap,
                                                  C.byref(n)))
     return xy[:n.value].copy(), sc[:n.value].copy()
+
+
+def unproject_points(model, xy, device=0):
+    """camera.unproject_one for (n, 2) float32 pixels -> (n, 2) float32 normalised coordinates (NaN outside)."""
+    xy = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+    out = np.empty_like(xy)
+    _check(load_library().rsvio_unproject_points(device, C.byref(model), xy, xy.shape[0], out))
+    return out
 
 
 def se2_exp(twists, device=0):
@@ -304,6 +333,22 @@ class _Tracker:
         cbuf = (C.c_int32 * g).from_address(cnt.value)
         return (np.frombuffer(rbuf, dtype=self.RECORD_DTYPE).reshape(g, c), np.frombuffer(cbuf, dtype=np.int32))
 
+    def set_camera(self, cam, model):
+        """camera model of cam 0 (left) / 1 (right): from the next frame on every record also carries its
+        unprojected coordinate (Feature.undistorted_coord, estimator/frame.rs:107-134)."""
+        _check(self._L.rsvio_tracker_set_camera(self._h, cam, C.byref(model)), self._h)
+
+    def undistorted_view(self):
+        """uxy[groups, cap, 2] float32 (zero-copy) for the records of result_view(), or None without a model."""
+        ptr = C.c_void_p()
+        groups, cap = C.c_int32(0), C.c_int32(0)
+        _check(self._L.rsvio_tracker_undistorted_view(self._h, C.byref(ptr), C.byref(groups), C.byref(cap)), self._h)
+        if not ptr.value:
+            return None
+        g, c = groups.value, cap.value
+        buf = (C.c_float * (g * c * 2)).from_address(ptr.value)
+        return np.frombuffer(buf, dtype=np.float32).reshape(g, c, 2)
+
     def transforms(self, cam=0, stream=0):
         ids = np.zeros(self._cap, np.uint64)
         T = np.zeros((self._cap, 6), np.float32)
@@ -350,10 +395,14 @@ class StereoPatchTracker(_Tracker):
         _check(self._L.rsvio_tracker_process_stereo(self._h, C.c_void_p(l.ctypes.data), C.c_void_p(r.ctypes.data),
                                                     self.width), self._h)
         if frame is not None:
+            uxy = self.undistorted_view()
             for cam, add in ((0, frame.add_left_feature), (1, frame.add_right_feature)):
                 ids, xy = self.tracks(cam)
-                for i, p in zip(ids.tolist(), xy.tolist()):
-                    add(Feature(i, (p[0], p[1])))
+                und = uxy[cam * self.n_streams, :len(ids)].tolist() if uxy is not None else None
+                for k, (i, p) in enumerate(zip(ids.tolist(), xy.tolist())):
+                    # with a camera model set the unprojection of Frame::add_*_feature (frame.rs:118-119) is
+                    # already done on the device; otherwise the reference's placeholder (-1, -1) stays
+                    add(Feature(i, (p[0], p[1]), tuple(und[k]) if und is not None else (-1.0, -1.0)))
 
     def get_track_points(self, stream=0):
         """[ {id: (x, y)} for cam0, cam1 ]  (feature_tracker.rs:188-200)"""

@@ -31,6 +31,18 @@ pub struct rsvio_track_record {
     pub y: f32,
 }
 
+pub const RSVIO_CAMERA_NONE: i32 = 0;
+pub const RSVIO_CAMERA_PINHOLE_RADTAN: i32 = 1;
+pub const RSVIO_CAMERA_EUCM: i32 = 2;
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct rsvio_camera_model {
+    pub model: i32,
+    pub reserved: i32,
+    pub params: [f64; 9],
+}
+
 #[repr(C)]
 pub struct rsvio_tracker {
     _private: [u8; 0],
@@ -90,6 +102,13 @@ extern "C" {
                                   grid_size: u32, cur_xy: *const u32, n_cur: i32, out_xy: *mut u32,
                                   out_score: *mut f32, cap: usize, n: *mut usize) -> rsvio_status;
     pub fn rsvio_se2_exp(device: i32, twists: *const f32, n: i32, out9: *mut f32) -> rsvio_status;
+
+    // ---- unprojection of the tracked pixels (Feature::undistorted_coord) ----
+    pub fn rsvio_tracker_set_camera(t: *mut rsvio_tracker, cam: i32, model: *const rsvio_camera_model) -> rsvio_status;
+    pub fn rsvio_tracker_undistorted_view(t: *mut rsvio_tracker, uxy: *mut *const f32, groups: *mut i32,
+                                          capacity: *mut i32) -> rsvio_status;
+    pub fn rsvio_unproject_points(device: i32, model: *const rsvio_camera_model, xy: *const f32, n: i32,
+                                  out_xy: *mut f32) -> rsvio_status;
 }
 
 pub const RSVIO_N_STAGES: usize = 8;

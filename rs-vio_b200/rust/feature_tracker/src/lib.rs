@@ -40,6 +40,7 @@ struct Handle {
     ptr: *mut ffi::rsvio_tracker,
     dims: (u32, u32),
     cfg: ffi::rsvio_config,
+    cameras: [Option<ffi::rsvio_camera_model>; 2],
 }
 // one handle == one CUDA stream; `&mut self` on every call gives the exclusivity the C ABI asks for
 unsafe impl Send for Handle {}
@@ -53,7 +54,7 @@ impl Handle {
         cfg.max_iterations = max_it as i32;
         cfg.convergence_threshold = thr;
         cfg.mode = mode;
-        Self { ptr: std::ptr::null_mut(), dims: (0, 0), cfg }
+        Self { ptr: std::ptr::null_mut(), dims: (0, 0), cfg, cameras: [None, None] }
     }
     /// The reference learns the image size from the first frame; so does the handle.
     fn ensure(&mut self, w: u32, h: u32) {
@@ -67,6 +68,12 @@ impl Handle {
         let st = unsafe { ffi::rsvio_tracker_create(&cfg, &mut self.ptr) };
         assert!(st == ffi::RSVIO_OK, "rsvio_tracker_create: {}", status_text(st));
         self.dims = (w, h);
+        for cam in 0..2 {
+            if let Some(model) = self.cameras[cam] {
+                let st = unsafe { ffi::rsvio_tracker_set_camera(self.ptr, cam as i32, &model) };
+                self.check(st, "rsvio_tracker_set_camera");
+            }
+        }
     }
     fn check(&self, st: ffi::rsvio_status, what: &str) {
         if st != ffi::RSVIO_OK {
@@ -74,7 +81,40 @@ impl Handle {
             panic!("{what}: {} ({detail})", status_text(st));
         }
     }
-    /// zero-copy view of the host-mapped result the merge kernel wrote
+    /// Camera model of one camera (0 = left, 1 = right); applied when the handle exists (the reference builds its
+    /// models from the YAML config, src/datasets/mod.rs:93-163).  With a model set, `process_frame` hands out
+    /// features whose `undistorted_coord` is already filled (what `Frame::add_*_feature` computes on the CPU).
+    fn set_camera(&mut self, cam: usize, model: ffi::rsvio_camera_model) {
+        self.cameras[cam] = Some(model);
+        if !self.ptr.is_null() {
+            let st = unsafe { ffi::rsvio_tracker_set_camera(self.ptr, cam as i32, &model) };
+            self.check(st, "rsvio_tracker_set_camera");
+        }
+    }
+    /// zero-copy view of the host-mapped result the export kernel wrote; `u` is the unprojected coordinate or
+    /// `[-1, -1]` (the reference's placeholder) when no camera model is set
+    fn for_each_feature(&self, cam: usize, mut f: impl FnMut(Feature)) {
+        if self.ptr.is_null() {
+            return;
+        }
+        let mut uxy: *const f32 = std::ptr::null();
+        let (mut g2, mut c2) = (0i32, 0i32);
+        let have_u = unsafe { ffi::rsvio_tracker_undistorted_view(self.ptr, &mut uxy, &mut g2, &mut c2) } == ffi::RSVIO_OK
+            && !uxy.is_null();
+        let cap = c2 as usize;
+        let groups = g2 as usize;
+        let mut k = 0usize;
+        self.for_each(cam, |id, x, y| {
+            let mut feat = Feature::new(id, [x, y]);
+            if have_u {
+                let base = (cam * (groups / 2) * cap + k) * 2;
+                feat.undistorted_coord = unsafe { [*uxy.add(base), *uxy.add(base + 1)] };
+            }
+            k += 1;
+            f(feat);
+        });
+    }
+    /// zero-copy view of the host-mapped result the export kernel wrote
     fn for_each(&self, cam: usize, mut f: impl FnMut(usize, f32, f32)) {
         if self.ptr.is_null() {
             return;
@@ -140,8 +180,21 @@ impl<const LEVELS: u32> StereoPatchTracker<LEVELS> {
                                               w as usize)
         };
         self.h.check(st, "rsvio_tracker_process_stereo");
-        self.h.for_each(0, |id, x, y| frame.add_left_feature(Feature::new(id, [x, y])));
-        self.h.for_each(1, |id, x, y| frame.add_right_feature(Feature::new(id, [x, y])));
+        self.h.for_each_feature(0, |f| frame.add_left_feature(f));
+        self.h.for_each_feature(1, |f| frame.add_right_feature(f));
+    }
+
+    /// Optional: pinhole-radtan parameters `[fx, fy, cx, cy, k1, k2, p1, p2, k3]` of one camera (0 = left,
+    /// 1 = right).  The features handed to `frame` then carry `undistorted_coord` and `Frame::add_*_feature`
+    /// can skip its own `unproject_one` (src/estimator/frame.rs:118,131).
+    pub fn set_pinhole_radtan(&mut self, cam: usize, params: [f64; 9]) {
+        self.h.set_camera(cam, ffi::rsvio_camera_model { model: ffi::RSVIO_CAMERA_PINHOLE_RADTAN, reserved: 0, params });
+    }
+
+    /// Optional: EUCM parameters `[fx, fy, cx, cy, alpha, beta]` of one camera.
+    pub fn set_eucm(&mut self, cam: usize, p: [f64; 6]) {
+        let params = [p[0], p[1], p[2], p[3], p[4], p[5], 0.0, 0.0, 0.0];
+        self.h.set_camera(cam, ffi::rsvio_camera_model { model: ffi::RSVIO_CAMERA_EUCM, reserved: 0, params });
     }
 
     pub fn get_track_points(&self) -> [HashMap<usize, (f32, f32)>; 2] {
