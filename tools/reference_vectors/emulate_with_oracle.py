@@ -50,6 +50,15 @@ def main():
         tr.process_mono(scene(w, h, 2 * t, t, seed))
         xy = tr.get_tracks(0)[1][:, [2, 5]]
         out.append(f"track {w} {h} {seed} {t} {len(xy)} : " + " ".join(f"{bits(x)},{bits(y)}" for x, y in xy))
+    from test_reference_vectors import EUROC_L, TUMVI_L
+
+    def b64(x):
+        return "%016x" % int(np.array([x], np.float64).view(np.uint64)[0])
+    for model, P, pts in ((1, EUROC_L, ((367.215, 248.375), (10.0, 10.0), (740.0, 470.0), (100.5, 300.25))),
+                          (2, TUMVI_L, ((254.9226487139376, 256.8780365577954), (100.5, 300.25), (400.0, 120.0)))):
+        for u, v in pts:
+            x, y = oracle.unproject(model, P, [[u, v]])[0]
+            out.append(f"unproject {model} {b64(u)} {b64(v)} : {b64(x)} {b64(y)} {b64(1.0)}")
     path = sys.argv[1] if len(sys.argv) > 1 else "reference_vectors_oracle.txt"
     open(path, "w").write("\n".join(out) + "\n")
     print("wrote", path)
