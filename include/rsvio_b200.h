@@ -105,6 +105,16 @@ rsvio_status rsvio_tracker_reset(rsvio_tracker *t);
  * id merge.  Host pointers (pinned or pageable).  Synchronous. */
 rsvio_status rsvio_tracker_process_stereo(rsvio_tracker *t, const uint8_t *left, const uint8_t *right,
                                           size_t stride);
+/* Same, for a frame as the decoder delivers it (ingest row f-3): the dataset players of the reference call
+ * `DynamicImage::to_luma8()` on the CPU before the tracker sees the frame (datasets/euroc_player.rs:227-231,
+ * tum_vi_player.rs:227-231); here the raw buffer is uploaded and converted on the device.
+ *   RSVIO_PIXEL_LUMA8  1 byte per pixel  (identical to rsvio_tracker_process_stereo)
+ *   RSVIO_PIXEL_LUMA16 native-endian u16 (TUM-VI PNGs): (c + 128) / 257
+ *   RSVIO_PIXEL_RGB8   r, g, b bytes:     (2126 r + 7152 g + 722 b) / 10000
+ * (`image` 0.25 arithmetic, not vendored in the reference: PARITY UNPINNED.)  stride in BYTES. */
+enum { RSVIO_PIXEL_LUMA8 = 0, RSVIO_PIXEL_LUMA16 = 1, RSVIO_PIXEL_RGB8 = 2 };
+rsvio_status rsvio_tracker_process_stereo_fmt(rsvio_tracker *t, const void *left, const void *right,
+                                              size_t stride_bytes, int32_t pixel_format);
 /* PatchTracker::process_frame (feature_tracker.rs:43-77) */
 rsvio_status rsvio_tracker_process_mono(rsvio_tracker *t, const uint8_t *image, size_t stride);
 
@@ -225,6 +235,10 @@ rsvio_status rsvio_se2_exp(int32_t device, const float *twists, int32_t n, float
 /* unproject_one for n pixels (host pointers): xy = n x (u, v) float, out_xy = n x (x/z, y/z) float */
 rsvio_status rsvio_unproject_points(int32_t device, const rsvio_camera_model *model, const float *xy, int32_t n,
                                     float *out_xy);
+
+/* DynamicImage::to_luma8 for one decoded frame (host pointers); out = height x width bytes, dense */
+rsvio_status rsvio_convert_to_luma8(int32_t device, const void *src, int32_t width, int32_t height,
+                                    size_t stride_bytes, int32_t pixel_format, uint8_t *out);
 
 #ifdef __cplusplus
 }

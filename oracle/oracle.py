@@ -117,6 +117,21 @@ def se2_exp(a):
     return out.reshape(3, 3)
 
 
+PIXEL_LUMA8, PIXEL_LUMA16, PIXEL_RGB8 = 0, 1, 2
+
+
+def to_luma8(img, fmt):
+    """DynamicImage::to_luma8: img = (h, w) uint16 for PIXEL_LUMA16, (h, w, 3) uint8 for PIXEL_RGB8."""
+    a = np.ascontiguousarray(img)
+    h, w = a.shape[:2]
+    out = np.empty((h, w), np.uint8)
+    f = lib().orc_to_luma8
+    f.restype = None
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_int, _u8p]
+    f(a.ctypes.data, w, h, a.strides[0], fmt, out)
+    return out
+
+
 CAMERA_PINHOLE_RADTAN, CAMERA_EUCM = 1, 2
 
 

@@ -730,6 +730,25 @@ void orc_se2_exp(const float a[3], float out[9]) {
     out[8] = 1.0f;
 }
 
+void orc_to_luma8(const uint8_t *src, int w, int h, size_t stride_bytes, int fmt, uint8_t *out) {
+    for (int y = 0; y < h; ++y) {
+        const uint8_t *row = src + (size_t)y * stride_bytes;
+        for (int x = 0; x < w; ++x) {
+            uint32_t v;
+            if (fmt == 1) {
+                uint16_t c;
+                std::memcpy(&c, row + 2 * x, 2);  // native-endian u16, as ImageBuffer<Luma<u16>> stores it
+                v = ((uint32_t)c + 128u) / 257u;
+            } else if (fmt == 2) {
+                v = (2126u * row[3 * x] + 7152u * row[3 * x + 1] + 722u * row[3 * x + 2]) / 10000u;
+            } else {
+                v = row[x];
+            }
+            out[(size_t)y * w + x] = (uint8_t)v;
+        }
+    }
+}
+
 int orc_project(int model, const double p[9], double x, double y, double out_uv[2]) {
     double xd, yd;
     if (model == 1) {

@@ -88,6 +88,8 @@ struct rsvio_tracker {
     // unprojection (row f-1): camera models and the host-mapped coordinate ring, allocated when a model is set
     CameraModelDev cam_model[2]{};
     float *h_uxy[kSlots] = {nullptr, nullptr}, *d_uxy[kSlots] = {nullptr, nullptr};
+    uint8_t *d_raw = nullptr;  // decoded-frame staging for process_stereo_fmt (2 images), grown on demand
+    size_t raw_bytes = 0;
     cudaEvent_t ev_h2d[kSlots]{}, ev_in_free[kSlots]{}, ev_done[kSlots]{}, ev_merged[kSlots]{};
     int next_slot = 0, oldest_slot = 0, inflight = 0, result_slot = -1;
     uint64_t host_launches = 0;
@@ -163,6 +165,7 @@ void free_all(rsvio_tracker *t) {
         cudaFree(t->tab[i].T6);
         cudaFree(t->tab[i].counts);
     }
+    cudaFree(t->d_raw);
     cudaFree(t->d_lk_T6);
     cudaFree(t->d_lk_status);
     cudaFree(t->d_occ);
@@ -632,6 +635,56 @@ rsvio_status rsvio_tracker_process_stereo(rsvio_tracker *t, const uint8_t *left,
     if (t->S != 1 || !t->stereo) return fail(t, RSVIO_ERR_INVALID_ARG, "handle is not a 1-stream stereo tracker");
     const uint8_t *l[1] = {left}, *r[1] = {right};
     return rsvio_tracker_process_batch(t, l, r, stride);
+}
+
+rsvio_status rsvio_tracker_process_stereo_fmt(rsvio_tracker *t, const void *left, const void *right,
+                                              size_t stride_bytes, int32_t pixel_format) {
+    if (!t) return RSVIO_ERR_INVALID_ARG;
+    if (pixel_format == RSVIO_PIXEL_LUMA8)
+        return rsvio_tracker_process_stereo(t, (const uint8_t *)left, (const uint8_t *)right, stride_bytes);
+    if (t->S != 1 || !t->stereo) return fail(t, RSVIO_ERR_INVALID_ARG, "handle is not a 1-stream stereo tracker");
+    const int bpp = pixel_bytes(pixel_format);
+    if (bpp == 0) return fail(t, RSVIO_ERR_INVALID_ARG, "unknown pixel format");
+    if (!left || !right) return fail(t, RSVIO_ERR_INVALID_ARG, "null image pointer");
+    const int w = t->cfg.width, h = t->cfg.height;
+    const size_t row = (size_t)w * bpp;
+    if (stride_bytes < row) return fail(t, RSVIO_ERR_INVALID_ARG, "stride smaller than a row");
+    if (t->inflight >= kSlots) return fail(t, RSVIO_ERR_STATE, "two frames already in flight: call rsvio_tracker_sync");
+    DeviceScope dev_scope;
+    CU_TRY(t, dev_scope.enter(t->cfg.device));
+    const size_t need = 2 * row * (size_t)h;
+    if (t->raw_bytes < need) {
+        CU_TRY(t, cudaStreamSynchronize(t->copy_st));
+        cudaFree(t->d_raw);
+        t->d_raw = nullptr;
+        t->raw_bytes = 0;
+        CU_TRY(t, cudaMalloc((void **)&t->d_raw, need));
+        t->raw_bytes = need;
+    }
+    const int slot = t->next_slot;
+    // raw upload and conversion on the copy stream: the conversion writes the slot the pyramid kernel reads
+    CU_TRY(t, cudaStreamWaitEvent(t->copy_st, t->ev_in_free[slot], 0));
+    if (t->profiling) cudaEventRecord(t->ev_up[slot][0], t->copy_st);
+    const void *src[2] = {left, right};
+    for (int cam = 0; cam < 2; ++cam) {
+        uint8_t *raw = t->d_raw + (size_t)cam * row * h;
+        CU_TRY(t, cudaMemcpy2DAsync(raw, row, src[cam], stride_bytes, row, (size_t)h, cudaMemcpyHostToDevice, t->copy_st));
+        CU_TRY(t, convert_to_luma8(raw, row, w, h, pixel_format, t->d_in[slot] + (size_t)cam * t->img_bytes, t->copy_st));
+    }
+    t->stage_launches[0] += 4;
+    t->host_launches += 2;
+    if (t->profiling) cudaEventRecord(t->ev_up[slot][1], t->copy_st);
+    t->up_valid[slot] = t->profiling;
+    CU_TRY(t, cudaEventRecord(t->ev_h2d[slot], t->copy_st));
+    CU_TRY(t, cudaStreamWaitEvent(t->st, t->ev_h2d[slot], 0));
+    if (t->pyr_st != t->st) CU_TRY(t, cudaStreamWaitEvent(t->pyr_st, t->ev_h2d[slot], 0));
+    rsvio_status rs = enqueue_frame(t, slot, t->d_in[slot], t->d_in[slot] + t->img_bytes, (size_t)w, t->img_bytes);
+    if (rs != RSVIO_OK) return rs;
+    t->next_slot ^= 1;
+    t->inflight += 1;
+    // the caller may reuse its buffers when this returns: pageable sources have been staged by the runtime,
+    // pinned ones are read by the DMA that the sync below waits for
+    return rsvio_tracker_sync(t);
 }
 
 rsvio_status rsvio_tracker_process_mono(rsvio_tracker *t, const uint8_t *image, size_t stride) {
@@ -1109,6 +1162,27 @@ rsvio_status rsvio_unproject_points(int32_t device, const rsvio_camera_model *mo
 done:
     cudaFree(d_in);
     cudaFree(d_out);
+    return rs;
+}
+
+rsvio_status rsvio_convert_to_luma8(int32_t device, const void *src, int32_t width, int32_t height, size_t stride_bytes,
+                                    int32_t pixel_format, uint8_t *out) {
+    const int bpp = pixel_bytes(pixel_format);
+    if (!src || !out || width < 1 || height < 1 || bpp == 0 || stride_bytes < (size_t)width * bpp)
+        return RSVIO_ERR_INVALID_ARG;
+    rsvio_status rs = RSVIO_OK;
+    DeviceScope dev_scope;
+    uint8_t *d_src = nullptr, *d_dst = nullptr;
+    const size_t row = (size_t)width * bpp;
+    CU_TRY0(dev_scope.enter(device));
+    CU_TRY0(cudaMalloc((void **)&d_src, row * (size_t)height));
+    CU_TRY0(cudaMalloc((void **)&d_dst, (size_t)width * height));
+    CU_TRY0(cudaMemcpy2D(d_src, row, src, stride_bytes, row, (size_t)height, cudaMemcpyHostToDevice));
+    CU_TRY0(convert_to_luma8(d_src, row, width, height, pixel_format, d_dst, 0));
+    CU_TRY0(cudaMemcpy(out, d_dst, (size_t)width * height, cudaMemcpyDeviceToHost));
+done:
+    cudaFree(d_src);
+    cudaFree(d_dst);
     return rs;
 }
 

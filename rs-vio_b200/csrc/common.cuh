@@ -180,5 +180,10 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// decoded frames (16-bit grey, RGB8) -> dense 8-bit luma (DynamicImage::to_luma8 of the dataset players)
+int pixel_bytes(int fmt);
+cudaError_t convert_to_luma8(const uint8_t *d_src, size_t stride_bytes, int w, int h, int fmt, uint8_t *d_dst,
+                             cudaStream_t st);
+
 }  // namespace rsvio
 #endif

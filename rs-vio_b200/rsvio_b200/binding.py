@@ -37,7 +37,10 @@ ABI_SYMBOLS = (
     "rsvio_pyramid_bytes", "rsvio_pyramid_device_bytes", "rsvio_build_pyramid_u8",
     "rsvio_build_pyramid_u8_device", "rsvio_track_points", "rsvio_detect_keypoints", "rsvio_se2_exp",
     "rsvio_tracker_set_camera", "rsvio_tracker_undistorted_view", "rsvio_unproject_points",
+    "rsvio_tracker_process_stereo_fmt", "rsvio_convert_to_luma8",
 )
+
+PIXEL_LUMA8, PIXEL_LUMA16, PIXEL_RGB8 = 0, 1, 2
 
 CAMERA_NONE, CAMERA_PINHOLE_RADTAN, CAMERA_EUCM = 0, 1, 2
 
@@ -148,6 +151,8 @@ def load_library():
     L.rsvio_tracker_set_camera.argtypes = [H, C.c_int32, C.POINTER(CameraModel)]
     L.rsvio_tracker_undistorted_view.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.rsvio_unproject_points.argtypes = [C.c_int32, C.POINTER(CameraModel), _f32p, C.c_int32, _f32p]
+    L.rsvio_tracker_process_stereo_fmt.argtypes = [H, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32]
+    L.rsvio_convert_to_luma8.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_size_t, C.c_int32, _u8p]
     _lib = L
     return L
 
@@ -218,6 +223,15 @@ def detect_keypoints(image, grid, cur_xy=None, device=0):
     _check(load_library().rsvio_detect_keypoints(device, img, w, h, w, grid, cur_arg, cur.shape[0], xy, sc, cap,
                                                  C.byref(n)))
     return xy[:n.value].copy(), sc[:n.value].copy()
+
+
+def convert_to_luma8(img, fmt, device=0):
+    """DynamicImage::to_luma8 on the device: (h, w) uint16 for PIXEL_LUMA16, (h, w, 3) uint8 for PIXEL_RGB8."""
+    a = np.ascontiguousarray(img)
+    h, w = a.shape[:2]
+    out = np.empty((h, w), np.uint8)
+    _check(load_library().rsvio_convert_to_luma8(device, C.c_void_p(a.ctypes.data), w, h, a.strides[0], fmt, out))
+    return out
 
 
 def unproject_points(model, xy, device=0):
@@ -403,6 +417,15 @@ class StereoPatchTracker(_Tracker):
                     # with a camera model set the unprojection of Frame::add_*_feature (frame.rs:118-119) is
                     # already done on the device; otherwise the reference's placeholder (-1, -1) stays
                     add(Feature(i, (p[0], p[1]), tuple(und[k]) if und is not None else (-1.0, -1.0)))
+
+    def process_decoded(self, left, right, fmt):
+        """process_frame for frames as the decoder delivers them: (h, w) uint16 (PIXEL_LUMA16) or (h, w, 3) uint8
+        (PIXEL_RGB8); the to_luma8() of the reference's dataset players runs on the device."""
+        l, r = np.ascontiguousarray(left), np.ascontiguousarray(right)
+        if l.shape[:2] != (self.height, self.width) or r.shape != l.shape:
+            raise ValueError("image shape does not match the tracker")
+        _check(self._L.rsvio_tracker_process_stereo_fmt(self._h, C.c_void_p(l.ctypes.data), C.c_void_p(r.ctypes.data),
+                                                        l.strides[0], fmt), self._h)
 
     def get_track_points(self, stream=0):
         """[ {id: (x, y)} for cam0, cam1 ]  (feature_tracker.rs:188-200)"""

@@ -31,6 +31,9 @@ pub struct rsvio_track_record {
     pub y: f32,
 }
 
+pub const RSVIO_PIXEL_LUMA8: i32 = 0;
+pub const RSVIO_PIXEL_LUMA16: i32 = 1;
+pub const RSVIO_PIXEL_RGB8: i32 = 2;
 pub const RSVIO_CAMERA_NONE: i32 = 0;
 pub const RSVIO_CAMERA_PINHOLE_RADTAN: i32 = 1;
 pub const RSVIO_CAMERA_EUCM: i32 = 2;
@@ -109,6 +112,12 @@ extern "C" {
                                           capacity: *mut i32) -> rsvio_status;
     pub fn rsvio_unproject_points(device: i32, model: *const rsvio_camera_model, xy: *const f32, n: i32,
                                   out_xy: *mut f32) -> rsvio_status;
+
+    // ---- decoded frames (16-bit grey, RGB8): DynamicImage::to_luma8 on the device ----
+    pub fn rsvio_tracker_process_stereo_fmt(t: *mut rsvio_tracker, left: *const c_void, right: *const c_void,
+                                            stride_bytes: usize, pixel_format: i32) -> rsvio_status;
+    pub fn rsvio_convert_to_luma8(device: i32, src: *const c_void, width: i32, height: i32, stride_bytes: usize,
+                                  pixel_format: i32, out: *mut u8) -> rsvio_status;
 }
 
 pub const RSVIO_N_STAGES: usize = 8;

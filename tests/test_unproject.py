@@ -95,3 +95,44 @@ def test_tracker_exports_undistorted_coordinates(rsvio, oracle):
     tr.set_camera(1, rsvio.CameraModel(rsvio.CAMERA_NONE))
     tr.process_frame(*seq.frame(3))
     assert tr.undistorted_view() is None
+
+
+# ---- ingest row f-3: decoded frames (DynamicImage::to_luma8 of the dataset players) -------------------------
+def test_oracle_to_luma8_known_values(oracle):
+    g16 = np.array([[0, 128, 129, 257, 65535, 32768, 385, 386]], np.uint16)
+    assert oracle.to_luma8(g16, oracle.PIXEL_LUMA16).tolist() == [[0, 0, 1, 1, 255, 128, 1, 2]]   # (c + 128) // 257
+    rgb = np.array([[[255, 255, 255], [255, 0, 0], [0, 255, 0], [0, 0, 255], [10, 20, 30]]], np.uint8)
+    want = [[255, 2126 * 255 // 10000, 7152 * 255 // 10000, 722 * 255 // 10000,
+             (2126 * 10 + 7152 * 20 + 722 * 30) // 10000]]
+    assert oracle.to_luma8(rgb, oracle.PIXEL_RGB8).tolist() == want
+
+
+@pytest.mark.gpu
+def test_gpu_to_luma8_and_decoded_frames(rsvio, oracle):
+    from rsvio_b200.synth import StereoSequence
+    rng = np.random.default_rng(5)
+    g16 = rng.integers(0, 65536, (97, 131), dtype=np.uint16)
+    rgb = rng.integers(0, 256, (97, 131, 3), dtype=np.uint8)
+    assert np.array_equal(rsvio.convert_to_luma8(g16, rsvio.PIXEL_LUMA16), oracle.to_luma8(g16, oracle.PIXEL_LUMA16))
+    assert np.array_equal(rsvio.convert_to_luma8(rgb, rsvio.PIXEL_RGB8), oracle.to_luma8(rgb, oracle.PIXEL_RGB8))
+    # a tracker fed 16-bit / RGB frames == a tracker fed their to_luma8()
+    w, h = 376, 240
+    seq = StereoSequence("C1", w=w, h=h)
+    for fmt, ofmt in ((rsvio.PIXEL_LUMA16, oracle.PIXEL_LUMA16), (rsvio.PIXEL_RGB8, oracle.PIXEL_RGB8)):
+        a = rsvio.StereoPatchTracker(40, 20, 0.01, width=w, height=h, levels=3)
+        b = rsvio.StereoPatchTracker(40, 20, 0.01, width=w, height=h, levels=3)
+        for t in range(3):
+            l8, r8 = seq.frame(t)
+            if fmt == rsvio.PIXEL_LUMA16:
+                lraw = l8.astype(np.uint16) * 257 + rng.integers(-100, 100, l8.shape).clip(0).astype(np.uint16)
+                rraw = r8.astype(np.uint16) * 257
+            else:
+                lraw = np.stack([l8, l8, l8], 2)
+                rraw = np.stack([r8, (r8 // 2 + 60).astype(np.uint8), r8], 2)
+            a.process_decoded(lraw, rraw, fmt)
+            b.process_frame(oracle.to_luma8(lraw, ofmt), oracle.to_luma8(rraw, ofmt))
+            for cam in (0, 1):
+                ia, Ta = a.transforms(cam)
+                ib, Tb = b.transforms(cam)
+                assert np.array_equal(ia, ib) and np.array_equal(Ta, Tb)
+        assert a.num_tracks(0) > 20
