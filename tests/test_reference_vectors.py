@@ -169,6 +169,33 @@ def test_gpu_unproject_matches_the_reference(rsvio):
     _unproject(fn)
 
 
+def _to_luma8(convert16, convert_rgb):
+    seen = 0
+    for head, tail in load():
+        if head[0] not in ("luma16", "rgb8"):
+            continue
+        seen += 1
+        w, h = int(head[1]), int(head[2])
+        raw = np.frombuffer(bytes.fromhex(tail[0]), np.uint8)
+        want = np.frombuffer(bytes.fromhex(tail[1]), np.uint8).reshape(h, w)
+        if head[0] == "luma16":
+            got = convert16(raw.view("<u2").reshape(h, w).astype(np.uint16))
+        else:
+            got = convert_rgb(raw.reshape(h, w, 3))
+        assert np.array_equal(got, want), head[0]
+    if not seen:
+        pytest.skip("no to_luma8 records")
+
+
+def test_oracle_to_luma8_matches_the_reference(oracle):
+    _to_luma8(lambda a: oracle.to_luma8(a, oracle.PIXEL_LUMA16), lambda a: oracle.to_luma8(a, oracle.PIXEL_RGB8))
+
+
+@pytest.mark.gpu
+def test_gpu_to_luma8_matches_the_reference(rsvio):
+    _to_luma8(lambda a: rsvio.convert_to_luma8(a, rsvio.PIXEL_LUMA16), lambda a: rsvio.convert_to_luma8(a, rsvio.PIXEL_RGB8))
+
+
 def _tracks(make_tracker):
     frames = {}
     for head, tail in load():

@@ -59,6 +59,13 @@ def main():
         for u, v in pts:
             x, y = oracle.unproject(model, P, [[u, v]])[0]
             out.append(f"unproject {model} {b64(u)} {b64(v)} : {b64(x)} {b64(y)} {b64(1.0)}")
+    from test_reference_vectors import mix
+    yy, xx = np.mgrid[0:8, 0:64]
+    g16 = (mix(xx, yy, 51) >> np.uint64(16)).astype(np.uint16)
+    out.append(f"luma16 64 8 51 : {g16.astype('<u2').tobytes().hex()} {oracle.to_luma8(g16, oracle.PIXEL_LUMA16).tobytes().hex()}")
+    m = mix(xx, yy, 52)
+    rgb = np.stack([(m >> np.uint64(24)) & np.uint64(255), (m >> np.uint64(16)) & np.uint64(255), (m >> np.uint64(8)) & np.uint64(255)], 2).astype(np.uint8)
+    out.append(f"rgb8 64 8 52 : {rgb.tobytes().hex()} {oracle.to_luma8(rgb, oracle.PIXEL_RGB8).tobytes().hex()}")
     path = sys.argv[1] if len(sys.argv) > 1 else "reference_vectors_oracle.txt"
     open(path, "w").write("\n".join(out) + "\n")
     print("wrote", path)
