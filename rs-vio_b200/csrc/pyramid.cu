@@ -423,30 +423,44 @@ __device__ __forceinline__ void ring_rows_horizontal(const FastParams &P, const 
     }
 }
 
-// border columns of level LEV: item = side * (TH / r) + row of the tile; interior rows only
+// border column `side` (0: ox = 0, 1: ox = wl - 1) of level LEV, interior rows only.  A group of GL adjacent lanes
+// owns one output: lane kx runs the vertical chain of window column kx (2r taps), then the CX column values are
+// combined in tap order through shuffles.  All NTA threads work (one pass per level and side), the lanes of a group
+// read the same shared-memory words (broadcast), and no block barrier is needed.  (The first version gave each
+// output to one thread: 48 serial taps at level 2, 192 at level 3, 8- to 15-way bank conflicts, and every border
+// tile waited for that one warp: 23 % of the kernel's time.)
 template <int LEV>
-__device__ __forceinline__ void ring_cols(const FastParams &P, const RingTile &rt, uint8_t *__restrict__ out, bool left,
-                                          bool right, int item) {
+__device__ __forceinline__ void ring_cols(const FastParams &P, const RingTile &rt, uint8_t *__restrict__ out, int side,
+                                          int tid) {
     constexpr int r = 1 << LEV, CX = r + (r >> 1), CY = 2 * r, ROWS = TH / r;
-    const int side = item / ROWS, ly = item % ROWS;
-    if (side == 0 ? !left : !right) return;
+    constexpr int GL = CX <= 4 ? 4 : (CX <= 8 ? 8 : 16);  // lanes per output
+    static_assert((ROWS * GL) % 32 == 0 && 32 % GL == 0, "groups must not straddle warps");
     const int wl = P.pd.lv[LEV].w, hl = P.pd.lv[LEV].h, w0 = P.pd.lv[0].w;
-    const int oy = rt.Y0 / r + ly, ox = side == 0 ? 0 : wl - 1;
-    if (oy < 1 || oy > hl - 2 || ox * r < rt.X0 || ox * r >= rt.X0 + TW) return;
+    const int ox = side == 0 ? 0 : wl - 1;
+    if (ox * r < rt.X0 || ox * r >= rt.X0 + TW) return;  // uniform
     float wy[CY];
 #pragma unroll
     for (int k = 0; k < CY; ++k) wy[k] = P.ring[LEV].inner[k];
-    const int c0 = (side == 0 ? 0 : w0 - CX) - rt.X0 + 16, row0 = oy * r - (r >> 1) - rt.Y0 + rt.ytop;
-    float t = 0.0f;
-#pragma unroll(LEV < 3 ? CX : 1)
-    for (int kx = 0; kx < CX; ++kx) {
-        const uint8_t *__restrict__ s = rt.at(row0, c0 + kx);
+    const int c0 = (side == 0 ? 0 : w0 - CX) - rt.X0 + 16;
+    for (int item = tid; item < ROWS * GL; item += NTA) {  // whole warps enter and leave together
+        const int ly = item / GL, kx = item % GL;
+        const int oy = rt.Y0 / r + ly;
+        const bool live = oy >= 1 && oy <= hl - 2;
         float v = 0.0f;
+        if (live && kx < CX) {
+            const uint8_t *__restrict__ s = rt.at(oy * r - (r >> 1) - rt.Y0 + rt.ytop, c0 + kx);
 #pragma unroll
-        for (int ky = 0; ky < CY; ++ky) v = __fadd_rn(v, __fmul_rn((float)s[ky * RW], wy[ky]));
-        t = __fadd_rn(t, __fmul_rn(v, side == 0 ? P.ring[LEV].first[kx] : P.ring[LEV].last[kx]));
+            for (int ky = 0; ky < CY; ++ky) v = __fadd_rn(v, __fmul_rn((float)s[ky * RW], wy[ky]));
+        }
+        const int leader = (tid & 31) & ~(GL - 1);
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < CX; ++k) {
+            const float vk = __shfl_sync(0xffffffffu, v, leader + k);
+            t = __fadd_rn(t, __fmul_rn(vk, side == 0 ? P.ring[LEV].first[k] : P.ring[LEV].last[k]));
+        }
+        if (live && kx == 0) out[P.pd.lv[LEV].off + (size_t)oy * wl + ox] = ring_round(t);
     }
-    out[P.pd.lv[LEV].off + (size_t)oy * wl + ox] = ring_round(t);
 }
 
 template <int NA>
@@ -584,15 +598,15 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
             if (NA >= 2) ring_rows_horizontal<2>(P, rt, vbuf[NA >= 2 ? 1 : 0], out, side, (tid + 64) % NTA);
             if (NA >= 3) ring_rows_horizontal<3>(P, rt, vbuf[NA >= 3 ? 2 : 0], out, side, (tid + 32) % NTA);
         }
-        // border columns (ox = 0 for left tiles, ox = wl - 1 for right tiles) without the corner rows:
-        // one thread per (level, side, row); a warp holds one level
-        static_assert(4 * NTA >= 7 * TH, "ring column items (TH + TH/2 + TH/4) are mapped to thread ranges");
-        if (left || right) {
-            if (tid < TH) ring_cols<1>(P, rt, out, left, right, tid);
-            else if (tid < TH + TH / 2) { if (NA >= 2) ring_cols<2>(P, rt, out, left, right, tid - TH); }
-            else if (tid < TH + TH / 2 + TH / 4) { if (NA >= 3) ring_cols<3>(P, rt, out, left, right, tid - TH - TH / 2); }
+        // border columns (ox = 0 for left tiles, ox = wl - 1 for right tiles) without the corner rows
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+            if (side == 0 ? !left : !right) continue;
+            ring_cols<1>(P, rt, out, side, tid);
+            if (NA >= 2) ring_cols<2>(P, rt, out, side, tid);
+            if (NA >= 3) ring_cols<3>(P, rt, out, side, tid);
         }
-            __syncthreads();  // vbuf shares its bytes with g2, which stage 1 writes next
+        if (top || bottom) __syncthreads();  // vbuf shares its bytes with g2, which stage 1 writes next
     }
 
     // ---- stage 1: level-1 output O_2 (global) and G_2 (smem); 4 chained DP4A per value.
