@@ -589,7 +589,9 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
 #pragma unroll 1
         for (int side = 0; side < 2; ++side) {  // border rows: oy = 0 (top tiles), oy = hl - 1 (bottom tiles)
             if (side == 0 ? !top : !bottom) continue;
-            __syncthreads();
+            // vbuf lives in the bytes of g2: the previous tile's readers passed the end-of-tile barrier; only a tile
+            // that is both top and bottom reuses vbuf within this block
+            if (side == 1 && top) __syncthreads();
             ring_rows_vertical<1>(P, rt, vbuf[0], side, tid);
             if (NA >= 2) ring_rows_vertical<2>(P, rt, vbuf[NA >= 2 ? 1 : 0], side, tid);
             if (NA >= 3) ring_rows_vertical<3>(P, rt, vbuf[NA >= 3 ? 2 : 0], side, tid);
