@@ -104,8 +104,10 @@ list_empty_cells_kernel(GridDesc gd, int streams, const uint8_t *__restrict__ oc
     if (empty) list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)item;
 }
 
-// One CTA per empty cell: the (g-6)^2 candidates are spread over 128 threads, block-wide packed-key max.
-constexpr int kDetThreads = 128;
+// One CTA per empty cell: the (g-6)^2 candidates are spread over 256 threads, block-wide packed-key max.
+// (128 threads: 4 % slower on the bench step; one WARP per cell, no block barriers: 40 % slower -- a lane then
+// tests 36 candidates in sequence.)
+constexpr int kDetThreads = 256;
 constexpr int kDetChunk = 2048;  // candidates per compaction pass (a 40-px cell has 1156)
 __global__ void __launch_bounds__(kDetThreads)
 detect_list_kernel(GridDesc gd, const uint8_t *__restrict__ img0, size_t stride, size_t pitch,
