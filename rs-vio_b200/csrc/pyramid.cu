@@ -438,20 +438,21 @@ __device__ __forceinline__ void ring_cols(const FastParams &P, const RingTile &r
     const int wl = P.pd.lv[LEV].w, hl = P.pd.lv[LEV].h, w0 = P.pd.lv[0].w;
     const int ox = side == 0 ? 0 : wl - 1;
     if (ox * r < rt.X0 || ox * r >= rt.X0 + TW) return;  // uniform
-    float wy[CY];
-#pragma unroll
-    for (int k = 0; k < CY; ++k) wy[k] = P.ring[LEV].inner[k];
     const int c0 = (side == 0 ? 0 : w0 - CX) - rt.X0 + 16;
     for (int item = tid; item < ROWS * GL; item += NTA) {  // whole warps enter and leave together
         const int ly = item / GL, kx = item % GL;
         const int oy = rt.Y0 / r + ly;
         const bool live = oy >= 1 && oy <= hl - 2;
-        float v = 0.0f;
+        // The vertical window of an interior row is complete: its weights are the dyadic tent (2k+1) / (2 r^2), every
+        // product and partial sum of the reference's f32 chain is exact (< 2^15 in units of 1 / (2 r^2)), so the chain
+        // is the integer sum below, scaled once -- one IMAD per tap instead of convert, multiply, add.
+        uint32_t nv = 0;
         if (live && kx < CX) {
             const uint8_t *__restrict__ s = rt.at(oy * r - (r >> 1) - rt.Y0 + rt.ytop, c0 + kx);
 #pragma unroll
-            for (int ky = 0; ky < CY; ++ky) v = __fadd_rn(v, __fmul_rn((float)s[ky * RW], wy[ky]));
+            for (int ky = 0; ky < CY; ++ky) nv += (uint32_t)(ky < r ? 2 * ky + 1 : 2 * (CY - 1 - ky) + 1) * s[ky * RW];
         }
+        const float v = __fmul_rn((float)nv, 1.0f / (float)(2 * r * r));
         const int leader = (tid & 31) & ~(GL - 1);
         float t = 0.0f;
 #pragma unroll
