@@ -58,7 +58,34 @@ def main():
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_small.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
+    rows_f()
+
+
+def rows_f():
+    """rows f-1 / f-3 (golden_rows_f.npz): unprojection with the cameras of the reference's configs and
+    DynamicImage::to_luma8 of 16-bit / RGB frames, by the oracle."""
+    out = {}
+    rng = np.random.default_rng(20261018)
+    euroc = [458.654, 457.296, 367.215, 248.375, -0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0]
+    tumvi = [191.75556798912652, 191.74816751185256, 254.9226487139376, 256.8780365577954, 0.6246288732884442,
+             1.0598071085569876, 0.0, 0.0, 0.0]
+    for name, model, P, (w, h) in (("euroc", orc.CAMERA_PINHOLE_RADTAN, euroc, (752, 480)),
+                                   ("tumvi", orc.CAMERA_EUCM, tumvi, (512, 512))):
+        uv = rng.uniform([0, 0], [w, h], (400, 2)).astype(np.float32)
+        out[f"unproject_{name}_params"] = np.array(P)
+        out[f"unproject_{name}_uv"] = uv
+        out[f"unproject_{name}_xy"] = orc.unproject(model, P, uv.astype(np.float64))
+    g16 = rng.integers(0, 65536, (33, 47), dtype=np.uint16)
+    rgb = rng.integers(0, 256, (33, 47, 3), dtype=np.uint8)
+    out["luma16_in"], out["luma16_out"] = g16, orc.to_luma8(g16, orc.PIXEL_LUMA16)
+    out["rgb8_in"], out["rgb8_out"] = rgb, orc.to_luma8(rgb, orc.PIXEL_RGB8)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_rows_f.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":
-    main()
+    if "--rows-f" in sys.argv:   # only the second file (golden_small.npz stays byte-identical)
+        rows_f()
+    else:
+        main()

@@ -136,3 +136,20 @@ def test_gpu_to_luma8_and_decoded_frames(rsvio, oracle):
                 ib, Tb = b.transforms(cam)
                 assert np.array_equal(ia, ib) and np.array_equal(Ta, Tb)
         assert a.num_tracks(0) > 20
+
+
+@pytest.mark.gpu
+def test_gpu_matches_golden_rows_f(rsvio):
+    import os
+    from util import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, "golden_rows_f.npz"))
+    for name, mk in (("euroc", rsvio.CAMERA_PINHOLE_RADTAN), ("tumvi", rsvio.CAMERA_EUCM)):
+        P = g[f"unproject_{name}_params"]
+        cm = rsvio.CameraModel(mk, 0, (rsvio.binding.C.c_double * 9)(*P))
+        got = rsvio.unproject_points(cm, g[f"unproject_{name}_uv"]).astype(np.float64)
+        want = g[f"unproject_{name}_xy"]
+        ok = np.isfinite(want).all(axis=1)
+        assert np.array_equal(np.isfinite(got).all(axis=1), ok)
+        assert np.abs(got[ok] - want[ok]).max() <= 2e-7 * (1.0 + np.abs(want[ok]).max())
+    assert np.array_equal(rsvio.convert_to_luma8(g["luma16_in"], rsvio.PIXEL_LUMA16), g["luma16_out"])
+    assert np.array_equal(rsvio.convert_to_luma8(g["rgb8_in"], rsvio.PIXEL_RGB8), g["rgb8_out"])
