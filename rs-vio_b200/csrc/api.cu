@@ -79,7 +79,7 @@ struct rsvio_tracker {
     int32_t *d_st_status = nullptr;
     unsigned long long *d_last_id = nullptr, *d_counters = nullptr, *d_rm = nullptr;
     int rm_cap = 0;
-    int *d_err = nullptr;
+    int *d_err = nullptr;  // one overflow flag per slot: a full table is reported for the frame that overflowed only
     unsigned *d_work = nullptr;  // [0,1] temporal LK counters, [2,3] stereo LK counters
     int lk_par[2] = {0, 0}, det_par = 0;
     // host-mapped output ring: records [groups][cap] and counts [groups] (+1 error flag)
@@ -195,7 +195,7 @@ rsvio_status clear_state(rsvio_tracker *t) {
     for (int i = 0; i < 2; ++i) CU_TRY(t, cudaMemsetAsync(t->tab[i].counts, 0, sizeof(int) * t->groups, t->st));
     CU_TRY(t, cudaMemsetAsync(t->d_last_id, 0, sizeof(unsigned long long) * t->S, t->st));
     CU_TRY(t, cudaMemsetAsync(t->d_counters, 0, sizeof(unsigned long long) * CNT_N, t->st));
-    CU_TRY(t, cudaMemsetAsync(t->d_err, 0, sizeof(int), t->st));
+    CU_TRY(t, cudaMemsetAsync(t->d_err, 0, sizeof(int) * kSlots, t->st));
     CU_TRY(t, cudaMemsetAsync(t->d_new_count, 0, sizeof(int) * t->S, t->st));
     CU_TRY(t, cudaMemsetAsync(t->d_work, 0, sizeof(unsigned) * 4, t->st));
     CU_TRY(t, cudaMemsetAsync(t->d_cell_list_n, 0, sizeof(int) * 2, t->st));
@@ -270,7 +270,7 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
     CU_TRY(t, cudaEventRecord(t->ev_lk_done, st));  // `prev` may be overwritten from here on
     mark(++stage);  // 3: compaction + occupancy
     CU_TRY(t, compact_tracks(tin, t->d_lk_T6, t->d_lk_status, tout, t->groups, t->cap, t->S, t->gd, t->d_occ,
-                             t->have_prev ? 1 : 0, t->d_counters, st));
+                             t->have_prev ? 1 : 0, t->d_counters, t->d_err + slot, st));
     count(3, 1);
     mark(++stage);  // 4: detection (level 0 of the current left pyramid is the input image)
     CU_TRY(t, detect_cells(t->gd, cur + t->pd.lv[0].off, (size_t)t->pd.lv[0].w, (size_t)t->pd.pyr_stride, t->S,
@@ -302,7 +302,7 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
     }
     mark(++stage);  // 6: merge (ids, table append)
     CU_TRY(t, merge_new_points(tout, t->S, t->cap, t->stereo, t->d_new_T6, t->d_st_T6, t->d_st_status,
-                               t->d_new_count, t->new_cap, t->d_last_id, t->d_err, st));
+                               t->d_new_count, t->new_cap, t->d_last_id, t->d_err + slot, st));
     count(6, 1);
     // 7: download -- packed records into mapped host memory + the error flag.  With many streams this runs on
     // its own CUDA stream beside the next frame (the table it reads is not written again before the frame after
@@ -317,7 +317,7 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
     CU_TRY(t, export_records(tout, t->groups, t->cap, t->S, t->d_out[slot], t->d_cnt[slot], t->cam_model[0], t->cam_model[1],
                              t->d_uxy[slot], xs));
     count(7, 1);
-    CU_TRY(t, cudaMemcpyAsync(t->h_cnt[slot] + t->groups, t->d_err, sizeof(int), cudaMemcpyDeviceToHost, xs));
+    CU_TRY(t, cudaMemcpyAsync(t->h_cnt[slot] + t->groups, t->d_err + slot, sizeof(int), cudaMemcpyDeviceToHost, xs));
     ++stage;
     if (prof) cudaEventRecord(t->ev_stage[slot][stage], xs);  // end
     t->stage_valid[slot] = prof;
@@ -532,7 +532,7 @@ rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) 
         CU_TRY(t, dmalloc(&t->d_st_status, S * (size_t)t->new_cap));
         CU_TRY(t, dmalloc(&t->d_last_id, S));
         CU_TRY(t, dmalloc(&t->d_counters, (size_t)CNT_N));
-        CU_TRY(t, dmalloc(&t->d_err, (size_t)1));
+        CU_TRY(t, dmalloc(&t->d_err, (size_t)kSlots));
         CU_TRY(t, dmalloc(&t->d_work, (size_t)4));
         return clear_state(t);
     };

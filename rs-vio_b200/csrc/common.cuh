@@ -139,7 +139,7 @@ struct TableView {
 // groups < streams (camera 0) also rebuild the occupancy grid of their stream.
 cudaError_t compact_tracks(const TableView &in, const float *lk_T6, const int32_t *lk_status, const TableView &out,
                            int groups, int cap, int streams, const GridDesc &gd, uint8_t *occ, int have_prev,
-                           unsigned long long *counters, cudaStream_t st);
+                           unsigned long long *counters, int *err_clear, cudaStream_t st);
 // packed output record written to (mapped) host memory
 struct OutRecord {
     unsigned long long id;

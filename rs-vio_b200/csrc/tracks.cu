@@ -43,7 +43,9 @@ __device__ __forceinline__ int block_rank(bool keep, int *warp_tot, int *base) {
 __global__ void __launch_bounds__(kThreads)
 compact_tracks_kernel(TableView in, const float *__restrict__ lk_T6, const int32_t *__restrict__ lk_status,
                       TableView out, int cap, int streams, GridDesc gd, uint8_t *__restrict__ occ, int have_prev,
-                      unsigned long long *counters) {
+                      unsigned long long *counters, int *__restrict__ err_clear) {
+    // the overflow flag the merge kernel of this frame may raise (its previous use, two frames ago, has been read)
+    if (err_clear && blockIdx.x == 0 && threadIdx.x == 0) *err_clear = 0;
     __shared__ int warp_tot[kWarps];
     __shared__ int base;
     const int g = blockIdx.x;
@@ -208,9 +210,9 @@ remove_ids_kernel(TableView in, TableView out, int cap, int streams, int stream,
 
 cudaError_t compact_tracks(const TableView &in, const float *lk_T6, const int32_t *lk_status, const TableView &out,
                            int groups, int cap, int streams, const GridDesc &gd, uint8_t *occ, int have_prev,
-                           unsigned long long *counters, cudaStream_t st) {
+                           unsigned long long *counters, int *err_clear, cudaStream_t st) {
     compact_tracks_kernel<<<groups, kThreads, 0, st>>>(in, lk_T6, lk_status, out, cap, streams, gd, occ, have_prev,
-                                                       counters);
+                                                       counters, err_clear);
     return cudaGetLastError();
 }
 
