@@ -194,6 +194,21 @@ def workload_config(args, S, n_gpus):
 
 
 # ------------------------------------------------------------------------------------------------
+def ncu_dram_traffic(same_workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the pyramid kernel, per launch, from the committed
+    `ncu --set full` capture of this same workload (profiles/r1_pyr_fast_kernel.txt); None for other workloads."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_pyr_fast_kernel.txt")
+    if not same_workload or not os.path.exists(path):
+        return None, None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    for line in open(path):
+        f = line.split()
+        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[2] in scale:
+            tot += float(f[1]) * scale[f[2]]
+    return (tot, "profiles/r1_pyr_fast_kernel.txt (ncu --set full, cold L2, one launch of 128 images)") if tot else (None, None)
+
+
 def bind_to_gpu_numa_node(local_rank):
     """Multi-GPU runs: keep this rank's threads -- and with them the first-touch pages of the pinned frame ring --
     on the CPUs NVML reports as local to its GPU, so that the uploads do not cross the socket interconnect.
@@ -405,9 +420,11 @@ def main():
     alg_bytes_launch = 2 * S * (w * h + rsvio_b200.pyramid_bytes(w, h, p["levels"]))
     peak, peak_src = measured_peaks()
     achieved = alg_bytes_launch / (pyr_ms * 1e-3) / 1e9 if pyr_ms > 0 else 0.0
+    ncu_traffic, ncu_traffic_src = ncu_dram_traffic(S == 64 and args.config == "C5")
     roofline = {"kernel": "pyr_fast_kernel (pyramid build of one step: %d launch(es), both cameras, all streams)" % pyr_launches,
                 "bound": "hbm", "achieved": achieved,
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic,
+                "traffic_source": ncu_traffic_src,
                 "alg_bytes_per_launch": alg_bytes_launch, "ms_per_launch": pyr_ms, "launches_per_step": pyr_launches,
                 "share_of_step": stages["pyramid"][0] / total_stage_ms if total_stage_ms else None}
     stage_share = {k: (v[0] / prof_steps, v[0] / total_stage_ms if (total_stage_ms and k != "upload") else None)
