@@ -73,3 +73,12 @@ def test_rust_ffi_declares_every_header_symbol():
     in_header = set(_declared_functions())
     in_ffi = set(re.findall(r"pub fn (rsvio_[a-z0-9_]+)", ffi))
     assert in_header == in_ffi, (sorted(in_header - in_ffi), sorted(in_ffi - in_header))
+
+
+def test_rust_build_script_lists_every_cuda_source():
+    """build.rs (--features build-cuda) must compile the same .cu files as the Makefile"""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    mk = open(os.path.join(root, "rs-vio_b200", "Makefile")).read()
+    srcs = set(re.findall(r"csrc/(\w+\.cu)", re.search(r"^SRCS\s*:=\s*(.*)$", mk, re.M).group(1)))
+    rs = open(os.path.join(root, "rs-vio_b200", "rust", "feature_tracker", "build.rs")).read()
+    assert srcs and srcs == set(re.findall(r'"(\w+\.cu)"', rs))
