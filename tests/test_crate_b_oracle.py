@@ -92,3 +92,74 @@ def test_tracking_recovers_a_known_shift():
     for k, T in out.items():
         moved = T.apply(pts[k]) - np.array(pts[k], np.float32)
         assert np.abs(moved - np.array([1.3, -0.7], np.float32)).max() < 0.05, moved
+
+
+# ---- vectors of the real crate (tools/reference_vectors_b; absent here: no cargo) --------------------------------
+VECTORS_B = os.environ.get("RSVIO_REFERENCE_VECTORS_B",
+                           os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors_b.txt"))
+M32 = np.uint64(0xFFFFFFFF)
+
+
+def mix(x, y, seed):
+    x, y = np.asarray(x, np.uint64), np.asarray(y, np.uint64)
+    s = ((x * np.uint64(0x9E3779B1)) & M32) ^ ((y * np.uint64(0x85EBCA77)) & M32) ^ np.uint64((seed * 0xC2B2AE3D) & 0xFFFFFFFF)
+    s ^= s >> np.uint64(15)
+    s = (s * np.uint64(0x2C1B3C6D)) & M32
+    s ^= s >> np.uint64(12)
+    s = (s * np.uint64(0x297A2D39)) & M32
+    s ^= s >> np.uint64(15)
+    return s
+
+
+def scene_b(w, h, seed):
+    y, x = np.mgrid[0:h, 0:w]
+    block = (mix(x // 8, y // 8, seed) >> np.uint64(24)) & np.uint64(0xE0)
+    noise = mix(x, y, seed ^ 0x5555) >> np.uint64(28)
+    return ((block + noise).astype(np.float32) / np.float32(255.0)).astype(np.float32)
+
+
+def _f32s(tokens):
+    return np.array([int(t, 16) for t in tokens], np.uint32).view(np.float32)
+
+
+def test_scene_b_generator():
+    a = scene_b(40, 30, 61)
+    assert a.dtype == np.float32 and a.shape == (30, 40) and 0.0 <= a.min() and a.max() <= 1.0
+    assert np.array_equal(a, scene_b(40, 30, 61)) and len(np.unique(a)) > 20
+
+
+def test_crate_b_oracle_matches_the_reference_vectors():
+    import pytest
+    if not os.path.exists(VECTORS_B):
+        pytest.skip("tests/golden/reference_vectors_b.txt not generated (needs cargo: tools/reference_vectors_b)")
+    for line in open(VECTORS_B):
+        if line.startswith("#") or ":" not in line:
+            continue
+        head, _, tail = line.partition(":")
+        head = head.split()
+        if head[0] == "pyr_b":
+            w, h, seed, levels = map(int, head[1:5])
+            ratio, blur, lev, lw, lh = float(_f32s([head[5]])[0]), int(head[6]), int(head[8]), int(head[9]), int(head[10])
+            if blur:
+                continue                                   # imageops::blur is not restated yet
+            pyr = B.build_image_pyramid(scene_b(w, h, seed), levels, ratio)
+            want = _f32s(tail.split()).reshape(lh, lw)
+            assert pyr[lev].shape == (lh, lw)
+            assert np.abs(pyr[lev] - want).max() <= 1e-6, f"pyramid {w}x{h} level {lev}"
+        elif head[0] == "bicubic":
+            w, h, seed = map(int, head[1:4])
+            x, y, ok = _f32s([head[4]])[0], _f32s([head[5]])[0], int(head[6])
+            r = B.d_interpolate_bicubic(scene_b(w, h, seed), x, y)
+            assert (r is not None) == bool(ok)
+            if ok:
+                v, v2, gx, gy = _f32s(tail.split())
+                assert abs(r[0] - v) <= 1e-6 and abs(B.interpolate_bicubic(scene_b(w, h, seed), x, y) - v2) <= 1e-6
+                assert np.abs(r[1] - np.array([gx, gy], np.float32)).max() <= 1e-5
+        elif head[0] == "patch_b":
+            w, h, seed = map(int, head[1:4])
+            x, y = _f32s([head[4]])[0], _f32s([head[5]])[0]
+            d, j, hi = (_f32s(part.split()) for part in tail.split("|"))
+            p = B.Patch52(scene_b(w, h, seed), (x, y), 0.1)
+            assert np.abs(p.intensities - d).max() <= 1e-6
+            assert np.abs(p.J - j.reshape(52, 3)).max() <= 1e-3 * max(1.0, np.abs(j).max())
+            assert np.abs(p.Hinv - hi.reshape(3, 3)).max() <= 1e-3 * np.abs(hi).max()

@@ -71,5 +71,36 @@ def main():
     print("wrote", path)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--crate-b" not in sys.argv:
     main()
+
+
+def crate_b(path):
+    """same for tools/reference_vectors_b (crate B): `python emulate_with_oracle.py --crate-b /tmp/vec_b.txt`, then
+    RSVIO_REFERENCE_VECTORS_B=/tmp/vec_b.txt python -m pytest tests/test_crate_b_oracle.py"""
+    from oracle import crate_b as B
+    from test_crate_b_oracle import scene_b
+
+    def dump(v):
+        return " ".join(bits(x) for x in np.asarray(v, np.float32).ravel())
+    out = ["# oracle-made stand-in for the crate B vectors (pins nothing)"]
+    for w, h, seed, levels, ratio in ((120, 60, 61, 3, 2.0), (97, 75, 62, 4, 2.0), (96, 64, 63, 3, 1.5)):
+        pyr = B.build_image_pyramid(scene_b(w, h, seed), levels, ratio)
+        for l, lv in enumerate(pyr):
+            out.append(f"pyr_b {w} {h} {seed} {levels} {bits(ratio)} 0 {bits(0.0)} {l} {lv.shape[1]} {lv.shape[0]} : {dump(lv)}")
+    img = scene_b(96, 72, 64)
+    for x, y in ((10.0, 10.0), (20.25, 31.75), (47.5, 35.5), (80.125, 60.875), (0.5, 3.0), (93.2, 10.0)):
+        r = B.d_interpolate_bicubic(img, x, y)
+        if r is None:
+            out.append(f"bicubic 96 72 64 {bits(x)} {bits(y)} 0 :")
+        else:
+            out.append(f"bicubic 96 72 64 {bits(x)} {bits(y)} 1 : {bits(r[0])} {bits(B.interpolate_bicubic(img, x, y))} {bits(r[1][0])} {bits(r[1][1])}")
+    for x, y in ((30.0, 30.0), (48.5, 36.25), (4.0, 4.0)):
+        p = B.Patch52(img, (x, y), 0.1)
+        out.append(f"patch_b 96 72 64 {bits(x)} {bits(y)} : {dump(p.intensities)} | {dump(p.J)} | {dump(p.Hinv)}")
+    open(path, "w").write("\n".join(out) + "\n")
+    print("wrote", path)
+
+
+if __name__ == "__main__" and "--crate-b" in sys.argv:
+    crate_b(sys.argv[-1])
