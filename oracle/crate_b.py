@@ -24,15 +24,14 @@ import numpy as np
 
 F = np.float32
 
-PATTERN_RAW = np.array(
-    [[-3, 7], [-1, 7], [1, 7], [3, 7],
-     [-5, 5], [-3, 5], [-1, 5], [1, 5], [3, 5], [5, 5],
-     [-7, 3], [-5, 3], [-3, 3], [-1, 3], [1, 3], [3, 3], [5, 3], [7, 3],
-     [-7, 1], [-5, 1], [-3, 1], [-1, 1], [1, 1], [3, 1], [5, 1], [7, 1],
-     [-7, -1], [-5, -1], [-3, -1], [-1, -1], [1, -1], [3, -1], [5, -1], [7, -1],
-     [-7, -3], [-5, -3], [-3, -3], [-1, -3], [1, -3], [3, -3], [5, -3], [7, -3],
-     [-5, -5], [-3, -5], [-1, -5], [1, -5], [3, -5], [5, -5],
-     [-3, -7], [-1, -7], [1, -7], [3, -7]], np.float32)          # patch.rs:259-277 (raw_indexes: not divided by 2)
+def _pattern():
+    """the 52 offsets of patch.rs:259-277: rows y = 7, 5, .., -7 with 4, 6, 8, 8, 8, 8, 6, 4 samples at odd x, left to
+    right (raw_indexes() returns them un-halved: the patch spans +-7 px)"""
+    half_widths = (3, 5, 7, 7, 7, 7, 5, 3)
+    return np.array([[x, 7 - 2 * r] for r, hw in enumerate(half_widths) for x in range(-hw, hw + 1, 2)], np.float32)
+
+
+PATTERN_RAW = _pattern()
 
 
 # ---- SE(2) --------------------------------------------------------------------------------------------------
