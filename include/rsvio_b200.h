@@ -240,6 +240,18 @@ rsvio_status rsvio_unproject_points(int32_t device, const rsvio_camera_model *mo
 rsvio_status rsvio_convert_to_luma8(int32_t device, const void *src, int32_t width, int32_t height,
                                     size_t stride_bytes, int32_t pixel_format, uint8_t *out);
 
+/* ---- row f-2, first slice: the tracking core of the reference's second tracker (`feature_tracker` crate) ----
+ * track_points (feature_tracker/src/feature_tracker/feature_tracking.rs:16-59) for n points between two f32
+ * pyramids (host pointers; level l is heights[l] x widths[l] floats, dense): bicubic sampler, SSD patch of 52
+ * samples (radius 7 px), LM-damped Gauss-Newton on SE(2) with twist [theta, vx, vy], forward-backward test
+ * (< 2 px).  out_T4[i] = (cos, sin, tx, ty) of the forward isometry; status[i]: 0 tracked, 1 forward pass left
+ * the image, 2 backward pass left the image, 3 forward-backward distance >= 2 px.  The pyramids (crate B's
+ * chained f32 `resize`, optional blur) and the detection are not on the device yet. */
+rsvio_status rsvio_b_track_points(int32_t device, const float *const *pyr0, const float *const *pyr1,
+                                  const int32_t *widths, const int32_t *heights, int32_t levels,
+                                  const float *points_xy, int32_t n, int32_t max_iteration, float lm_lambda,
+                                  float *out_T4, int32_t *status);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1186,4 +1186,47 @@ done:
     return rs;
 }
 
+rsvio_status rsvio_b_track_points(int32_t device, const float *const *pyr0, const float *const *pyr1,
+                                  const int32_t *widths, const int32_t *heights, int32_t levels,
+                                  const float *points_xy, int32_t n, int32_t max_iteration, float lm_lambda,
+                                  float *out_T4, int32_t *status) {
+    if (!pyr0 || !pyr1 || !widths || !heights || levels < 1 || levels > RSVIO_MAX_LEVELS || !points_xy || n < 0 ||
+        max_iteration < 0 || !out_T4 || !status)
+        return RSVIO_ERR_INVALID_ARG;
+    for (int l = 0; l < levels; ++l)
+        if (!pyr0[l] || !pyr1[l] || widths[l] < 1 || heights[l] < 1) return RSVIO_ERR_INVALID_ARG;
+    if (n == 0) return RSVIO_OK;
+    rsvio_status rs = RSVIO_OK;
+    DeviceScope dev_scope;
+    float *d_lv[2][RSVIO_MAX_LEVELS] = {};
+    float *d_pts = nullptr, *d_T = nullptr;
+    int32_t *d_st = nullptr;
+    int w[RSVIO_MAX_LEVELS], h[RSVIO_MAX_LEVELS];
+    CU_TRY0(dev_scope.enter(device));
+    for (int l = 0; l < levels; ++l) {
+        w[l] = widths[l];
+        h[l] = heights[l];
+        const size_t bytes = sizeof(float) * (size_t)w[l] * h[l];
+        for (int k = 0; k < 2; ++k) {
+            CU_TRY0(cudaMalloc((void **)&d_lv[k][l], bytes));
+            CU_TRY0(cudaMemcpy(d_lv[k][l], (k == 0 ? pyr0 : pyr1)[l], bytes, cudaMemcpyHostToDevice));
+        }
+    }
+    CU_TRY0(cudaMalloc((void **)&d_pts, sizeof(float) * 2 * (size_t)n));
+    CU_TRY0(cudaMalloc((void **)&d_T, sizeof(float) * 4 * (size_t)n));
+    CU_TRY0(cudaMalloc((void **)&d_st, sizeof(int32_t) * (size_t)n));
+    CU_TRY0(cudaMemcpy(d_pts, points_xy, sizeof(float) * 2 * (size_t)n, cudaMemcpyHostToDevice));
+    CU_TRY0(trackb_points(d_lv[0], d_lv[1], w, h, levels, d_pts, n, max_iteration, lm_lambda, d_T, d_st, 0));
+    CU_TRY0(cudaDeviceSynchronize());
+    CU_TRY0(cudaMemcpy(out_T4, d_T, sizeof(float) * 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    CU_TRY0(cudaMemcpy(status, d_st, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+done:
+    for (int l = 0; l < RSVIO_MAX_LEVELS; ++l)
+        for (int k = 0; k < 2; ++k) cudaFree(d_lv[k][l]);
+    cudaFree(d_pts);
+    cudaFree(d_T);
+    cudaFree(d_st);
+    return rs;
+}
+
 }  // extern "C"

@@ -185,5 +185,10 @@ int pixel_bytes(int fmt);
 cudaError_t convert_to_luma8(const uint8_t *d_src, size_t stride_bytes, int w, int h, int fmt, uint8_t *d_dst,
                              cudaStream_t st);
 
+// row f-2, first slice: crate B's tracking core (trackb.cu).  Device pointers; out_T4 = n x (cos, sin, tx, ty)
+cudaError_t trackb_points(const float *const *d_a, const float *const *d_b, const int *w, const int *h, int levels,
+                          const float *d_pts, int n, int max_it, float lambda, float *d_out_T4, int32_t *d_status,
+                          cudaStream_t st);
+
 }  // namespace rsvio
 #endif

@@ -37,7 +37,7 @@ ABI_SYMBOLS = (
     "rsvio_pyramid_bytes", "rsvio_pyramid_device_bytes", "rsvio_build_pyramid_u8",
     "rsvio_build_pyramid_u8_device", "rsvio_track_points", "rsvio_detect_keypoints", "rsvio_se2_exp",
     "rsvio_tracker_set_camera", "rsvio_tracker_undistorted_view", "rsvio_unproject_points",
-    "rsvio_tracker_process_stereo_fmt", "rsvio_convert_to_luma8",
+    "rsvio_tracker_process_stereo_fmt", "rsvio_convert_to_luma8", "rsvio_b_track_points",
 )
 
 PIXEL_LUMA8, PIXEL_LUMA16, PIXEL_RGB8 = 0, 1, 2
@@ -153,6 +153,8 @@ def load_library():
     L.rsvio_unproject_points.argtypes = [C.c_int32, C.POINTER(CameraModel), _f32p, C.c_int32, _f32p]
     L.rsvio_tracker_process_stereo_fmt.argtypes = [H, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32]
     L.rsvio_convert_to_luma8.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_size_t, C.c_int32, _u8p]
+    L.rsvio_b_track_points.argtypes = [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i32p, _i32p, C.c_int32,
+                                       _f32p, C.c_int32, C.c_int32, C.c_float, _f32p, _i32p]
     _lib = L
     return L
 
@@ -223,6 +225,26 @@ def detect_keypoints(image, grid, cur_xy=None, device=0):
     _check(load_library().rsvio_detect_keypoints(device, img, w, h, w, grid, cur_arg, cur.shape[0], xy, sc, cap,
                                                  C.byref(n)))
     return xy[:n.value].copy(), sc[:n.value].copy()
+
+
+def b_track_points(pyr0, pyr1, points, max_iteration=10, lm_lambda=0.1, device=0):
+    """crate B's track_points (row f-2, first slice): pyr0 / pyr1 = lists of (h, w) float32 levels, points (n, 2).
+    Returns (T4[n, 4] = cos, sin, tx, ty of the forward isometry, status[n])."""
+    lv0 = [np.ascontiguousarray(a, np.float32) for a in pyr0]
+    lv1 = [np.ascontiguousarray(a, np.float32) for a in pyr1]
+    L = len(lv0)
+    if len(lv1) != L or any(a.shape != b.shape for a, b in zip(lv0, lv1)):
+        raise ValueError("the two pyramids must have the same level shapes")
+    p0 = (C.c_void_p * L)(*[a.ctypes.data for a in lv0])
+    p1 = (C.c_void_p * L)(*[a.ctypes.data for a in lv1])
+    ws = np.array([a.shape[1] for a in lv0], np.int32)
+    hs = np.array([a.shape[0] for a in lv0], np.int32)
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 2)
+    n = pts.shape[0]
+    T = np.zeros((n, 4), np.float32)
+    st = np.zeros(n, np.int32)
+    _check(load_library().rsvio_b_track_points(device, p0, p1, ws, hs, L, pts, n, max_iteration, lm_lambda, T, st))
+    return T, st
 
 
 def convert_to_luma8(img, fmt, device=0):

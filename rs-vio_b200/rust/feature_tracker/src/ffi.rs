@@ -118,6 +118,11 @@ extern "C" {
                                             stride_bytes: usize, pixel_format: i32) -> rsvio_status;
     pub fn rsvio_convert_to_luma8(device: i32, src: *const c_void, width: i32, height: i32, stride_bytes: usize,
                                   pixel_format: i32, out: *mut u8) -> rsvio_status;
+
+    // ---- row f-2, first slice: crate B's track_points between two f32 pyramids ----
+    pub fn rsvio_b_track_points(device: i32, pyr0: *const *const f32, pyr1: *const *const f32, widths: *const i32,
+                                heights: *const i32, levels: i32, points_xy: *const f32, n: i32, max_iteration: i32,
+                                lm_lambda: f32, out_t4: *mut f32, status: *mut i32) -> rsvio_status;
 }
 
 pub const RSVIO_N_STAGES: usize = 8;
