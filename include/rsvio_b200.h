@@ -251,6 +251,14 @@ rsvio_status rsvio_b_track_points(int32_t device, const float *const *pyr0, cons
                                   const int32_t *widths, const int32_t *heights, int32_t levels,
                                   const float *points_xy, int32_t n, int32_t max_iteration, float lm_lambda,
                                   float *out_T4, int32_t *status);
+/* crate B's build_image_pyramid without the preprocessing blur (feature_tracker/src/image_operations.rs:47-78):
+ * level 0 = image (h x w floats in [0, 1]), level l = Triangle resize of level l-1 to
+ * round(w / ratio^l) x round(h / ratio^l).  rsvio_b_pyramid_dims fills the level sizes; out_levels[l] must hold
+ * heights[l] * widths[l] floats (host pointers). */
+rsvio_status rsvio_b_pyramid_dims(int32_t width, int32_t height, int32_t levels, double ratio, int32_t *widths,
+                                  int32_t *heights);
+rsvio_status rsvio_b_build_pyramid(int32_t device, const float *image, int32_t width, int32_t height, int32_t levels,
+                                   double ratio, float *const *out_levels);
 
 #ifdef __cplusplus
 }

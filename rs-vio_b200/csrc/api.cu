@@ -9,6 +9,7 @@
 // with no host round trip in between.  There is no CPU fallback anywhere in this file.
 #include <cstdio>
 #include <cstring>
+#include <cmath>
 #include <new>
 #include <string>
 #include <vector>
@@ -1183,6 +1184,47 @@ rsvio_status rsvio_convert_to_luma8(int32_t device, const void *src, int32_t wid
 done:
     cudaFree(d_src);
     cudaFree(d_dst);
+    return rs;
+}
+
+rsvio_status rsvio_b_pyramid_dims(int32_t width, int32_t height, int32_t levels, double ratio, int32_t *widths,
+                                  int32_t *heights) {
+    if (width < 1 || height < 1 || levels < 1 || levels > RSVIO_MAX_LEVELS || !(ratio > 1.0) || !widths || !heights)
+        return RSVIO_ERR_INVALID_ARG;
+    double f = 1.0;
+    for (int l = 0; l < levels; ++l) {
+        // (w0 as f64 / ratio.powi(l)).round() as u32 -- round half away from zero
+        widths[l] = (int32_t)std::floor((double)width / f + 0.5);
+        heights[l] = (int32_t)std::floor((double)height / f + 0.5);
+        if (widths[l] < 1 || heights[l] < 1) return RSVIO_ERR_INVALID_ARG;
+        f *= ratio;
+    }
+    return RSVIO_OK;
+}
+
+rsvio_status rsvio_b_build_pyramid(int32_t device, const float *image, int32_t width, int32_t height, int32_t levels,
+                                   double ratio, float *const *out_levels) {
+    int32_t w[RSVIO_MAX_LEVELS], h[RSVIO_MAX_LEVELS];
+    if (!image || !out_levels) return RSVIO_ERR_INVALID_ARG;
+    rsvio_status rs = rsvio_b_pyramid_dims(width, height, levels, ratio, w, h);
+    if (rs != RSVIO_OK) return rs;
+    for (int l = 0; l < levels; ++l)
+        if (!out_levels[l]) return RSVIO_ERR_INVALID_ARG;
+    DeviceScope dev_scope;
+    float *d_lv[RSVIO_MAX_LEVELS] = {};
+    float *d_tmp = nullptr;
+    CU_TRY0(dev_scope.enter(device));
+    for (int l = 0; l < levels; ++l) CU_TRY0(cudaMalloc((void **)&d_lv[l], sizeof(float) * (size_t)w[l] * h[l]));
+    CU_TRY0(cudaMalloc((void **)&d_tmp, sizeof(float) * (size_t)w[0] * h[0]));
+    CU_TRY0(cudaMemcpy(d_lv[0], image, sizeof(float) * (size_t)w[0] * h[0], cudaMemcpyHostToDevice));
+    for (int l = 1; l < levels; ++l)
+        CU_TRY0(resize_triangle_f32(d_lv[l - 1], w[l - 1], h[l - 1], d_tmp, d_lv[l], w[l], h[l], 0));
+    CU_TRY0(cudaDeviceSynchronize());
+    for (int l = 0; l < levels; ++l)
+        CU_TRY0(cudaMemcpy(out_levels[l], d_lv[l], sizeof(float) * (size_t)w[l] * h[l], cudaMemcpyDeviceToHost));
+done:
+    for (int l = 0; l < RSVIO_MAX_LEVELS; ++l) cudaFree(d_lv[l]);
+    cudaFree(d_tmp);
     return rs;
 }
 

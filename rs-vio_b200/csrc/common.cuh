@@ -190,5 +190,9 @@ cudaError_t trackb_points(const float *const *d_a, const float *const *d_b, cons
                           const float *d_pts, int n, int max_it, float lambda, float *d_out_T4, int32_t *d_status,
                           cudaStream_t st);
 
+// one level of crate B's pyramid: Triangle resize of an f32 image (d_tmp: h_out x w_in floats of scratch)
+cudaError_t resize_triangle_f32(const float *d_src, int w_in, int h_in, float *d_tmp, float *d_dst, int w_out, int h_out,
+                                cudaStream_t st);
+
 }  // namespace rsvio
 #endif

@@ -315,3 +315,70 @@ cudaError_t trackb_points(const float *const *d_a, const float *const *d_b, cons
 }
 
 }  // namespace rsvio
+
+// ---- crate B's pyramid: level l = resize(level l-1, round(w0 / ratio^l), round(h0 / ratio^l), Triangle) on f32 ----
+// (feature_tracker/src/image_operations.rs:47-78; `image` 0.25.9 resize on Luma<f32>, not vendored: restated as
+// SURVEY.md Appendix A -- vertical pass first, weights tent((i - c') / sratio) normalised by their f32 sum,
+// `t += pix * w` in tap order, no rounding, clamp to [0, 1] after the horizontal pass.  PARITY UNPINNED.)
+// Correctness-first: one thread per output sample, the window and its weights recomputed per thread.
+namespace rsvio {
+
+namespace {
+
+struct Taps {
+    int left, right;
+    float cc, sratio, sum;
+};
+__device__ __forceinline__ Taps taps_for(int o, int n_in, int n_out) {
+    Taps t;
+    const float ratio = (float)n_in / (float)n_out;
+    t.sratio = fmaxf(ratio, 1.0f);
+    const float support = 1.0f * t.sratio;
+    const float c = ((float)o + 0.5f) * ratio;
+    const long long l0 = (long long)floorf(c - support), r0 = (long long)ceilf(c + support);
+    t.left = (int)min(max(l0, 0ll), (long long)n_in - 1);
+    t.right = (int)min(max(r0, (long long)t.left + 1), (long long)n_in);
+    t.cc = c - 0.5f;
+    float s = 0.0f;
+    for (int i = t.left; i < t.right; ++i) {
+        const float xx = fabsf(((float)i - t.cc) / t.sratio);
+        s = s + (xx < 1.0f ? 1.0f - xx : 0.0f);
+    }
+    t.sum = s;
+    return t;
+}
+__device__ __forceinline__ float tap_weight(const Taps &t, int i) {
+    const float xx = fabsf(((float)i - t.cc) / t.sratio);
+    return (xx < 1.0f ? 1.0f - xx : 0.0f) / t.sum;
+}
+
+// src: h_in x w, dst: h_out x w
+__global__ void resize_f32_vertical(const float *__restrict__ src, int w, int h_in, int h_out, float *__restrict__ dst) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, o = blockIdx.y;
+    if (x >= w) return;
+    const Taps t = taps_for(o, h_in, h_out);
+    float acc = 0.0f;
+    for (int i = t.left; i < t.right; ++i) acc = acc + src[(size_t)i * w + x] * tap_weight(t, i);
+    dst[(size_t)o * w + x] = acc;
+}
+// src: h x w_in, dst: h x w_out, clamped to [0, 1]
+__global__ void resize_f32_horizontal(const float *__restrict__ src, int w_in, int w_out, int h, float *__restrict__ dst) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (o >= w_out) return;
+    const Taps t = taps_for(o, w_in, w_out);
+    float acc = 0.0f;
+    for (int i = t.left; i < t.right; ++i) acc = acc + src[(size_t)y * w_in + i] * tap_weight(t, i);
+    dst[(size_t)y * w_out + o] = fminf(fmaxf(acc, 0.0f), 1.0f);
+}
+
+}  // namespace
+
+cudaError_t resize_triangle_f32(const float *d_src, int w_in, int h_in, float *d_tmp, float *d_dst, int w_out, int h_out,
+                                cudaStream_t st) {
+    if (w_in < 1 || h_in < 1 || w_out < 1 || h_out < 1) return cudaErrorInvalidValue;
+    resize_f32_vertical<<<dim3((unsigned)((w_in + 127) / 128), (unsigned)h_out, 1), 128, 0, st>>>(d_src, w_in, h_in, h_out, d_tmp);
+    resize_f32_horizontal<<<dim3((unsigned)((w_out + 127) / 128), (unsigned)h_out, 1), 128, 0, st>>>(d_tmp, w_in, w_out, h_out, d_dst);
+    return cudaGetLastError();
+}
+
+}  // namespace rsvio

@@ -38,6 +38,7 @@ ABI_SYMBOLS = (
     "rsvio_build_pyramid_u8_device", "rsvio_track_points", "rsvio_detect_keypoints", "rsvio_se2_exp",
     "rsvio_tracker_set_camera", "rsvio_tracker_undistorted_view", "rsvio_unproject_points",
     "rsvio_tracker_process_stereo_fmt", "rsvio_convert_to_luma8", "rsvio_b_track_points",
+    "rsvio_b_pyramid_dims", "rsvio_b_build_pyramid",
 )
 
 PIXEL_LUMA8, PIXEL_LUMA16, PIXEL_RGB8 = 0, 1, 2
@@ -153,6 +154,9 @@ def load_library():
     L.rsvio_unproject_points.argtypes = [C.c_int32, C.POINTER(CameraModel), _f32p, C.c_int32, _f32p]
     L.rsvio_tracker_process_stereo_fmt.argtypes = [H, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32]
     L.rsvio_convert_to_luma8.argtypes = [C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_size_t, C.c_int32, _u8p]
+    L.rsvio_b_pyramid_dims.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_double, _i32p, _i32p]
+    L.rsvio_b_build_pyramid.argtypes = [C.c_int32, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_double,
+                                        C.POINTER(C.c_void_p)]
     L.rsvio_b_track_points.argtypes = [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i32p, _i32p, C.c_int32,
                                        _f32p, C.c_int32, C.c_int32, C.c_float, _f32p, _i32p]
     _lib = L
@@ -225,6 +229,19 @@ def detect_keypoints(image, grid, cur_xy=None, device=0):
     _check(load_library().rsvio_detect_keypoints(device, img, w, h, w, grid, cur_arg, cur.shape[0], xy, sc, cap,
                                                  C.byref(n)))
     return xy[:n.value].copy(), sc[:n.value].copy()
+
+
+def b_build_pyramid(image, levels, ratio=2.0, device=0):
+    """crate B's build_image_pyramid (no blur) on the device: image (h, w) float32 in [0, 1] -> list of levels."""
+    img = np.ascontiguousarray(image, np.float32)
+    h, w = img.shape
+    ws, hs = np.zeros(levels, np.int32), np.zeros(levels, np.int32)
+    L = load_library()
+    _check(L.rsvio_b_pyramid_dims(w, h, levels, float(ratio), ws, hs))
+    out = [np.empty((int(hs[l]), int(ws[l])), np.float32) for l in range(levels)]
+    ptrs = (C.c_void_p * levels)(*[a.ctypes.data for a in out])
+    _check(L.rsvio_b_build_pyramid(device, img, w, h, levels, float(ratio), ptrs))
+    return out
 
 
 def b_track_points(pyr0, pyr1, points, max_iteration=10, lm_lambda=0.1, device=0):

@@ -120,6 +120,10 @@ extern "C" {
                                   pixel_format: i32, out: *mut u8) -> rsvio_status;
 
     // ---- row f-2, first slice: crate B's track_points between two f32 pyramids ----
+    pub fn rsvio_b_pyramid_dims(width: i32, height: i32, levels: i32, ratio: f64, widths: *mut i32, heights: *mut i32)
+        -> rsvio_status;
+    pub fn rsvio_b_build_pyramid(device: i32, image: *const f32, width: i32, height: i32, levels: i32, ratio: f64,
+                                 out_levels: *const *mut f32) -> rsvio_status;
     pub fn rsvio_b_track_points(device: i32, pyr0: *const *const f32, pyr1: *const *const f32, widths: *const i32,
                                 heights: *const i32, levels: i32, points_xy: *const f32, n: i32, max_iteration: i32,
                                 lm_lambda: f32, out_t4: *mut f32, status: *mut i32) -> rsvio_status;

@@ -67,3 +67,23 @@ def test_crate_b_tracking_core_matches_oracle(rsvio):
     # and both recover the synthetic motion of the interior points
     flow = moved_g[:24] - pts[:24]
     assert np.abs(np.median(flow, axis=0) - np.array([1.3, -0.7])).max() < 0.1
+
+
+def test_crate_b_pyramid_matches_oracle(rsvio):
+    """f32 chained Triangle resize: same operations in the same order as the numpy restatement -> same bits"""
+    rng = np.random.default_rng(8)
+    for (h, w, levels, ratio) in ((60, 120, 3, 2.0), (75, 97, 4, 2.0), (64, 96, 3, 1.5), (33, 41, 2, 3.0)):
+        img = rng.uniform(0.0, 1.0, (h, w)).astype(np.float32)
+        want = B.build_image_pyramid(img, levels, ratio)
+        got = rsvio.b_build_pyramid(img, levels, ratio)
+        assert [g.shape for g in got] == [x.shape for x in want]
+        for l in range(levels):
+            assert np.abs(got[l] - want[l]).max() <= 1e-7, (h, w, ratio, l, np.abs(got[l] - want[l]).max())
+    # the device pyramid feeds the device tracker
+    a, b = scene(96, 128), scene(96, 128, 1.3, -0.7)
+    pa, pb = rsvio.b_build_pyramid(a, 3, 2.0), rsvio.b_build_pyramid(b, 3, 2.0)
+    pts = np.array([[40.0, 40.0], [64.0, 50.0], [90.0, 60.0]], np.float32)
+    T, st = rsvio.b_track_points(pa, pb, pts, 10, 0.1)
+    flow = np.stack([T[:, 0] * pts[:, 0] - T[:, 1] * pts[:, 1] + T[:, 2],
+                     T[:, 1] * pts[:, 0] + T[:, 0] * pts[:, 1] + T[:, 3]], 1) - pts     # T p - p, not T's translation
+    assert (st == 0).all() and np.abs(flow - np.array([1.3, -0.7])).max() < 0.05
