@@ -152,6 +152,18 @@ class StereoPatchTracker {
         detail::check(rsvio_tracker_process_stereo(h_.get(), image0.data, image1.data, image0.width), h_.get(),
                       "rsvio_tracker_process_stereo");
     }
+    // the same for frames as the decoder delivers them (RSVIO_PIXEL_LUMA16 / RSVIO_PIXEL_RGB8): the
+    // DynamicImage::to_luma8() of the reference's dataset players (src/datasets/euroc_player.rs:231) runs on the device
+    void process_decoded(const void *image0, const void *image1, std::uint32_t width, std::uint32_t height,
+                         std::size_t stride_bytes, std::int32_t pixel_format) {
+        const bool created = h_.ensure(cfg_, width, height);
+        if (created)
+            for (int cam = 0; cam < 2; ++cam)
+                if (have_cam_[cam])
+                    detail::check(rsvio_tracker_set_camera(h_.get(), cam, &cams_[cam]), h_.get(), "rsvio_tracker_set_camera");
+        detail::check(rsvio_tracker_process_stereo_fmt(h_.get(), image0, image1, stride_bytes, pixel_format), h_.get(),
+                      "rsvio_tracker_process_stereo_fmt");
+    }
     // get_track_points(&self) -> [HashMap<usize, (f32, f32)>; 2]
     std::pair<std::unordered_map<std::size_t, std::pair<float, float>>, std::unordered_map<std::size_t, std::pair<float, float>>>
     get_track_points() const {
