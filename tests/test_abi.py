@@ -82,3 +82,15 @@ def test_rust_build_script_lists_every_cuda_source():
     srcs = set(re.findall(r"csrc/(\w+\.cu)", re.search(r"^SRCS\s*:=\s*(.*)$", mk, re.M).group(1)))
     rs = open(os.path.join(root, "rs-vio_b200", "rust", "feature_tracker", "build.rs")).read()
     assert srcs and srcs == set(re.findall(r'"(\w+\.cu)"', rs))
+
+
+def test_tools_and_entry_points_compile():
+    """bench.py, __graft_entry__.py and every script under tools/ at least parse (they only run on a GPU box)"""
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")]
+    for d, _, names in os.walk(os.path.join(root, "tools")):
+        files += [os.path.join(d, n) for n in names if n.endswith(".py")]
+    assert len(files) > 8
+    for f in files:
+        py_compile.compile(f, doraise=True)
