@@ -69,7 +69,8 @@ typedef struct rsvio_config {
     int32_t levels;                /* N of StereoPatchTracker<N>; level i is (w >> i, h >> i) */
     uint32_t grid_size;            /* feature_detection.grid_size (config/euroc_vio.yaml:42) */
     int32_t max_iterations;        /* optical_flow_max_iterations */
-    float convergence_threshold;   /* optical_flow_convergence_threshold */
+    float convergence_threshold;   /* optical_flow_convergence_threshold; must be finite, <= 0 never converges early
+                                      (as `inc.norm() < thr`, feature_tracker.rs:374) */
     int32_t mode;                  /* RSVIO_MODE_STEREO | RSVIO_MODE_MONO (PatchTracker<N>) */
     int32_t n_streams;             /* independent sequences batched on this handle; 1 == reference */
     int32_t device;                /* CUDA device ordinal */
@@ -184,6 +185,13 @@ rsvio_status rsvio_tracker_undistorted_view(rsvio_tracker *t, const float **uxy,
  * [2] LK iterations evaluated                   [3] Pattern52 templates built
  * [4] kernels launched by this handle           [5] points detected by grid replenishment */
 rsvio_status rsvio_tracker_counters(rsvio_tracker *t, uint64_t out[6]);
+
+/* RSVIO_ERR_CAPACITY from rsvio_tracker_sync / process_* is NOT fatal: the frame has been processed, its result
+ * views are valid and the state has advanced; only the newly detected points that did not fit the track table
+ * (rsvio_config.max_tracks) were dropped.  The reference's HashMaps are unbounded (feature_tracker.rs:93-96), so
+ * its signatures cannot fail this way: callers (the Rust / C++ / Python mirrors do) should deliver the frame and
+ * surface a warning.  *n = frames since create/reset that dropped points. */
+rsvio_status rsvio_tracker_overflow_frames(rsvio_tracker *t, uint64_t *n);
 
 /* per-stage device time (CUDA events on the handle's stream), accumulated since the last call
  * with reset != 0.  ms[0..7]: upload, pyramid, temporal LK, compaction+occupancy, detection,

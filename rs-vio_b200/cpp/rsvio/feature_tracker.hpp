@@ -12,6 +12,7 @@
 #pragma once
 
 #include <cstdint>
+#include <cstdio>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -44,6 +45,18 @@ namespace detail {
 inline void check(rsvio_status s, rsvio_tracker *t, const char *what) {
     if (s != RSVIO_OK)
         throw Error(s, std::string(what) + ": " + rsvio_status_string(s) + (t ? std::string(" / ") + rsvio_tracker_last_error(t) : ""));
+}
+// status of a process_* call: a full track table is not an error -- the frame was processed and is delivered, only
+// new points were dropped (the reference's maps are unbounded, its process_frame cannot fail); one warning on
+// stderr per handle, the count stays queryable through rsvio_tracker_overflow_frames
+inline void check_frame(rsvio_status s, rsvio_tracker *t, const char *what) {
+    if (s == RSVIO_ERR_CAPACITY) {
+        std::uint64_t n = 0;
+        if (rsvio_tracker_overflow_frames(t, &n) == RSVIO_OK && n == 1)
+            std::fprintf(stderr, "rsvio: %s: %s\n", what, rsvio_tracker_last_error(t));
+        return;
+    }
+    check(s, t, what);
 }
 
 class Handle {
@@ -149,8 +162,8 @@ class StereoPatchTracker {
             for (int cam = 0; cam < 2; ++cam)
                 if (have_cam_[cam])
                     detail::check(rsvio_tracker_set_camera(h_.get(), cam, &cams_[cam]), h_.get(), "rsvio_tracker_set_camera");
-        detail::check(rsvio_tracker_process_stereo(h_.get(), image0.data, image1.data, image0.width), h_.get(),
-                      "rsvio_tracker_process_stereo");
+        detail::check_frame(rsvio_tracker_process_stereo(h_.get(), image0.data, image1.data, image0.width), h_.get(),
+                            "rsvio_tracker_process_stereo");
     }
     // the same for frames as the decoder delivers them (RSVIO_PIXEL_LUMA16 / RSVIO_PIXEL_RGB8): the
     // DynamicImage::to_luma8() of the reference's dataset players (src/datasets/euroc_player.rs:231) runs on the device
@@ -161,8 +174,8 @@ class StereoPatchTracker {
             for (int cam = 0; cam < 2; ++cam)
                 if (have_cam_[cam])
                     detail::check(rsvio_tracker_set_camera(h_.get(), cam, &cams_[cam]), h_.get(), "rsvio_tracker_set_camera");
-        detail::check(rsvio_tracker_process_stereo_fmt(h_.get(), image0, image1, stride_bytes, pixel_format), h_.get(),
-                      "rsvio_tracker_process_stereo_fmt");
+        detail::check_frame(rsvio_tracker_process_stereo_fmt(h_.get(), image0, image1, stride_bytes, pixel_format), h_.get(),
+                            "rsvio_tracker_process_stereo_fmt");
     }
     // get_track_points(&self) -> [HashMap<usize, (f32, f32)>; 2]
     std::pair<std::unordered_map<std::size_t, std::pair<float, float>>, std::unordered_map<std::size_t, std::pair<float, float>>>
@@ -190,7 +203,7 @@ class PatchTracker {
     }
     void process_frame(const GrayImageView &image) {
         h_.ensure(cfg_, image.width, image.height);
-        detail::check(rsvio_tracker_process_mono(h_.get(), image.data, image.width), h_.get(), "rsvio_tracker_process_mono");
+        detail::check_frame(rsvio_tracker_process_mono(h_.get(), image.data, image.width), h_.get(), "rsvio_tracker_process_mono");
     }
     std::unordered_map<std::size_t, std::pair<float, float>> get_track_points() const { return h_.tracks(0); }
     void remove_id(const std::vector<std::size_t> &ids) { h_.remove(ids); }

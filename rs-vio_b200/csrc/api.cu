@@ -101,6 +101,10 @@ struct rsvio_tracker {
     bool stage_valid[kSlots] = {false, false}, up_valid[kSlots] = {false, false};
     double stage_ms[RSVIO_N_STAGES] = {0};
     uint64_t stage_launches[RSVIO_N_STAGES] = {0};
+    // a CUDA failure may leave a frame half enqueued (tables partly written, events unrecorded): the handle refuses
+    // further frames until rsvio_tracker_reset has rebuilt a consistent state
+    bool poisoned = false;
+    uint64_t overflow_frames = 0;  // frames whose new points did not all fit the track table (sticky count)
     std::string err;
 };
 
@@ -112,6 +116,7 @@ rsvio_status fail_cuda(rsvio_tracker *t, cudaError_t e, const char *what, int li
         char buf[512];
         snprintf(buf, sizeof(buf), "CUDA error %d (%s) at api.cu:%d: %s", (int)e, cudaGetErrorString(e), line, what);
         t->err = buf;
+        t->poisoned = true;
     }
     return RSVIO_ERR_CUDA;
 }
@@ -212,6 +217,8 @@ rsvio_status clear_state(rsvio_tracker *t) {
     t->next_slot = t->oldest_slot = 0;
     t->result_slot = -1;
     t->host_launches = 0;
+    t->overflow_frames = 0;
+    t->poisoned = false;
     return RSVIO_OK;
 }
 
@@ -260,12 +267,12 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
         b.counters = t->d_counters;
         b.work_counter = t->d_work;
         b.work_parity = t->lk_par[0];
-        t->lk_par[0] ^= 1;
         b.groups = t->stereo ? t->groups : t->S;
         b.cap = t->cap;
         b.max_it = t->cfg.max_iterations;
         b.thr = t->cfg.convergence_threshold;
         CU_TRY(t, lk_track(t->pd, b, st));
+        t->lk_par[0] ^= 1;  // only a launch that went out has cleared the other counter
         count(2, 1);
     }
     CU_TRY(t, cudaEventRecord(t->ev_lk_done, st));  // `prev` may be overwritten from here on
@@ -293,12 +300,12 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
         b.counters = t->d_counters;
         b.work_counter = t->d_work + 2;
         b.work_parity = t->lk_par[1];
-        t->lk_par[1] ^= 1;
         b.groups = t->S;
         b.cap = t->new_cap;
         b.max_it = t->cfg.max_iterations;
         b.thr = t->cfg.convergence_threshold;
         CU_TRY(t, lk_track(t->pd, b, st));
+        t->lk_par[1] ^= 1;
         count(5, 1);
     }
     mark(++stage);  // 6: merge (ids, table append)
@@ -382,6 +389,7 @@ rsvio_status check_batch_args(rsvio_tracker *t, const uint8_t *const *left, cons
     if (stride < (size_t)t->cfg.width) return fail(t, RSVIO_ERR_INVALID_ARG, "stride smaller than width");
     for (int s = 0; s < t->S; ++s)
         if (!left[s] || (t->stereo && !right[s])) return fail(t, RSVIO_ERR_INVALID_ARG, "null image pointer");
+    if (t->poisoned) return fail(t, RSVIO_ERR_STATE, "an earlier CUDA error left the handle inconsistent: call rsvio_tracker_reset");
     if (t->inflight >= kSlots) return fail(t, RSVIO_ERR_STATE, "two frames already in flight: call rsvio_tracker_sync");
     return RSVIO_OK;
 }
@@ -453,6 +461,7 @@ rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) 
         cfg->levels > RSVIO_MAX_LEVELS || (cfg->width >> (cfg->levels - 1)) < 1 ||
         (cfg->height >> (cfg->levels - 1)) < 1 || cfg->grid_size < 7 || cfg->grid_size > 1024 ||
         cfg->max_iterations < 0 || cfg->n_streams < 1 || cfg->max_tracks < 0 ||
+        !std::isfinite(cfg->convergence_threshold) ||  // NaN never compares; a negative one is legal (never converges early)
         (cfg->mode != RSVIO_MODE_STEREO && cfg->mode != RSVIO_MODE_MONO))
         return RSVIO_ERR_INVALID_ARG;
     int ndev = 0;
@@ -583,6 +592,7 @@ rsvio_status rsvio_tracker_submit_device(rsvio_tracker *t, const void *d_left, c
     if (!d_left || (t->stereo && !d_right)) return fail(t, RSVIO_ERR_INVALID_ARG, "null device image pointer");
     if (stride < (size_t)t->cfg.width || pitch < stride * (size_t)(t->cfg.height - 1) + (size_t)t->cfg.width)
         return fail(t, RSVIO_ERR_INVALID_ARG, "stride/pitch too small");
+    if (t->poisoned) return fail(t, RSVIO_ERR_STATE, "an earlier CUDA error left the handle inconsistent: call rsvio_tracker_reset");
     if (t->inflight >= kSlots) return fail(t, RSVIO_ERR_STATE, "two frames already in flight: call rsvio_tracker_sync");
     DeviceScope dev_scope;
     CU_TRY(t, dev_scope.enter(t->cfg.device));
@@ -601,7 +611,14 @@ rsvio_status rsvio_tracker_sync(rsvio_tracker *t) {
     DeviceScope dev_scope;
     CU_TRY(t, dev_scope.enter(t->cfg.device));
     const int slot = t->oldest_slot;
-    CU_TRY(t, cudaEventSynchronize(t->ev_done[slot]));
+    {
+        const cudaError_t e = cudaEventSynchronize(t->ev_done[slot]);
+        if (e != cudaSuccess) {  // the frame is lost: retire it (so a reset is possible) and poison the handle
+            t->oldest_slot ^= 1;
+            t->inflight -= 1;
+            return fail_cuda(t, e, "cudaEventSynchronize(ev_done)", __LINE__);
+        }
+    }
     if (t->stage_valid[slot]) {
         for (int k = 1; k < RSVIO_N_STAGES; ++k) {
             float ms = 0.0f;
@@ -619,8 +636,13 @@ rsvio_status rsvio_tracker_sync(rsvio_tracker *t) {
     t->oldest_slot ^= 1;
     t->inflight -= 1;
     t->result_slot = slot;
-    if (t->h_cnt[slot][t->groups] != 0)
-        return fail(t, RSVIO_ERR_CAPACITY, "track table full: raise rsvio_config.max_tracks");
+    if (t->h_cnt[slot][t->groups] != 0) {
+        // not fatal: the frame has been processed and its result is valid, only the new points that did not fit
+        // were dropped (the reference's maps are unbounded).  The status tells the caller for THIS frame; the count
+        // stays queryable (rsvio_tracker_overflow_frames).
+        t->overflow_frames += 1;
+        return fail(t, RSVIO_ERR_CAPACITY, "track table full, new points dropped: raise rsvio_config.max_tracks");
+    }
     return RSVIO_OK;
 }
 
@@ -650,6 +672,7 @@ rsvio_status rsvio_tracker_process_stereo_fmt(rsvio_tracker *t, const void *left
     const int w = t->cfg.width, h = t->cfg.height;
     const size_t row = (size_t)w * bpp;
     if (stride_bytes < row) return fail(t, RSVIO_ERR_INVALID_ARG, "stride smaller than a row");
+    if (t->poisoned) return fail(t, RSVIO_ERR_STATE, "an earlier CUDA error left the handle inconsistent: call rsvio_tracker_reset");
     if (t->inflight >= kSlots) return fail(t, RSVIO_ERR_STATE, "two frames already in flight: call rsvio_tracker_sync");
     DeviceScope dev_scope;
     CU_TRY(t, dev_scope.enter(t->cfg.device));
@@ -723,6 +746,7 @@ rsvio_status rsvio_tracker_get_tracks(rsvio_tracker *t, int32_t stream, int32_t 
     *n = (size_t)cnt;
     if ((size_t)cnt > cap) return fail(t, RSVIO_ERR_CAPACITY, "output arrays too small");
     if (cnt > 0 && (!ids || !xy)) return RSVIO_ERR_INVALID_ARG;
+    if (cnt <= 0) return RSVIO_OK;  // also: no frame yet (result_slot < 0), nothing to index
     const OutRecord *r = t->h_out[t->result_slot] + (size_t)g * t->cap;
     for (int k = 0; k < cnt; ++k) {
         ids[k] = r[k].id;
@@ -831,8 +855,9 @@ rsvio_status rsvio_tracker_remove_ids(rsvio_tracker *t, int32_t stream, const ui
         std::vector<unsigned long long> hid(cnt[g] > 0 ? cnt[g] : 1);
         std::vector<float> hT((size_t)(cnt[g] > 0 ? cnt[g] : 1) * 6);
         if (cnt[g] > 0) {
-            CU_TRY(t, cudaMemcpy(hid.data(), tv.ids + (size_t)g * t->cap, sizeof(uint64_t) * cnt[g], cudaMemcpyDeviceToHost));
-            CU_TRY(t, cudaMemcpy(hT.data(), tv.T6 + (size_t)g * t->cap * 6, sizeof(float) * 6 * cnt[g], cudaMemcpyDeviceToHost));
+            CU_TRY(t, cudaMemcpyAsync(hid.data(), tv.ids + (size_t)g * t->cap, sizeof(uint64_t) * cnt[g], cudaMemcpyDeviceToHost, t->st));
+            CU_TRY(t, cudaMemcpyAsync(hT.data(), tv.T6 + (size_t)g * t->cap * 6, sizeof(float) * 6 * cnt[g], cudaMemcpyDeviceToHost, t->st));
+            CU_TRY(t, cudaStreamSynchronize(t->st));
         }
         OutRecord *r = t->h_out[slot] + (size_t)g * t->cap;
         for (int k = 0; k < cnt[g]; ++k) {
@@ -866,6 +891,12 @@ rsvio_status rsvio_tracker_counters(rsvio_tracker *t, uint64_t out[6]) {
     out[3] = c[CNT_TEMPLATES];
     out[4] = t->host_launches;
     out[5] = c[CNT_DETECTED];
+    return RSVIO_OK;
+}
+
+rsvio_status rsvio_tracker_overflow_frames(rsvio_tracker *t, uint64_t *n) {
+    if (!t || !n) return RSVIO_ERR_INVALID_ARG;
+    *n = t->overflow_frames;
     return RSVIO_OK;
 }
 
@@ -909,6 +940,19 @@ size_t rsvio_pyramid_bytes(int32_t width, int32_t height, int32_t levels) {
             goto done;                                                                                  \
         }                                                                                               \
     } while (0)
+
+// The stateless calls run on a private non-blocking stream (never the legacy default stream, which would
+// serialise with every blocking stream of the host application and stall its tracker handles) and wait for
+// that stream only.  Copies are stream-ordered on it as well.
+struct CallStream {
+    cudaStream_t s = nullptr;
+    cudaError_t create() { return cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking); }
+    ~CallStream() {
+        if (s) cudaStreamDestroy(s);
+    }
+};
+#define H2D(dst, src, bytes) cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, cs.s)
+#define D2H(dst, src, bytes) cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, cs.s)
 
 static bool pyr_args_ok(int32_t n_images, int32_t width, int32_t height, size_t stride, size_t pitch, int32_t levels) {
     return n_images >= 1 && width >= 1 && height >= 1 && width <= 65535 && height <= 65535 && levels >= 1 &&
@@ -961,25 +1005,28 @@ rsvio_status rsvio_build_pyramid_u8(int32_t device, const uint8_t *images, int32
     if (!images || !out || !pyr_args_ok(n_images, width, height, stride, pitch, levels)) return RSVIO_ERR_INVALID_ARG;
     rsvio_status rs = RSVIO_OK;
     DeviceScope dev_scope;
+    CallStream cs;
     const PyrDesc pd = make_pyr_desc(width, height, levels);
     const size_t dense = rsvio_pyramid_bytes(width, height, levels);
     uint8_t *d_in = nullptr, *d_out = nullptr;
     const size_t in_bytes = (size_t)(n_images - 1) * pitch + stride * (size_t)(height - 1) + (size_t)width;
     CU_TRY0(dev_scope.enter(device));
+    CU_TRY0(cs.create());
     CU_TRY0(cudaMalloc((void **)&d_in, in_bytes));
     CU_TRY0(cudaMalloc((void **)&d_out, (size_t)n_images * pd.pyr_stride));
-    CU_TRY0(cudaMemcpy(d_in, images, in_bytes, cudaMemcpyHostToDevice));
+    CU_TRY0(H2D(d_in, images, in_bytes));
+    CU_TRY0(cudaStreamSynchronize(cs.s));  // the device variant launches on a stream of its own
     rs = rsvio_build_pyramid_u8_device(device, d_in, n_images, width, height, stride, pitch, levels, d_out, 1, nullptr);
     if (rs != RSVIO_OK) goto done;
     for (int j = 0; j < n_images; ++j) {
         size_t o = 0;
         for (int i = 0; i < levels; ++i) {
             const size_t nb = (size_t)pd.lv[i].w * pd.lv[i].h;
-            CU_TRY0(cudaMemcpy(out + (size_t)j * dense + o, d_out + (size_t)j * pd.pyr_stride + pd.lv[i].off, nb,
-                               cudaMemcpyDeviceToHost));
+            CU_TRY0(D2H(out + (size_t)j * dense + o, d_out + (size_t)j * pd.pyr_stride + pd.lv[i].off, nb));
             o += nb;
         }
     }
+    CU_TRY0(cudaStreamSynchronize(cs.s));
 done:
     cudaFree(d_in);
     cudaFree(d_out);
@@ -989,25 +1036,28 @@ done:
 rsvio_status rsvio_track_points(int32_t device, const uint8_t *pyr_a, const uint8_t *pyr_b, int32_t width,
                                 int32_t height, int32_t levels, int32_t n, const float *in_T6, int32_t max_iterations,
                                 float convergence_threshold, float *out_T6, int32_t *status, int32_t *iters) {
-    if (!pyr_a || !pyr_b || n < 0 || !pyr_args_ok(1, width, height, (size_t)width, 0, levels) || max_iterations < 0)
+    if (!pyr_a || !pyr_b || n < 0 || !pyr_args_ok(1, width, height, (size_t)width, 0, levels) || max_iterations < 0 ||
+        !std::isfinite(convergence_threshold))
         return RSVIO_ERR_INVALID_ARG;
     if (n == 0) return RSVIO_OK;
     if (!in_T6 || !out_T6 || !status) return RSVIO_ERR_INVALID_ARG;
     rsvio_status rs = RSVIO_OK;
     DeviceScope dev_scope;
+    CallStream cs;
     const PyrDesc pd = make_pyr_desc(width, height, levels);
     uint8_t *d_pyr = nullptr;
     float *d_in = nullptr, *d_out = nullptr;
     int32_t *d_status = nullptr, *d_iters = nullptr;
     int *d_count = nullptr;
     CU_TRY0(dev_scope.enter(device));
+    CU_TRY0(cs.create());
     CU_TRY0(cudaMalloc((void **)&d_pyr, 2 * (size_t)pd.pyr_stride));
     {
         size_t o = 0;
         for (int i = 0; i < levels; ++i) {
             const size_t nb = (size_t)pd.lv[i].w * pd.lv[i].h;
-            CU_TRY0(cudaMemcpy(d_pyr + pd.lv[i].off, pyr_a + o, nb, cudaMemcpyHostToDevice));
-            CU_TRY0(cudaMemcpy(d_pyr + pd.pyr_stride + pd.lv[i].off, pyr_b + o, nb, cudaMemcpyHostToDevice));
+            CU_TRY0(H2D(d_pyr + pd.lv[i].off, pyr_a + o, nb));
+            CU_TRY0(H2D(d_pyr + pd.pyr_stride + pd.lv[i].off, pyr_b + o, nb));
             o += nb;
         }
     }
@@ -1016,8 +1066,8 @@ rsvio_status rsvio_track_points(int32_t device, const uint8_t *pyr_a, const uint
     CU_TRY0(cudaMalloc((void **)&d_status, sizeof(int32_t) * n));
     CU_TRY0(cudaMalloc((void **)&d_iters, sizeof(int32_t) * 2 * n));
     CU_TRY0(cudaMalloc((void **)&d_count, sizeof(int)));
-    CU_TRY0(cudaMemcpy(d_in, in_T6, sizeof(float) * 6 * n, cudaMemcpyHostToDevice));
-    CU_TRY0(cudaMemcpy(d_count, &n, sizeof(int), cudaMemcpyHostToDevice));
+    CU_TRY0(H2D(d_in, in_T6, sizeof(float) * 6 * n));
+    CU_TRY0(H2D(d_count, &n, sizeof(int)));
     {
         LkBatch b{};
         b.pyr_a = d_pyr;
@@ -1033,12 +1083,13 @@ rsvio_status rsvio_track_points(int32_t device, const uint8_t *pyr_a, const uint
         b.cap = n;
         b.max_it = max_iterations;
         b.thr = convergence_threshold;
-        CU_TRY0(lk_track(pd, b, 0));
+        CU_TRY0(lk_track(pd, b, cs.s));
     }
-    CU_TRY0(cudaDeviceSynchronize());
-    CU_TRY0(cudaMemcpy(out_T6, d_out, sizeof(float) * 6 * n, cudaMemcpyDeviceToHost));
-    CU_TRY0(cudaMemcpy(status, d_status, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
-    if (iters) CU_TRY0(cudaMemcpy(iters, d_iters, sizeof(int32_t) * 2 * n, cudaMemcpyDeviceToHost));
+    CU_TRY0(cudaStreamSynchronize(cs.s));
+    CU_TRY0(D2H(out_T6, d_out, sizeof(float) * 6 * n));
+    CU_TRY0(D2H(status, d_status, sizeof(int32_t) * n));
+    if (iters) CU_TRY0(D2H(iters, d_iters, sizeof(int32_t) * 2 * n));
+    CU_TRY0(cudaStreamSynchronize(cs.s));
 done:
     cudaFree(d_pyr);
     cudaFree(d_in);
@@ -1057,6 +1108,7 @@ rsvio_status rsvio_detect_keypoints(int32_t device, const uint8_t *image, int32_
         return RSVIO_ERR_INVALID_ARG;
     rsvio_status rs = RSVIO_OK;
     DeviceScope dev_scope;
+    CallStream cs;
     const GridDesc gd = make_grid_desc(width, height, grid_size);
     const int cells = gd.ncx * gd.ncy;
     *n = 0;
@@ -1069,14 +1121,15 @@ rsvio_status rsvio_detect_keypoints(int32_t device, const uint8_t *image, int32_
     int cnt = 0;
     std::vector<float> hT, hs;
     CU_TRY0(dev_scope.enter(device));
+    CU_TRY0(cs.create());
     CU_TRY0(cudaMalloc((void **)&d_img, (size_t)width * height));
-    CU_TRY0(cudaMemcpy2D(d_img, (size_t)width, image, stride, (size_t)width, (size_t)height, cudaMemcpyHostToDevice));
+    CU_TRY0(cudaMemcpy2DAsync(d_img, (size_t)width, image, stride, (size_t)width, (size_t)height, cudaMemcpyHostToDevice, cs.s));
     CU_TRY0(cudaMalloc((void **)&d_occ, (size_t)gd.occ_rows * gd.occ_cols));
-    CU_TRY0(cudaMemset(d_occ, 0, (size_t)gd.occ_rows * gd.occ_cols));
+    CU_TRY0(cudaMemsetAsync(d_occ, 0, (size_t)gd.occ_rows * gd.occ_cols, cs.s));
     if (n_cur > 0) {
         CU_TRY0(cudaMalloc((void **)&d_xy, sizeof(uint32_t) * 2 * n_cur));
-        CU_TRY0(cudaMemcpy(d_xy, cur_xy, sizeof(uint32_t) * 2 * n_cur, cudaMemcpyHostToDevice));
-        CU_TRY0(mark_occupancy_xy(gd, d_xy, n_cur, d_occ, 0));
+        CU_TRY0(H2D(d_xy, cur_xy, sizeof(uint32_t) * 2 * n_cur));
+        CU_TRY0(mark_occupancy_xy(gd, d_xy, n_cur, d_occ, cs.s));
     }
     CU_TRY0(cudaMalloc((void **)&d_cell, sizeof(uint32_t) * cells));
     CU_TRY0(cudaMalloc((void **)&d_score, sizeof(float) * cells));
@@ -1085,11 +1138,11 @@ rsvio_status rsvio_detect_keypoints(int32_t device, const uint8_t *image, int32_
     CU_TRY0(cudaMalloc((void **)&d_cnt, sizeof(int)));
     CU_TRY0(cudaMalloc((void **)&d_list, sizeof(uint32_t) * cells));
     CU_TRY0(cudaMalloc((void **)&d_list_n, 2 * sizeof(int)));
-    CU_TRY0(cudaMemset(d_list_n, 0, 2 * sizeof(int)));
-    CU_TRY0(detect_cells(gd, d_img, (size_t)width, 0, 1, d_occ, d_cell, d_score, d_list, d_list_n, 0, 0));
-    CU_TRY0(collect_new_points(gd, 1, d_cell, d_score, d_T6, d_nscore, d_cnt, cells, nullptr, 0));
-    CU_TRY0(cudaDeviceSynchronize());
-    CU_TRY0(cudaMemcpy(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost));
+    CU_TRY0(cudaMemsetAsync(d_list_n, 0, 2 * sizeof(int), cs.s));
+    CU_TRY0(detect_cells(gd, d_img, (size_t)width, 0, 1, d_occ, d_cell, d_score, d_list, d_list_n, 0, cs.s));
+    CU_TRY0(collect_new_points(gd, 1, d_cell, d_score, d_T6, d_nscore, d_cnt, cells, nullptr, cs.s));
+    CU_TRY0(D2H(&cnt, d_cnt, sizeof(int)));
+    CU_TRY0(cudaStreamSynchronize(cs.s));
     *n = (size_t)cnt;
     if ((size_t)cnt > cap) {
         rs = RSVIO_ERR_CAPACITY;
@@ -1102,8 +1155,9 @@ rsvio_status rsvio_detect_keypoints(int32_t device, const uint8_t *image, int32_
         }
         hT.resize((size_t)cnt * 6);
         hs.resize((size_t)cnt);
-        CU_TRY0(cudaMemcpy(hT.data(), d_T6, sizeof(float) * 6 * cnt, cudaMemcpyDeviceToHost));
-        CU_TRY0(cudaMemcpy(hs.data(), d_nscore, sizeof(float) * cnt, cudaMemcpyDeviceToHost));
+        CU_TRY0(D2H(hT.data(), d_T6, sizeof(float) * 6 * cnt));
+        CU_TRY0(D2H(hs.data(), d_nscore, sizeof(float) * cnt));
+        CU_TRY0(cudaStreamSynchronize(cs.s));
         for (int k = 0; k < cnt; ++k) {
             out_xy[2 * k] = (uint32_t)hT[(size_t)k * 6 + 2];
             out_xy[2 * k + 1] = (uint32_t)hT[(size_t)k * 6 + 5];
@@ -1129,14 +1183,17 @@ rsvio_status rsvio_se2_exp(int32_t device, const float *twists, int32_t n, float
     if (n == 0) return RSVIO_OK;
     rsvio_status rs = RSVIO_OK;
     DeviceScope dev_scope;
+    CallStream cs;
     float *d_in = nullptr, *d_out = nullptr;
     CU_TRY0(dev_scope.enter(device));
+    CU_TRY0(cs.create());
     CU_TRY0(cudaMalloc((void **)&d_in, sizeof(float) * 3 * n));
     CU_TRY0(cudaMalloc((void **)&d_out, sizeof(float) * 9 * n));
-    CU_TRY0(cudaMemcpy(d_in, twists, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
-    CU_TRY0(se2_exp_batch(d_in, n, d_out, 0));
-    CU_TRY0(cudaDeviceSynchronize());
-    CU_TRY0(cudaMemcpy(out9, d_out, sizeof(float) * 9 * n, cudaMemcpyDeviceToHost));
+    CU_TRY0(H2D(d_in, twists, sizeof(float) * 3 * n));
+    CU_TRY0(se2_exp_batch(d_in, n, d_out, cs.s));
+    CU_TRY0(cudaStreamSynchronize(cs.s));
+    CU_TRY0(D2H(out9, d_out, sizeof(float) * 9 * n));
+    CU_TRY0(cudaStreamSynchronize(cs.s));
 done:
     cudaFree(d_in);
     cudaFree(d_out);
@@ -1150,16 +1207,19 @@ rsvio_status rsvio_unproject_points(int32_t device, const rsvio_camera_model *mo
     if (n == 0) return RSVIO_OK;
     rsvio_status rs = RSVIO_OK;
     DeviceScope dev_scope;
+    CallStream cs;
     float *d_in = nullptr, *d_out = nullptr;
     CameraModelDev cm{};
     cm.model = model->model;
     for (int k = 0; k < 9; ++k) cm.p[k] = model->params[k];
     CU_TRY0(dev_scope.enter(device));
+    CU_TRY0(cs.create());
     CU_TRY0(cudaMalloc((void **)&d_in, sizeof(float) * 2 * (size_t)n));
     CU_TRY0(cudaMalloc((void **)&d_out, sizeof(float) * 2 * (size_t)n));
-    CU_TRY0(cudaMemcpy(d_in, xy, sizeof(float) * 2 * (size_t)n, cudaMemcpyHostToDevice));
-    CU_TRY0(unproject_points(cm, d_in, n, d_out, 0));
-    CU_TRY0(cudaMemcpy(out_xy, d_out, sizeof(float) * 2 * (size_t)n, cudaMemcpyDeviceToHost));
+    CU_TRY0(H2D(d_in, xy, sizeof(float) * 2 * (size_t)n));
+    CU_TRY0(unproject_points(cm, d_in, n, d_out, cs.s));
+    CU_TRY0(D2H(out_xy, d_out, sizeof(float) * 2 * (size_t)n));
+    CU_TRY0(cudaStreamSynchronize(cs.s));
 done:
     cudaFree(d_in);
     cudaFree(d_out);
@@ -1173,14 +1233,17 @@ rsvio_status rsvio_convert_to_luma8(int32_t device, const void *src, int32_t wid
         return RSVIO_ERR_INVALID_ARG;
     rsvio_status rs = RSVIO_OK;
     DeviceScope dev_scope;
+    CallStream cs;
     uint8_t *d_src = nullptr, *d_dst = nullptr;
     const size_t row = (size_t)width * bpp;
     CU_TRY0(dev_scope.enter(device));
+    CU_TRY0(cs.create());
     CU_TRY0(cudaMalloc((void **)&d_src, row * (size_t)height));
     CU_TRY0(cudaMalloc((void **)&d_dst, (size_t)width * height));
-    CU_TRY0(cudaMemcpy2D(d_src, row, src, stride_bytes, row, (size_t)height, cudaMemcpyHostToDevice));
-    CU_TRY0(convert_to_luma8(d_src, row, width, height, pixel_format, d_dst, 0));
-    CU_TRY0(cudaMemcpy(out, d_dst, (size_t)width * height, cudaMemcpyDeviceToHost));
+    CU_TRY0(cudaMemcpy2DAsync(d_src, row, src, stride_bytes, row, (size_t)height, cudaMemcpyHostToDevice, cs.s));
+    CU_TRY0(convert_to_luma8(d_src, row, width, height, pixel_format, d_dst, cs.s));
+    CU_TRY0(D2H(out, d_dst, (size_t)width * height));
+    CU_TRY0(cudaStreamSynchronize(cs.s));
 done:
     cudaFree(d_src);
     cudaFree(d_dst);
@@ -1211,17 +1274,20 @@ rsvio_status rsvio_b_build_pyramid(int32_t device, const float *image, int32_t w
     for (int l = 0; l < levels; ++l)
         if (!out_levels[l]) return RSVIO_ERR_INVALID_ARG;
     DeviceScope dev_scope;
+    CallStream cs;
     float *d_lv[RSVIO_MAX_LEVELS] = {};
     float *d_tmp = nullptr;
     CU_TRY0(dev_scope.enter(device));
+    CU_TRY0(cs.create());
     for (int l = 0; l < levels; ++l) CU_TRY0(cudaMalloc((void **)&d_lv[l], sizeof(float) * (size_t)w[l] * h[l]));
     CU_TRY0(cudaMalloc((void **)&d_tmp, sizeof(float) * (size_t)w[0] * h[0]));
-    CU_TRY0(cudaMemcpy(d_lv[0], image, sizeof(float) * (size_t)w[0] * h[0], cudaMemcpyHostToDevice));
+    CU_TRY0(H2D(d_lv[0], image, sizeof(float) * (size_t)w[0] * h[0]));
     for (int l = 1; l < levels; ++l)
-        CU_TRY0(resize_triangle_f32(d_lv[l - 1], w[l - 1], h[l - 1], d_tmp, d_lv[l], w[l], h[l], 0));
-    CU_TRY0(cudaDeviceSynchronize());
+        CU_TRY0(resize_triangle_f32(d_lv[l - 1], w[l - 1], h[l - 1], d_tmp, d_lv[l], w[l], h[l], cs.s));
+    CU_TRY0(cudaStreamSynchronize(cs.s));
     for (int l = 0; l < levels; ++l)
-        CU_TRY0(cudaMemcpy(out_levels[l], d_lv[l], sizeof(float) * (size_t)w[l] * h[l], cudaMemcpyDeviceToHost));
+        CU_TRY0(D2H(out_levels[l], d_lv[l], sizeof(float) * (size_t)w[l] * h[l]));
+    CU_TRY0(cudaStreamSynchronize(cs.s));
 done:
     for (int l = 0; l < RSVIO_MAX_LEVELS; ++l) cudaFree(d_lv[l]);
     cudaFree(d_tmp);
@@ -1240,28 +1306,31 @@ rsvio_status rsvio_b_track_points(int32_t device, const float *const *pyr0, cons
     if (n == 0) return RSVIO_OK;
     rsvio_status rs = RSVIO_OK;
     DeviceScope dev_scope;
+    CallStream cs;
     float *d_lv[2][RSVIO_MAX_LEVELS] = {};
     float *d_pts = nullptr, *d_T = nullptr;
     int32_t *d_st = nullptr;
     int w[RSVIO_MAX_LEVELS], h[RSVIO_MAX_LEVELS];
     CU_TRY0(dev_scope.enter(device));
+    CU_TRY0(cs.create());
     for (int l = 0; l < levels; ++l) {
         w[l] = widths[l];
         h[l] = heights[l];
         const size_t bytes = sizeof(float) * (size_t)w[l] * h[l];
         for (int k = 0; k < 2; ++k) {
             CU_TRY0(cudaMalloc((void **)&d_lv[k][l], bytes));
-            CU_TRY0(cudaMemcpy(d_lv[k][l], (k == 0 ? pyr0 : pyr1)[l], bytes, cudaMemcpyHostToDevice));
+            CU_TRY0(H2D(d_lv[k][l], (k == 0 ? pyr0 : pyr1)[l], bytes));
         }
     }
     CU_TRY0(cudaMalloc((void **)&d_pts, sizeof(float) * 2 * (size_t)n));
     CU_TRY0(cudaMalloc((void **)&d_T, sizeof(float) * 4 * (size_t)n));
     CU_TRY0(cudaMalloc((void **)&d_st, sizeof(int32_t) * (size_t)n));
-    CU_TRY0(cudaMemcpy(d_pts, points_xy, sizeof(float) * 2 * (size_t)n, cudaMemcpyHostToDevice));
-    CU_TRY0(trackb_points(d_lv[0], d_lv[1], w, h, levels, d_pts, n, max_iteration, lm_lambda, d_T, d_st, 0));
-    CU_TRY0(cudaDeviceSynchronize());
-    CU_TRY0(cudaMemcpy(out_T4, d_T, sizeof(float) * 4 * (size_t)n, cudaMemcpyDeviceToHost));
-    CU_TRY0(cudaMemcpy(status, d_st, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+    CU_TRY0(H2D(d_pts, points_xy, sizeof(float) * 2 * (size_t)n));
+    CU_TRY0(trackb_points(d_lv[0], d_lv[1], w, h, levels, d_pts, n, max_iteration, lm_lambda, d_T, d_st, cs.s));
+    CU_TRY0(cudaStreamSynchronize(cs.s));
+    CU_TRY0(D2H(out_T4, d_T, sizeof(float) * 4 * (size_t)n));
+    CU_TRY0(D2H(status, d_st, sizeof(int32_t) * (size_t)n));
+    CU_TRY0(cudaStreamSynchronize(cs.s));
 done:
     for (int l = 0; l < RSVIO_MAX_LEVELS; ++l)
         for (int k = 0; k < 2; ++k) cudaFree(d_lv[k][l]);

@@ -18,7 +18,26 @@ namespace rsvio {
 
 constexpr int kMaxLevels = RSVIO_MAX_LEVELS;
 constexpr int kPattern = RSVIO_PATTERN_SIZE;
-constexpr int kNumSMs = 148;  // B200
+constexpr int kNumSMs = 148;  // B200 (fallback only: launches size their grids with sm_count())
+
+// SM count of the calling thread's current device (grids are sized in multiples of it)
+inline int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+        cudaGetLastError();
+        return kNumSMs;
+    }
+    if (cached[dev] <= 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            return kNumSMs;
+        }
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
 
 struct LevelDesc {
     int w, h;

@@ -253,7 +253,8 @@ cudaError_t detect_cells(const GridDesc &gd, const uint8_t *img0, size_t stride,
                                                                              cnt, other);
     // one resident wave of CTAs looping over the list (measured: 23 us; one CTA per candidate cell, most of
     // them exiting at once, 31 us)
-    long long blocks = total < (long long)kNumSMs * 8 ? total : (long long)kNumSMs * 8;
+    const long long wave = (long long)sm_count() * 8;
+    long long blocks = total < wave ? total : wave;
     detect_list_kernel<<<(unsigned)blocks, kDetThreads, 0, st>>>(gd, img0, stride, pitch, list, cnt, cell_pt,
                                                                  cell_score);
     return cudaGetLastError();

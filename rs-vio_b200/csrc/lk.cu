@@ -338,7 +338,8 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
         float wlim = (float)((uint32_t)ib.w - 2u), hlim = (float)((uint32_t)ib.h - 2u);
         asm volatile("mov.b32 %0, %0;" : "+f"(wlim));  // kept in registers across the iterations, as the base and pitch below
         asm volatile("mov.b32 %0, %0;" : "+f"(hlim));
-        const float thr2 = thr * thr;
+        // `inc.norm() < thr` (feature_tracker.rs:374) is never true for thr <= 0
+        const float thr2 = thr > 0.0f ? thr * thr : 0.0f;
         // the level base and row pitch stay in registers across the iterations (opaque to rematerialisation)
         const uint8_t *ibp = ib.p;
         uint32_t ibw = (uint32_t)ib.w;
@@ -563,7 +564,7 @@ cudaError_t lk_track(const PyrDesc &pd, const LkBatch &b, cudaStream_t st) {
     long long blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const bool dynamic = b.work_counter != nullptr && b.groups <= kMaxGroupsSmem;
     // dynamic scheduling: one resident wave (64 registers -> 8 CTAs per SM); static striding: up to 16 per SM
-    const long long max_blocks = (long long)kNumSMs * (dynamic ? 8 : 16);
+    const long long max_blocks = (long long)sm_count() * (dynamic ? 8 : 16);
     if (blocks > max_blocks) blocks = max_blocks;
     const size_t smem = dynamic ? sizeof(int) * (size_t)(b.groups + 1) : 0;
     lk_track_fb_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(pd, b);

@@ -1722,7 +1722,7 @@ cudaError_t pyr_build(const PyrPlan *p, const uint8_t *src0, const uint8_t *src1
             const long long items = (long long)n * ((long long)p->pd.lv[4].w * p->pd.lv[4].h +
                                                     (p->do5 ? (long long)p->pd.lv[5].w * p->pd.lv[5].h : 0));
             long long blocks = (items + kDeepThreads - 1) / kDeepThreads;
-            if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+            if (blocks > sm_count() * 8) blocks = sm_count() * 8;
             if (blocks < 1) blocks = 1;
             pyr_deep_kernel<<<(unsigned)blocks, kDeepThreads, 0, st>>>(p->pd, p->taps, p->d_g8, n, p->do5, s0, s1, sps,
                                                                         stride, pitch, d);

@@ -32,7 +32,8 @@ ABI_SYMBOLS = (
     "rsvio_tracker_submit_batch", "rsvio_tracker_sync", "rsvio_tracker_submit_device",
     "rsvio_tracker_num_tracks", "rsvio_tracker_get_tracks", "rsvio_tracker_result_view",
     "rsvio_tracker_get_transforms",
-    "rsvio_tracker_remove_ids", "rsvio_tracker_counters", "rsvio_tracker_set_profiling",
+    "rsvio_tracker_remove_ids", "rsvio_tracker_counters", "rsvio_tracker_overflow_frames",
+    "rsvio_tracker_set_profiling",
     "rsvio_tracker_stage_times",
     "rsvio_pyramid_bytes", "rsvio_pyramid_device_bytes", "rsvio_build_pyramid_u8",
     "rsvio_build_pyramid_u8_device", "rsvio_track_points", "rsvio_detect_keypoints", "rsvio_se2_exp",
@@ -134,6 +135,7 @@ def load_library():
                                                C.POINTER(C.c_size_t)]
     L.rsvio_tracker_remove_ids.argtypes = [H, C.c_int32, _u64p, C.c_size_t]
     L.rsvio_tracker_counters.argtypes = [H, _u64p]
+    L.rsvio_tracker_overflow_frames.argtypes = [H, C.POINTER(C.c_uint64)]
     L.rsvio_tracker_set_profiling.argtypes = [H, C.c_int32]
     L.rsvio_tracker_stage_times.argtypes = [H, _f32p, _u64p, C.c_int32]
     L.rsvio_pyramid_bytes.restype = C.c_size_t
@@ -161,6 +163,20 @@ def load_library():
                                        _f32p, C.c_int32, C.c_int32, C.c_float, _f32p, _i32p]
     _lib = L
     return L
+
+
+class CapacityWarning(RuntimeWarning):
+    """new points did not fit the track table (rsvio_config.max_tracks); the frame itself was processed"""
+
+
+def _check_frame(status, handle):
+    """status of a process_* / sync call: a full track table is a warning, not an error -- the reference's maps
+    are unbounded (feature_tracker.rs:93-96) and its process_frame cannot fail, so the frame is delivered."""
+    if status == ERR_CAPACITY:
+        import warnings
+        warnings.warn(load_library().rsvio_tracker_last_error(handle).decode(), CapacityWarning, stacklevel=3)
+        return
+    _check(status, handle)
 
 
 def _check(status, handle=None):
@@ -344,7 +360,7 @@ class _Tracker:
             ra, rp = self._ptrs(right, self.n_streams, self.width, self.height)
         else:
             ra, rp = None, None
-        _check(self._L.rsvio_tracker_process_batch(self._h, lp, rp, self.width), self._h)
+        _check_frame(self._L.rsvio_tracker_process_batch(self._h, lp, rp, self.width), self._h)
 
     def submit_batch_ptr(self, left_ptrs, right_ptrs, stride=None):
         """left_ptrs/right_ptrs: ctypes arrays of host addresses (e.g. into pinned memory)."""
@@ -357,7 +373,13 @@ class _Tracker:
                                                    pitch), self._h)
 
     def sync(self):
-        _check(self._L.rsvio_tracker_sync(self._h), self._h)
+        _check_frame(self._L.rsvio_tracker_sync(self._h), self._h)
+
+    def overflow_frames(self):
+        """frames since create/reset whose new points did not all fit the track table"""
+        n = C.c_uint64(0)
+        _check(self._L.rsvio_tracker_overflow_frames(self._h, C.byref(n)), self._h)
+        return n.value
 
     def num_tracks(self, cam=0, stream=0):
         n = C.c_int32(0)
@@ -445,8 +467,8 @@ class StereoPatchTracker(_Tracker):
         r = np.ascontiguousarray(greyscale_image1, np.uint8)
         if l.shape != (self.height, self.width) or r.shape != l.shape:
             raise ValueError("image shape does not match the tracker")
-        _check(self._L.rsvio_tracker_process_stereo(self._h, C.c_void_p(l.ctypes.data), C.c_void_p(r.ctypes.data),
-                                                    self.width), self._h)
+        _check_frame(self._L.rsvio_tracker_process_stereo(self._h, C.c_void_p(l.ctypes.data),
+                                                          C.c_void_p(r.ctypes.data), self.width), self._h)
         if frame is not None:
             uxy = self.undistorted_view()
             for cam, add in ((0, frame.add_left_feature), (1, frame.add_right_feature)):
@@ -463,8 +485,8 @@ class StereoPatchTracker(_Tracker):
         l, r = np.ascontiguousarray(left), np.ascontiguousarray(right)
         if l.shape[:2] != (self.height, self.width) or r.shape != l.shape:
             raise ValueError("image shape does not match the tracker")
-        _check(self._L.rsvio_tracker_process_stereo_fmt(self._h, C.c_void_p(l.ctypes.data), C.c_void_p(r.ctypes.data),
-                                                        l.strides[0], fmt), self._h)
+        _check_frame(self._L.rsvio_tracker_process_stereo_fmt(self._h, C.c_void_p(l.ctypes.data),
+                                                              C.c_void_p(r.ctypes.data), l.strides[0], fmt), self._h)
 
     def get_track_points(self, stream=0):
         """[ {id: (x, y)} for cam0, cam1 ]  (feature_tracker.rs:188-200)"""
@@ -487,7 +509,7 @@ class PatchTracker(_Tracker):
         im = np.ascontiguousarray(greyscale_image, np.uint8)
         if im.shape != (self.height, self.width):
             raise ValueError("image shape does not match the tracker")
-        _check(self._L.rsvio_tracker_process_mono(self._h, C.c_void_p(im.ctypes.data), self.width), self._h)
+        _check_frame(self._L.rsvio_tracker_process_mono(self._h, C.c_void_p(im.ctypes.data), self.width), self._h)
 
     def get_track_points(self, stream=0):
         ids, xy = self.tracks(0, stream)

@@ -4,6 +4,7 @@ use std::os::raw::{c_char, c_void};
 
 pub type rsvio_status = i32;
 pub const RSVIO_OK: rsvio_status = 0;
+pub const RSVIO_ERR_CAPACITY: rsvio_status = -3;
 pub const RSVIO_MODE_STEREO: i32 = 0;
 pub const RSVIO_MODE_MONO: i32 = 1;
 
@@ -86,6 +87,7 @@ extern "C" {
 
     // ---- counters and per-stage device times ----
     pub fn rsvio_tracker_counters(t: *mut rsvio_tracker, out: *mut u64) -> rsvio_status; // out[6]
+    pub fn rsvio_tracker_overflow_frames(t: *mut rsvio_tracker, n: *mut u64) -> rsvio_status;
     pub fn rsvio_tracker_set_profiling(t: *mut rsvio_tracker, enabled: i32) -> rsvio_status;
     pub fn rsvio_tracker_stage_times(t: *mut rsvio_tracker, ms: *mut f32, launches: *mut u64, reset: i32)
         -> rsvio_status; // ms[RSVIO_N_STAGES], launches[RSVIO_N_STAGES]

@@ -81,6 +81,21 @@ impl Handle {
             panic!("{what}: {} ({detail})", status_text(st));
         }
     }
+    /// Status of a `process_*` call.  A full track table is not an error: the frame was processed and is delivered,
+    /// only new points were dropped (the reference's maps are unbounded and its `process_frame` cannot fail,
+    /// feature_tracker.rs:93-96,116).  One warning on stderr per handle; the count stays queryable
+    /// (`rsvio_tracker_overflow_frames`).
+    fn check_frame(&self, st: ffi::rsvio_status, what: &str) {
+        if st == ffi::RSVIO_ERR_CAPACITY {
+            let mut n: u64 = 0;
+            if unsafe { ffi::rsvio_tracker_overflow_frames(self.ptr, &mut n) } == ffi::RSVIO_OK && n == 1 {
+                let detail = unsafe { CStr::from_ptr(ffi::rsvio_tracker_last_error(self.ptr)) }.to_string_lossy().into_owned();
+                eprintln!("rsvio: {what}: {detail}");
+            }
+            return;
+        }
+        self.check(st, what);
+    }
     /// Camera model of one camera (0 = left, 1 = right); applied when the handle exists (the reference builds its
     /// models from the YAML config, src/datasets/mod.rs:93-163).  With a model set, `process_frame` hands out
     /// features whose `undistorted_coord` is already filled (what `Frame::add_*_feature` computes on the CPU).
@@ -179,7 +194,7 @@ impl<const LEVELS: u32> StereoPatchTracker<LEVELS> {
             ffi::rsvio_tracker_process_stereo(self.h.ptr, greyscale_image0.as_raw().as_ptr(), greyscale_image1.as_raw().as_ptr(),
                                               w as usize)
         };
-        self.h.check(st, "rsvio_tracker_process_stereo");
+        self.h.check_frame(st, "rsvio_tracker_process_stereo");
         self.h.for_each_feature(0, |f| frame.add_left_feature(f));
         self.h.for_each_feature(1, |f| frame.add_right_feature(f));
     }
@@ -228,7 +243,7 @@ impl<const LEVELS: u32> PatchTracker<LEVELS> {
         let (w, h) = greyscale_image.dimensions();
         self.h.ensure(w, h);
         let st = unsafe { ffi::rsvio_tracker_process_mono(self.h.ptr, greyscale_image.as_raw().as_ptr(), w as usize) };
-        self.h.check(st, "rsvio_tracker_process_mono");
+        self.h.check_frame(st, "rsvio_tracker_process_mono");
     }
     pub fn get_track_points(&self) -> HashMap<usize, (f32, f32)> {
         let mut out = HashMap::new();

@@ -84,7 +84,8 @@ def record(stats):
 
 
 @pytest.mark.parametrize("w,h,levels,max_it,grid", [(752, 480, 3, 20, 40), (512, 512, 4, 10, 30),
-                                                    (800, 400, 6, 10, 12), (752, 480, 6, 20, 50)])
+                                                    (800, 400, 6, 10, 12), (752, 480, 6, 20, 50),
+                                                    (1920, 1200, 5, 20, 15)])
 def test_lk_matches_oracle_on_detected_corners(rsvio, oracle, w, h, levels, max_it, grid):
     a, b = scene_pair(w, h, 1000 + levels, (1.37, -0.62))
     xs, ys, _ = oracle.detect_key_points(a, grid, np.zeros((0, 2), np.uint32))
