@@ -136,19 +136,21 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 def cpu_run(config, frames, n_streams, n_frames, warm_frames, threads):
     """oracle StereoTracker per stream, streams spread over `threads` host threads (ctypes releases the
-    GIL), frames [0, warm) untimed.  Returns (tracks, stereo_frames, seconds)."""
+    GIL), frames [0, warm) untimed.  A single stream gets all threads inside the tracker instead (levels and
+    points in parallel, as the reference's rayon calls).  Returns (tracks, stereo_frames, seconds)."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle as orc
     orc.build()
     p = CONFIGS[config]
-    trackers = [orc.StereoTracker(p["levels"], p["grid"], p["max_it"], p["thr"], nthreads=1) for _ in range(n_streams)]
+    inner = threads if n_streams == 1 else 1
+    trackers = [orc.StereoTracker(p["levels"], p["grid"], p["max_it"], p["thr"], nthreads=inner) for _ in range(n_streams)]
 
     def advance(s, t0, t1):
         for t in range(t0, t1):
             k = ring_index(t, frames.shape[0])
             trackers[s].process_frame(frames[k, 0, s], frames[k, 1, s])
 
-    with ThreadPoolExecutor(max_workers=threads) as ex:
+    with ThreadPoolExecutor(max_workers=max(1, min(threads, n_streams))) as ex:
         list(ex.map(lambda s: advance(s, 0, warm_frames), range(n_streams)))
         before = sum(t.counters()[0] for t in trackers)
         t0 = time.perf_counter()
@@ -190,23 +192,30 @@ def workload_config(args, S, n_gpus):
             "streams_per_gpu": S, "total_streams": total, "frame_ring": RING,
             "l2": "per step the kernels touch previous+current pyramids and the input ring slot "
                   "(> 230 MB at 64 streams), larger than the 126 MB L2; no explicit flush",
-            "parallelism": f"{n_gpus} x independent replicas (streams sharded, no collective)"}
+            "parallelism": f"{n_gpus} x independent replicas (streams sharded, no data-path collective; "
+                           "torch.distributed/NCCL carries only the timing barrier and the final counter reduction)"}
 
 
 # ------------------------------------------------------------------------------------------------
 def ncu_dram_traffic(same_workload):
     """dram__bytes_read.sum + dram__bytes_write.sum of the pyramid kernel, per launch, from the committed
-    `ncu --set full` capture of this same workload (profiles/r1_pyr_fast_kernel.txt); None for other workloads."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_pyr_fast_kernel.txt")
-    if not same_workload or not os.path.exists(path):
+    `ncu --set full` capture of this same workload (profiles/r2_pyr_fast_kernel.txt, else round 1's); None for
+    other workloads.  A number taken under a profiler is evidence, never a bench value: only `traffic` uses it."""
+    if not same_workload:
         return None, None
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    tot = 0.0
-    for line in open(path):
-        f = line.split()
-        if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[2] in scale:
-            tot += float(f[1]) * scale[f[2]]
-    return (tot, "profiles/r1_pyr_fast_kernel.txt (ncu --set full, cold L2, one launch of 128 images)") if tot else (None, None)
+    for name in ("r2_pyr_fast_kernel.txt", "r1_pyr_fast_kernel.txt"):
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        tot = 0.0
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and f[2] in scale:
+                tot += float(f[1]) * scale[f[2]]
+        if tot:
+            return tot, f"profiles/{name} (ncu --set full, cold L2, one launch of 128 images)"
+    return None, None
 
 
 def bind_to_gpu_numa_node(local_rank):
@@ -231,6 +240,151 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
+class Runner:
+    """One tracker handle on one GPU fed from a ring of synthetic frames: device-resident steps (`value`),
+    host-frame steps through the reference-facing submit/sync calls (`e2e`), per-stage profiling."""
+
+    def __init__(self, torch, rsvio_b200, config, frames_np, local_rank, stream, host_kind="wc"):
+        import ctypes as C
+        self.torch, self.rs, self.C = torch, rsvio_b200, C
+        self.p = CONFIGS[config]
+        self.w, self.h = self.p["w"], self.p["h"]
+        self.S = frames_np.shape[2]
+        self.ring = frames_np.shape[0]
+        self.stream = stream
+        dev = torch.device("cuda", local_rank)
+        # Pinned frame ring [ring][cam][S][h][w].  "wc": rsvio_host_alloc_flags(WRITE_COMBINED) -- the CPU only writes
+        # these pages, the DMA engine reads them without snooping CPU caches; "pinned": torch.pin_memory().
+        self.host_kind = host_kind
+        if host_kind == "wc":
+            self.hostbuf = rsvio_b200.HostBuffer(frames_np.shape, write_combined=True)
+            np.copyto(self.hostbuf.array, frames_np)
+            base = self.hostbuf.ptr
+        else:
+            self.hostbuf = torch.from_numpy(frames_np).pin_memory()
+            base = self.hostbuf.data_ptr()
+        self.dev = torch.from_numpy(frames_np).to(dev)
+        img = self.w * self.h
+        self.img_bytes = img
+        self.host_ptrs = []
+        for k in range(self.ring):
+            lp = (C.c_void_p * self.S)(*[base + ((k * 2 + 0) * self.S + s) * img for s in range(self.S)])
+            rp = (C.c_void_p * self.S)(*[base + ((k * 2 + 1) * self.S + s) * img for s in range(self.S)])
+            self.host_ptrs.append((lp, rp))
+        with torch.cuda.stream(stream):
+            self.tr = rsvio_b200.StereoPatchTracker(self.p["grid"], self.p["max_it"], self.p["thr"], width=self.w,
+                                                    height=self.h, levels=self.p["levels"], n_streams=self.S,
+                                                    device=local_rank, cuda_stream=stream.cuda_stream)
+        self.read_sum = 0.0
+
+    def close(self):
+        self.tr.close()
+        if self.host_kind == "wc":
+            self.hostbuf.close()
+
+    def _submit(self, kind, i):
+        k = ring_index(i, self.ring)
+        if kind == "device":
+            self.tr.submit_device(self.dev[k, 0].data_ptr(), self.dev[k, 1].data_ptr(), self.w, self.img_bytes)
+        else:
+            lp, rp = self.host_ptrs[k]
+            self.tr.submit_batch_ptr(lp, rp, self.w)
+
+    def _consume(self):
+        """read the WHOLE result of the step on the host (zero-copy view of host-mapped pinned memory)"""
+        rec, cnt = self.tr.result_view()
+        n = 0
+        for g in range(cnt.shape[0]):
+            c = int(cnt[g])
+            if c:
+                self.read_sum += float(rec["x"][g, :c].sum()) + float(rec["y"][g, :c].sum())
+            n += c
+        return n
+
+    def run(self, kind, first, n, consume=False):
+        """n pipelined steps (<= 2 in flight); returns the number of records read"""
+        recs = 0
+        self._submit(kind, first)
+        for i in range(first + 1, first + n):
+            self._submit(kind, i)
+            self.tr.sync()
+            if consume:
+                recs += self._consume()
+        self.tr.sync()
+        if consume:
+            recs += self._consume()
+        return recs
+
+    def timed(self, kind, first, n, barrier, sampler=None):
+        """(counter deltas, device ms between events on the handle's stream, wall s, records read)"""
+        torch = self.torch
+        barrier()
+        c0 = self.tr.counters()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        if sampler is not None:
+            sampler.active = True
+        t0 = time.perf_counter()
+        e0.record(self.stream)
+        recs = self.run(kind, first, n, consume=(kind == "host"))
+        e1.record(self.stream)
+        e1.synchronize()
+        wall = time.perf_counter() - t0
+        if sampler is not None:
+            sampler.active = False
+        barrier()
+        c1 = self.tr.counters()
+        return {k: c1[k] - c0[k] for k in c1}, e0.elapsed_time(e1), wall, recs
+
+    def stages(self, kind, first, n):
+        """per-stage device ms per step: profiling mode puts everything on one stream with CUDA events between
+        the stages, so a stage time is that stage's kernels alone on the device"""
+        self.tr.set_profiling(True)
+        self.tr.stage_times(reset=True)
+        self.run(kind, first, n)
+        st = self.tr.stage_times(reset=True)
+        self.tr.set_profiling(False)
+        return {k: v[0] / n for k, v in st.items()}, {k: v[1] // n for k, v in st.items()}
+
+
+def per_config_results(torch, rsvio_b200, local_rank, stream, cores, which, steps=24, warmup=6):
+    """value / e2e / cpu_baseline of the single-stream BASELINE configs (C1..C4 and the estimator's shipped L = 6
+    setting): one stereo stream through one handle, short runs, same definitions as the headline numbers."""
+    out = []
+    for config in which:
+        try:
+            p = CONFIGS[config]
+            frames = generate_frames(config, [0], RING, 1)
+            r = Runner(torch, rsvio_b200, config, frames, local_rank, stream)
+            sync = torch.cuda.synchronize
+            r.run("device", 0, warmup)
+            d, ms, _, _ = r.timed("device", warmup, steps, sync)
+            stage_ms, _ = r.stages("device", warmup + steps, 12)
+            r.tr.reset()
+            r.run("host", 0, warmup)
+            dh, msh, wallh, recs = r.timed("host", warmup, steps, sync)
+            msh = max(msh, wallh * 1e3)
+            alive = int(r.tr.result_view()[1].sum())
+            r.close()
+            ct, cf, cdt = cpu_run(config, frames, 1, 8, 3, cores)
+            alg = 2 * (p["w"] * p["h"] + rsvio_b200.pyramid_bytes(p["w"], p["h"], p["levels"]))
+            out.append({
+                "config": config, "shape": f"{p['w']}x{p['h']} L{p['levels']} grid {p['grid']}", "streams": 1,
+                "value": d["tracks"] / (ms * 1e-3), "unit": "tracks/s", "ms_per_frame": ms / steps,
+                "stereo_frames_per_sec": steps / (ms * 1e-3), "tracks_alive": alive,
+                "e2e": {"value": dh["tracks"] / (msh * 1e-3), "ms_per_frame": msh / steps,
+                        "h2d_bytes_per_step": 2 * p["w"] * p["h"], "d2h_bytes_per_step": recs * 16 / steps},
+                "stage_ms": stage_ms,
+                "pyramid_latency": {"ms": stage_ms["pyramid"], "alg_bytes": alg,
+                                    "note": "2 images: latency-bound, not a bandwidth number"},
+                "cpu_baseline": {"value": ct / cdt, "unit": "tracks/s", "cores": cores, "kind": "port",
+                                 "stereo_frames_per_sec": cf / cdt, "sample": "1 stream x 8 frames after 3 warm-up frames"},
+            })
+        except Exception as ex:  # the headline line does not depend on these
+            out.append({"config": config, "error": repr(ex)})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -242,8 +396,11 @@ def main():
                     help="weak scaling (default): every GPU runs this many streams (C5: 64)")
     ap.add_argument("--total-streams", type=int, default=None,
                     help="strong scaling: this many streams block-partitioned over the GPUs")
+    ap.add_argument("--host-memory", default="wc", choices=["wc", "pinned"],
+                    help="frame ring: write-combined pinned pages from rsvio_host_alloc_flags (default) or torch.pin_memory")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pyramid-roofline", action="store_true")
+    ap.add_argument("--no-per-config", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -305,118 +462,41 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    host = torch.from_numpy(frames_np).pin_memory()                  # [ring][cam][S][h][w]
-    devbuf = host.to(dev)
-    img_bytes = w * h
     stream = torch.cuda.Stream(device=dev)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    run = Runner(torch, rsvio_b200, args.config, frames_np, local_rank, stream, args.host_memory)
+    img_bytes = w * h
 
-    import ctypes as C
-    host_ptrs = []
-    for k in range(RING):
-        lp = (C.c_void_p * S)(*[host[k, 0, s].data_ptr() for s in range(S)])
-        rp = (C.c_void_p * S)(*[host[k, 1, s].data_ptr() for s in range(S)])
-        host_ptrs.append((lp, rp))
+    # ---- device-resident throughput (`value`) ---------------------------------------------------
+    run.run("device", 0, args.warmup)
+    d, ms, _, _ = run.timed("device", args.warmup, args.steps, barrier, sampler)
+    tracks_dev, frames_dev, iters_dev, ms_dev = sharding.aggregate(dist, dev, d["tracks"], S * args.steps,
+                                                                   d["iterations"], ms)
+    templ_dev = reduce_sum(d["templates"])
+    launches = d["launches"]
+    n_tracks_alive = int(run.tr.result_view()[1].sum())
 
-    with torch.cuda.stream(stream):
-        tr = rsvio_b200.StereoPatchTracker(p["grid"], p["max_it"], p["thr"], width=w, height=h, levels=p["levels"],
-                                           n_streams=S, device=local_rank, cuda_stream=stream.cuda_stream)
+    # ---- per-stage device times of that path (profiling mode, device-resident frames) -----------
+    prof_steps = max(10, min(50, args.steps))
+    sampler.active = True
+    stages, stage_launches = run.stages("device", args.warmup + args.steps, prof_steps)
+    sampler.active = False
 
-        def submit_dev(i):
-            k = ring_index(i)
-            tr.submit_device(devbuf[k, 0].data_ptr(), devbuf[k, 1].data_ptr(), w, img_bytes)
+    # ---- end to end: pinned host frames in, host-mapped result out (`e2e`) -----------------------
+    run.tr.reset()
+    run.run("host", 0, args.warmup)
+    dh, ms_e2e_dev, wall_e2e, recs = run.timed("host", args.warmup, args.steps, barrier, sampler)
+    ms_e2e_dev = reduce_max(ms_e2e_dev)
+    ms_e2e = max(ms_e2e_dev, reduce_max(wall_e2e * 1e3))   # host reads are part of the step
+    tracks_e2e, frames_e2e, _, _ = sharding.aggregate(dist, dev, dh["tracks"], S * args.steps, 0, 0.0)
+    d2h_per_step = (recs * 16 + 2 * S * 4) / args.steps
+    stages_host, _ = run.stages("host", args.warmup + args.steps, min(prof_steps, 20))
+    h2d_gbs_rank = 2 * S * img_bytes / (ms_e2e / args.steps * 1e-3) / 1e9
 
-        def run_device(first, n):
-            """n pipelined steps (<= 2 in flight) from device-resident frames"""
-            submit_dev(first)
-            for i in range(first + 1, first + n):
-                submit_dev(i)
-                tr.sync()
-            tr.sync()
-
-        # ---- device-resident throughput --------------------------------------------------------
-        run_device(0, args.warmup)
-        barrier()
-        c0 = tr.counters()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        sampler.active = True
-        e0.record(stream)
-        run_device(args.warmup, args.steps)
-        e1.record(stream)
-        e1.synchronize()
-        sampler.active = False
-        barrier()
-        c1 = tr.counters()
-        tracks_dev, frames_dev, iters_dev, ms_dev = sharding.aggregate(
-            dist, dev, c1["tracks"] - c0["tracks"], S * args.steps, c1["iterations"] - c0["iterations"],
-            e0.elapsed_time(e1))
-        templ_dev = reduce_sum(c1["templates"] - c0["templates"])
-        launches = c1["launches"] - c0["launches"]
-        n_tracks_alive = int(tr.result_view()[1].sum())
-
-        # ---- end to end: pinned host frames in, host-mapped result out ---------------------------
-        tr.reset()
-
-        def submit_host(i):
-            lp, rp = host_ptrs[ring_index(i)]
-            tr.submit_batch_ptr(lp, rp, w)
-
-        consumed = [0, 0.0]
-
-        def consume():
-            rec, cnt = tr.result_view()              # zero-copy view of host-mapped pinned memory
-            n = int(cnt.sum())
-            consumed[0] += n
-            # read the step's result on the host: x of the first track of every group
-            consumed[1] += float(rec["x"][:, 0].sum())
-            return n
-
-        def run_host(first, n):
-            d2h = 0
-            submit_host(first)
-            for i in range(first + 1, first + n):
-                submit_host(i)
-                tr.sync()
-                d2h += consume()
-            tr.sync()
-            d2h += consume()
-            return d2h
-
-        run_host(0, args.warmup)
-        barrier()
-        c2 = tr.counters()
-        barrier()
-        sampler.active = True
-        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        e2.record(stream)
-        recs = run_host(args.warmup, args.steps)
-        e3.record(stream)
-        e3.synchronize()
-        wall_e2e = time.perf_counter() - t0
-        sampler.active = False
-        barrier()
-        ms_e2e_dev = reduce_max(e2.elapsed_time(e3))
-        ms_e2e = max(ms_e2e_dev, reduce_max(wall_e2e * 1e3))   # host reads are part of the step
-        c3 = tr.counters()
-        tracks_e2e, frames_e2e, _, _ = sharding.aggregate(dist, dev, c3["tracks"] - c2["tracks"], S * args.steps, 0, 0.0)
-        d2h_per_step = (recs * 16 + 2 * S * 4) / args.steps
-
-        # ---- per-stage device times (CUDA events inside the library, same stream) ----------------
-        prof_steps = max(10, min(50, args.steps))
-        tr.set_profiling(True)
-        tr.stage_times(reset=True)
-        sampler.active = True
-        run_host(args.warmup + args.steps, prof_steps)
-        sampler.active = False
-        stages = tr.stage_times(reset=True)
-        tr.set_profiling(False)
-
-    total_stage_ms = sum(v[0] for k, v in stages.items() if k != "upload")
-    pyr_launches = max(1, stages["pyramid"][1] // prof_steps)     # kernels per pyramid build
-    pyr_ms = stages["pyramid"][0] / prof_steps                    # all of them: the whole pyramid of a step
+    total_stage_ms = sum(v for k, v in stages.items() if k != "upload")
+    pyr_launches = max(1, stage_launches["pyramid"])          # kernels per pyramid build
+    pyr_ms = stages["pyramid"]                                 # all of them: the whole pyramid of a step
     alg_bytes_launch = 2 * S * (w * h + rsvio_b200.pyramid_bytes(w, h, p["levels"]))
     peak, peak_src = measured_peaks()
     achieved = alg_bytes_launch / (pyr_ms * 1e-3) / 1e9 if pyr_ms > 0 else 0.0
@@ -425,32 +505,56 @@ def main():
                 "bound": "hbm", "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic,
                 "traffic_source": ncu_traffic_src,
+                "traffic_over_algorithmic": (ncu_traffic / alg_bytes_launch) if ncu_traffic else None,
                 "alg_bytes_per_launch": alg_bytes_launch, "ms_per_launch": pyr_ms, "launches_per_step": pyr_launches,
-                "share_of_step": stages["pyramid"][0] / total_stage_ms if total_stage_ms else None}
-    stage_share = {k: (v[0] / prof_steps, v[0] / total_stage_ms if (total_stage_ms and k != "upload") else None)
-                   for k, v in stages.items()}
+                "how": "CUDA events on the handle's stream around the pyramid launch of every profiled step "
+                       "(device-resident frames, input ring of 8 frames x 46 MB: cold inputs)",
+                "share_of_step": pyr_ms / total_stage_ms if total_stage_ms else None}
+
+    # ---- LK: not HBM-bound; against the FP32 issue rate measured in this run ---------------------
+    lk_ms = stages["lk_temporal"] + stages["lk_stereo"]
+    lk_roofline = None
+    try:
+        ffma_tf, split_tf = rsvio_b200.microbench_fp32(local_rank)
+        step_ms = ms_dev / args.steps
+        flops_step = (6.3e3 * templ_dev + 1.8e3 * iters_dev) / args.steps / max(world, 1)
+        lk_roofline = {"kernel": "lk_track_fb_kernel (temporal + stereo launch of a step)", "bound": "fp32 issue",
+                       "achieved": flops_step / (lk_ms * 1e-3) / 1e12 if lk_ms > 0 else None, "unit": "TFLOP/s",
+                       "peak_ffma": ffma_tf, "peak_fmul_fadd": split_tf,
+                       "frac_of_ffma": flops_step / (lk_ms * 1e-3) / 1e12 / ffma_tf if lk_ms > 0 and ffma_tf else None,
+                       "algorithmic_flops": "6.3 kflop per template + 1.8 kflop per iteration (SURVEY 8d), counted by the kernel",
+                       "ms_per_step": lk_ms, "share_of_step": lk_ms / total_stage_ms if total_stage_ms else None,
+                       "tracks_per_step": tracks_dev / args.steps / max(world, 1),
+                       "note": "warp-instruction counts per track: profiles/ (ncu); most issue slots are addressing, "
+                               "u8 gathers + conversions, predicates and shuffles, not flops"}
+        del step_ms
+    except Exception as ex:
+        lk_roofline = {"error": repr(ex)}
 
     # ---- pyramid kernels alone on batches far larger than L2 (>= 512 MB per launch) --------
     extra_roofline = None
     if not args.no_pyramid_roofline and rank == 0 and world == 1:
+        import ctypes as C
         extra_roofline = []
         L = rsvio_b200.load_library()
-        for cw, ch, cl, n_img, label in ((w, h, p["levels"], 640, "bench shape"), (1920, 1200, 5, 96, "C4 shape")):
+        for cw, ch, cl, n_img, label in ((w, h, p["levels"], 640, "bench shape"), (1920, 1200, 5, 96, "C4 shape"),
+                                         (752, 480, 6, 128, "shipped EuRoC L6, one step's batch"),
+                                         (800, 400, 6, 128, "C3 L6")):
             try:
                 src = torch.randint(0, 256, (n_img, ch, cw), dtype=torch.uint8, device=dev)
                 pb = L.rsvio_pyramid_device_bytes(cw, ch, cl)
                 dst = torch.empty(n_img * pb, dtype=torch.uint8, device=dev)
-                ms = C.c_float(0)
+                msv = C.c_float(0)
                 for rep in (3, 10):
                     st = L.rsvio_build_pyramid_u8_device(local_rank, C.c_void_p(src.data_ptr()), n_img, cw, ch, cw, cw * ch,
-                                                         cl, C.c_void_p(dst.data_ptr()), rep, C.byref(ms))
+                                                         cl, C.c_void_p(dst.data_ptr()), rep, C.byref(msv))
                     if st != 0:
                         raise RuntimeError(f"status {st}")
                 ab = n_img * (cw * ch + rsvio_b200.pyramid_bytes(cw, ch, cl))
                 extra_roofline.append({"workload": f"{n_img} x {cw}x{ch} {cl}-level pyramids per launch set "
                                                    f"({ab / 1e6:.0f} MB algorithmic, {label})",
-                                       "achieved": ab / (ms.value * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                       "frac": ab / (ms.value * 1e-3) / 1e9 / peak, "ms_per_launch_set": ms.value})
+                                       "achieved": ab / (msv.value * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": ab / (msv.value * 1e-3) / 1e9 / peak, "ms_per_launch_set": msv.value})
                 del src, dst
             except Exception as ex:  # the headline number does not depend on this microbenchmark
                 extra_roofline.append({"error": str(ex)})
@@ -458,24 +562,40 @@ def main():
     # ---- latency of ONE stream through the synchronous reference-facing call (the drop-in use case) ----
     single = None
     if rank == 0:
-        try:
-            tr1 = rsvio_b200.StereoPatchTracker(p["grid"], p["max_it"], p["thr"], width=w, height=h, levels=p["levels"],
-                                                device=local_rank)
-            lat = []
-            for i in range(60):
-                k = ring_index(i)
-                lp, rp = host[k, 0, 0], host[k, 1, 0]
-                t0 = time.perf_counter()
-                rsvio_b200.binding._check(tr1._L.rsvio_tracker_process_stereo(tr1._h, C.c_void_p(lp.data_ptr()),
-                                                                                C.c_void_p(rp.data_ptr()), w), tr1._h)
-                lat.append(time.perf_counter() - t0)
-            lat = np.array(lat[10:]) * 1e3
-            single = {"ms_per_frame_median": float(np.median(lat)), "ms_per_frame_p95": float(np.percentile(lat, 95)),
-                      "stereo_frames_per_sec": float(1e3 / np.median(lat)), "tracks_alive": tr1.num_tracks(0) + tr1.num_tracks(1),
-                      "what": "1 stream, rsvio_tracker_process_stereo per frame (upload + 9 kernels + result), host wall clock"}
-            tr1.close()
-        except Exception as ex:
-            single = {"error": str(ex)}
+        import ctypes as C
+        single = {}
+        for name, lv, grid in (("L3", p["levels"], p["grid"]), ("shipped_L6", 6, 50)):
+            try:
+                tr1 = rsvio_b200.StereoPatchTracker(grid, p["max_it"], p["thr"], width=w, height=h, levels=lv,
+                                                    device=local_rank)
+                base = run.hostbuf.ptr if run.host_kind == "wc" else run.hostbuf.data_ptr()
+                lat = []
+                for i in range(60):
+                    k = ring_index(i)
+                    lp = base + (k * 2 + 0) * S * img_bytes
+                    rp = base + (k * 2 + 1) * S * img_bytes
+                    t0 = time.perf_counter()
+                    st = tr1._L.rsvio_tracker_process_stereo(tr1._h, C.c_void_p(lp), C.c_void_p(rp), w)
+                    lat.append(time.perf_counter() - t0)
+                    if st != 0:
+                        raise RuntimeError(f"status {st}")
+                lat = np.array(lat[10:]) * 1e3
+                single[name] = {"ms_per_frame_median": float(np.median(lat)), "ms_per_frame_p95": float(np.percentile(lat, 95)),
+                                "stereo_frames_per_sec": float(1e3 / np.median(lat)),
+                                "tracks_alive": tr1.num_tracks(0) + tr1.num_tracks(1),
+                                "what": f"1 stream, {lv} levels, grid {grid}: rsvio_tracker_process_stereo per frame "
+                                        "(upload + kernels + result), host wall clock"}
+                tr1.close()
+            except Exception as ex:
+                single[name] = {"error": str(ex)}
+
+    run.close()
+
+    # ---- the other BASELINE configs, one stream each (short) ---------------------------------------
+    per_config = None
+    if rank == 0 and world == 1 and not args.no_per_config:
+        per_config = per_config_results(torch, rsvio_b200, local_rank, stream, cores,
+                                        ("C1", "C2", "C3", "C4", "EUROC_SHIPPED"))
 
     sampler.stop_flag = True
     clocks = sampler.summary()
@@ -508,12 +628,17 @@ def main():
             "e2e": {"value": tracks_e2e / (ms_e2e * 1e-3), "unit": "tracks/s",
                     "stereo_frames_per_sec": frames_e2e / (ms_e2e * 1e-3),
                     "ms_per_step": ms_e2e / args.steps, "ms_per_step_device_events": ms_e2e_dev / args.steps,
-                    "h2d_bytes_per_step": 2 * S * img_bytes, "d2h_bytes_per_step": d2h_per_step},
+                    "h2d_bytes_per_step": 2 * S * img_bytes, "d2h_bytes_per_step": d2h_per_step,
+                    "h2d_gbs_per_gpu": h2d_gbs_rank, "h2d_gbs_all_gpus": h2d_gbs_rank * world,
+                    "host_memory": args.host_memory, "result_read": "every record of every step (x and y summed on the host)"},
             "gpu_launches": int(launches),
             "roofline": roofline,
+            "roofline_lk": lk_roofline,
             "roofline_pyramid_batch": extra_roofline,
-            "stage_ms_per_step": {k: v[0] for k, v in stage_share.items()},
-            "stage_share": {k: v[1] for k, v in stage_share.items()},
+            "stage_ms_per_step": stages,
+            "stage_share": {k: (v / total_stage_ms if (total_stage_ms and k != "upload") else None) for k, v in stages.items()},
+            "stage_ms_per_step_host_frames": stages_host,
+            "per_config": per_config,
             "cpu_baseline": cpu_baseline,
             "single_stream_latency": single,
             "clocks": clocks,

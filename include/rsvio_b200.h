@@ -91,6 +91,10 @@ void rsvio_config_default(rsvio_config *cfg);
 /* pinned host memory for image hand-off without a staging copy (ingest row f-3;
  * replaces the `to_vec()` copies at estimator.rs:131,143) */
 rsvio_status rsvio_host_alloc(void **ptr, size_t bytes);
+/* the same with RSVIO_HOST_WRITE_COMBINED: pages the CPU only ever writes (decoded frames on their way to the
+ * device) -- the DMA engine reads them without snooping the CPU caches; CPU reads of such memory are very slow */
+#define RSVIO_HOST_WRITE_COMBINED 1u
+rsvio_status rsvio_host_alloc_flags(void **ptr, size_t bytes, uint32_t flags);
 rsvio_status rsvio_host_free(void *ptr);
 
 /* ---- stateful tracker: StereoPatchTracker<N> / PatchTracker<N> ------------------------- */
@@ -239,6 +243,11 @@ rsvio_status rsvio_detect_keypoints(int32_t device, const uint8_t *image, int32_
 /* se2_exp_matrix (image_utilities.rs:82-106) evaluated by the device code: n twists
  * [vx, vy, theta] -> n row-major 3x3 matrices */
 rsvio_status rsvio_se2_exp(int32_t device, const float *twists, int32_t n, float *out9);
+
+/* In-run FP32 microbenchmark (the denominator of the LK kernel's roofline): TFLOP/s of
+ * dependent-chain FFMA and of separately rounded FMUL + FADD pairs (2 flop per multiply-add) on `device`, at the
+ * clocks of the moment.  Takes a few milliseconds. */
+rsvio_status rsvio_microbench_fp32(int32_t device, float *ffma_tflops, float *fmul_fadd_tflops);
 
 /* unproject_one for n pixels (host pointers): xy = n x (u, v) float, out_xy = n x (x/z, y/z) float */
 rsvio_status rsvio_unproject_points(int32_t device, const rsvio_camera_model *model, const float *xy, int32_t n,

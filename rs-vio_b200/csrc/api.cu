@@ -315,7 +315,7 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
     // 7: download -- packed records into mapped host memory + the error flag.  With many streams this runs on
     // its own CUDA stream beside the next frame (the table it reads is not written again before the frame after
     // next, which cannot be submitted until this one has been synced).
-    cudaStream_t xs = t->exp_st;
+    cudaStream_t xs = prof ? st : t->exp_st;  // profiling: one stream, every stage alone on the device
     if (xs != st) {
         CU_TRY(t, cudaEventRecord(t->ev_merged[slot], st));
         CU_TRY(t, cudaStreamWaitEvent(xs, t->ev_merged[slot], 0));
@@ -323,9 +323,8 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
     ++stage;
     if (prof) cudaEventRecord(t->ev_stage[slot][stage], xs);
     CU_TRY(t, export_records(tout, t->groups, t->cap, t->S, t->d_out[slot], t->d_cnt[slot], t->cam_model[0], t->cam_model[1],
-                             t->d_uxy[slot], xs));
+                             t->d_uxy[slot], t->d_err + slot, xs));
     count(7, 1);
-    CU_TRY(t, cudaMemcpyAsync(t->h_cnt[slot] + t->groups, t->d_err + slot, sizeof(int), cudaMemcpyDeviceToHost, xs));
     ++stage;
     if (prof) cudaEventRecord(t->ev_stage[slot][stage], xs);  // end
     t->stage_valid[slot] = prof;
@@ -438,6 +437,18 @@ void rsvio_config_default(rsvio_config *cfg) {
 rsvio_status rsvio_host_alloc(void **ptr, size_t bytes) {
     if (!ptr) return RSVIO_ERR_INVALID_ARG;
     if (cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        *ptr = nullptr;
+        return RSVIO_ERR_CUDA;
+    }
+    return RSVIO_OK;
+}
+
+rsvio_status rsvio_host_alloc_flags(void **ptr, size_t bytes, uint32_t flags) {
+    if (!ptr || (flags & ~(uint32_t)RSVIO_HOST_WRITE_COMBINED)) return RSVIO_ERR_INVALID_ARG;
+    unsigned f = cudaHostAllocPortable;
+    if (flags & RSVIO_HOST_WRITE_COMBINED) f |= cudaHostAllocWriteCombined;
+    if (cudaHostAlloc(ptr, bytes ? bytes : 1, f) != cudaSuccess) {
         cudaGetLastError();
         *ptr = nullptr;
         return RSVIO_ERR_CUDA;
@@ -1197,6 +1208,18 @@ rsvio_status rsvio_se2_exp(int32_t device, const float *twists, int32_t n, float
 done:
     cudaFree(d_in);
     cudaFree(d_out);
+    return rs;
+}
+
+rsvio_status rsvio_microbench_fp32(int32_t device, float *ffma_tflops, float *fmul_fadd_tflops) {
+    if (!ffma_tflops || !fmul_fadd_tflops) return RSVIO_ERR_INVALID_ARG;
+    rsvio_status rs = RSVIO_OK;
+    DeviceScope dev_scope;
+    CallStream cs;
+    CU_TRY0(dev_scope.enter(device));
+    CU_TRY0(cs.create());
+    CU_TRY0(fp32_rate(ffma_tflops, fmul_fadd_tflops, cs.s));
+done:
     return rs;
 }
 

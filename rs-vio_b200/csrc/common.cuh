@@ -114,6 +114,9 @@ struct LkBatch {
 cudaError_t lk_track(const PyrDesc &pd, const LkBatch &b, cudaStream_t st);
 cudaError_t se2_exp_batch(const float *d_twists, int n, float *d_out9, cudaStream_t st);
 
+// microbench.cu: measured FP32 multiply-add rates (TFLOP/s), fused and as separately rounded FMUL + FADD
+cudaError_t fp32_rate(float *ffma_tflops, float *fmul_fadd_tflops, cudaStream_t st);
+
 // detect.cu
 struct GridDesc {
     int w, h;
@@ -171,7 +174,8 @@ cudaError_t merge_new_points(const TableView &tab, int streams, int cap, int ste
 // packed (id, x, y) records and counts of every group -> out_rec / out_counts (mapped host memory); with a camera
 // model (groups < streams: cam0, else cam1) also the unprojected coordinate of every record -> out_uxy
 cudaError_t export_records(const TableView &tab, int groups, int cap, int streams, OutRecord *out_rec, int *out_counts,
-                           const CameraModelDev &cam0, const CameraModelDev &cam1, float *out_uxy, cudaStream_t st);
+                           const CameraModelDev &cam0, const CameraModelDev &cam1, float *out_uxy, const int *err_flag,
+                           cudaStream_t st);  // err_flag (device, may be null) -> out_counts[groups]
 cudaError_t unproject_points(const CameraModelDev &cm, const float *d_xy, int n, float *d_out, cudaStream_t st);
 cudaError_t remove_ids(const TableView &in, const TableView &out, int groups, int cap, int streams, int stream,
                        const unsigned long long *d_ids, int n, cudaStream_t st);

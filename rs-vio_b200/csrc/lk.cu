@@ -23,6 +23,27 @@ namespace rsvio {
 namespace {
 
 constexpr float kEps = 1.1920929e-07f;  // f32::EPSILON
+
+// FMA policy of this file.  The library is compiled with -fmad=false (the pyramid must be bit-exact), so nothing is
+// contracted behind our back; the LK bar is 1e-3 px, not bit-exactness, and the kernel is issue-bound, so the
+// multiply-add chains below are fused EXPLICITLY (one rounding instead of two per step: never less accurate than
+// the reference's separately rounded chain).  -DRSVIO_LK_FMA=0 restores the reference's operation-by-operation
+// rounding for A/B runs.
+#ifndef RSVIO_LK_FMA
+#define RSVIO_LK_FMA 1
+#endif
+__device__ __forceinline__ float mad(float a, float b, float c) {  // a * b + c
+#if RSVIO_LK_FMA
+    return fmaf(a, b, c);
+#else
+    return a * b + c;
+#endif
+}
+// w00 p00 + w01 p01 + w10 p10 + w11 p11 in the reference's order (image_utilities.rs:30, patch.rs:203)
+__device__ __forceinline__ float bilin(float w00, float w01, float w10, float w11, float p00, float p01, float p10,
+                                       float p11) {
+    return mad(w11, p11, mad(w10, p10, mad(w01, p01, w00 * p00)));
+}
 constexpr int kWarpsPerBlock = 4;
 constexpr int kMaxGroupsSmem = 2048;  // groups whose live-point prefix fits the shared-memory table
 
@@ -51,6 +72,19 @@ __device__ __forceinline__ void pattern_offset(int i, float &ox, float &oy) {
     oy = (float)y / 2.0f;
 }
 
+// hardware reciprocal / reciprocal square root with one Newton step (<= 1 ulp for normal arguments): the IEEE
+// sequences behind __frcp_rn / sqrtf cost 10-25 instructions each with their range handling
+[[maybe_unused]] __device__ __forceinline__ float rcp_nr(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+[[maybe_unused]] __device__ __forceinline__ float rsqrt_nr(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(0.5f * r, fmaf(-x * r, r, 1.0f), r);
+}
+
 // image_grad -- image_utilities.rs:5-66 (same products and sum order).  `ok` == the sample passed the
 // inbound test; otherwise the 12 gathers are redirected to clamped in-image addresses (results unused),
 // which keeps the warp free of divergent branches.
@@ -72,12 +106,12 @@ __device__ __forceinline__ void image_grad(const Img &im, float x, float y, bool
     const float p20 = (float)__ldg(r0 + 2), p21 = (float)__ldg(r1 + 2);
     const float p0m = (float)__ldg(rm), p1m = (float)__ldg(rm + 1);
     const float p02 = (float)__ldg(r2), p12 = (float)__ldg(r2 + 1);
-    v = w00 * p00 + w01 * p01 + w10 * p10 + w11 * p11;
-    const float res_mx = w00 * pm0 + w01 * pm1 + w10 * p00 + w11 * p01;
-    const float res_px = w00 * p10 + w01 * p11 + w10 * p20 + w11 * p21;
+    v = bilin(w00, w01, w10, w11, p00, p01, p10, p11);
+    const float res_mx = bilin(w00, w01, w10, w11, pm0, pm1, p00, p01);
+    const float res_px = bilin(w00, w01, w10, w11, p10, p11, p20, p21);
     gx = 0.5f * (res_px - res_mx);
-    const float res_my = w00 * p0m + w01 * p00 + w10 * p1m + w11 * p10;
-    const float res_py = w00 * p01 + w01 * p02 + w10 * p11 + w11 * p12;
+    const float res_my = bilin(w00, w01, w10, w11, p0m, p00, p1m, p10);
+    const float res_py = bilin(w00, w01, w10, w11, p01, p02, p11, p12);
     gy = 0.5f * (res_py - res_my);
 }
 
@@ -100,9 +134,13 @@ __device__ __forceinline__ bool chol3_inverse(const float H[3][3], float Hinv[3]
         }
         const float diag = m[j][j];
         ok = ok && (diag != 0.0f) && (diag >= 0.0f);
+#if RSVIO_LK_FMA
+        inv[j] = rsqrt_nr(diag);  // only 1 / L_jj is used below (the divisions by the pivot are multiplications)
+#else
         const float denom = sqrtf(diag);
         m[j][j] = denom;
         inv[j] = __frcp_rn(denom);  // one IEEE reciprocal per pivot, multiplications below
+#endif
 #pragma unroll
         for (int i = j + 1; i < 3; ++i) m[i][j] = m[i][j] * inv[j];
     }
@@ -130,9 +168,9 @@ __device__ __forceinline__ void se2_exp(const float a[3], float m[6]) {
     const float theta = a[2];
     float sn, cs;
     if (fabsf(theta) < 0.5f) {
-        // LK increments are small rotations: Taylor polynomials (truncation < 2e-11, i.e. below half an
-        // ulp of the result) instead of the general-range sincosf; explicitly fused, the reference's
-        // libm sinf/cosf are not reproducible bit for bit anyway
+        // LK increments are small rotations: Taylor polynomials (truncation < 2e-11, i.e. below half an ulp of the
+        // result) instead of the general-range sincosf; explicitly fused, the reference's libm sinf/cosf are not
+        // reproducible bit for bit anyway
         const float t2 = theta * theta;
         float ps = fmaf(t2, 2.7557319e-06f, -1.9841270e-04f);
         ps = fmaf(ps, t2, 8.3333333e-03f);
@@ -152,7 +190,15 @@ __device__ __forceinline__ void se2_exp(const float a[3], float m[6]) {
         s_by_t = 1.0f - 1.0f / 6.0f * t2;
         omc_by_t = 0.5f * theta - 1.0f / 24.0f * theta * t2;
     } else {
+        // The reference's `(1 - cos t) / t` (image_utilities.rs:96) cancels: for t = 1e-3 the numerator keeps 3
+        // digits, and that rounding noise (up to 6e-8 / t, times the translation increment) is part of what the
+        // reference computes.  It is reproduced here from the correctly rounded f32 cosine -- a cancellation-free
+        // series would be more accurate and 1e-4 px away from the reference (measured: 28 of 9645 points off).
+#if RSVIO_LK_FMA
+        const float inv_t = rcp_nr(theta);     // |t| >= EPSILON: normal range; <= 1 ulp
+#else
         const float inv_t = __frcp_rn(theta);  // one IEEE reciprocal instead of two divisions
+#endif
         s_by_t = sn * inv_t;
         omc_by_t = (1.0f - cs) * inv_t;
     }
@@ -160,8 +206,8 @@ __device__ __forceinline__ void se2_exp(const float a[3], float m[6]) {
     m[1] = -sn;
     m[3] = sn;
     m[4] = cs;
-    m[2] = s_by_t * a[0] - omc_by_t * a[1];
-    m[5] = omc_by_t * a[0] + s_by_t * a[1];
+    m[2] = mad(s_by_t, a[0], -(omc_by_t * a[1]));
+    m[5] = mad(omc_by_t, a[0], s_by_t * a[1]);
 }
 
 __device__ __forceinline__ bool finite3(const float a[3]) {
@@ -262,7 +308,7 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
                 // columns are exact for finite gradients and are not spelled out
                 J[k][0] = gx;
                 J[k][1] = gy;
-                J[k][2] = gx * (-o.y) + gy * o.x;
+                J[k][2] = mad(gy, o.x, gx * (-o.y));
                 sum += v;
                 g0 += J[k][0];
                 g1 += J[k][1];
@@ -273,16 +319,28 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
         }
         ++n_templates;
         warp_sum4(sum, g0, g1, g2, lane);
+#if RSVIO_LK_FMA
+        const float inv_sum = rcp_nr(sum);  // sum == 0 (black patch): inf -> NaN below -> template invalid, as the reference's mean test
+        const float mean_inv = (float)n_valid * inv_sum;
+#else
         const float mean_inv = (float)n_valid / sum;
         const float inv_sum = __frcp_rn(sum);
+#endif
         float h00 = 0.f, h01 = 0.f, h02 = 0.f, h11 = 0.f, h12 = 0.f, h22 = 0.f;
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             const bool first = k == 0;  // every lane holds sample 0: its products start the sums (no 0 + x)
             if (d[k] >= 0.0f) {
+#if RSVIO_LK_FMA
+                const float dn = -(d[k] * inv_sum);
+                J[k][0] = fmaf(g0, dn, J[k][0]);
+                J[k][1] = fmaf(g1, dn, J[k][1]);
+                J[k][2] = fmaf(g2, dn, J[k][2]);
+#else
                 J[k][0] += -(g0 * d[k] * inv_sum);
                 J[k][1] += -(g1 * d[k] * inv_sum);
                 J[k][2] += -(g2 * d[k] * inv_sum);
+#endif
                 d[k] *= mean_inv;
             } else {
                 J[k][0] = J[k][1] = J[k][2] = 0.0f;
@@ -298,12 +356,12 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
                 h12 = J[k][1] * J[k][2];
                 h22 = J[k][2] * J[k][2];
             } else if (ln.has[k]) {
-                h00 += J[k][0] * J[k][0];
-                h01 += J[k][0] * J[k][1];
-                h02 += J[k][0] * J[k][2];
-                h11 += J[k][1] * J[k][1];
-                h12 += J[k][1] * J[k][2];
-                h22 += J[k][2] * J[k][2];
+                h00 = mad(J[k][0], J[k][0], h00);
+                h01 = mad(J[k][0], J[k][1], h01);
+                h02 = mad(J[k][0], J[k][2], h02);
+                h11 = mad(J[k][1], J[k][1], h11);
+                h12 = mad(J[k][1], J[k][2], h12);
+                h22 = mad(J[k][2], J[k][2], h22);
             }
         }
         float H[3][3], Hinv[3][3];
@@ -324,7 +382,7 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
         for (int k = 0; k < 2; ++k) {
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                M[k][r] = Hinv[r][0] * J[k][0] + Hinv[r][1] * J[k][1] + Hinv[r][2] * J[k][2];
+                M[k][r] = mad(Hinv[r][2], J[k][2], mad(Hinv[r][1], J[k][1], Hinv[r][0] * J[k][0]));
                 fin = fin && (!ln.has[k] || isfinite(M[k][r]));
             }
             fin = fin && (!ln.has[k] || isfinite(d[k]));
@@ -339,7 +397,8 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
         asm volatile("mov.b32 %0, %0;" : "+f"(wlim));  // kept in registers across the iterations, as the base and pitch below
         asm volatile("mov.b32 %0, %0;" : "+f"(hlim));
         // `inc.norm() < thr` (feature_tracker.rs:374) is never true for thr <= 0
-        const float thr2 = thr > 0.0f ? thr * thr : 0.0f;
+        float thr2 = thr > 0.0f ? thr * thr : 0.0f;
+        asm volatile("mov.b32 %0, %0;" : "+f"(thr2));  // in a register across the iterations, not re-derived from the constant bank
         // the level base and row pitch stay in registers across the iterations (opaque to rematerialisation)
         const uint8_t *ibp = ib.p;
         uint32_t ibw = (uint32_t)ib.w;
@@ -351,11 +410,16 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
             float rsum = 0.0f;
             int nv = 0;
             unsigned cmask[2];
+            bool okk[2];
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 const float2 o = ln.offset(k);
-                const float x = (T1[0] * o.x + T1[1] * o.y) + T1[2];
-                const float y = (T1[3] * o.x + T1[4] * o.y) + T1[5];
+                // (R o) + t in the reference's association (feature_tracker.rs:356-360): the rotated offset (a few px)
+                // is summed first and then added to the translation (hundreds of px).  Folding t into the chain
+                // instead rounds twice at the magnitude of t: measured, half of all tracks then differ from the
+                // reference in the last bit and six times as many convergence tests flip.
+                const float x = mad(T1[0], o.x, T1[1] * o.y) + T1[2];
+                const float y = mad(T1[3], o.x, T1[4] * o.y) + T1[5];
                 const bool ok = ln.has[k] && x >= 2.0f && y >= 2.0f && x < wlim && y < hlim;
                 // branch-free gather: rejected samples read pixels (0,0)..(1,1), unused; accepted ones have
                 // ix + 1 <= w - 2 and iy + 1 <= h - 2, so nothing needs clamping
@@ -366,9 +430,9 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
                 const uint8_t *__restrict__ q1 = q0 + ibw;
                 const float p00 = (float)__ldg(q0), p10 = (float)__ldg(q0 + 1);
                 const float p01 = (float)__ldg(q1), p11 = (float)__ldg(q1 + 1);
-                const float val = ddx * ddy * p00 + ddx * dy * p01 + dx * ddy * p10 + dx * dy * p11;
-                r[k] = ok ? val : -1.0f;
-                rsum = k == 0 ? (ok ? val : 0.0f) : rsum + (ok ? val : 0.0f);
+                r[k] = bilin(ddx * ddy, ddx * dy, dx * ddy, dx * dy, p00, p01, p10, p11);
+                okk[k] = ok;
+                rsum = k == 0 ? (ok ? r[k] : 0.0f) : rsum + (ok ? r[k] : 0.0f);
                 cmask[k] = __ballot_sync(0xffffffffu, ok);
                 nv += __popc(cmask[k]);
             }
@@ -377,38 +441,56 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
             // residuals exist where the sample is valid in the template and in the current image
             const int nres = __popc(cmask[0] & tmask[0]) + __popc(cmask[1] & tmask[1]);
             float i0 = 0.0f, i1 = 0.0f, i2 = 0.0f;
+#if RSVIO_LK_FMA
+            // n / sum once per iteration (warp-uniform).  eps <= sum <= 52 * 255: always a normal number, so the
+            // hardware reciprocal with one Newton step (<= 1 ulp) needs none of __frcp_rn's range handling
+            const float rscale = (float)nv * rcp_nr(rsum);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                // a sample that is invalid in the template has a zero row in H^-1 J^T (J row = 0, M finite), so only
+                // the current image's validity needs a select
+                const float res = okk[k] ? fmaf(r[k], rscale, -d[k]) : 0.0f;
+                i0 = k == 0 ? (-M[k][0]) * res : fmaf(-M[k][0], res, i0);
+                i1 = k == 0 ? (-M[k][1]) * res : fmaf(-M[k][1], res, i1);
+                i2 = k == 0 ? (-M[k][2]) * res : fmaf(-M[k][2], res, i2);
+            }
+#else
             const float inv_rsum = __frcp_rn(rsum);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const bool both = r[k] >= 0.0f && d[k] >= 0.0f;
+                const bool both = okk[k] && d[k] >= 0.0f;
                 const float res = both ? (float)nv * r[k] * inv_rsum - d[k] : 0.0f;
                 i0 = k == 0 ? (-M[k][0]) * res : i0 + (-M[k][0]) * res;
                 i1 = k == 0 ? (-M[k][1]) * res : i1 + (-M[k][1]) * res;
                 i2 = k == 0 ? (-M[k][2]) * res : i2 + (-M[k][2]) * res;
             }
+#endif
             if (nres <= kPattern / 2) return RSVIO_FAIL_RESIDUAL;
             float inc[3], i3 = 0.0f;
             warp_sum4(i0, i1, i2, i3, lane);
             inc[0] = i0;
             inc[1] = i1;
             inc[2] = i2;
-            if (!finite3(inc)) return RSVIO_FAIL_NONFINITE;
             // |inc| > 1e6 and |inc| < thr (feature_tracker.rs:369-376) on the squared norm: no square root on the
-            // per-iteration path; the two forms can only disagree within an ulp of the threshold itself
-            const float norm2 = inc[0] * inc[0] + inc[1] * inc[1] + inc[2] * inc[2];
-            if (norm2 > 1e12f) return RSVIO_FAIL_DIVERGED;
+            // per-iteration path; the two forms can only disagree within an ulp of the threshold itself.  A
+            // non-finite increment (feature_tracker.rs:366) makes the squared norm NaN or +inf: one compare
+            // catches both exits, the (rare) failure path tells them apart.
+            const float norm2 = mad(inc[2], inc[2], mad(inc[1], inc[1], inc[0] * inc[0]));
+            if (!(norm2 <= 1e12f)) return finite3(inc) ? RSVIO_FAIL_DIVERGED : RSVIO_FAIL_NONFINITE;
             if (norm2 < thr2) break;  // converged: increment not applied (feature_tracker.rs:374-376)
             float E[6], N[6];
             se2_exp(inc, E);
-            N[0] = T1[0] * E[0] + T1[1] * E[3];
-            N[1] = T1[0] * E[1] + T1[1] * E[4];
-            N[2] = T1[0] * E[2] + T1[1] * E[5] + T1[2];
-            N[3] = T1[3] * E[0] + T1[4] * E[3];
-            N[4] = T1[3] * E[1] + T1[4] * E[4];
-            N[5] = T1[3] * E[2] + T1[4] * E[5] + T1[5];
+            N[0] = mad(T1[1], E[3], T1[0] * E[0]);
+            N[1] = mad(T1[1], E[4], T1[0] * E[1]);
+            N[2] = mad(T1[0], E[2], T1[1] * E[5]) + T1[2];  // same association as the reference's 3x3 product
+            N[3] = mad(T1[4], E[3], T1[3] * E[0]);
+            N[4] = mad(T1[4], E[4], T1[3] * E[1]);
+            N[5] = mad(T1[3], E[2], T1[4] * E[5]) + T1[5];
 #pragma unroll
             for (int k = 0; k < 6; ++k) T1[k] = N[k];
-            if (!inbound(ib.w, ib.h, T1[2], T1[5], 2)) return RSVIO_FAIL_OOB;
+            // inbound(.., 2) (feature_tracker.rs:380-388) in the float domain: round-half-away(x) >= 2 <=> x >= 1.5 and
+            // round-half-away(x) <= w - 3 <=> x < w - 2.5 (exact for every float, NaN fails both forms)
+            if (!(T1[2] >= 1.5f && T1[5] >= 1.5f && T1[2] < wlim - 0.5f && T1[5] < hlim - 0.5f)) return RSVIO_FAIL_OOB;
         }
         T1[2] = T1[2] * s;
         T1[5] = T1[5] * s;

@@ -193,6 +193,16 @@ pyr_generic_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ P
 // ------------------------------------------------------------------------------------------
 // fast dyadic kernel: levels 0..NA (NA <= 3) from one shared-memory tile
 // ------------------------------------------------------------------------------------------
+// experiment switches (A/B builds: make VARIANT=x EXTRA="-DPYR_STAGE0=0 ...")
+#ifndef PYR_STAGE0
+#define PYR_STAGE0 1        // 1: unpredicated level-0 copy of full-height tiles, loads batched before the stores
+#endif
+#ifndef PYR_RING_NOINLINE
+#define PYR_RING_NOINLINE 0 // 1: border ring as an out-of-line function
+#endif
+#ifndef PYR_OROUND
+#define PYR_OROUND 1        // 1: rounding constant folded into the O accumulators
+#endif
 constexpr int TW = 256, TH = 64;          // base-image tile owned by one CTA (TH = 32 with NSEG = 2 measured the same on C1, slower with NA = 3)
 constexpr int PITCH = TW + 32;            // tile columns [X0 - 16, X0 + TW + 16), bytes per smem row
 constexpr int NCOL = TW / 8;              // stage-1 column threads: 4 level-1 columns (8 px) each = one warp
@@ -276,6 +286,8 @@ __device__ __forceinline__ RingTap ring_tap(const RingWeights &rw, int o, int n_
 // accumulators), else row 2t.  Flags select which accumulators are live (peeled first/last rows).
 // GS = false: the G columns are j0-2 .. j0+1 (words wm1, w01.x, w01.y); GS = true: j0 .. j0+3 (words
 // w01.x, w01.y, wp2), the streaming kernel's mapping.
+// the O accumulators start from the rounding constant of `(N + 32) >> 6` (round half up of N / 64): the store is a shift
+constexpr uint32_t kORound = PYR_OROUND ? 32u : 0u;
 template <bool ROW_A, bool ON, bool OO, bool GN, bool GM, bool GO, bool GS = false>
 __device__ __forceinline__ void stage1_words(uint32_t wm1, uint2 w01, uint32_t wp2, uint32_t (&aOn)[4],
                                              uint32_t (&aOo)[4], uint32_t (&aGn)[4], uint32_t (&aGm)[4],
@@ -284,11 +296,11 @@ __device__ __forceinline__ void stage1_words(uint32_t wm1, uint2 w01, uint32_t w
     if (ON || OO) {
         const uint32_t v0 = __funnelshift_r(wm1, w01.x, 24), v1 = __funnelshift_r(w01.x, w01.y, 8);
         const uint32_t v2 = __funnelshift_r(w01.x, w01.y, 24), v3 = __funnelshift_r(w01.y, wp2, 8);
-        if (ON) {  // O_t: row 2t-1 starts it with weight 1, row 2t adds weight 3
-            aOn[0] = dp4a_u(v0, ROW_A ? k1 : k3, ROW_A ? 0u : aOn[0]);
-            aOn[1] = dp4a_u(v1, ROW_A ? k1 : k3, ROW_A ? 0u : aOn[1]);
-            aOn[2] = dp4a_u(v2, ROW_A ? k1 : k3, ROW_A ? 0u : aOn[2]);
-            aOn[3] = dp4a_u(v3, ROW_A ? k1 : k3, ROW_A ? 0u : aOn[3]);
+        if (ON) {  // O_t: row 2t-1 starts it with weight 1 (on top of the rounding constant), row 2t adds weight 3
+            aOn[0] = dp4a_u(v0, ROW_A ? k1 : k3, ROW_A ? kORound : aOn[0]);
+            aOn[1] = dp4a_u(v1, ROW_A ? k1 : k3, ROW_A ? kORound : aOn[1]);
+            aOn[2] = dp4a_u(v2, ROW_A ? k1 : k3, ROW_A ? kORound : aOn[2]);
+            aOn[3] = dp4a_u(v3, ROW_A ? k1 : k3, ROW_A ? kORound : aOn[3]);
         }
         if (OO) {  // O_{t-1}: rows 2t-1 (weight 3) and 2t (weight 1, completes it)
             aOo[0] = dp4a_u(v0, ROW_A ? k3 : k1, aOo[0]);
@@ -464,6 +476,44 @@ __device__ __forceinline__ void ring_cols(const FastParams &P, const RingTile &r
     }
 }
 
+// The border ring of one tile: the reference's f32 chains (truncated windows are renormalised by a non-dyadic
+// sum, so nothing is exact there), read from the staged tile.  sides: bit 0 top, 1 bottom, 2 left, 3 right.
+#if PYR_RING_NOINLINE
+#define PYR_RING_ATTR __noinline__
+#else
+#define PYR_RING_ATTR __forceinline__
+#endif
+template <int NA>
+__device__ PYR_RING_ATTR void ring_of_tile(const FastParams &P, const uint8_t *tA, int delta, int X0, int Y0,
+                                          float (*vbuf)[PITCH], uint8_t *__restrict__ out, int sides, int tid) {
+    using C = FastCfg<NA>;
+    const bool top = sides & 1, bottom = sides & 2, left = sides & 4, right = sides & 8;
+    const RingTile rt{tA, delta, X0, Y0, C::ytop};
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {  // border rows: oy = 0 (top tiles), oy = hl - 1 (bottom tiles)
+        if (side == 0 ? !top : !bottom) continue;
+        // vbuf lives in the bytes of g2: the previous tile's readers passed the end-of-tile barrier; only a tile
+        // that is both top and bottom reuses vbuf within this block
+        if (side == 1 && top) __syncthreads();
+        ring_rows_vertical<1>(P, rt, vbuf[0], side, tid);
+        if (NA >= 2) ring_rows_vertical<2>(P, rt, vbuf[NA >= 2 ? 1 : 0], side, tid);
+        if (NA >= 3) ring_rows_vertical<3>(P, rt, vbuf[NA >= 3 ? 2 : 0], side, tid);
+        __syncthreads();
+        ring_rows_horizontal<1>(P, rt, vbuf[0], out, side, tid);
+        if (NA >= 2) ring_rows_horizontal<2>(P, rt, vbuf[NA >= 2 ? 1 : 0], out, side, (tid + 64) % NTA);
+        if (NA >= 3) ring_rows_horizontal<3>(P, rt, vbuf[NA >= 3 ? 2 : 0], out, side, (tid + 32) % NTA);
+    }
+    // border columns (ox = 0 for left tiles, ox = wl - 1 for right tiles) without the corner rows
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+        if (side == 0 ? !left : !right) continue;
+        ring_cols<1>(P, rt, out, side, tid);
+        if (NA >= 2) ring_cols<2>(P, rt, out, side, tid);
+        if (NA >= 3) ring_cols<3>(P, rt, out, side, tid);
+    }
+    if (top || bottom) __syncthreads();  // vbuf shares its bytes with g2, which stage 1 writes next
+}
+
 template <int NA>
 struct FastSmem {
     using C = FastCfg<NA>;
@@ -554,6 +604,9 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
     } else if (tid == 0 && tile_id + (int)gridDim.x < total) {
         issue_load(tile_id + gridDim.x, buf ^ 1);  // prefetch
     }
+    // Plain image-major, row-major tile order.  Tried and dropped: longest-processing-time-first orders (border tiles of
+    // all images first; or position-major over cost-sorted positions): no gain at 128 images, 35-50 % slower at 640
+    // (neighbouring tiles share halo rows and DRAM pages; concurrent CTAs a whole image apart share nothing).
     const int img = magic_div(tile_id, tiles_per_img, P.magic_tpi), tl = tile_id - img * tiles_per_img;
     const int tile_y = magic_div(tl, P.tiles_x, P.magic_tx), tile_x = tl - tile_y * P.tiles_x;
     const int X0 = tile_x * TW, Y0 = tile_y * TH;
@@ -564,7 +617,8 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
     mbar_wait(mbar0 + 8u * buf, (dbl ? (it >> 1) : it) & 1);
 
     // ---- stage 0: level 0 == input, 16-byte copies from the staged tile.  A thread owns one 16-byte
-    // column and every (NTA/16)-th row: one pointer pair, constant strides.
+    // column and every (NTA/16)-th row: constant row offsets on the shared side, one global pointer advanced by
+    // a constant stride; full-height tiles (uniform) run without row predicates.
     {
         constexpr int VPT = TW / 16, RPP = NTA / VPT;  // vectors per row, rows per pass
         const int nrow = min(TH, h0 - Y0), nvec = min(VPT, (w0 - X0) >> 4);
@@ -573,44 +627,34 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
             const uint8_t *__restrict__ s0 = trow(y0 + C::ytop, 16 + vx * 16);
             uint8_t *__restrict__ d0 = out + (size_t)(Y0 + y0) * w0 + X0 + vx * 16;
             const size_t dstep = (size_t)RPP * w0;
+#if PYR_STAGE0 == 1
+            if (nrow == TH) {
+                uint4 q[TH / RPP];
 #pragma unroll
-            for (int k = 0; k < TH / RPP; ++k)
-                if (y0 + k * RPP < nrow)
-                    *reinterpret_cast<uint4 *>(d0 + k * dstep) = *reinterpret_cast<const uint4 *>(s0 + k * RPP * RW);
+                for (int k = 0; k < TH / RPP; ++k) q[k] = *reinterpret_cast<const uint4 *>(s0 + k * RPP * RW);
+#pragma unroll
+                for (int k = 0; k < TH / RPP; ++k) {
+                    *reinterpret_cast<uint4 *>(d0) = q[k];
+                    d0 += dstep;
+                }
+            } else
+#endif
+            {
+#pragma unroll
+                for (int k = 0; k < TH / RPP; ++k)
+                    if (y0 + k * RPP < nrow)
+                        *reinterpret_cast<uint4 *>(d0 + k * dstep) = *reinterpret_cast<const uint4 *>(s0 + k * RPP * RW);
+            }
         }
     }
 
     // ---- border ring of levels 1..NA owned by this tile (before stage 1: its scratch row vbuf lives in the
-    // bytes of g2): the reference's f32 chains (truncated
-    // windows are renormalised by a non-dyadic sum, so nothing is exact there), read from the tile.
-    const bool top = Y0 == 0, bottom = Y0 + TH >= h0 && Y0 < h0;
-    const bool left = X0 == 0, right = X0 + TW >= w0 && X0 < w0;
-    if (top || bottom || left || right) {
-        const RingTile rt{tA, S::region - RB, X0, Y0, C::ytop};
-#pragma unroll 1
-        for (int side = 0; side < 2; ++side) {  // border rows: oy = 0 (top tiles), oy = hl - 1 (bottom tiles)
-            if (side == 0 ? !top : !bottom) continue;
-            // vbuf lives in the bytes of g2: the previous tile's readers passed the end-of-tile barrier; only a tile
-            // that is both top and bottom reuses vbuf within this block
-            if (side == 1 && top) __syncthreads();
-            ring_rows_vertical<1>(P, rt, vbuf[0], side, tid);
-            if (NA >= 2) ring_rows_vertical<2>(P, rt, vbuf[NA >= 2 ? 1 : 0], side, tid);
-            if (NA >= 3) ring_rows_vertical<3>(P, rt, vbuf[NA >= 3 ? 2 : 0], side, tid);
-            __syncthreads();
-            ring_rows_horizontal<1>(P, rt, vbuf[0], out, side, tid);
-            if (NA >= 2) ring_rows_horizontal<2>(P, rt, vbuf[NA >= 2 ? 1 : 0], out, side, (tid + 64) % NTA);
-            if (NA >= 3) ring_rows_horizontal<3>(P, rt, vbuf[NA >= 3 ? 2 : 0], out, side, (tid + 32) % NTA);
-        }
-        // border columns (ox = 0 for left tiles, ox = wl - 1 for right tiles) without the corner rows
-#pragma unroll 1
-        for (int side = 0; side < 2; ++side) {
-            if (side == 0 ? !left : !right) continue;
-            ring_cols<1>(P, rt, out, side, tid);
-            if (NA >= 2) ring_cols<2>(P, rt, out, side, tid);
-            if (NA >= 3) ring_cols<3>(P, rt, out, side, tid);
-        }
-        if (top || bottom) __syncthreads();  // vbuf shares its bytes with g2, which stage 1 writes next
-    }
+    // bytes of g2).  Out of line: only border tiles pay for it, and none of its address arithmetic leaks into the
+    // common path.
+    const bool top = tile_y == 0, bottom = tile_y == P.tiles_y - 1;
+    const bool left = tile_x == 0, right = tile_x == P.tiles_x - 1;
+    if (top || bottom || left || right)
+        ring_of_tile<NA>(P, tA, S::region - RB, X0, Y0, vbuf, out, (top ? 1 : 0) | (bottom ? 2 : 0) | (left ? 4 : 0) | (right ? 8 : 0), tid);
 
     // ---- stage 1: level-1 output O_2 (global) and G_2 (smem); 4 chained DP4A per value.
     // Warp = one row segment, lane c = level-1 columns j0 .. j0+3, j0 = X0/2 - 2 + 4c, both phases (the tile
@@ -640,8 +684,8 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
         constexpr int RWW = RW / 8;  // row pitch in 8-byte units
         auto store_o = [&](int to) {  // O_{to} complete -> level 1, round half up: (N + 32) >> 6
             if (to >= o_lo && to < o_hi) {
-                const uint32_t b0 = (aOo[0] + 32u) >> 6, b1 = (aOo[1] + 32u) >> 6;
-                const uint32_t b2 = (aOo[2] + 32u) >> 6, b3 = (aOo[3] + 32u) >> 6;
+                constexpr uint32_t kR = 32u - kORound;  // what of the rounding constant is not in the accumulator yet
+                const uint32_t b0 = (aOo[0] + kR) >> 6, b1 = (aOo[1] + kR) >> 6, b2 = (aOo[2] + kR) >> 6, b3 = (aOo[3] + kR) >> 6;
                 if (!o_edge) {  // j0 = 2 (mod 4): two aligned 16-bit stores
                     reinterpret_cast<uint16_t *>(orow)[0] = (uint16_t)(b0 | (b1 << 8));
                     reinterpret_cast<uint16_t *>(orow)[1] = (uint16_t)(b2 | (b3 << 8));
@@ -842,354 +886,6 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------
-// streaming variant of the fast path: one WARP per work item, no block barriers.
-//
-// A warp walks down a 256-pixel-wide strip over `rbh` base rows.  Rows stream through a private
-// shared-memory ring of 8-row chunks fetched by TMA three chunks ahead (two 144-byte-wide boxes per
-// chunk: lanes 0-15 read the first, lanes 16-31 the second; a lane's 16 bytes are two aligned
-// LDS.64, conflict free).  Stage 1 runs exactly like in the tile kernel but its warm-up rows are paid
-// once per row block instead of once per 16 output rows, and the G_2 / G_4 rows it emits go to small
-// rings from which the warp itself produces the level-2 / level-3 rows as soon as their three input
-// rows exist.  Level 0 is copied global -> global with 16-byte accesses when a chunk has landed
-// (L2 hits).  The border ring of each level is a separate kind of work item in the same launch.
-// ------------------------------------------------------------------------------------------
-constexpr int SCH = 8;            // base rows per chunk
-constexpr int SNB = 4;            // chunks in the ring (previous, current, two in flight)
-constexpr int SBW = 160;          // bytes per row of one TMA box
-constexpr int SG2 = 8, SG4 = 4;   // rows in the G_2 / G_4 rings
-constexpr int SG4P = 68;          // G_4 ring pitch (66 used)
-
-struct StreamParams {
-    PyrDesc pd;
-    RingWeights ring[4];
-    const uint8_t *src0, *src1;
-    size_t stride, pitch;
-    int split, n_images;
-    uint8_t *dst;
-    uint32_t *g8;
-    int strips, blocks_y, rbh;    // 256-px strips per image, row blocks per strip, base rows per block
-    int n_main;                   // n_images * strips * blocks_y
-    int ring_per_image;           // border work items per image
-    int ring_first[4];            // prefix of border items per level (index = level - 1)
-    int ring_rows[4];             // row-segment items per side of that level (128 outputs each)
-    int ring_cols[4];             // column-segment items per side (32 outputs each)
-};
-
-// border outputs of one level: faithful f32 chains straight from global memory (L2 resident)
-__device__ __forceinline__ void stream_ring_item(const StreamParams &P, int item, float *vbuf, int lane) {
-    const int img = item / P.ring_per_image;
-    int k = item - img * P.ring_per_image;
-    int lev = 1;
-    while (lev < 3 && k >= P.ring_first[lev]) ++lev;   // ring_first[lev] = prefix before level lev+1
-    k -= P.ring_first[lev - 1];
-    const int r = 1 << lev, wl = P.pd.lv[lev].w, hl = P.pd.lv[lev].h, w0 = P.pd.lv[0].w;
-    const RingWeights &rw = P.ring[lev];
-    const uint8_t *__restrict__ src = image_ptr(P.src0, P.src1, P.split, img, P.pitch);
-    uint8_t *__restrict__ lo = P.dst + (size_t)img * P.pd.pyr_stride + P.pd.lv[lev].off;
-    const int nr = P.ring_rows[lev - 1], nc = P.ring_cols[lev - 1];
-    if (k < 2 * nr) {  // border row: side = top / bottom, segment of 128 outputs
-        const int side = k / nr, seg = k - side * nr;
-        const int oy = side == 0 ? 0 : hl - 1;
-        const int ox0 = seg * 128, ox1 = min(ox0 + 128, wl);
-        const RingTap ty = ring_tap(rw, oy, hl, r);
-        const int xl = max(ox0 * r - (r >> 1), 0), xr = min(ox1 * r + (r >> 1), w0);
-        for (int x = xl + lane; x < xr; x += 32) {
-            const uint8_t *__restrict__ p = src + (size_t)ty.left * P.stride + x;
-            float v = 0.0f;
-            for (int t = 0; t < ty.cnt; ++t) v = __fadd_rn(v, __fmul_rn((float)__ldg(p + (size_t)t * P.stride), ty.w[t]));
-            vbuf[x - xl] = v;
-        }
-        __syncwarp();
-        for (int ox = ox0 + lane; ox < ox1; ox += 32) {
-            const RingTap tx = ring_tap(rw, ox, wl, r);
-            float t = 0.0f;
-            for (int q = 0; q < tx.cnt; ++q) t = __fadd_rn(t, __fmul_rn(vbuf[tx.left + q - xl], tx.w[q]));
-            t = fminf(fmaxf(t, 0.0f), 255.0f);
-            lo[(size_t)oy * wl + ox] = (uint8_t)__float2uint_rz(roundf(t));
-        }
-        __syncwarp();
-    } else {           // border column: side = left / right, 32 outputs, one per lane
-        k -= 2 * nr;
-        const int side = k / nc, seg = k - side * nc;
-        const int ox = side == 0 ? 0 : wl - 1;
-        const int oy = 1 + seg * 32 + lane;
-        if (oy <= hl - 2) {
-            const RingTap tx = ring_tap(rw, ox, wl, r), ty = ring_tap(rw, oy, hl, r);
-            float t = 0.0f;
-            for (int q = 0; q < tx.cnt; ++q) {
-                const uint8_t *__restrict__ p = src + (size_t)ty.left * P.stride + (tx.left + q);
-                float v = 0.0f;
-                for (int u = 0; u < ty.cnt; ++u)
-                    v = __fadd_rn(v, __fmul_rn((float)__ldg(p + (size_t)u * P.stride), ty.w[u]));
-                t = __fadd_rn(t, __fmul_rn(v, tx.w[q]));
-            }
-            t = fminf(fmaxf(t, 0.0f), 255.0f);
-            lo[(size_t)oy * wl + ox] = (uint8_t)__float2uint_rz(roundf(t));
-        }
-    }
-}
-
-template <int NA>
-__global__ void __launch_bounds__(32)
-pyr_stream_kernel(const __grid_constant__ StreamParams P, const __grid_constant__ CUtensorMap map0,
-                  const __grid_constant__ CUtensorMap map1) {
-    using C = FastCfg<NA>;
-    __shared__ __align__(128) uint8_t chunks[SNB][2][SCH][SBW];
-    __shared__ __align__(16) uint16_t g2[SG2][G2P];
-    __shared__ __align__(16) uint32_t g4[NA >= 3 ? SG4 : 1][SG4P];
-    __shared__ __align__(8) unsigned long long mbar_mem[SNB];
-
-    const int lane = threadIdx.x;
-    const int w0 = P.pd.lv[0].w, h0 = P.pd.lv[0].h;
-    const int w1 = P.pd.lv[1].w, h1 = P.pd.lv[1].h;
-    const uint32_t mbar0 = smem_u32(mbar_mem);
-    if (lane == 0) {
-#pragma unroll
-        for (int q = 0; q < SNB; ++q) mbar_init(mbar0 + 8u * q, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    uint32_t n_done = 0;  // chunks consumed so far by this warp (all items): ring slot and phase follow from it
-
-    const int total = P.n_main + P.n_images * P.ring_per_image;
-    for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        if (item >= P.n_main) {
-            stream_ring_item(P, item - P.n_main, reinterpret_cast<float *>(&chunks[0][0][0][0]), lane);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes before later TMA writes
-            __syncwarp();
-            continue;
-        }
-        const int img = item / (P.strips * P.blocks_y);
-        const int rem = item - img * (P.strips * P.blocks_y);
-        const int by = rem / P.strips, kx = rem - by * P.strips;
-        const int X0 = kx * TW, Y0 = by * P.rbh;
-        const int rows_blk = min(P.rbh, h0 - Y0);
-        const uint8_t *__restrict__ src = image_ptr(P.src0, P.src1, P.split, img, P.pitch);
-        uint8_t *__restrict__ out = P.dst + (size_t)img * P.pd.pyr_stride;
-        const CUtensorMap *map = img < P.split ? &map0 : &map1;
-        const int z = img < P.split ? img : img - P.split;
-
-        const int T_lo = Y0 / 2, T_hi = (Y0 + rows_blk) / 2;     // level-1 rows owned by the block
-        const int ts = T_lo - C::et, te = T_hi + C::eb;          // level-1 rows emitted (O and / or G)
-        const int r0 = 2 * ts - 1;                               // first base row fetched
-        const int n_it = te + 2 - ts;                            // iterations tau = ts .. te+1
-        const int n_chunks = (2 * (n_it - 1) + 1 + SCH - 1) / SCH;
-        const uint32_t base_done = n_done;
-
-        auto issue = [&](int ci) {  // lane 0: both boxes of chunk ci
-            const uint32_t slot = (base_done + (uint32_t)ci) % SNB;
-            const uint32_t mbar = mbar0 + 8u * slot;
-            const uint32_t dstA = smem_u32(&chunks[slot][0][0][0]);
-            mbar_expect_tx(mbar, 2u * SCH * SBW);
-            // box starts must be 16-byte aligned in global memory: tile columns [0, 160) and [128, 288) of
-            // the tile that begins at x = X0 - 16
-            tma_load_3d(dstA, map, X0 - 16, r0 + ci * SCH, z, mbar);
-            tma_load_3d(dstA + SCH * SBW, map, X0 - 16 + 128, r0 + ci * SCH, z, mbar);
-        };
-        if (lane == 0)
-            for (int q = 0; q < SNB - 1 && q < n_chunks; ++q) issue(q);
-
-        // lane geometry: level-1 columns j0..j0+3 with j0 = X0/2 - 2 + 4 lane, both phases (O and G).  The
-        // lane's pixels 2 j0 - 4 .. 2 j0 + 11 are 16 bytes at box offset boff: two aligned 8-byte loads.
-        const int j0 = X0 / 2 - 2 + 4 * lane;
-        const int box = lane >> 4, boff = 8 * (lane & 15) + 8;
-        const int o_lo = max(T_lo, 1), o_hi = (j0 < w1 && j0 + 3 >= 1) ? min(T_hi, h1 - 1) : o_lo;
-        const bool o_edge = j0 < 1 || j0 + 3 > w1 - 2;
-        uint32_t aOo[4] = {0, 0, 0, 0}, aOn[4] = {0, 0, 0, 0}, aGo[4] = {0, 0, 0, 0}, aGm[4] = {0, 0, 0, 0},
-                 aGn[4] = {0, 0, 0, 0};
-        uint8_t *__restrict__ orow = out + P.pd.lv[1].off + (ptrdiff_t)(ts - 1) * w1 + j0;  // row tau - 1
-        constexpr bool G = NA >= 2;
-
-        auto store_o = [&](int to) {  // O_{to} complete -> level 1, round half up: (N + 32) >> 6
-            if (to >= o_lo && to < o_hi) {
-                const uint32_t b0 = (aOo[0] + 32u) >> 6, b1 = (aOo[1] + 32u) >> 6;
-                const uint32_t b2 = (aOo[2] + 32u) >> 6, b3 = (aOo[3] + 32u) >> 6;
-                if (!o_edge) {  // j0 = 2 (mod 4): two aligned 16-bit stores
-                    reinterpret_cast<uint16_t *>(orow)[0] = (uint16_t)(b0 | (b1 << 8));
-                    reinterpret_cast<uint16_t *>(orow)[1] = (uint16_t)(b2 | (b3 << 8));
-                } else {
-                    if (j0 + 0 >= 1 && j0 + 0 <= w1 - 2) orow[0] = (uint8_t)b0;
-                    if (j0 + 1 >= 1 && j0 + 1 <= w1 - 2) orow[1] = (uint8_t)b1;
-                    if (j0 + 2 >= 1 && j0 + 2 <= w1 - 2) orow[2] = (uint8_t)b2;
-                    if (j0 + 3 >= 1 && j0 + 3 <= w1 - 2) orow[3] = (uint8_t)b3;
-                }
-            }
-        };
-        // levels 2 and 3 from the rings, called when G_2 row tg (all columns) is in the ring
-        auto after_g2_row = [&](int tg) {
-            if (!G) return;
-            __syncwarp();
-            const uint32_t kA[3] = {0x0100u, 0x0200u, 0x0100u}, kB[3] = {0x0102u, 0x0204u, 0x0102u};
-            const uint32_t kC[3] = {0x0201u, 0x0402u, 0x0201u}, kD[3] = {0x0001u, 0x0002u, 0x0001u};
-            if (tg & 1) {  // O_4 row oy = (tg - 1) / 2 from G_2 rows tg-2 .. tg
-                const int oy = (tg - 1) >> 1;
-                const int w2 = P.pd.lv[2].w, h2 = P.pd.lv[2].h;
-                if (oy >= Y0 / 4 && oy < (Y0 + rows_blk) / 4 && oy >= 1 && oy <= h2 - 2 && lane < 16) {
-                    uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-#pragma unroll
-                    for (int rr = 0; rr < 3; ++rr) {
-                        const uint32_t *__restrict__ gw =
-                            reinterpret_cast<const uint32_t *>(&g2[(tg - 2 + rr + 64) & (SG2 - 1)][0]) + 4 * lane;
-                        const uint4 a = *reinterpret_cast<const uint4 *>(gw);
-                        const uint32_t a4 = gw[4];
-                        n0 = __dp2a_lo(a.y, kB[rr], __dp2a_lo(a.x, kA[rr], n0));
-                        n1 = __dp2a_lo(a.z, kB[rr], __dp2a_lo(a.y, kA[rr], n1));
-                        n2 = __dp2a_lo(a.w, kB[rr], __dp2a_lo(a.z, kA[rr], n2));
-                        n3 = __dp2a_lo(a4, kB[rr], __dp2a_lo(a.w, kA[rr], n3));
-                    }
-                    const int ox = X0 / 4 + 4 * lane;
-                    if (ox < w2) {
-                        const uint32_t b0 = (n0 + 512u) >> 10, b1 = (n1 + 512u) >> 10;
-                        const uint32_t b2 = (n2 + 512u) >> 10, b3 = (n3 + 512u) >> 10;
-                        uint8_t *__restrict__ dp = out + P.pd.lv[2].off + (size_t)oy * w2 + ox;
-                        if (ox >= 1 && ox + 3 <= w2 - 2) {
-                            *reinterpret_cast<uint32_t *>(dp) = __byte_perm(b0 | (b1 << 8), b2 | (b3 << 8), 0x5410);
-                        } else {
-                            if (ox + 0 >= 1 && ox + 0 <= w2 - 2) dp[0] = (uint8_t)b0;
-                            if (ox + 1 >= 1 && ox + 1 <= w2 - 2) dp[1] = (uint8_t)b1;
-                            if (ox + 2 >= 1 && ox + 2 <= w2 - 2) dp[2] = (uint8_t)b2;
-                            if (ox + 3 >= 1 && ox + 3 <= w2 - 2) dp[3] = (uint8_t)b3;
-                        }
-                    }
-                }
-            } else if (NA >= 3) {  // G_4 row s = (tg - 2) / 2 from G_2 rows tg-2 .. tg, then level 3
-                const int s = (tg - 2) >> 1;
-                if (s >= Y0 / 4 - 1 && s <= (Y0 + rows_blk) / 4) {
-                    // 66 values G_4[X0/4 - 1 + gm]: window of gm starts at g2 column 2 gm; lane: gm = 2 lane, 2 lane + 1
-                    uint32_t n0 = 0, n1 = 0, n2 = 0;
-#pragma unroll
-                    for (int rr = 0; rr < 3; ++rr) {
-                        const uint32_t *__restrict__ gw =
-                            reinterpret_cast<const uint32_t *>(&g2[(tg - 2 + rr + 64) & (SG2 - 1)][0]) + 2 * lane;
-                        const uint32_t a0 = gw[0], a1 = gw[1], a2 = gw[2];
-                        n0 = __dp2a_lo(a1, kD[rr], __dp2a_lo(a0, kC[rr], n0));
-                        n1 = __dp2a_lo(a2, kD[rr], __dp2a_lo(a1, kC[rr], n1));
-                        if (lane < 2) {  // columns 64, 65
-                            const uint32_t b0 = gw[64 - 2 * lane + lane], b1 = gw[65 - 2 * lane + lane];
-                            n2 = __dp2a_lo(b1, kD[rr], __dp2a_lo(b0, kC[rr], n2));
-                        }
-                    }
-                    uint32_t *__restrict__ g4r = &g4[(s + 64) & (SG4 - 1)][0];
-                    g4r[2 * lane] = n0;
-                    g4r[2 * lane + 1] = n1;
-                    if (lane < 2) g4r[64 + lane] = n2;
-                    __syncwarp();
-                    // level 3: O_8 row o8 when s == 2 o8 + 1, G_8 row m8 when s == 2 m8 + 2
-                    const int w3 = P.pd.lv[3].w, h3 = P.pd.lv[3].h, w8 = w0 / 8, h8 = h0 / 8;
-                    const bool is_o = s & 1;
-                    const int row8 = is_o ? (s - 1) >> 1 : (s - 2) >> 1;
-                    if (row8 >= Y0 / 8 && row8 < (Y0 + rows_blk) / 8) {
-                        const int mc = 2 * lane + 1 + (is_o ? 0 : 1);   // window centre in g4 columns
-                        const uint32_t *q0 = &g4[(s - 2 + 64) & (SG4 - 1)][mc - 1];
-                        const uint32_t *q1 = &g4[(s - 1 + 64) & (SG4 - 1)][mc - 1];
-                        const uint32_t *q2 = &g4[(s + 64) & (SG4 - 1)][mc - 1];
-                        const uint32_t n = q0[0] + 2u * q0[1] + q0[2] + 2u * (q1[0] + 2u * q1[1] + q1[2]) + q2[0] +
-                                           2u * q2[1] + q2[2];
-                        const int ox = X0 / 8 + lane;
-                        if (is_o) {
-                            if (ox >= 1 && ox <= w3 - 2 && row8 >= 1 && row8 <= h3 - 2)
-                                out[P.pd.lv[3].off + (size_t)row8 * w3 + ox] = (uint8_t)((n + 8192u) >> 14);
-                        } else if (P.g8 && ox < w8 && row8 < h8) {
-                            P.g8[((size_t)img * h8 + row8) * w8 + ox] = n;
-                        }
-                    }
-                }
-            }
-        };
-
-        for (int ci = 0; ci < n_chunks; ++ci) {
-            const uint32_t cnum = base_done + (uint32_t)ci;
-            const uint32_t slot = cnum % SNB;
-            mbar_wait(mbar0 + 8u * slot, (cnum / SNB) & 1u);
-            // ---- level 0 == input: rows of this chunk owned by the block, global -> global (L2 hits)
-            {
-                const int v = lane & 15, rr0 = lane >> 4;
-                const int x = X0 + 16 * v;
-                if (x < w0) {
-#pragma unroll
-                    for (int q = 0; q < SCH / 2; ++q) {
-                        const int y = r0 + ci * SCH + rr0 + 2 * q;
-                        if (y >= Y0 && y < Y0 + rows_blk)
-                            *reinterpret_cast<uint4 *>(out + (size_t)y * w0 + x) =
-                                __ldg(reinterpret_cast<const uint4 *>(src + (size_t)y * P.stride + x));
-                    }
-                }
-            }
-            // ---- G_2 columns right of the warp's 128: rows t = ts + 4 ci - 2 .. + 1 (base rows 2t .. 2t+3 lie
-            // in the previous and the current chunk)
-            if (G && lane < 4 * C::GX) {
-                constexpr int GXD = C::GX > 0 ? C::GX : 1;
-                const int gx = lane % GXD, tq = lane / GXD;
-                const int t = ts + 4 * ci - 2 + tq;
-                if (t >= ts && t < te) {
-                    const int pb = 140 + 2 * gx;  // byte offset of pixel 2j (j = X0/2 + 126 + gx) in box 1
-                    uint32_t acc = 0;
-#pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) {
-                        const int rel = 2 * (t - ts) + 1 + rr;              // row index relative to r0
-                        const uint32_t sl = (base_done + (uint32_t)(rel / SCH)) % SNB;
-                        const uint32_t *__restrict__ wq =
-                            reinterpret_cast<const uint32_t *>(&chunks[sl][1][rel % SCH][0]) + (pb >> 2);
-                        const uint32_t vv = (pb & 2) ? __funnelshift_r(wq[0], wq[1], 16) : wq[0];
-                        acc = dp4a_u(vv, (rr == 0 || rr == 3) ? 0x01030301u : 0x03090903u, acc);
-                    }
-                    g2[(t + 64) & (SG2 - 1)][TW / 2 + gx] = (uint16_t)acc;
-                }
-            }
-            __syncwarp();
-            if (lane == 0 && ci + SNB - 1 < n_chunks) issue(ci + SNB - 1);  // refill the slot of chunk ci - 1
-
-            // ---- stage 1: the 4 iterations of this chunk
-#pragma unroll
-            for (int q = 0; q < SCH / 2; ++q) {
-                const int i = ci * (SCH / 2) + q;
-                if (i >= n_it) break;
-                const int tau = ts + i;
-                const uint2 *__restrict__ ra = reinterpret_cast<const uint2 *>(&chunks[slot][box][2 * q][boff]);
-                const uint2 *__restrict__ rb = reinterpret_cast<const uint2 *>(&chunks[slot][box][2 * q + 1][boff]);
-                const uint2 a01 = ra[0], a23 = ra[1];
-                // roles of the two rows as in the tile kernel; first / last iterations feed fewer accumulators
-                if (i == 0) {
-                    stage1_words<true, true, false, false, false, false, true>(a01.x, make_uint2(a01.y, a23.x), a23.y, aOn, aOo, aGn, aGm, aGo);
-                } else if (i == 1) {
-                    stage1_words<true, true, true, false, G, false, true>(a01.x, make_uint2(a01.y, a23.x), a23.y, aOn, aOo, aGn, aGm, aGo);
-                } else {
-                    stage1_words<true, true, true, false, G, G, true>(a01.x, make_uint2(a01.y, a23.x), a23.y, aOn, aOo, aGn, aGm, aGo);
-                    if (G) {
-                        const int tg = tau - 2;  // G_{tau-2} complete
-                        if (tg < te) {
-                            *reinterpret_cast<uint2 *>(&g2[(tg + 64) & (SG2 - 1)][4 * lane]) =
-                                make_uint2(aGo[0] | (aGo[1] << 16), aGo[2] | (aGo[3] << 16));
-                            after_g2_row(tg);
-                        }
-                    }
-                }
-                if (i < n_it - 1) {
-                    const uint2 b01 = rb[0], b23 = rb[1];
-                    if (i == 0)
-                        stage1_words<false, true, false, G, false, false, true>(b01.x, make_uint2(b01.y, b23.x), b23.y, aOn, aOo, aGn, aGm, aGo);
-                    else
-                        stage1_words<false, true, true, G, G, false, true>(b01.x, make_uint2(b01.y, b23.x), b23.y, aOn, aOo, aGn, aGm, aGo);
-                    if (i >= 1) store_o(tau - 1);
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        aOo[u] = aOn[u];
-                        if (G) {
-                            aGo[u] = aGm[u];
-                            aGm[u] = aGn[u];
-                        }
-                    }
-                    orow += w1;
-                }
-            }
-            __syncwarp();
-        }
-        n_done = base_done + (uint32_t)n_chunks;
-        __syncwarp();
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // deep dyadic levels (4, 5) from the exported G_8; near ties fall back to the faithful chains
 // ------------------------------------------------------------------------------------------
 constexpr int kDeepThreads = 256;
@@ -1336,17 +1032,6 @@ static cudaError_t fast_kernel_setup(int *grid, int nbuf, int *smem_bytes) {
     return cudaSuccess;
 }
 
-template <int NA>
-static cudaError_t stream_kernel_setup(int *grid) {
-    int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pyr_stream_kernel<NA>, 32, 0);
-    if (e != cudaSuccess) return e;
-    int dev = 0, sms = kNumSMs;
-    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    *grid = sms * (occ > 0 ? occ : 1);
-    return cudaSuccess;
-}
-
 struct PyrPlan {
     PyrDesc pd;
     PyrTaps taps;
@@ -1364,8 +1049,6 @@ struct PyrPlan {
     int fast_nbuf, fast_smem;  // tile buffers per CTA and the resulting dynamic shared memory
     unsigned *d_tile_counter;  // two counters used alternately
     int tile_parity;
-    int use_stream;  // streaming warp-per-strip kernel instead of the CTA-tile kernel
-    int stream_grid; // resident warps (1-warp CTAs) on the device
     RingWeights ring[4];
     void *d_tables;
     // scratch for deep levels (grown on demand)
@@ -1488,8 +1171,6 @@ cudaError_t pyr_plan_create(int w, int h, int levels, cudaStream_t st, PyrPlan *
     p->tiles_y = (h + TH - 1) / TH;
     p->fast_rows = 0;
     p->fast_grid = kNumSMs;
-    p->use_stream = 0;
-    p->stream_grid = kNumSMs;
     if (p->n_fast >= 1 && !encode_tiled_fn()) p->n_fast = 0;  // no TMA descriptor encoder: generic path
     p->n_a = p->n_fast < 3 ? p->n_fast : 3;
     p->do4 = p->n_fast >= 4;
@@ -1512,17 +1193,6 @@ cudaError_t pyr_plan_create(int w, int h, int levels, cudaStream_t st, PyrPlan *
             return e;
         }
         p->fast_rows = p->n_a == 1 ? FastCfg<1>::ROWS : (p->n_a == 2 ? FastCfg<2>::ROWS : FastCfg<3>::ROWS);
-        // RSVIO_PYR_KERNEL=stream selects the experimental warp-per-strip kernel (bit-exact too, currently
-        // slower: 64 us vs 43 us on 128 x C1); the CTA-tile kernel is the default
-        const char *env = getenv("RSVIO_PYR_KERNEL");
-        p->use_stream = env && strcmp(env, "stream") == 0;
-        p->stream_grid = kNumSMs;
-        e = p->n_a == 1 ? stream_kernel_setup<1>(&p->stream_grid)
-                        : (p->n_a == 2 ? stream_kernel_setup<2>(&p->stream_grid) : stream_kernel_setup<3>(&p->stream_grid));
-        if (e != cudaSuccess) {
-            pyr_plan_destroy(p);
-            return e;
-        }
     }
     // faithful border weights of the dyadic levels handled by pyr_fast_kernel: they depend on the
     // ratio only; take them from the x table (outputs 0, 1 and n-1) as computed on the device
@@ -1623,63 +1293,7 @@ cudaError_t pyr_build(const PyrPlan *p, const uint8_t *src0, const uint8_t *src1
             if (n_launches) ++*n_launches;
             continue;
         }
-        if (p->use_stream) {
-            StreamParams sp;
-            sp.pd = p->pd;
-            memcpy(sp.ring, p->ring, sizeof(sp.ring));
-            sp.src0 = s0;
-            sp.src1 = s1;
-            sp.stride = stride;
-            sp.pitch = pitch;
-            sp.split = sps;
-            sp.n_images = n;
-            sp.dst = d;
-            sp.g8 = p->do4 ? p->d_g8 : nullptr;
-            const int w0 = p->pd.lv[0].w, h0 = p->pd.lv[0].h;
-            sp.strips = (w0 / 2 + 2 + TW / 2 - 1) / (TW / 2);   // a strip owns level-1 columns [128 k - 2, 128 k + 126)
-            // rows per block (multiple of 16): the smallest height whose item count still fits one wave of
-            // resident warps (short blocks pay the 2-3 warm-up rows more often); big batches use 128
-            int rbh = 128;
-            for (int cand = 32; cand <= 512; cand += 16) {
-                const long long items = (long long)n * sp.strips * ((h0 + cand - 1) / cand);
-                if (items <= (long long)p->stream_grid) {
-                    rbh = cand;
-                    break;
-                }
-            }
-            if (const char *ev = getenv("RSVIO_PYR_RBH")) rbh = atoi(ev) > 0 ? (atoi(ev) + 15) / 16 * 16 : rbh;
-            sp.rbh = rbh;
-            sp.blocks_y = (h0 + rbh - 1) / rbh;
-            sp.n_main = n * sp.strips * sp.blocks_y;
-            int tot = 0;
-            for (int i = 0; i < 4; ++i) {
-                sp.ring_first[i] = tot;
-                sp.ring_rows[i] = sp.ring_cols[i] = 0;
-                const int lev = i + 1;
-                if (lev <= p->n_a) {
-                    sp.ring_rows[i] = (p->pd.lv[lev].w + 127) / 128;
-                    sp.ring_cols[i] = (p->pd.lv[lev].h - 2 + 31) / 32;
-                    tot += 2 * sp.ring_rows[i] + 2 * sp.ring_cols[i];
-                }
-            }
-            sp.ring_per_image = tot;
-            CUtensorMap m0, m1;
-            const int n0 = sps < n ? sps : n;
-            const uint8_t *b1 = sps < n ? s1 : s0;
-            const int n1 = sps < n ? n - sps : 1;
-            if (!make_tile_map(&m0, n0 > 0 ? s0 : b1, w0, h0, n0 > 0 ? n0 : 1, stride, pitch, SCH, SBW) ||
-                !make_tile_map(&m1, b1, w0, h0, n1, stride, pitch, SCH, SBW))
-                return cudaErrorInvalidValue;
-            const long long total = (long long)sp.n_main + (long long)n * sp.ring_per_image;
-            const int blocks = (int)(total < p->stream_grid ? total : p->stream_grid);
-            if (p->n_a == 1)
-                pyr_stream_kernel<1><<<blocks, 32, 0, st>>>(sp, m0, m1);
-            else if (p->n_a == 2)
-                pyr_stream_kernel<2><<<blocks, 32, 0, st>>>(sp, m0, m1);
-            else
-                pyr_stream_kernel<3><<<blocks, 32, 0, st>>>(sp, m0, m1);
-            if (n_launches) ++*n_launches;
-        } else {
+        {
         FastParams fp;
         fp.pd = p->pd;
         memcpy(fp.ring, p->ring, sizeof(fp.ring));

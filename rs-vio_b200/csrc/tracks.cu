@@ -145,10 +145,12 @@ constexpr int kExportChunks = 4;
 __global__ void __launch_bounds__(kThreads)
 export_records_kernel(TableView tab, int cap, int streams, OutRecord *__restrict__ out_rec, int *__restrict__ out_counts,
                       const __grid_constant__ CameraModelDev cam0, const __grid_constant__ CameraModelDev cam1,
-                      float2 *__restrict__ out_uxy) {
+                      float2 *__restrict__ out_uxy, const int *__restrict__ err_flag) {
     const int g = blockIdx.x;
     const int n = tab.counts[g];
     if (blockIdx.y == 0 && threadIdx.x == 0) out_counts[g] = n;
+    // the frame's overflow flag rides along behind the counts: no memcpy on the per-frame path at all
+    if (g == 0 && blockIdx.y == 0 && threadIdx.x == 0 && err_flag) out_counts[gridDim.x] = *err_flag;
     const CameraModelDev &cm = g < streams ? cam0 : cam1;
     const bool unproject = out_uxy != nullptr && cm.model != RSVIO_CAMERA_NONE;
     for (int k = blockIdx.y * kThreads + threadIdx.x; k < n; k += kExportChunks * kThreads) {
@@ -225,9 +227,10 @@ cudaError_t merge_new_points(const TableView &tab, int streams, int cap, int ste
 }
 
 cudaError_t export_records(const TableView &tab, int groups, int cap, int streams, OutRecord *out_rec, int *out_counts,
-                           const CameraModelDev &cam0, const CameraModelDev &cam1, float *out_uxy, cudaStream_t st) {
+                           const CameraModelDev &cam0, const CameraModelDev &cam1, float *out_uxy, const int *err_flag,
+                           cudaStream_t st) {
     export_records_kernel<<<dim3((unsigned)groups, kExportChunks, 1), kThreads, 0, st>>>(
-        tab, cap, streams, out_rec, out_counts, cam0, cam1, reinterpret_cast<float2 *>(out_uxy));
+        tab, cap, streams, out_rec, out_counts, cam0, cam1, reinterpret_cast<float2 *>(out_uxy), err_flag);
     return cudaGetLastError();
 }
 

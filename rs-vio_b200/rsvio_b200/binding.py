@@ -14,7 +14,8 @@ import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)                      # rs-vio_b200/
-_LIB_PATH = os.path.join(_ROOT, "lib", "librsvio_b200.so")
+# RSVIO_LIB: another build of the same library (A/B runs of kernel variants); still the CUDA library, never a fallback
+_LIB_PATH = os.environ.get("RSVIO_LIB") or os.path.join(_ROOT, "lib", "librsvio_b200.so")
 
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_CAPACITY, ERR_STATE, ERR_ALLOC = 0, -1, -2, -3, -4, -5
 TRACK_OK, FAIL_TEMPLATE, FAIL_RESIDUAL, FAIL_NONFINITE, FAIL_DIVERGED, FAIL_OOB, FAIL_FB = range(7)
@@ -26,7 +27,7 @@ STAGE_NAMES = ("upload", "pyramid", "lk_temporal", "compact", "detect", "lk_ster
 # every symbol include/rsvio_b200.h declares
 ABI_SYMBOLS = (
     "rsvio_abi_version", "rsvio_status_string", "rsvio_device_count", "rsvio_config_default",
-    "rsvio_host_alloc", "rsvio_host_free",
+    "rsvio_host_alloc", "rsvio_host_alloc_flags", "rsvio_host_free",
     "rsvio_tracker_create", "rsvio_tracker_destroy", "rsvio_tracker_last_error", "rsvio_tracker_reset",
     "rsvio_tracker_process_stereo", "rsvio_tracker_process_mono", "rsvio_tracker_process_batch",
     "rsvio_tracker_submit_batch", "rsvio_tracker_sync", "rsvio_tracker_submit_device",
@@ -39,7 +40,7 @@ ABI_SYMBOLS = (
     "rsvio_build_pyramid_u8_device", "rsvio_track_points", "rsvio_detect_keypoints", "rsvio_se2_exp",
     "rsvio_tracker_set_camera", "rsvio_tracker_undistorted_view", "rsvio_unproject_points",
     "rsvio_tracker_process_stereo_fmt", "rsvio_convert_to_luma8", "rsvio_b_track_points",
-    "rsvio_b_pyramid_dims", "rsvio_b_build_pyramid",
+    "rsvio_b_pyramid_dims", "rsvio_b_build_pyramid", "rsvio_microbench_fp32",
 )
 
 PIXEL_LUMA8, PIXEL_LUMA16, PIXEL_RGB8 = 0, 1, 2
@@ -114,6 +115,7 @@ def load_library():
     L.rsvio_config_default.restype = None
     L.rsvio_config_default.argtypes = [C.POINTER(Config)]
     L.rsvio_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_size_t]
+    L.rsvio_host_alloc_flags.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_uint32]
     L.rsvio_host_free.argtypes = [C.c_void_p]
     L.rsvio_tracker_create.argtypes = [C.POINTER(Config), C.POINTER(H)]
     L.rsvio_tracker_destroy.restype = None
@@ -151,6 +153,7 @@ def load_library():
     L.rsvio_detect_keypoints.argtypes = [C.c_int32, _u8p, C.c_int32, C.c_int32, C.c_size_t, C.c_uint32, _u32p,
                                          C.c_int32, _u32p, _f32p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.rsvio_se2_exp.argtypes = [C.c_int32, _f32p, C.c_int32, _f32p]
+    L.rsvio_microbench_fp32.argtypes = [C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.rsvio_tracker_set_camera.argtypes = [H, C.c_int32, C.POINTER(CameraModel)]
     L.rsvio_tracker_undistorted_view.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.rsvio_unproject_points.argtypes = [C.c_int32, C.POINTER(CameraModel), _f32p, C.c_int32, _f32p]
@@ -194,6 +197,31 @@ def device_count():
     n = C.c_int32(0)
     load_library().rsvio_device_count(C.byref(n))
     return n.value
+
+
+HOST_WRITE_COMBINED = 1
+
+
+class HostBuffer:
+    """Pinned host memory from rsvio_host_alloc[_flags] as a numpy uint8 array (`.array`), freed on close()."""
+
+    def __init__(self, shape, write_combined=False):
+        self.nbytes = int(np.prod(shape))
+        self._p = C.c_void_p()
+        _check(load_library().rsvio_host_alloc_flags(C.byref(self._p), self.nbytes,
+                                                     HOST_WRITE_COMBINED if write_combined else 0))
+        buf = (C.c_uint8 * self.nbytes).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=np.uint8).reshape(shape)
+
+    @property
+    def ptr(self):
+        return self._p.value
+
+    def close(self):
+        if self._p:
+            self.array = None
+            load_library().rsvio_host_free(self._p)
+            self._p = C.c_void_p()
 
 
 # ---- stateless entry points ---------------------------------------------------------------
@@ -295,6 +323,13 @@ def unproject_points(model, xy, device=0):
     out = np.empty_like(xy)
     _check(load_library().rsvio_unproject_points(device, C.byref(model), xy, xy.shape[0], out))
     return out
+
+
+def microbench_fp32(device=0):
+    """(FFMA TFLOP/s, separately rounded FMUL + FADD TFLOP/s) measured on the device right now"""
+    a, b = C.c_float(0), C.c_float(0)
+    _check(load_library().rsvio_microbench_fp32(device, C.byref(a), C.byref(b)))
+    return a.value, b.value
 
 
 def se2_exp(twists, device=0):

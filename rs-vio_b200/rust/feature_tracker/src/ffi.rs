@@ -57,6 +57,7 @@ extern "C" {
     pub fn rsvio_status_string(s: rsvio_status) -> *const c_char;
     pub fn rsvio_config_default(cfg: *mut rsvio_config);
     pub fn rsvio_host_alloc(ptr: *mut *mut c_void, bytes: usize) -> rsvio_status;
+    pub fn rsvio_host_alloc_flags(ptr: *mut *mut c_void, bytes: usize, flags: u32) -> rsvio_status;
     pub fn rsvio_host_free(ptr: *mut c_void) -> rsvio_status;
     pub fn rsvio_tracker_create(cfg: *const rsvio_config, out: *mut *mut rsvio_tracker) -> rsvio_status;
     pub fn rsvio_tracker_destroy(t: *mut rsvio_tracker);
@@ -106,6 +107,7 @@ extern "C" {
     pub fn rsvio_detect_keypoints(device: i32, image: *const u8, width: i32, height: i32, stride: usize,
                                   grid_size: u32, cur_xy: *const u32, n_cur: i32, out_xy: *mut u32,
                                   out_score: *mut f32, cap: usize, n: *mut usize) -> rsvio_status;
+    pub fn rsvio_microbench_fp32(device: i32, ffma_tflops: *mut f32, fmul_fadd_tflops: *mut f32) -> rsvio_status;
     pub fn rsvio_se2_exp(device: i32, twists: *const f32, n: i32, out9: *mut f32) -> rsvio_status;
 
     // ---- unprojection of the tracked pixels (Feature::undistorted_coord) ----
