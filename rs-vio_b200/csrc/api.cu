@@ -8,6 +8,7 @@
 //   occupancy -> FAST detection -> collect -> stereo LK -> merge + packed output
 // with no host round trip in between.  There is no CPU fallback anywhere in this file.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <new>
@@ -75,6 +76,7 @@ struct rsvio_tracker {
     float *d_cell_score = nullptr;
     uint32_t *d_cell_list = nullptr;
     int *d_cell_list_n = nullptr;
+    int *d_cell_work = nullptr;  // [0, S): listed empty cells per stream, [S, 2S): finished ones (zero between frames)
     float *d_new_T6 = nullptr, *d_st_T6 = nullptr;
     int *d_new_count = nullptr;
     int32_t *d_st_status = nullptr;
@@ -103,6 +105,16 @@ struct rsvio_tracker {
     uint64_t stage_launches[RSVIO_N_STAGES] = {0};
     // a CUDA failure may leave a frame half enqueued (tables partly written, events unrecorded): the handle refuses
     // further frames until rsvio_tracker_reset has rebuilt a consistent state
+    // CUDA graphs of the per-frame launch sequence (single-stream handles: everything is on one stream there, and the
+    // launch overhead of 7 kernels is a third of a frame).  One executable graph per state of the ping-pong buffers.
+    struct FrameGraph {
+        int slot, pcur, tcur, lk0, lk1, det, have_prev, plan_parity, plan_delta;
+        const uint8_t *src0, *src1;
+        size_t stride, pitch;
+        cudaGraphExec_t exec;
+    };
+    std::vector<FrameGraph> graphs;
+    bool use_graphs = false;
     bool poisoned = false;
     uint64_t overflow_frames = 0;  // frames whose new points did not all fit the track table (sticky count)
     std::string err;
@@ -140,6 +152,12 @@ cudaError_t dmalloc(T **p, size_t n) {
     return cudaMalloc((void **)p, n * sizeof(T) > 0 ? n * sizeof(T) : 16);
 }
 
+void drop_graphs(rsvio_tracker *t) {
+    for (auto &g : t->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    t->graphs.clear();
+}
+
 void free_all(rsvio_tracker *t) {
     if (!t) return;
     DeviceScope dev_scope;
@@ -148,6 +166,7 @@ void free_all(rsvio_tracker *t) {
     if (t->copy_st) cudaStreamSynchronize(t->copy_st);
     if (t->own_exp && t->exp_st) cudaStreamSynchronize(t->exp_st);
     if (t->own_pyr && t->pyr_st) cudaStreamSynchronize(t->pyr_st);
+    drop_graphs(t);
     pyr_plan_destroy(t->plan);
     for (int i = 0; i < kSlots; ++i) {
         cudaFree(t->d_in[i]);
@@ -179,6 +198,7 @@ void free_all(rsvio_tracker *t) {
     cudaFree(t->d_cell_score);
     cudaFree(t->d_cell_list);
     cudaFree(t->d_cell_list_n);
+    cudaFree(t->d_cell_work);
     cudaFree(t->d_new_T6);
     cudaFree(t->d_st_T6);
     cudaFree(t->d_new_count);
@@ -205,6 +225,7 @@ rsvio_status clear_state(rsvio_tracker *t) {
     CU_TRY(t, cudaMemsetAsync(t->d_new_count, 0, sizeof(int) * t->S, t->st));
     CU_TRY(t, cudaMemsetAsync(t->d_work, 0, sizeof(unsigned) * 4, t->st));
     CU_TRY(t, cudaMemsetAsync(t->d_cell_list_n, 0, sizeof(int) * 2, t->st));
+    CU_TRY(t, cudaMemsetAsync(t->d_cell_work, 0, sizeof(int) * 2 * t->S, t->st));
     t->lk_par[0] = t->lk_par[1] = t->det_par = 0;
     if (t->own_exp) CU_TRY(t, cudaStreamSynchronize(t->exp_st));
     if (t->own_pyr) CU_TRY(t, cudaStreamSynchronize(t->pyr_st));
@@ -222,16 +243,20 @@ rsvio_status clear_state(rsvio_tracker *t) {
     return RSVIO_OK;
 }
 
-// one frame, enqueued on t->st.  src0/src1: device images of camera 0 / 1 (S each).
-rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, const uint8_t *src1, size_t stride,
-                           size_t pitch) {
+// The launches of one frame on t->st (and the side streams of batched handles).  src0/src1: device images of camera
+// 0 / 1 (S each).  Changes no host state of the handle: frame_advance() does, once the launches are out.  With
+// `capturing` the stream is being captured into a graph: everything is on t->st and no event is recorded (the
+// caller records them after the graph launch).
+rsvio_status frame_launches(rsvio_tracker *t, int slot, const uint8_t *src0, const uint8_t *src1, size_t stride,
+                            size_t pitch, bool capturing) {
     cudaStream_t st = t->st;
-    const bool prof = t->profiling;
+    const bool prof = t->profiling && !capturing;
     int stage = 1;  // stage 0 (upload) is timed on the copy stream
     auto mark = [&](int k) {
         if (prof) cudaEventRecord(t->ev_stage[slot][k], st);
     };
     auto count = [&](int stg, int n) {
+        if (capturing) return;  // replays are counted by the caller
         t->host_launches += (uint64_t)n;
         t->stage_launches[stg] += (uint64_t)n;
     };
@@ -243,13 +268,13 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
     // the low-occupancy tail (compaction, detection, stereo LK, merge) of the previous one.  It overwrites the
     // set that was the previous frame's `prev`, last read by that frame's temporal LK.  Profiling keeps
     // everything on one stream (stage times would overlap otherwise).
-    cudaStream_t ps = prof ? st : t->pyr_st;
+    cudaStream_t ps = (prof || capturing) ? st : t->pyr_st;
     if (ps != st) CU_TRY(t, cudaStreamWaitEvent(ps, t->ev_lk_done, 0));
     mark(stage);
     int nl = 0;
     CU_TRY(t, pyr_build(t->plan, src0, src1, t->S, n_img, stride, pitch, cur, ps, &nl));
     count(1, nl);
-    CU_TRY(t, cudaEventRecord(t->ev_in_free[slot], ps));
+    if (!capturing) CU_TRY(t, cudaEventRecord(t->ev_in_free[slot], ps));
     if (ps != st) {
         CU_TRY(t, cudaEventRecord(t->ev_pyr[slot], ps));
         CU_TRY(t, cudaStreamWaitEvent(st, t->ev_pyr[slot], 0));
@@ -272,21 +297,26 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
         b.max_it = t->cfg.max_iterations;
         b.thr = t->cfg.convergence_threshold;
         CU_TRY(t, lk_track(t->pd, b, st));
-        t->lk_par[0] ^= 1;  // only a launch that went out has cleared the other counter
         count(2, 1);
     }
-    CU_TRY(t, cudaEventRecord(t->ev_lk_done, st));  // `prev` may be overwritten from here on
-    mark(++stage);  // 3: compaction + occupancy
+    if (!capturing) CU_TRY(t, cudaEventRecord(t->ev_lk_done, st));  // `prev` may be overwritten from here on
+    mark(++stage);  // 3: compaction + occupancy + the list of empty cells
+    CellWork cw{};
+    cw.cell_pt = t->d_cell_pt;
+    cw.cell_score = t->d_cell_score;
+    cw.list = t->d_cell_list;
+    cw.list_count = t->d_cell_list_n + t->det_par;
+    cw.next_count = t->d_cell_list_n + (t->det_par ^ 1);
+    cw.n_empty = t->d_cell_work;
+    cw.done = t->d_cell_work + t->S;
+    cw.new_count = t->d_new_count;
     CU_TRY(t, compact_tracks(tin, t->d_lk_T6, t->d_lk_status, tout, t->groups, t->cap, t->S, t->gd, t->d_occ,
-                             t->have_prev ? 1 : 0, t->d_counters, t->d_err + slot, st));
+                             t->have_prev ? 1 : 0, t->d_counters, t->d_err + slot, cw, st));
     count(3, 1);
-    mark(++stage);  // 4: detection (level 0 of the current left pyramid is the input image)
+    mark(++stage);  // 4: detection (level 0 of the current left pyramid is the input image) + ordered collection
     CU_TRY(t, detect_cells(t->gd, cur + t->pd.lv[0].off, (size_t)t->pd.lv[0].w, (size_t)t->pd.pyr_stride, t->S,
-                           t->d_occ, t->d_cell_pt, t->d_cell_score, t->d_cell_list, t->d_cell_list_n, t->det_par, st));
-    t->det_par ^= 1;
-    CU_TRY(t, collect_new_points(t->gd, t->S, t->d_cell_pt, t->d_cell_score, t->d_new_T6, nullptr, t->d_new_count,
-                                 t->new_cap, t->d_counters, st));
-    count(4, 3);
+                           t->d_occ, cw, t->d_new_T6, nullptr, t->new_cap, t->d_counters, false, st));
+    count(4, 1);
     mark(++stage);  // 5: stereo LK (left -> right of the current frame)
     if (t->stereo) {
         LkBatch b{};
@@ -305,7 +335,6 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
         b.max_it = t->cfg.max_iterations;
         b.thr = t->cfg.convergence_threshold;
         CU_TRY(t, lk_track(t->pd, b, st));
-        t->lk_par[1] ^= 1;
         count(5, 1);
     }
     mark(++stage);  // 6: merge (ids, table append)
@@ -315,7 +344,7 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
     // 7: download -- packed records into mapped host memory + the error flag.  With many streams this runs on
     // its own CUDA stream beside the next frame (the table it reads is not written again before the frame after
     // next, which cannot be submitted until this one has been synced).
-    cudaStream_t xs = prof ? st : t->exp_st;  // profiling: one stream, every stage alone on the device
+    cudaStream_t xs = (prof || capturing) ? st : t->exp_st;  // profiling: one stream, every stage alone on the device
     if (xs != st) {
         CU_TRY(t, cudaEventRecord(t->ev_merged[slot], st));
         CU_TRY(t, cudaStreamWaitEvent(xs, t->ev_merged[slot], 0));
@@ -327,11 +356,77 @@ rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, cons
     count(7, 1);
     ++stage;
     if (prof) cudaEventRecord(t->ev_stage[slot][stage], xs);  // end
-    t->stage_valid[slot] = prof;
-    CU_TRY(t, cudaEventRecord(t->ev_done[slot], xs));
+    if (!capturing) {
+        t->stage_valid[slot] = prof;
+        CU_TRY(t, cudaEventRecord(t->ev_done[slot], xs));
+    }
+    return RSVIO_OK;
+}
+
+// host state after the launches of a frame went out: the ping-pong sets and the counter pairs switch sides
+void frame_advance(rsvio_tracker *t) {
+    if (t->have_prev) t->lk_par[0] ^= 1;  // only a launch that went out has cleared the other counter
+    if (t->stereo) t->lk_par[1] ^= 1;
+    t->det_par ^= 1;
     t->tcur ^= 1;
     t->pcur ^= 1;
     t->have_prev = true;
+}
+
+// Single-stream handles: the frame as one CUDA graph launch.  Graphs are captured lazily, one per state of the
+// ping-pong buffers (two in steady state), and replayed while that state recurs.
+rsvio_status enqueue_frame_graph(rsvio_tracker *t, int slot, const uint8_t *src0, const uint8_t *src1, size_t stride,
+                                 size_t pitch) {
+    const int parity = pyr_plan_parity(t->plan);
+    rsvio_tracker::FrameGraph *hit = nullptr;
+    for (auto &g : t->graphs)
+        if (g.slot == slot && g.pcur == t->pcur && g.tcur == t->tcur && g.lk0 == t->lk_par[0] && g.lk1 == t->lk_par[1] &&
+            g.det == t->det_par && g.have_prev == (t->have_prev ? 1 : 0) && g.plan_parity == parity && g.src0 == src0 &&
+            g.src1 == src1 && g.stride == stride && g.pitch == pitch) {
+            hit = &g;
+            break;
+        }
+    if (!hit) {
+        if (t->graphs.size() >= 16) drop_graphs(t);  // callers that keep changing their buffers: start over
+        CU_TRY(t, cudaStreamBeginCapture(t->st, cudaStreamCaptureModeThreadLocal));
+        const rsvio_status rs = frame_launches(t, slot, src0, src1, stride, pitch, true);
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ec = cudaStreamEndCapture(t->st, &graph);
+        const int after = pyr_plan_parity(t->plan);
+        pyr_plan_set_parity(t->plan, parity);  // nothing ran yet: the host copy follows the replays below
+        if (rs != RSVIO_OK || ec != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            return rs != RSVIO_OK ? rs : fail_cuda(t, ec != cudaSuccess ? ec : cudaErrorUnknown, "cudaStreamEndCapture", __LINE__);
+        }
+        rsvio_tracker::FrameGraph g{slot, t->pcur, t->tcur, t->lk_par[0], t->lk_par[1], t->det_par, t->have_prev ? 1 : 0,
+                                    parity, after ^ parity, src0, src1, stride, pitch, nullptr};
+        const cudaError_t ei = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) return fail_cuda(t, ei, "cudaGraphInstantiate", __LINE__);
+        t->graphs.push_back(g);
+        hit = &t->graphs.back();
+    }
+    CU_TRY(t, cudaGraphLaunch(hit->exec, t->st));
+    pyr_plan_set_parity(t->plan, parity ^ hit->plan_delta);
+    const int n_launch = 5 + (t->have_prev ? 1 : 0) + (t->stereo ? 1 : 0);
+    t->host_launches += (uint64_t)n_launch;
+    t->stage_launches[1] += 1;
+    CU_TRY(t, cudaEventRecord(t->ev_in_free[slot], t->st));
+    CU_TRY(t, cudaEventRecord(t->ev_lk_done, t->st));
+    t->stage_valid[slot] = false;
+    CU_TRY(t, cudaEventRecord(t->ev_done[slot], t->st));
+    return RSVIO_OK;
+}
+
+rsvio_status enqueue_frame(rsvio_tracker *t, int slot, const uint8_t *src0, const uint8_t *src1, size_t stride,
+                           size_t pitch) {
+    rsvio_status rs;
+    if (t->use_graphs && !t->profiling && t->pyr_st == t->st && t->exp_st == t->st)
+        rs = enqueue_frame_graph(t, slot, src0, src1, stride, pitch);
+    else
+        rs = frame_launches(t, slot, src0, src1, stride, pitch, false);
+    if (rs != RSVIO_OK) return rs;
+    frame_advance(t);
     return RSVIO_OK;
 }
 
@@ -514,6 +609,8 @@ rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) 
         } else {
             t->exp_st = t->st;
             t->pyr_st = t->st;
+            const char *ng = getenv("RSVIO_NO_GRAPH");
+            t->use_graphs = !(ng && ng[0] == '1');
         }
         CU_TRY(t, cudaEventCreateWithFlags(&t->ev_lk_done, cudaEventDisableTiming));
         CU_TRY(t, pyr_plan_create(cfg->width, cfg->height, cfg->levels, t->st, &t->plan));
@@ -547,6 +644,7 @@ rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) 
         CU_TRY(t, dmalloc(&t->d_cell_score, S * (size_t)t->new_cap));
         CU_TRY(t, dmalloc(&t->d_cell_list, S * (size_t)t->new_cap));
         CU_TRY(t, dmalloc(&t->d_cell_list_n, (size_t)2));
+        CU_TRY(t, dmalloc(&t->d_cell_work, 2 * S));
         CU_TRY(t, dmalloc(&t->d_new_T6, S * (size_t)t->new_cap * 6));
         CU_TRY(t, dmalloc(&t->d_st_T6, S * (size_t)t->new_cap * 6));
         CU_TRY(t, dmalloc(&t->d_new_count, S));
@@ -800,6 +898,7 @@ rsvio_status rsvio_tracker_set_camera(rsvio_tracker *t, int32_t cam, const rsvio
     }
     t->cam_model[cam].model = model->model;
     for (int k = 0; k < 9; ++k) t->cam_model[cam].p[k] = model->params[k];
+    drop_graphs(t);  // the export kernel's parameters are baked into the captured frames
     return RSVIO_OK;
 }
 
@@ -1127,7 +1226,7 @@ rsvio_status rsvio_detect_keypoints(int32_t device, const uint8_t *image, int32_
     uint8_t *d_img = nullptr, *d_occ = nullptr;
     uint32_t *d_xy = nullptr, *d_cell = nullptr;
     float *d_score = nullptr, *d_T6 = nullptr, *d_nscore = nullptr;
-    int *d_cnt = nullptr, *d_list_n = nullptr;
+    int *d_cnt = nullptr, *d_list_n = nullptr;  // d_list_n: [0,1] list counters, [2] listed cells, [3] finished cells
     uint32_t *d_list = nullptr;
     int cnt = 0;
     std::vector<float> hT, hs;
@@ -1148,10 +1247,21 @@ rsvio_status rsvio_detect_keypoints(int32_t device, const uint8_t *image, int32_
     CU_TRY0(cudaMalloc((void **)&d_nscore, sizeof(float) * cells));
     CU_TRY0(cudaMalloc((void **)&d_cnt, sizeof(int)));
     CU_TRY0(cudaMalloc((void **)&d_list, sizeof(uint32_t) * cells));
-    CU_TRY0(cudaMalloc((void **)&d_list_n, 2 * sizeof(int)));
-    CU_TRY0(cudaMemsetAsync(d_list_n, 0, 2 * sizeof(int), cs.s));
-    CU_TRY0(detect_cells(gd, d_img, (size_t)width, 0, 1, d_occ, d_cell, d_score, d_list, d_list_n, 0, cs.s));
-    CU_TRY0(collect_new_points(gd, 1, d_cell, d_score, d_T6, d_nscore, d_cnt, cells, nullptr, cs.s));
+    CU_TRY0(cudaMalloc((void **)&d_list_n, 4 * sizeof(int)));
+    CU_TRY0(cudaMemsetAsync(d_list_n, 0, 4 * sizeof(int), cs.s));
+    CU_TRY0(cudaMemsetAsync(d_cnt, 0, sizeof(int), cs.s));  // stays 0 when no cell is empty
+    {
+        CellWork cw{};
+        cw.cell_pt = d_cell;
+        cw.cell_score = d_score;
+        cw.list = d_list;
+        cw.list_count = d_list_n;
+        cw.next_count = d_list_n + 1;
+        cw.n_empty = d_list_n + 2;
+        cw.done = d_list_n + 3;
+        cw.new_count = d_cnt;
+        CU_TRY0(detect_cells(gd, d_img, (size_t)width, 0, 1, d_occ, cw, d_T6, d_nscore, cells, nullptr, true, cs.s));
+    }
     CU_TRY0(D2H(&cnt, d_cnt, sizeof(int)));
     CU_TRY0(cudaStreamSynchronize(cs.s));
     *n = (size_t)cnt;

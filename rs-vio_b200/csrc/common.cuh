@@ -89,6 +89,10 @@ struct PyrPlan;  // owns the tap tables and tile lists of one (w, h, levels)
 cudaError_t pyr_plan_create(int w, int h, int levels, cudaStream_t st, PyrPlan **out);
 void pyr_plan_destroy(PyrPlan *p);
 const PyrDesc &pyr_plan_desc(const PyrPlan *p);
+// which of the plan's two tile counters the next fast-path launch draws from (a launch flips it): a captured launch
+// sequence that is replayed must see the parity it was captured with, and the host copy must follow the replays
+int pyr_plan_parity(const PyrPlan *p);
+void pyr_plan_set_parity(PyrPlan *p, int parity);
 // scratch for the deep dyadic levels (>= 4) of up to n_images images per pyr_build call
 cudaError_t pyr_plan_reserve(PyrPlan *p, int n_images);
 // n_images source images: image j at src[j < split ? 0 : 1] + (j < split ? j : j - split) * pitch
@@ -138,16 +142,25 @@ inline GridDesc make_grid_desc(int w, int h, uint32_t g) {
     d.y_start = ((uint32_t)h % g) / 2;
     return d;
 }
-// occ: [streams][occ_rows*occ_cols] bytes, cell_pt: [streams][ncx*ncy] packed (y << 16 | x) or ~0,
-// cell_score: [streams][ncx*ncy].  img of stream s = img0 + s * pitch.
-// list / list_count: scratch for the work list of empty cells ([streams * cells] and one int).  3 launches.
+// Detection work shared by the compaction kernel (producer of the list) and the detection kernel:
+//   cell_pt [streams][cells]  packed (y << 16 | x) of the chosen corner or ~0; cell_score the same layout
+//   list / list_count         empty cells of all streams (item = stream * cells + cell), count; next_count is the other
+//                             counter of the pair (cleared for the next frame)
+//   n_empty [streams]         listed cells per stream; done [streams] counts finished ones (zero between frames):
+//                             the CTA that finishes a stream's last cell compacts that stream's new points
+struct CellWork {
+    uint32_t *cell_pt;
+    float *cell_score;
+    uint32_t *list;
+    int *list_count, *next_count;
+    int *n_empty, *done;
+    int *new_count;  // [streams]
+};
+// occ: [streams][occ_rows*occ_cols] bytes.  img of stream s = img0 + s * pitch.  Stateless form: lists the empty cells
+// itself (1 extra launch) before the detection launch.
 cudaError_t detect_cells(const GridDesc &gd, const uint8_t *img0, size_t stride, size_t pitch, int streams,
-                         const uint8_t *occ, uint32_t *cell_pt, float *cell_score, uint32_t *list, int *list_count,
-                         int parity, cudaStream_t st);  // list_count: 2 ints used alternately (parity), zero at first use
-// ordered compaction of the per-cell results into identity transforms new_T6[s][k], new_count[s]
-cudaError_t collect_new_points(const GridDesc &gd, int streams, const uint32_t *cell_pt, const float *cell_score,
-                               float *new_T6, float *new_score, int *new_count, int new_cap,
-                               unsigned long long *counters, cudaStream_t st);
+                         const uint8_t *occ, const CellWork &cw, float *new_T6, float *new_score, int new_cap,
+                         unsigned long long *counters, bool list_first, cudaStream_t st);
 // marks cells holding one of n (x, y) rounded positions (stateless API); occ must be zeroed
 cudaError_t mark_occupancy_xy(const GridDesc &gd, const uint32_t *d_xy, int n, uint8_t *occ, cudaStream_t st);
 
@@ -161,7 +174,7 @@ struct TableView {
 // groups < streams (camera 0) also rebuild the occupancy grid of their stream.
 cudaError_t compact_tracks(const TableView &in, const float *lk_T6, const int32_t *lk_status, const TableView &out,
                            int groups, int cap, int streams, const GridDesc &gd, uint8_t *occ, int have_prev,
-                           unsigned long long *counters, int *err_clear, cudaStream_t st);
+                           unsigned long long *counters, int *err_clear, const CellWork &cw, cudaStream_t st);
 // packed output record written to (mapped) host memory
 struct OutRecord {
     unsigned long long id;

@@ -83,7 +83,7 @@ __device__ __forceinline__ int fast9_score_full(const uint8_t *__restrict__ p, i
 __global__ void __launch_bounds__(256)
 list_empty_cells_kernel(GridDesc gd, int streams, const uint8_t *__restrict__ occ, uint32_t *__restrict__ cell_pt,
                         float *__restrict__ cell_score, uint32_t *__restrict__ list, int *__restrict__ list_count,
-                        int *__restrict__ next_count) {
+                        int *__restrict__ next_count, int *__restrict__ n_empty) {
     if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;  // the other counter, for the next frame
     const int cells = gd.ncx * gd.ncy;
     const long long total = (long long)cells * streams;
@@ -102,25 +102,71 @@ list_empty_cells_kernel(GridDesc gd, int streams, const uint8_t *__restrict__ oc
     if (lane == 0 && m) base = atomicAdd(list_count, __popc(m));
     base = __shfl_sync(0xffffffffu, base, 0);
     if (empty) list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)item;
+    if (empty) atomicAdd(n_empty + (int)(item / cells), 1);  // stateless path only (one image): not on the frame path
+}
+
+constexpr int kDetThreads = 256;
+constexpr int kDetChunk = 2048;  // candidates per compaction pass (a 40-px cell has 1156)
+
+// ordered compaction of one stream's cells (visiting order: x outer, y inner) into identity transforms, by one CTA.
+// The cell results were written by other CTAs of this launch (fenced before their `done` increment): read past L1.
+__device__ void collect_stream(const GridDesc &gd, int s, const uint32_t *cell_pt, const float *cell_score,
+                               float *__restrict__ new_T6, float *__restrict__ new_score, int *__restrict__ new_count,
+                               int new_cap, unsigned long long *counters, uint32_t *warp_tot /* >= 8 shared words */) {
+    __shared__ int base;
+    const int cells = gd.ncx * gd.ncy;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < cells; c0 += kDetThreads) {
+        const int c = c0 + threadIdx.x;
+        const uint32_t pt = c < cells ? __ldcg(cell_pt + (size_t)s * cells + c) : 0xFFFFFFFFu;
+        const bool has = pt != 0xFFFFFFFFu;
+        const unsigned m = __ballot_sync(0xffffffffu, has);
+        if (lane == 0) warp_tot[wid] = (uint32_t)__popc(m);
+        __syncthreads();
+        int off = base;
+        for (int k = 0; k < wid; ++k) off += (int)warp_tot[k];
+        const int rank = off + __popc(m & ((1u << lane) - 1u));
+        if (has && rank < new_cap) {
+            float *T = new_T6 + ((size_t)s * new_cap + rank) * 6;
+            T[0] = 1.0f; T[1] = 0.0f; T[2] = (float)(pt & 0xFFFFu);
+            T[3] = 0.0f; T[4] = 1.0f; T[5] = (float)(pt >> 16);
+            if (new_score) new_score[(size_t)s * new_cap + rank] = __ldcg(cell_score + (size_t)s * cells + c);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int k = 0; k < kDetThreads / 32; ++k) t += (int)warp_tot[k];
+            base += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const int n = base < new_cap ? base : new_cap;
+        new_count[s] = n;
+        if (counters) atomicAdd(counters + CNT_DETECTED, (unsigned long long)n);
+    }
 }
 
 // One CTA per empty cell: the (g-6)^2 candidates are spread over 256 threads, block-wide packed-key max.
 // (128 threads: 4 % slower on the bench step; one WARP per cell, no block barriers: 40 % slower -- a lane then
 // tests 36 candidates in sequence.)
-constexpr int kDetThreads = 256;
-constexpr int kDetChunk = 2048;  // candidates per compaction pass (a 40-px cell has 1156)
 __global__ void __launch_bounds__(kDetThreads)
-detect_list_kernel(GridDesc gd, const uint8_t *__restrict__ img0, size_t stride, size_t pitch,
-                   const uint32_t *__restrict__ list, const int *__restrict__ list_count,
-                   uint32_t *__restrict__ cell_pt, float *__restrict__ cell_score) {
+detect_list_kernel(GridDesc gd, const uint8_t *__restrict__ img0, size_t stride, size_t pitch, CellWork cw,
+                   float *__restrict__ new_T6, float *__restrict__ new_score, int new_cap, unsigned long long *counters) {
+    const uint32_t *__restrict__ list = cw.list;
+    uint32_t *__restrict__ cell_pt = cw.cell_pt;
+    float *__restrict__ cell_score = cw.cell_score;
     __shared__ uint32_t wbest[kDetThreads / 32];
     __shared__ uint32_t surv[kDetChunk];
     __shared__ int n_surv;
+    __shared__ int s_last;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int cells = gd.ncx * gd.ncy;
     const int g = (int)gd.g;
     const int side = g - 6;  // candidates per axis
-    const int n = *list_count;
+    const int n = *cw.list_count;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const uint32_t item = __ldg(list + i);
         const int s = (int)(item / (uint32_t)cells), cell = (int)(item - (uint32_t)s * (uint32_t)cells);
@@ -184,51 +230,17 @@ detect_list_kernel(GridDesc gd, const uint8_t *__restrict__ img0, size_t stride,
                 cell_pt[item] = (gy << 16) | gx;
                 cell_score[item] = (float)sc;
             }
+            // the CTA that finishes the last listed cell of a stream compacts that stream's new points (below)
+            __threadfence();
+            s_last = atomicAdd(cw.done + s, 1) + 1 == __ldg(cw.n_empty + s) ? 1 : 0;
         }
         __syncthreads();
-    }
-}
-
-// ordered compaction of one stream's cells (visiting order) into identity transforms
-__global__ void __launch_bounds__(256)
-collect_new_kernel(GridDesc gd, const uint32_t *__restrict__ cell_pt, const float *__restrict__ cell_score,
-                   float *__restrict__ new_T6, float *__restrict__ new_score, int *__restrict__ new_count,
-                   int new_cap, unsigned long long *counters) {
-    __shared__ int warp_tot[8];
-    __shared__ int base;
-    const int s = blockIdx.x;
-    const int cells = gd.ncx * gd.ncy;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (threadIdx.x == 0) base = 0;
-    __syncthreads();
-    for (int c0 = 0; c0 < cells; c0 += 256) {
-        const int c = c0 + threadIdx.x;
-        const uint32_t pt = c < cells ? __ldg(cell_pt + (size_t)s * cells + c) : 0xFFFFFFFFu;
-        const bool has = pt != 0xFFFFFFFFu;
-        const unsigned m = __ballot_sync(0xffffffffu, has);
-        if (lane == 0) warp_tot[wid] = __popc(m);
-        __syncthreads();
-        int off = base;
-        for (int k = 0; k < wid; ++k) off += warp_tot[k];
-        const int rank = off + __popc(m & ((1u << lane) - 1u));
-        if (has && rank < new_cap) {
-            float *T = new_T6 + ((size_t)s * new_cap + rank) * 6;
-            T[0] = 1.0f; T[1] = 0.0f; T[2] = (float)(pt & 0xFFFFu);
-            T[3] = 0.0f; T[4] = 1.0f; T[5] = (float)(pt >> 16);
-            if (new_score) new_score[(size_t)s * new_cap + rank] = __ldg(cell_score + (size_t)s * cells + c);
+        if (s_last) {
+            __threadfence();
+            collect_stream(gd, s, cell_pt, cell_score, new_T6, new_score, cw.new_count, new_cap, counters, wbest);
+            if (threadIdx.x == 0) cw.done[s] = 0;  // ready for the next frame
+            __syncthreads();
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            int t = 0;
-            for (int k = 0; k < 8; ++k) t += warp_tot[k];
-            base += t;
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        const int n = base < new_cap ? base : new_cap;
-        new_count[s] = n;
-        if (counters) atomicAdd(counters + CNT_DETECTED, (unsigned long long)n);
     }
 }
 
@@ -244,28 +256,20 @@ __global__ void mark_occupancy_xy_kernel(GridDesc gd, const uint32_t *__restrict
 }  // namespace
 
 cudaError_t detect_cells(const GridDesc &gd, const uint8_t *img0, size_t stride, size_t pitch, int streams,
-                         const uint8_t *occ, uint32_t *cell_pt, float *cell_score, uint32_t *list, int *list_count,
-                         int parity, cudaStream_t st) {
+                         const uint8_t *occ, const CellWork &cw, float *new_T6, float *new_score, int new_cap,
+                         unsigned long long *counters, bool list_first, cudaStream_t st) {
     const long long total = (long long)gd.ncx * gd.ncy * streams;
     if (total <= 0) return cudaSuccess;
-    int *cnt = list_count + (parity & 1), *other = list_count + ((parity & 1) ^ 1);
-    list_empty_cells_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gd, streams, occ, cell_pt, cell_score, list,
-                                                                             cnt, other);
+    if (list_first)  // stateless path: the frame path gets its list from the compaction kernel
+        list_empty_cells_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gd, streams, occ, cw.cell_pt, cw.cell_score,
+                                                                                 cw.list, cw.list_count, cw.next_count,
+                                                                                 cw.n_empty);
     // one resident wave of CTAs looping over the list (measured: 23 us; one CTA per candidate cell, most of
     // them exiting at once, 31 us)
     const long long wave = (long long)sm_count() * 8;
     long long blocks = total < wave ? total : wave;
-    detect_list_kernel<<<(unsigned)blocks, kDetThreads, 0, st>>>(gd, img0, stride, pitch, list, cnt, cell_pt,
-                                                                 cell_score);
-    return cudaGetLastError();
-}
-
-cudaError_t collect_new_points(const GridDesc &gd, int streams, const uint32_t *cell_pt, const float *cell_score,
-                               float *new_T6, float *new_score, int *new_count, int new_cap,
-                               unsigned long long *counters, cudaStream_t st) {
-    if (streams <= 0) return cudaSuccess;
-    collect_new_kernel<<<streams, 256, 0, st>>>(gd, cell_pt, cell_score, new_T6, new_score, new_count, new_cap,
-                                                counters);
+    detect_list_kernel<<<(unsigned)blocks, kDetThreads, 0, st>>>(gd, img0, stride, pitch, cw, new_T6, new_score, new_cap,
+                                                                 counters);
     return cudaGetLastError();
 }
 

@@ -1258,6 +1258,9 @@ void pyr_plan_destroy(PyrPlan *p) {
 
 const PyrDesc &pyr_plan_desc(const PyrPlan *p) { return p->pd; }
 
+int pyr_plan_parity(const PyrPlan *p) { return p->tile_parity; }
+void pyr_plan_set_parity(PyrPlan *p, int parity) { p->tile_parity = parity & 1; }
+
 cudaError_t pyr_plan_reserve(PyrPlan *p, int n_images) {
     if (!p->do4 || (size_t)n_images <= p->g8_images) return cudaSuccess;
     if (p->d_g8) cudaFree(p->d_g8);

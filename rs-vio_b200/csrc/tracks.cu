@@ -43,7 +43,7 @@ __device__ __forceinline__ int block_rank(bool keep, int *warp_tot, int *base) {
 __global__ void __launch_bounds__(kThreads)
 compact_tracks_kernel(TableView in, const float *__restrict__ lk_T6, const int32_t *__restrict__ lk_status,
                       TableView out, int cap, int streams, GridDesc gd, uint8_t *__restrict__ occ, int have_prev,
-                      unsigned long long *counters, int *__restrict__ err_clear) {
+                      unsigned long long *counters, int *__restrict__ err_clear, CellWork cw) {
     // the overflow flag the merge kernel of this frame may raise (its previous use, two frames ago, has been read)
     if (err_clear && blockIdx.x == 0 && threadIdx.x == 0) *err_clear = 0;
     __shared__ int warp_tot[kWarps];
@@ -85,6 +85,35 @@ compact_tracks_kernel(TableView in, const float *__restrict__ lk_T6, const int32
     if (threadIdx.x == 0) {
         out.counts[g] = base;
         if (counters && g == 0) atomicAdd(counters + CNT_FRAMES, (unsigned long long)streams);
+    }
+    // The work list of the detection kernel (detect_key_points visits the cells without a tracked point,
+    // image_utilities.rs:141-149): the CTA that built a stream's occupancy grid appends that stream's empty cells
+    // (any order: results are per cell) and initialises every cell to "no point".
+    if (cw.list && cam0) {
+        if (g == 0 && threadIdx.x == 0) *cw.next_count = 0;  // the other counter of the pair, for the next frame
+        __syncthreads();  // occupancy complete (written by this CTA)
+        const int cells = gd.ncx * gd.ncy;
+        const int lane = threadIdx.x & 31;
+        int n_empty = 0;
+        for (int c0 = 0; c0 < cells; c0 += kThreads) {
+            const int cell = c0 + threadIdx.x;
+            bool empty = false;
+            if (cell < cells) {
+                const int cx = cell / gd.ncy, cy = cell - cx * gd.ncy;  // visiting order: x outer, y inner
+                empty = my_occ[(size_t)cy * gd.occ_cols + cx] == 0;
+                cw.cell_pt[(size_t)g * cells + cell] = 0xFFFFFFFFu;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, empty);
+            int at = 0;
+            if (lane == 0 && m) at = atomicAdd(cw.list_count, __popc(m));
+            at = __shfl_sync(0xffffffffu, at, 0);
+            if (empty) cw.list[at + __popc(m & ((1u << lane) - 1u))] = (uint32_t)((size_t)g * cells + cell);
+            n_empty += __syncthreads_count(empty);
+        }
+        if (threadIdx.x == 0) {
+            cw.n_empty[g] = n_empty;
+            if (n_empty == 0) cw.new_count[g] = 0;  // nobody will collect this stream
+        }
     }
 }
 
@@ -212,9 +241,9 @@ remove_ids_kernel(TableView in, TableView out, int cap, int streams, int stream,
 
 cudaError_t compact_tracks(const TableView &in, const float *lk_T6, const int32_t *lk_status, const TableView &out,
                            int groups, int cap, int streams, const GridDesc &gd, uint8_t *occ, int have_prev,
-                           unsigned long long *counters, int *err_clear, cudaStream_t st) {
+                           unsigned long long *counters, int *err_clear, const CellWork &cw, cudaStream_t st) {
     compact_tracks_kernel<<<groups, kThreads, 0, st>>>(in, lk_T6, lk_status, out, cap, streams, gd, occ, have_prev,
-                                                       counters, err_clear);
+                                                       counters, err_clear, cw);
     return cudaGetLastError();
 }
 
