@@ -26,7 +26,8 @@
 //  pyr_deep_kernel    levels 4 and 5 from G_8 (exact integers).  There the reference's horizontal
 //      f32 accumulation is no longer exact (26 > 24 bits), but its error is < 2^-10 grey levels,
 //      so round(N / D) is the reference's byte unless frac(N / D) is within 2^-10 of 1/2; those
-//      rare outputs are recomputed on the spot, warp-cooperatively, with the faithful f32 chains.
+//      rare outputs go to a queue that extra CTAs of the following pyr_generic_kernel launch drain as
+//      1x1 tiles with the faithful f32 chains.
 //  pyr_generic_kernel faithful f32 chains, one CTA per tile descriptor: the outermost ring of every
 //      dyadic level (truncated windows: weights are renormalised by a non-power-of-two sum,
 //      nothing is exact) as 1-row / 1-column tiles, whole levels whose ratio is not a power of
@@ -94,16 +95,14 @@ struct TileDesc {
     int32_t ox0, oy0;
 };
 
-__global__ void __launch_bounds__(kGenThreads)
-pyr_generic_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ PyrTaps taps,
-                   const TileDesc *__restrict__ tiles, const uint8_t *__restrict__ src0,
-                   const uint8_t *__restrict__ src1, int split, size_t stride, size_t pitch,
-                   uint8_t *__restrict__ dst) {
-    __shared__ __align__(16) float v[kGenSmemFloats];
-    const int img = blockIdx.y;
+// a near-tie output of the deep dyadic kernel, queued for the faithful chains: x = image, y = lev << 28 | oy << 14 | ox
+typedef uint2 TieEntry;
+
+__device__ __forceinline__ void generic_tile(const PyrDesc &pd, const PyrTaps &taps, const TileDesc td, int img,
+                                             const uint8_t *__restrict__ src0, const uint8_t *__restrict__ src1, int split,
+                                             size_t stride, size_t pitch, uint8_t *__restrict__ dst, float *__restrict__ v) {
     const uint8_t *__restrict__ src = image_ptr(src0, src1, split, img, pitch);
     uint8_t *__restrict__ out = dst + (size_t)img * pd.pyr_stride;
-    const TileDesc td = tiles[blockIdx.x];
     const int lev = td.lev;
     const int w0 = pd.lv[0].w;
 
@@ -149,7 +148,7 @@ pyr_generic_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ P
             // u8 -> f32 without the quarter-rate I2F: one PRMT drops byte j into the mantissa of 2^23
             // (0x4B0000bb == 8388608 + b), one exact FADD removes the 2^23.  This loop is conversion-bound otherwise.
             constexpr float kTwo23 = 8388608.0f;
-#pragma unroll 8  // the loads do not depend on the f32 chains: 8 in flight per thread
+#pragma unroll 16  // the loads do not depend on the f32 chains: 16 in flight per thread
             for (int k = 0; k < n; ++k) {
                 const uint32_t q = __ldg(reinterpret_cast<const uint32_t *>(p + (size_t)k * stride));
                 const float wk = __ldg(wy + k);
@@ -190,6 +189,60 @@ pyr_generic_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ P
     }
 }
 
+// One CTA per static tile descriptor (blockIdx.x < n_static, image blockIdx.y); the remaining CTAs of the grid drain
+// the tie queue of pyr_deep_kernel (any image).
+__global__ void __launch_bounds__(kGenThreads)
+pyr_generic_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ PyrTaps taps,
+                   const TileDesc *__restrict__ tiles, int n_static, const TieEntry *__restrict__ tie_queue,
+                   const unsigned *__restrict__ tie_count, const uint8_t *__restrict__ src0,
+                   const uint8_t *__restrict__ src1, int split, size_t stride, size_t pitch,
+                   uint8_t *__restrict__ dst) {
+    __shared__ __align__(16) float v[kGenSmemFloats];
+    if ((int)blockIdx.x < n_static) {
+        generic_tile(pd, taps, tiles[blockIdx.x], blockIdx.y, src0, src1, split, stride, pitch, dst, v);
+        return;
+    }
+    // Tie workers: one WARP per queued output (an interior output of dyadic level 4 or 5: complete 2r x 2r window).
+    // A lane runs the vertical f32 chain of window column `lane` (and lane + 32 at level 5) with all its loads in
+    // flight at once, then every lane walks the horizontal chain in tap order over shuffled column values.
+    const int lane = threadIdx.x & 31, wpb = kGenThreads / 32;
+    const unsigned workers = (gridDim.x - n_static) * gridDim.y * wpb;
+    const unsigned cnt = *tie_count;
+    for (unsigned i = (blockIdx.y * (gridDim.x - n_static) + (blockIdx.x - n_static)) * wpb + (threadIdx.x >> 5); i < cnt;
+         i += workers) {
+        const TieEntry e = tie_queue[i];
+        const int lev = (int)(e.y >> 28), ox = (int)(e.y & 0x3fffu), oy = (int)((e.y >> 14) & 0x3fffu), img = (int)e.x;
+        const uint8_t *__restrict__ src = image_ptr(src0, src1, split, img, pitch);
+        const TapTable tx = taps.x[lev], ty = taps.y[lev];
+        const int left = __ldg(tx.left + ox), nx = __ldg(tx.cnt + ox), top = __ldg(ty.left + oy), ny = __ldg(ty.cnt + oy);
+        const float *__restrict__ wy = ty.w + (size_t)oy * ty.kmax;
+        const float *__restrict__ wx = tx.w + (size_t)ox * tx.kmax;
+        float vc[2], wc[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int kx = lane + 32 * h;
+            float t = 0.0f;
+            if (kx < nx) {
+                const uint8_t *__restrict__ p = src + (size_t)top * stride + (left + kx);
+#pragma unroll 16
+                for (int ky = 0; ky < ny; ++ky) t = __fadd_rn(t, __fmul_rn((float)__ldg(p + (size_t)ky * stride), __ldg(wy + ky)));
+            }
+            vc[h] = t;
+            wc[h] = kx < nx ? __ldg(wx + kx) : 0.0f;
+        }
+        float t = 0.0f;
+        for (int k = 0; k < nx; ++k) {  // nx <= 64 (levels 4, 5)
+            const float vk = __shfl_sync(0xffffffffu, k < 32 ? vc[0] : vc[1], k & 31);
+            const float wk = __shfl_sync(0xffffffffu, k < 32 ? wc[0] : wc[1], k & 31);
+            t = __fadd_rn(t, __fmul_rn(vk, wk));
+        }
+        if (lane == 0) {
+            t = fminf(fmaxf(t, 0.0f), 255.0f);
+            dst[(size_t)img * pd.pyr_stride + pd.lv[lev].off + (size_t)oy * pd.lv[lev].w + ox] = (uint8_t)__float2uint_rz(roundf(t));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // fast dyadic kernel: levels 0..NA (NA <= 3) from one shared-memory tile
 // ------------------------------------------------------------------------------------------
@@ -203,7 +256,13 @@ pyr_generic_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ P
 #ifndef PYR_OROUND
 #define PYR_OROUND 1        // 1: rounding constant folded into the O accumulators
 #endif
-constexpr int TW = 256, TH = 64;          // base-image tile owned by one CTA (TH = 32 with NSEG = 2 measured the same on C1, slower with NA = 3)
+#ifndef PYR_TH
+#define PYR_TH 48
+#endif
+// base-image tile owned by one CTA.  TH = 48: 480 and 1200 rows divide evenly (no half-empty bottom tiles) and the
+// 3-level variant fits 8 CTAs per SM instead of 7; measured against 64 / 32 on 128 x 752x480: 36.7 / 39.5 / 37.4 us,
+// no shape slower (gpurun_out/r2/pyr1/ab.log).
+constexpr int TW = 256, TH = PYR_TH;
 constexpr int PITCH = TW + 32;            // tile columns [X0 - 16, X0 + TW + 16), bytes per smem row
 constexpr int NCOL = TW / 8;              // stage-1 column threads: 4 level-1 columns (8 px) each = one warp
 constexpr int NSEG = 4;                   // stage-1 row segments = warps per CTA
@@ -242,6 +301,7 @@ struct FastParams {
     int nbuf;             // tile buffers per CTA: 2 = next tile prefetched during compute, 1 = more CTAs per SM
     unsigned *tile_counter;  // single-buffer mode: tiles are handed out dynamically from this counter ...
     unsigned *tile_counter_next;  // ... and the other one of the pair is cleared for the next launch
+    unsigned *tie_count;     // deep levels follow: their tie queue is emptied here (stream order: before pyr_deep_kernel)
 };
 
 // n / d with the host-made multiplier m = ceil(2^32 / d); exact while n * d < 2^32 (the host checks)
@@ -528,8 +588,13 @@ struct FastSmem {
     static constexpr int bytes = off_mbar + 16 + 128;                    // + slack for the 128-B base alignment
 };
 
+#ifdef PYR_MINB
+#define PYR_BOUNDS __launch_bounds__(NTA, PYR_MINB)
+#else
+#define PYR_BOUNDS __launch_bounds__(NTA)
+#endif
 template <int NA>
-__global__ void __launch_bounds__(NTA)
+__global__ void PYR_BOUNDS
 pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CUtensorMap map0,
                 const __grid_constant__ CUtensorMap map1) {
     using C = FastCfg<NA>;
@@ -569,6 +634,7 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
         mbar_init(mbar0, 1);
         mbar_init(mbar0 + 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (blockIdx.x == 0 && P.tie_count) *P.tie_count = 0u;
     }
     __syncthreads();
     const bool dbl = P.nbuf == 2;
@@ -891,22 +957,16 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
 constexpr int kDeepThreads = 256;
 
 __global__ void __launch_bounds__(kDeepThreads)
-pyr_deep_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ PyrTaps taps,
-                const uint32_t *__restrict__ g8, int n_images, int do5, const uint8_t *__restrict__ src0,
-                const uint8_t *__restrict__ src1, int split, size_t stride, size_t pitch, uint8_t *__restrict__ dst) {
-    __shared__ float vbuf[kDeepThreads / 32][2 * 64 + 8];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+pyr_deep_kernel(const __grid_constant__ PyrDesc pd, const uint32_t *__restrict__ g8, int n_images, int do5,
+                TieEntry *__restrict__ tie_queue, unsigned *__restrict__ tie_count, uint8_t *__restrict__ dst) {
     const int w8 = pd.lv[0].w / 8, h8 = pd.lv[0].h / 8;
     const int w4 = pd.lv[4].w, h4 = pd.lv[4].h;
     const int n4 = max(w4 - 2, 0) * max(h4 - 2, 0);
     const int w5 = do5 ? pd.lv[5].w : 0, h5 = do5 ? pd.lv[5].h : 0;
     const int n5 = do5 ? max(w5 - 2, 0) * max(h5 - 2, 0) : 0;
     const long long total = (long long)(n4 + n5) * n_images;
-    // warp-uniform trip count: the tie fix-up below is a warp-cooperative step
-    for (long long base = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < total;
-         base += (long long)gridDim.x * blockDim.x) {
-        const bool act = base + lane < total;
-        const long long idx = act ? base + lane : total - 1;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
         const int img = (int)(idx / (n4 + n5));
         int k = (int)(idx - (long long)img * (n4 + n5));
         const uint32_t *__restrict__ g = g8 + (size_t)img * w8 * h8;
@@ -939,39 +999,15 @@ pyr_deep_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ PyrT
         // at level 5: the outputs within 2^-11 resp. 2^-10 of a tie could round the other way (~0.2 % of them).
         const uint32_t frac = n & ((1u << shift) - 1u);
         const uint32_t dist = frac > half ? frac - half : half - frac;
-        const bool tie = act && dist <= (1u << (shift - (lev == 4 ? 11 : 10)));
-        if (act && !tie)
+        // Those outputs are not written here: they go to a queue that the extra CTAs of the following
+        // pyr_generic_kernel launch drain as 1x1 tiles with the reference's f32 chains from the base image.  (The first
+        // version recomputed them on the spot, one warp per tie: a 3-5 us serial detour for the unlucky warps, which
+        // decided the kernel's time -- 20-30 us for 3 MB of G_8.)
+        if (dist <= (1u << (shift - (lev == 4 ? 11 : 10)))) {
+            const unsigned slot = atomicAdd(tie_count, 1u);
+            tie_queue[slot] = make_uint2((unsigned)img, ((unsigned)lev << 28) | ((unsigned)oy << 14) | (unsigned)ox);
+        } else {
             dst[(size_t)img * pd.pyr_stride + pd.lv[lev].off + (size_t)oy * pd.lv[lev].w + ox] = (uint8_t)((n + half) >> shift);
-        // near ties: the warp recomputes them one by one with the reference's f32 chains from the base image
-        // (a lane per window column, then the horizontal chain in tap order)
-        unsigned todo = __ballot_sync(0xffffffffu, tie);
-        while (todo) {
-            const int from = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int f_img = __shfl_sync(0xffffffffu, img, from), f_lev = __shfl_sync(0xffffffffu, lev, from);
-            const int f_ox = __shfl_sync(0xffffffffu, ox, from), f_oy = __shfl_sync(0xffffffffu, oy, from);
-            const uint8_t *__restrict__ src = image_ptr(src0, src1, split, f_img, pitch);
-            const TapTable tx = taps.x[f_lev], ty = taps.y[f_lev];
-            const int left = tx.left[f_ox], nx = tx.cnt[f_ox];
-            const int top = ty.left[f_oy], ny = ty.cnt[f_oy];
-            const float *__restrict__ wy = ty.w + (size_t)f_oy * ty.kmax;
-            for (int kx = lane; kx < nx; kx += 32) {
-                const uint8_t *__restrict__ p = src + (size_t)top * stride + (left + kx);
-                float v = 0.0f;
-#pragma unroll 8  // independent loads: keep 8 in flight
-                for (int ky = 0; ky < ny; ++ky) v = __fadd_rn(v, __fmul_rn((float)__ldg(p + (size_t)ky * stride), wy[ky]));
-                vbuf[wib][kx] = v;
-            }
-            __syncwarp();
-            if (lane == 0) {
-                const float *__restrict__ wx = tx.w + (size_t)f_ox * tx.kmax;
-                float t = 0.0f;
-                for (int kx = 0; kx < nx; ++kx) t = __fadd_rn(t, __fmul_rn(vbuf[wib][kx], wx[kx]));
-                t = fminf(fmaxf(t, 0.0f), 255.0f);
-                dst[(size_t)f_img * pd.pyr_stride + pd.lv[f_lev].off + (size_t)f_oy * pd.lv[f_lev].w + f_ox] =
-                    (uint8_t)__float2uint_rz(roundf(t));
-            }
-            __syncwarp();
         }
     }
 }
@@ -1054,6 +1090,7 @@ struct PyrPlan {
     // scratch for deep levels (grown on demand)
     uint32_t *d_g8;
     size_t g8_images;
+    TieEntry *d_tie_queue;  // near-tie outputs of pyr_deep_kernel (capacity: every interior output of levels 4 / 5)
 };
 
 // tiles covering the output rectangle [x0, x0 + nx) x [y0, y0 + ny) of one level
@@ -1109,6 +1146,7 @@ cudaError_t pyr_plan_create(int w, int h, int levels, cudaStream_t st, PyrPlan *
     p->d_tiles = nullptr;
     p->d_g8 = nullptr;
     p->g8_images = 0;
+    p->d_tie_queue = nullptr;
     // one allocation for all tap tables
     size_t bytes = 0;
     struct Sz { int n_in, n_out, kmax; size_t off_left, off_cnt, off_w; };
@@ -1176,8 +1214,8 @@ cudaError_t pyr_plan_create(int w, int h, int levels, cudaStream_t st, PyrPlan *
     p->do4 = p->n_fast >= 4;
     p->do5 = p->n_fast >= 5;
     if (p->n_a >= 1) {
-        e = cudaMalloc((void **)&p->d_tile_counter, 2 * sizeof(unsigned));
-        if (e == cudaSuccess) e = cudaMemsetAsync(p->d_tile_counter, 0, 2 * sizeof(unsigned), st);
+        e = cudaMalloc((void **)&p->d_tile_counter, 4 * sizeof(unsigned));  // [0], [1]: tiles, [2]: tie queue length
+        if (e == cudaSuccess) e = cudaMemsetAsync(p->d_tile_counter, 0, 4 * sizeof(unsigned), st);
         p->tile_parity = 0;
         if (e != cudaSuccess) {
             pyr_plan_destroy(p);
@@ -1253,6 +1291,7 @@ void pyr_plan_destroy(PyrPlan *p) {
     if (p->d_tile_counter) cudaFree(p->d_tile_counter);
     if (p->d_tiles) cudaFree(p->d_tiles);
     if (p->d_g8) cudaFree(p->d_g8);
+    if (p->d_tie_queue) cudaFree(p->d_tie_queue);
     delete p;
 }
 
@@ -1264,9 +1303,14 @@ void pyr_plan_set_parity(PyrPlan *p, int parity) { p->tile_parity = parity & 1; 
 cudaError_t pyr_plan_reserve(PyrPlan *p, int n_images) {
     if (!p->do4 || (size_t)n_images <= p->g8_images) return cudaSuccess;
     if (p->d_g8) cudaFree(p->d_g8);
+    if (p->d_tie_queue) cudaFree(p->d_tie_queue);
     p->d_g8 = nullptr;
+    p->d_tie_queue = nullptr;
     const size_t per = (size_t)(p->pd.lv[0].w / 8) * (p->pd.lv[0].h / 8);
     cudaError_t e = cudaMalloc((void **)&p->d_g8, per * n_images * sizeof(uint32_t));
+    if (e != cudaSuccess) return e;
+    const size_t outs = (size_t)p->pd.lv[4].w * p->pd.lv[4].h + (p->do5 ? (size_t)p->pd.lv[5].w * p->pd.lv[5].h : 0);
+    e = cudaMalloc((void **)&p->d_tie_queue, outs * n_images * sizeof(TieEntry));
     if (e != cudaSuccess) return e;
     p->g8_images = (size_t)n_images;
     return cudaSuccess;
@@ -1292,7 +1336,8 @@ cudaError_t pyr_build(const PyrPlan *p, const uint8_t *src0, const uint8_t *src1
         uint8_t *d = dst + (size_t)first * p->pd.pyr_stride;
         if (!fast) {
             dim3 grid((unsigned)p->n_all, (unsigned)n, 1);
-            pyr_generic_kernel<<<grid, kGenThreads, 0, st>>>(p->pd, p->taps, p->d_tiles, s0, s1, sps, stride, pitch, d);
+            pyr_generic_kernel<<<grid, kGenThreads, 0, st>>>(p->pd, p->taps, p->d_tiles, p->n_all, nullptr, nullptr, s0, s1, sps,
+                                                             stride, pitch, d);
             if (n_launches) ++*n_launches;
             continue;
         }
@@ -1312,6 +1357,7 @@ cudaError_t pyr_build(const PyrPlan *p, const uint8_t *src0, const uint8_t *src1
             fp.magic_tx = magic_for((unsigned)p->tiles_x, tpi);
         }
         fp.nbuf = p->fast_nbuf;
+        fp.tie_count = p->do4 ? p->d_tile_counter + 2 : nullptr;
         {
             PyrPlan *mp = const_cast<PyrPlan *>(p);  // launches of one plan are stream ordered
             fp.tile_counter = p->d_tile_counter + mp->tile_parity;
@@ -1341,14 +1387,16 @@ cudaError_t pyr_build(const PyrPlan *p, const uint8_t *src0, const uint8_t *src1
             long long blocks = (items + kDeepThreads - 1) / kDeepThreads;
             if (blocks > sm_count() * 8) blocks = sm_count() * 8;
             if (blocks < 1) blocks = 1;
-            pyr_deep_kernel<<<(unsigned)blocks, kDeepThreads, 0, st>>>(p->pd, p->taps, p->d_g8, n, p->do5, s0, s1, sps,
-                                                                        stride, pitch, d);
+            pyr_deep_kernel<<<(unsigned)blocks, kDeepThreads, 0, st>>>(p->pd, p->d_g8, n, p->do5, p->d_tie_queue,
+                                                                        p->d_tile_counter + 2, d);
             if (n_launches) ++*n_launches;
         }
         if (p->n_rest > 0) {  // ring of the dyadic levels + whole non-dyadic levels
-            dim3 ggrid((unsigned)p->n_rest, (unsigned)n, 1);
-            pyr_generic_kernel<<<ggrid, kGenThreads, 0, st>>>(p->pd, p->taps, p->d_tiles + p->n_all, s0, s1, sps, stride,
-                                                             pitch, d);
+            // + the CTAs that drain the tie queue of pyr_deep_kernel: ~0.2 % of the level-4/5 outputs, ~2 us each
+            const int tie_ctas = p->do4 ? (n >= 64 ? 1 : (n >= 8 ? 2 : 4)) : 0;  // x 8 warps, one tie per warp at a time
+            dim3 ggrid((unsigned)(p->n_rest + tie_ctas), (unsigned)n, 1);
+            pyr_generic_kernel<<<ggrid, kGenThreads, 0, st>>>(p->pd, p->taps, p->d_tiles + p->n_all, p->n_rest, p->d_tie_queue,
+                                                             p->d_tile_counter + 2, s0, s1, sps, stride, pitch, d);
             if (n_launches) ++*n_launches;
         }
     }
