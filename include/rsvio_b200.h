@@ -257,13 +257,12 @@ rsvio_status rsvio_unproject_points(int32_t device, const rsvio_camera_model *mo
 rsvio_status rsvio_convert_to_luma8(int32_t device, const void *src, int32_t width, int32_t height,
                                     size_t stride_bytes, int32_t pixel_format, uint8_t *out);
 
-/* ---- row f-2, first slice: the tracking core of the reference's second tracker (`feature_tracker` crate) ----
+/* ---- row f-2: the tracking core of the reference's second tracker (`feature_tracker` crate) ----
  * track_points (feature_tracker/src/feature_tracker/feature_tracking.rs:16-59) for n points between two f32
  * pyramids (host pointers; level l is heights[l] x widths[l] floats, dense): bicubic sampler, SSD patch of 52
  * samples (radius 7 px), LM-damped Gauss-Newton on SE(2) with twist [theta, vx, vy], forward-backward test
  * (< 2 px).  out_T4[i] = (cos, sin, tx, ty) of the forward isometry; status[i]: 0 tracked, 1 forward pass left
- * the image, 2 backward pass left the image, 3 forward-backward distance >= 2 px.  The pyramids (crate B's
- * chained f32 `resize`, optional blur) and the detection are not on the device yet. */
+ * the image, 2 backward pass left the image, 3 forward-backward distance >= 2 px.  SSD cost. */
 rsvio_status rsvio_b_track_points(int32_t device, const float *const *pyr0, const float *const *pyr1,
                                   const int32_t *widths, const int32_t *heights, int32_t levels,
                                   const float *points_xy, int32_t n, int32_t max_iteration, float lm_lambda,
@@ -276,6 +275,67 @@ rsvio_status rsvio_b_pyramid_dims(int32_t width, int32_t height, int32_t levels,
                                   int32_t *heights);
 rsvio_status rsvio_b_build_pyramid(int32_t device, const float *image, int32_t width, int32_t height, int32_t levels,
                                    double ratio, float *const *out_levels);
+
+/* ---- row f-2: the rest of crate B -- preprocessing blur, LSSD cost, Shi-Tomasi detection, the stateful tracker ----
+ * matching cost of Patch52 (feature_tracker/src/patch.rs:4-8); FeatureTracker::process_frame hard-codes SSD
+ * (feature_tracker.rs:125), LSSD is reachable through the public `patch` module */
+#define RSVIO_B_COST_SSD 0
+#define RSVIO_B_COST_LSSD 1
+/* rsvio_b_track_points with the matching cost as a parameter */
+rsvio_status rsvio_b_track_points_cost(int32_t device, const float *const *pyr0, const float *const *pyr1,
+                                       const int32_t *widths, const int32_t *heights, int32_t levels,
+                                       const float *points_xy, int32_t n, int32_t max_iteration, float lm_lambda,
+                                       int32_t matching_cost, float *out_T4, int32_t *status);
+/* `image::imageops::blur(image, sigma)` as build_image_pyramid applies it (image_operations.rs:58-62); host
+ * pointers, height x width floats in [0, 1] */
+rsvio_status rsvio_b_blur(int32_t device, const float *image, int32_t width, int32_t height, float sigma, float *out);
+/* shi_tomasi_score (feature_tracker/src/feature_tracker/feature_detection.rs:83-165); host pointers */
+rsvio_status rsvio_b_shi_tomasi_score(int32_t device, const float *image, int32_t width, int32_t height,
+                                      float detection_blur, float *out_score);
+/* add_points (feature_detection.rs:48-80) on a finest-level image: block non-maximum suppression (radius 1) of the
+ * score map, the n_tracked tracked features injected with score max + 1, `local_maxima(min_dist)`, border filter.
+ * out_xy = (x, y) u32 pairs of the new corners in (y, x) order; *n = their number (at most cap are written). */
+rsvio_status rsvio_b_add_points(int32_t device, const float *image, int32_t width, int32_t height,
+                                const float *tracked_xy, int32_t n_tracked, float threshold, uint32_t min_dist,
+                                float detection_blur, uint32_t *out_xy, size_t cap, size_t *n);
+
+/* FeatureTrackingConfig (feature_tracker/src/feature_tracker.rs:24-38) + the image size, device and matching cost */
+typedef struct rsvio_b_config {
+    int32_t width, height;              /* fixed for the handle's lifetime */
+    int32_t nlevels;                    /* number of pyramid levels */
+    double ratio;                       /* ratio of size between levels */
+    int32_t preprocessing_blur;         /* bool */
+    float preprocessing_blur_sigma;
+    float detection_threshold;
+    uint32_t detection_min_dist;
+    float detection_blur;
+    int32_t optical_flow_max_iter;
+    float optical_flow_lm_lambda;
+    int32_t matching_cost;              /* RSVIO_B_COST_SSD (what process_frame uses) | RSVIO_B_COST_LSSD */
+    int32_t device;
+    int32_t max_features;               /* capacity of the feature table; 0 = derived from min_dist */
+} rsvio_b_config;
+/* the values of feature_tracker/config/config.yaml (5 levels, ratio 2, blur 2.0, threshold 2.5, min_dist 15,
+ * detection blur 6.0, 25 iterations, lambda 0.1), SSD */
+void rsvio_b_config_default(rsvio_b_config *cfg);
+
+typedef struct rsvio_b_tracker rsvio_b_tracker;
+/* FeatureTracker::new (feature_tracker.rs:59-69; the viewer is dropped) */
+rsvio_status rsvio_b_tracker_create(const rsvio_b_config *cfg, rsvio_b_tracker **out);
+void rsvio_b_tracker_destroy(rsvio_b_tracker *t);
+/* FeatureTracker::process_frame (feature_tracker.rs:77-185): image = height x width floats in [0, 1] (a
+ * FloatGrayImage, dense).  Synchronous like the reference: returns when the frame's features are on the host. */
+rsvio_status rsvio_b_tracker_process_frame(rsvio_b_tracker *t, const float *image, int64_t frame_id);
+/* the frame handed back by process_frame (`previous_frame_pyramid.0.features`): tracked features first, in their old
+ * order, then the new ones in (y, x) order with fresh ids; *n_new = how many of them are new */
+rsvio_status rsvio_b_tracker_num_features(const rsvio_b_tracker *t, int32_t *n, int32_t *n_new);
+rsvio_status rsvio_b_tracker_get_features(const rsvio_b_tracker *t, uint64_t *ids, float *xy, size_t cap, size_t *n);
+/* get_pyramid (feature_tracker.rs:190-193): level sizes and one level of the last frame's pyramid (host pointer,
+ * heights[l] x widths[l] floats); RSVIO_ERR_INVALID_ARG before the first frame */
+rsvio_status rsvio_b_tracker_pyramid_dims(const rsvio_b_tracker *t, int32_t *levels, int32_t *widths, int32_t *heights);
+rsvio_status rsvio_b_tracker_get_pyramid_level(rsvio_b_tracker *t, int32_t level, float *out);
+/* kernel time of the last process_frame (CUDA events on the handle's stream, upload and download excluded) */
+rsvio_status rsvio_b_tracker_last_frame_ms(const rsvio_b_tracker *t, float *ms);
 
 #ifdef __cplusplus
 }

@@ -1431,8 +1431,16 @@ rsvio_status rsvio_b_track_points(int32_t device, const float *const *pyr0, cons
                                   const int32_t *widths, const int32_t *heights, int32_t levels,
                                   const float *points_xy, int32_t n, int32_t max_iteration, float lm_lambda,
                                   float *out_T4, int32_t *status) {
+    return rsvio_b_track_points_cost(device, pyr0, pyr1, widths, heights, levels, points_xy, n, max_iteration, lm_lambda,
+                                     RSVIO_B_COST_SSD, out_T4, status);
+}
+
+rsvio_status rsvio_b_track_points_cost(int32_t device, const float *const *pyr0, const float *const *pyr1,
+                                       const int32_t *widths, const int32_t *heights, int32_t levels,
+                                       const float *points_xy, int32_t n, int32_t max_iteration, float lm_lambda,
+                                       int32_t matching_cost, float *out_T4, int32_t *status) {
     if (!pyr0 || !pyr1 || !widths || !heights || levels < 1 || levels > RSVIO_MAX_LEVELS || !points_xy || n < 0 ||
-        max_iteration < 0 || !out_T4 || !status)
+        max_iteration < 0 || !out_T4 || !status || (matching_cost != RSVIO_B_COST_SSD && matching_cost != RSVIO_B_COST_LSSD))
         return RSVIO_ERR_INVALID_ARG;
     for (int l = 0; l < levels; ++l)
         if (!pyr0[l] || !pyr1[l] || widths[l] < 1 || heights[l] < 1) return RSVIO_ERR_INVALID_ARG;
@@ -1459,7 +1467,7 @@ rsvio_status rsvio_b_track_points(int32_t device, const float *const *pyr0, cons
     CU_TRY0(cudaMalloc((void **)&d_T, sizeof(float) * 4 * (size_t)n));
     CU_TRY0(cudaMalloc((void **)&d_st, sizeof(int32_t) * (size_t)n));
     CU_TRY0(H2D(d_pts, points_xy, sizeof(float) * 2 * (size_t)n));
-    CU_TRY0(trackb_points(d_lv[0], d_lv[1], w, h, levels, d_pts, n, max_iteration, lm_lambda, d_T, d_st, cs.s));
+    CU_TRY0(trackb_points(d_lv[0], d_lv[1], w, h, levels, d_pts, n, max_iteration, lm_lambda, matching_cost, d_T, d_st, cs.s));
     CU_TRY0(cudaStreamSynchronize(cs.s));
     CU_TRY0(D2H(out_T4, d_T, sizeof(float) * 4 * (size_t)n));
     CU_TRY0(D2H(status, d_st, sizeof(int32_t) * (size_t)n));

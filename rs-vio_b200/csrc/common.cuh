@@ -222,13 +222,50 @@ cudaError_t convert_to_luma8(const uint8_t *d_src, size_t stride_bytes, int w, i
                              cudaStream_t st);
 
 // row f-2, first slice: crate B's tracking core (trackb.cu).  Device pointers; out_T4 = n x (cos, sin, tx, ty)
+// cost: RSVIO_B_COST_SSD / RSVIO_B_COST_LSSD
 cudaError_t trackb_points(const float *const *d_a, const float *const *d_b, const int *w, const int *h, int levels,
-                          const float *d_pts, int n, int max_it, float lambda, float *d_out_T4, int32_t *d_status,
-                          cudaStream_t st);
+                          const float *d_pts, int n, int max_it, float lambda, int cost, float *d_out_T4,
+                          int32_t *d_status, cudaStream_t st);
 
 // one level of crate B's pyramid: Triangle resize of an f32 image (d_tmp: h_out x w_in floats of scratch)
 cudaError_t resize_triangle_f32(const float *d_src, int w_in, int h_in, float *d_tmp, float *d_dst, int w_out, int h_out,
                                 cudaStream_t st);
+
+
+// ---- detectb.cu: crate B's blur, Shi-Tomasi detection and feature bookkeeping (device pointers) ----
+struct GaussTab {     // un-normalised gaussian(d, sigma) for d = -K .. K, made on the host (libm expf); support = 2 sigma
+    float g[2 * 64 + 1];
+    int K;
+    float support;
+};
+// imageops::blur: d_tmp and d_dst are h x w floats; d_dst may alias d_src's successor buffers but not d_src / d_tmp
+cudaError_t blurb_gaussian(const float *d_src, int w, int h, const GaussTab &G, float *d_tmp, float *d_dst, cudaStream_t st);
+// shi_tomasi_score: planes_a / planes_b are 3 x h x w floats of scratch, box_r the three box radii of fast_blur
+cudaError_t scoreb_map(const float *d_img, int w, int h, const int box_r[3], float *d_planes_a, float *d_planes_b,
+                       float *d_score, cudaStream_t st);
+enum { DB_NCAND = 0, DB_NSURV, DB_MAXSCORE, DB_LASTROW, DB_N };
+struct DetectB {
+    const float *score;       // h x w
+    int w, h;
+    float threshold;
+    int min_dist;
+    float *cand;              // h x w scratch
+    uint8_t *fmap;            // h x w scratch
+    uint32_t *list, *surv;    // ceil(w/2) * ceil(h/2) entries each
+    unsigned *cnt;            // DB_N counters, zero between frames
+    unsigned long long *ids;  // feature table of the frame: [0, *n_feat) tracked features, new ones are appended
+    float *xy;
+    int *n_feat;              // device
+    int n_tracked_host;       // upper bound of *n_feat known to the host (0: no tracked features)
+    int cap;
+    unsigned long long *last_id;  // device: next id
+    int *n_new;               // device: number of appended features
+    int *err;                 // device: set when the table overflowed
+};
+cudaError_t detectb_new_points(const DetectB &d, cudaStream_t st);
+// tracked features of the new frame: status 0, old order, xy = T * xy_in
+cudaError_t keepb_tracked(const unsigned long long *ids_in, const float *xy_in, int n, const float *T4, const int32_t *status,
+                          unsigned long long *ids_out, float *xy_out, int *n_out, cudaStream_t st);
 
 }  // namespace rsvio
 #endif

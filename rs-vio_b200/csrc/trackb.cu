@@ -1,5 +1,5 @@
-// trackb.cu -- first CUDA slice of row f-2: the tracking core of the reference's second tracker (the
-// `feature_tracker` crate, "crate B"), stateless.  One warp per point, forward and backward pass.
+// trackb.cu -- row f-2: the tracking core of the reference's second tracker (the `feature_tracker` crate,
+// "crate B") and its chained f32 pyramid.  One warp per point, forward and backward pass.
 //
 // Replaces (paths relative to the reference repository):
 //   track_points / track_point / track_point_at_level   feature_tracker/src/feature_tracker/feature_tracking.rs:16-192
@@ -7,10 +7,11 @@
 //   Patch52::new, jacobian, residuals_ssd               feature_tracker/src/patch.rs:57-164, 244-255
 //   interpolate_bicubic / d_interpolate_bicubic         feature_tracker/src/image_operations.rs:140-282
 //   in_bounds                                           image_operations.rs:4-7
-// The f32 pyramids are inputs here (crate B's chained `resize` and its blur are not on the device yet), and
-// neither detection nor the stateful FeatureTracker exist: this kernel is the LK skeleton of tracker A with a
-// 4x4 Catmull-Rom gather, absolute-coordinate Jacobians, an LM-damped Hessian and isometries instead of
-// affine matrices.  Checked against oracle/crate_b.py (itself pinned by the reference's own unit tests).
+//   residuals_lssd, compute_intensities_and_jacobian_lssd  patch.rs:84-105, 167-216
+// The kernel is the LK skeleton of tracker A with a 4x4 Catmull-Rom gather, absolute-coordinate Jacobians, an
+// LM-damped Hessian and isometries instead of affine matrices.  Blur, detection and the stateful FeatureTracker are
+// in detectb.cu / apib.cu.  Checked against oracle/crate_b.py (its tracking core is pinned by the reference's own
+// unit tests).
 #include "common.cuh"
 
 namespace rsvio {
@@ -147,8 +148,10 @@ __device__ __forceinline__ Iso exp_se2_b(float theta, float v0, float v1) {
 }
 
 // track_point_at_level; false == OutOfBound.  All lanes hold the same T and take the same exits.
+// cost: 0 SSD (patch.rs:69-83, 119-164), 1 LSSD (patch.rs:84-105, 167-216: target samples divided by their mean, the
+// template intensities stay raw, quotient-rule Jacobian)
 __device__ bool track_level_b(const float *__restrict__ img0, const float *__restrict__ img1, int w, int h, float cx,
-                              float cy, Iso &T, int max_it, float lambda, int lane) {
+                              float cy, Iso &T, int max_it, float lambda, int cost, int lane) {
     float sx[2], sy[2], inten[2], J[2][3];
     bool has[2], valid[2];
     float g_x[2], g_y[2];
@@ -182,10 +185,25 @@ __device__ bool track_level_b(const float *__restrict__ img0, const float *__res
             gx = j < 0 ? 0.0f : (j < 32 ? a0 : a1);
             gy = j < 0 ? 0.0f : (j < 32 ? b0 : b1);
         }
+        g_x[k] = has[k] ? gx : 0.0f;
+        g_y[k] = has[k] ? gy : 0.0f;
+    }
+    if (cost == 1) {  // dr/dpixel = (dI * mean - I * mean_dI) / mean^2
+        const float mean_i = warp_sum(inten[0] + inten[1]) / (float)kNP;
+        const float mean_gx = warp_sum(g_x[0] + g_x[1]) / (float)kNP, mean_gy = warp_sum(g_y[0] + g_y[1]) / (float)kNP;
+        const float m2 = mean_i * mean_i;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            g_x[k] = has[k] ? (g_x[k] * mean_i - inten[k] * mean_gx) / m2 : 0.0f;
+            g_y[k] = has[k] ? (g_y[k] * mean_i - inten[k] * mean_gy) / m2 : 0.0f;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
         // [gx gy] * [[-py, 1, 0], [px, 0, 1]]
-        J[k][0] = has[k] ? gx * (-sy[k]) + gy * sx[k] : 0.0f;
-        J[k][1] = has[k] ? gx : 0.0f;
-        J[k][2] = has[k] ? gy : 0.0f;
+        J[k][0] = has[k] ? g_x[k] * (-sy[k]) + g_y[k] * sx[k] : 0.0f;
+        J[k][1] = g_x[k];
+        J[k][2] = g_y[k];
     }
     // H = lambda I + J^T J, inverse by cofactors (nalgebra try_inverse of a 3x3)
     float h00 = 0, h01 = 0, h02 = 0, h11 = 0, h12 = 0, h22 = 0;
@@ -216,12 +234,19 @@ __device__ bool track_level_b(const float *__restrict__ img0, const float *__res
 
     for (int it = 0; it < max_it; ++it) {
         float b0 = 0.0f, b1 = 0.0f, b2 = 0.0f;
+        float tv[2];
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
             float px, py, v = 0.0f;
             iso_apply(T, sx[k], sy[k], px, py);
             const bool ok = has[k] && interp_b(img1, w, h, px, py, v);
-            const float res = has[k] ? (ok ? v : 0.0f) - inten[k] : 0.0f;
+            tv[k] = ok ? v : 0.0f;
+        }
+        float tmean = 1.0f;
+        if (cost == 1) tmean = warp_sum(tv[0] + tv[1]) / (float)kNP;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float res = has[k] ? (cost == 1 ? tv[k] / tmean : tv[k]) - inten[k] : 0.0f;
             b0 += J[k][0] * res;
             b1 += J[k][1] * res;
             b2 += J[k][2] * res;
@@ -246,7 +271,8 @@ __device__ bool track_level_b(const float *__restrict__ img0, const float *__res
     return true;
 }
 
-__device__ bool track_point_b(const PyrB &P, bool forward, float px, float py, Iso &T, int max_it, float lambda, int lane) {
+__device__ bool track_point_b(const PyrB &P, bool forward, float px, float py, Iso &T, int max_it, float lambda, int cost,
+                              int lane) {
     const float w0 = (float)P.w[0], h0 = (float)P.h[0];
     T.c = 1.0f;
     T.s = 0.0f;
@@ -256,7 +282,7 @@ __device__ bool track_point_b(const PyrB &P, bool forward, float px, float py, I
         const float scx = (float)wl / w0, scy = (float)hl / h0;
         const float cx = scx * (px + 0.5f) - 0.5f, cy = scy * (py + 0.5f) - 0.5f;
         const float *img0 = forward ? P.a[lev] : P.b[lev], *img1 = forward ? P.b[lev] : P.a[lev];
-        if (!track_level_b(img0, img1, wl, hl, cx, cy, T, max_it, lambda, lane)) return false;
+        if (!track_level_b(img0, img1, wl, hl, cx, cy, T, max_it, lambda, cost, lane)) return false;
         if (lev > 0) {
             T.tx = T.tx * ((float)P.w[lev - 1] / (float)wl);
             T.ty = T.ty * ((float)P.h[lev - 1] / (float)hl);
@@ -266,7 +292,7 @@ __device__ bool track_point_b(const PyrB &P, bool forward, float px, float py, I
 }
 
 __global__ void __launch_bounds__(128)
-trackb_kernel(const __grid_constant__ PyrB P, const float2 *__restrict__ pts, int n, int max_it, float lambda,
+trackb_kernel(const __grid_constant__ PyrB P, const float2 *__restrict__ pts, int n, int max_it, float lambda, int cost,
               float4 *__restrict__ out_T, int32_t *__restrict__ status) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -274,12 +300,12 @@ trackb_kernel(const __grid_constant__ PyrB P, const float2 *__restrict__ pts, in
     const float2 p = pts[warp];
     Iso T0, T1;
     int st = 0;
-    if (!track_point_b(P, true, p.x, p.y, T0, max_it, lambda, lane)) {
+    if (!track_point_b(P, true, p.x, p.y, T0, max_it, lambda, cost, lane)) {
         st = 1;  // forward pass left the image
     } else {
         float qx, qy;
         iso_apply(T0, p.x, p.y, qx, qy);
-        if (!track_point_b(P, false, qx, qy, T1, max_it, lambda, lane)) {
+        if (!track_point_b(P, false, qx, qy, T1, max_it, lambda, cost, lane)) {
             st = 2;  // backward pass left the image
         } else {
             float rx, ry;
@@ -297,8 +323,8 @@ trackb_kernel(const __grid_constant__ PyrB P, const float2 *__restrict__ pts, in
 }  // namespace
 
 cudaError_t trackb_points(const float *const *d_a, const float *const *d_b, const int *w, const int *h, int levels,
-                          const float *d_pts, int n, int max_it, float lambda, float *d_out_T4, int32_t *d_status,
-                          cudaStream_t st) {
+                          const float *d_pts, int n, int max_it, float lambda, int cost, float *d_out_T4,
+                          int32_t *d_status, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     PyrB P{};
     P.levels = levels;
@@ -310,7 +336,7 @@ cudaError_t trackb_points(const float *const *d_a, const float *const *d_b, cons
     }
     const int warps_per_block = 4;
     trackb_kernel<<<(n + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
-        P, reinterpret_cast<const float2 *>(d_pts), n, max_it, lambda, reinterpret_cast<float4 *>(d_out_T4), d_status);
+        P, reinterpret_cast<const float2 *>(d_pts), n, max_it, lambda, cost, reinterpret_cast<float4 *>(d_out_T4), d_status);
     return cudaGetLastError();
 }
 

@@ -41,7 +41,13 @@ ABI_SYMBOLS = (
     "rsvio_tracker_set_camera", "rsvio_tracker_undistorted_view", "rsvio_unproject_points",
     "rsvio_tracker_process_stereo_fmt", "rsvio_convert_to_luma8", "rsvio_b_track_points",
     "rsvio_b_pyramid_dims", "rsvio_b_build_pyramid", "rsvio_microbench_fp32",
+    "rsvio_b_track_points_cost", "rsvio_b_blur", "rsvio_b_shi_tomasi_score", "rsvio_b_add_points",
+    "rsvio_b_config_default", "rsvio_b_tracker_create", "rsvio_b_tracker_destroy", "rsvio_b_tracker_process_frame",
+    "rsvio_b_tracker_num_features", "rsvio_b_tracker_get_features", "rsvio_b_tracker_pyramid_dims",
+    "rsvio_b_tracker_get_pyramid_level", "rsvio_b_tracker_last_frame_ms",
 )
+
+B_COST_SSD, B_COST_LSSD = 0, 1
 
 PIXEL_LUMA8, PIXEL_LUMA16, PIXEL_RGB8 = 0, 1, 2
 
@@ -59,6 +65,15 @@ class Config(C.Structure):
                 ("max_iterations", C.c_int32), ("convergence_threshold", C.c_float), ("mode", C.c_int32),
                 ("n_streams", C.c_int32), ("device", C.c_int32), ("max_tracks", C.c_int32),
                 ("cuda_stream", C.c_void_p)]
+
+
+class BConfig(C.Structure):
+    """rsvio_b_config: crate B's FeatureTrackingConfig (feature_tracker/src/feature_tracker.rs:24-38) + size / device"""
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("nlevels", C.c_int32), ("ratio", C.c_double),
+                ("preprocessing_blur", C.c_int32), ("preprocessing_blur_sigma", C.c_float),
+                ("detection_threshold", C.c_float), ("detection_min_dist", C.c_uint32), ("detection_blur", C.c_float),
+                ("optical_flow_max_iter", C.c_int32), ("optical_flow_lm_lambda", C.c_float),
+                ("matching_cost", C.c_int32), ("device", C.c_int32), ("max_features", C.c_int32)]
 
 
 def library_path():
@@ -164,6 +179,25 @@ def load_library():
                                         C.POINTER(C.c_void_p)]
     L.rsvio_b_track_points.argtypes = [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i32p, _i32p, C.c_int32,
                                        _f32p, C.c_int32, C.c_int32, C.c_float, _f32p, _i32p]
+    L.rsvio_b_track_points_cost.argtypes = [C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i32p, _i32p, C.c_int32,
+                                            _f32p, C.c_int32, C.c_int32, C.c_float, C.c_int32, _f32p, _i32p]
+    L.rsvio_b_blur.argtypes = [C.c_int32, _f32p, C.c_int32, C.c_int32, C.c_float, _f32p]
+    L.rsvio_b_shi_tomasi_score.argtypes = [C.c_int32, _f32p, C.c_int32, C.c_int32, C.c_float, _f32p]
+    L.rsvio_b_add_points.argtypes = [C.c_int32, _f32p, C.c_int32, C.c_int32, _f32p, C.c_int32, C.c_float, C.c_uint32,
+                                     C.c_float, np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS"), C.c_size_t,
+                                     C.POINTER(C.c_size_t)]
+    L.rsvio_b_config_default.argtypes = [C.POINTER(BConfig)]
+    L.rsvio_b_config_default.restype = None
+    L.rsvio_b_tracker_create.argtypes = [C.POINTER(BConfig), C.POINTER(C.c_void_p)]
+    L.rsvio_b_tracker_destroy.argtypes = [C.c_void_p]
+    L.rsvio_b_tracker_destroy.restype = None
+    L.rsvio_b_tracker_process_frame.argtypes = [C.c_void_p, _f32p, C.c_int64]
+    L.rsvio_b_tracker_num_features.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.rsvio_b_tracker_get_features.argtypes = [C.c_void_p, np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS"), _f32p,
+                                               C.c_size_t, C.POINTER(C.c_size_t)]
+    L.rsvio_b_tracker_pyramid_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int32), _i32p, _i32p]
+    L.rsvio_b_tracker_get_pyramid_level.argtypes = [C.c_void_p, C.c_int32, _f32p]
+    L.rsvio_b_tracker_last_frame_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -306,6 +340,121 @@ def b_track_points(pyr0, pyr1, points, max_iteration=10, lm_lambda=0.1, device=0
     st = np.zeros(n, np.int32)
     _check(load_library().rsvio_b_track_points(device, p0, p1, ws, hs, L, pts, n, max_iteration, lm_lambda, T, st))
     return T, st
+
+
+def b_track_points_cost(pyr0, pyr1, points, max_iteration=10, lm_lambda=0.1, cost=B_COST_SSD, device=0):
+    """b_track_points with crate B's matching cost (B_COST_SSD | B_COST_LSSD, feature_tracker/src/patch.rs:4-8)"""
+    lv0 = [np.ascontiguousarray(a, np.float32) for a in pyr0]
+    lv1 = [np.ascontiguousarray(a, np.float32) for a in pyr1]
+    L = len(lv0)
+    if len(lv1) != L or any(a.shape != b.shape for a, b in zip(lv0, lv1)):
+        raise ValueError("the two pyramids must have the same level shapes")
+    p0 = (C.c_void_p * L)(*[a.ctypes.data for a in lv0])
+    p1 = (C.c_void_p * L)(*[a.ctypes.data for a in lv1])
+    ws = np.array([a.shape[1] for a in lv0], np.int32)
+    hs = np.array([a.shape[0] for a in lv0], np.int32)
+    pts = np.ascontiguousarray(points, np.float32).reshape(-1, 2)
+    n = pts.shape[0]
+    T = np.zeros((n, 4), np.float32)
+    st = np.zeros(n, np.int32)
+    _check(load_library().rsvio_b_track_points_cost(device, p0, p1, ws, hs, L, pts, n, max_iteration, lm_lambda, cost, T,
+                                                    st))
+    return T, st
+
+
+def b_blur(image, sigma, device=0):
+    """crate B's preprocessing blur (`image::imageops::blur`, image_operations.rs:58-62) on the device"""
+    img = np.ascontiguousarray(image, np.float32)
+    h, w = img.shape
+    out = np.empty_like(img)
+    _check(load_library().rsvio_b_blur(device, img, w, h, float(sigma), out))
+    return out
+
+
+def b_shi_tomasi_score(image, detection_blur, device=0):
+    """crate B's shi_tomasi_score (feature_detection.rs:83-165) on the device"""
+    img = np.ascontiguousarray(image, np.float32)
+    h, w = img.shape
+    out = np.empty_like(img)
+    _check(load_library().rsvio_b_shi_tomasi_score(device, img, w, h, float(detection_blur), out))
+    return out
+
+
+def b_add_points(image, tracked_xy, threshold, min_dist, detection_blur, device=0):
+    """crate B's add_points (feature_detection.rs:48-80): new corners (n, 2) uint32 in (y, x) order"""
+    img = np.ascontiguousarray(image, np.float32)
+    h, w = img.shape
+    tr = np.ascontiguousarray(tracked_xy, np.float32).reshape(-1, 2)
+    cap = ((w + 1) // 2) * ((h + 1) // 2)
+    out = np.zeros((cap, 2), np.uint32)
+    n = C.c_size_t(0)
+    tr_arg = tr if tr.shape[0] else np.zeros((1, 2), np.float32)
+    _check(load_library().rsvio_b_add_points(device, img, w, h, tr_arg, tr.shape[0], float(threshold), int(min_dist),
+                                             float(detection_blur), out, cap, C.byref(n)))
+    return out[:n.value].copy()
+
+
+class FeatureTrackerB:
+    """Mirror of crate B's `FeatureTracker` (feature_tracker/src/feature_tracker.rs:50-195) over rsvio_b_tracker_*:
+    process_frame(image) -> [(feature_id, x, y)], get_pyramid() -> list of levels or None."""
+
+    def __init__(self, width, height, nlevels=5, ratio=2.0, preprocessing_blur=True, preprocessing_blur_sigma=2.0,
+                 detection_threshold=2.5, detection_min_dist=15, detection_blur=6.0, optical_flow_max_iter=25,
+                 optical_flow_lm_lambda=0.1, matching_cost=B_COST_SSD, device=0, max_features=0):
+        L = load_library()
+        cfg = BConfig()
+        L.rsvio_b_config_default(C.byref(cfg))
+        cfg.width, cfg.height, cfg.nlevels, cfg.ratio = width, height, nlevels, ratio
+        cfg.preprocessing_blur, cfg.preprocessing_blur_sigma = int(bool(preprocessing_blur)), preprocessing_blur_sigma
+        cfg.detection_threshold, cfg.detection_min_dist = detection_threshold, detection_min_dist
+        cfg.detection_blur, cfg.optical_flow_max_iter = detection_blur, optical_flow_max_iter
+        cfg.optical_flow_lm_lambda, cfg.matching_cost, cfg.device = optical_flow_lm_lambda, matching_cost, device
+        cfg.max_features = max_features
+        self._L, self._h = L, C.c_void_p()
+        self.width, self.height, self._frames = width, height, 0
+        _check(L.rsvio_b_tracker_create(C.byref(cfg), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._L.rsvio_b_tracker_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def process_frame(self, image, frame_id=0):
+        img = np.ascontiguousarray(image, np.float32)
+        if img.shape != (self.height, self.width):
+            raise ValueError("image shape does not match the tracker")
+        _check(self._L.rsvio_b_tracker_process_frame(self._h, img, int(frame_id)))
+        self._frames += 1
+        return self.features()
+
+    def features(self):
+        n, n_new = C.c_int32(0), C.c_int32(0)
+        _check(self._L.rsvio_b_tracker_num_features(self._h, C.byref(n), C.byref(n_new)))
+        ids, xy = np.zeros(max(n.value, 1), np.uint64), np.zeros((max(n.value, 1), 2), np.float32)
+        got = C.c_size_t(0)
+        _check(self._L.rsvio_b_tracker_get_features(self._h, ids, xy, n.value, C.byref(got)))
+        self.n_new = n_new.value
+        return [(int(ids[i]), xy[i, 0], xy[i, 1]) for i in range(n.value)]
+
+    def get_pyramid(self):
+        if self._frames == 0:
+            return None
+        lv = C.c_int32(0)
+        ws, hs = np.zeros(8, np.int32), np.zeros(8, np.int32)
+        _check(self._L.rsvio_b_tracker_pyramid_dims(self._h, C.byref(lv), ws, hs))
+        out = []
+        for l in range(lv.value):
+            a = np.empty((int(hs[l]), int(ws[l])), np.float32)
+            _check(self._L.rsvio_b_tracker_get_pyramid_level(self._h, l, a))
+            out.append(a)
+        return out
+
+    def last_frame_ms(self):
+        ms = C.c_float(0)
+        _check(self._L.rsvio_b_tracker_last_frame_ms(self._h, C.byref(ms)))
+        return ms.value
 
 
 def convert_to_luma8(img, fmt, device=0):

@@ -12,7 +12,7 @@ fn main() {
         let csrc = pkg_root.join("csrc");
         let out = PathBuf::from(env::var("OUT_DIR").unwrap());
         let mut objs = Vec::new();
-        for f in ["pyramid.cu", "lk.cu", "detect.cu", "tracks.cu", "convert.cu", "trackb.cu", "microbench.cu", "api.cu"] {
+        for f in ["pyramid.cu", "lk.cu", "detect.cu", "tracks.cu", "convert.cu", "trackb.cu", "detectb.cu", "microbench.cu", "api.cu", "apib.cu"] {
             let obj = out.join(f.replace(".cu", ".o"));
             // same flags as rs-vio_b200/Makefile: sm_100a only, no FMA contraction (bit-exact pyramid)
             let st = Command::new(&nvcc)

@@ -131,6 +131,57 @@ extern "C" {
     pub fn rsvio_b_track_points(device: i32, pyr0: *const *const f32, pyr1: *const *const f32, widths: *const i32,
                                 heights: *const i32, levels: i32, points_xy: *const f32, n: i32, max_iteration: i32,
                                 lm_lambda: f32, out_t4: *mut f32, status: *mut i32) -> rsvio_status;
+
+    // ---- row f-2: the rest of crate B (blur, LSSD, Shi-Tomasi detection, stateful FeatureTracker) ----
+    pub fn rsvio_b_track_points_cost(device: i32, pyr0: *const *const f32, pyr1: *const *const f32, widths: *const i32,
+                                     heights: *const i32, levels: i32, points_xy: *const f32, n: i32,
+                                     max_iteration: i32, lm_lambda: f32, matching_cost: i32, out_t4: *mut f32,
+                                     status: *mut i32) -> rsvio_status;
+    pub fn rsvio_b_blur(device: i32, image: *const f32, width: i32, height: i32, sigma: f32, out: *mut f32) -> rsvio_status;
+    pub fn rsvio_b_shi_tomasi_score(device: i32, image: *const f32, width: i32, height: i32, detection_blur: f32,
+                                    out_score: *mut f32) -> rsvio_status;
+    pub fn rsvio_b_add_points(device: i32, image: *const f32, width: i32, height: i32, tracked_xy: *const f32,
+                              n_tracked: i32, threshold: f32, min_dist: u32, detection_blur: f32, out_xy: *mut u32,
+                              cap: usize, n: *mut usize) -> rsvio_status;
+    pub fn rsvio_b_config_default(cfg: *mut rsvio_b_config);
+    pub fn rsvio_b_tracker_create(cfg: *const rsvio_b_config, out: *mut *mut rsvio_b_tracker) -> rsvio_status;
+    pub fn rsvio_b_tracker_destroy(t: *mut rsvio_b_tracker);
+    pub fn rsvio_b_tracker_process_frame(t: *mut rsvio_b_tracker, image: *const f32, frame_id: i64) -> rsvio_status;
+    pub fn rsvio_b_tracker_num_features(t: *const rsvio_b_tracker, n: *mut i32, n_new: *mut i32) -> rsvio_status;
+    pub fn rsvio_b_tracker_get_features(t: *const rsvio_b_tracker, ids: *mut u64, xy: *mut f32, cap: usize,
+                                        n: *mut usize) -> rsvio_status;
+    pub fn rsvio_b_tracker_pyramid_dims(t: *const rsvio_b_tracker, levels: *mut i32, widths: *mut i32,
+                                        heights: *mut i32) -> rsvio_status;
+    pub fn rsvio_b_tracker_get_pyramid_level(t: *mut rsvio_b_tracker, level: i32, out: *mut f32) -> rsvio_status;
+    pub fn rsvio_b_tracker_last_frame_ms(t: *const rsvio_b_tracker, ms: *mut f32) -> rsvio_status;
+}
+
+pub const RSVIO_B_COST_SSD: i32 = 0;
+pub const RSVIO_B_COST_LSSD: i32 = 1;
+
+/// rsvio_b_config (include/rsvio_b200.h): crate B's FeatureTrackingConfig + image size, device, matching cost
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct rsvio_b_config {
+    pub width: i32,
+    pub height: i32,
+    pub nlevels: i32,
+    pub ratio: f64,
+    pub preprocessing_blur: i32,
+    pub preprocessing_blur_sigma: f32,
+    pub detection_threshold: f32,
+    pub detection_min_dist: u32,
+    pub detection_blur: f32,
+    pub optical_flow_max_iter: i32,
+    pub optical_flow_lm_lambda: f32,
+    pub matching_cost: i32,
+    pub device: i32,
+    pub max_features: i32,
+}
+
+#[repr(C)]
+pub struct rsvio_b_tracker {
+    _private: [u8; 0],
 }
 
 pub const RSVIO_N_STAGES: usize = 8;

@@ -11,6 +11,8 @@
 //!
 //! NOT COMPILED IN THIS REPOSITORY (no Rust toolchain in the image) -- INTEGRATION.md.
 pub mod ffi;
+/// the reference's standalone `feature_tracker` crate (mono, f32 pyramid, bicubic, Shi-Tomasi): row f-2
+pub mod crate_b;
 
 use image::GrayImage;
 use std::collections::HashMap;
@@ -170,7 +172,7 @@ impl Drop for Handle {
     }
 }
 
-fn status_text(st: ffi::rsvio_status) -> String {
+pub(crate) fn status_text(st: ffi::rsvio_status) -> String {
     unsafe { CStr::from_ptr(ffi::rsvio_status_string(st)) }.to_string_lossy().into_owned()
 }
 

@@ -163,3 +163,109 @@ def test_crate_b_oracle_matches_the_reference_vectors():
             assert np.abs(p.intensities - d).max() <= 1e-6
             assert np.abs(p.J - j.reshape(52, 3)).max() <= 1e-3 * max(1.0, np.abs(j).max())
             assert np.abs(p.Hinv - hi.reshape(3, 3)).max() <= 1e-3 * np.abs(hi).max()
+
+
+# ---- the rest of crate B in the oracle: blur, fast_blur, Shi-Tomasi, NMS, local_maxima, FeatureTracker ---------------
+def _texture(h, w, seed, dx=0.0, dy=0.0):
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:w].astype(np.float64)
+    x, y = x - dx, y - dy
+    v = 0.5 + 0.12 * np.sin(0.21 * x + 0.13 * y) + 0.1 * np.sin(0.09 * x - 0.17 * y + 1.0)
+    for _ in range(max(6, h * w // 900)):
+        cx, cy, s, a = rng.uniform(8, w - 8), rng.uniform(8, h - 8), rng.uniform(1.5, 3.5), rng.uniform(-0.3, 0.3)
+        v += a * np.exp(-((x - cx) ** 2 + (y - cy) ** 2) / (2 * s * s))
+    return np.clip(v, 0.0, 1.0).astype(np.float32)
+
+
+def test_blur_properties():
+    flat = np.full((20, 30), 0.4, np.float32)
+    assert np.abs(B.blur(flat, 2.0) - 0.4).max() < 1e-6                  # weights are normalised, also at the border
+    img = np.zeros((41, 41), np.float32)
+    img[20, 20] = 1.0
+    b = B.blur(img, 2.0)
+    assert abs(b.sum() - 1.0) < 1e-5 and b[20, 20] == b.max()
+    assert np.count_nonzero(b[20]) == 9 and np.count_nonzero(b[:, 20]) == 9   # support 2 sigma: taps -4 .. 4
+    assert np.allclose(b, b.T) and np.allclose(b, b[::-1, ::-1])
+    # against OpenCV's Gaussian (different truncation: 2 sigma here), interior only
+    import cv2
+    tex = _texture(60, 80, 1)
+    ref = cv2.GaussianBlur(tex, (9, 9), 2.0, borderType=cv2.BORDER_REPLICATE)
+    assert np.abs(B.blur(tex, 2.0) - ref)[6:-6, 6:-6].max() < 2e-3          # cv2 with the same 9 taps
+
+
+def test_fast_blur_boxes_and_properties():
+    assert B.boxes_for_gauss(6.0) == [11, 11, 13] and B.boxes_for_gauss(2.0) == [3, 3, 5] and B.boxes_for_gauss(1.0) == [1, 1, 3]
+    flat = np.full((17, 23), 0.3, np.float32)
+    assert np.abs(B.fast_blur(flat, 6.0) - 0.3).max() < 1e-6
+    img = np.zeros((31, 31), np.float32)
+    img[15, 15] = 1.0
+    b = B.fast_blur(img, 2.0)
+    assert b.shape == img.shape and abs(b.sum() - 1.0) < 1e-5 and b[15, 15] == b.max()
+    neg = np.full((9, 9), -0.5, np.float32)
+    assert (B.fast_blur(neg, 1.0) == 0).all()                             # values are clamped to the sample range [0, 1]
+
+
+def test_score_map_and_nms():
+    flat = np.full((30, 30), 0.5, np.float32)
+    assert (B.shi_tomasi_score(flat, 2.0) == 0).all()
+    img = B.blur(_texture(60, 80, 2), 1.5)
+    s = B.shi_tomasi_score(img, 2.0)
+    assert s.shape == img.shape and s.min() >= 0 and s.max() > 0.05
+    for thr in (0.0, 0.05):
+        a, b = B.suppress_non_maximum(s, 1, np.float32(thr)), B.suppress_non_maximum_r1(s, np.float32(thr))
+        assert a == b and len(a) > 5
+        for x, y, v in a[:20]:                                             # every kept pixel is the 3x3 maximum
+            assert v == s[max(y - 1, 0):y + 2, max(x - 1, 0):x + 2].max() and v >= thr
+    q = (np.round(s * 40) / 40).astype(np.float32)                         # many exact ties
+    assert B.suppress_non_maximum(q, 1, np.float32(0.0)) == B.suppress_non_maximum_r1(q, np.float32(0.0))
+
+
+def test_local_maxima_follows_imageproc():
+    items = [(10, 10, 1.0, "a"), (12, 11, 2.0, "b"), (30, 10, 1.0, "c"), (10, 13, 1.0, "d"), (50, 40, 0.5, "e")]
+    assert [t[3] for t in B.local_maxima(items, 3)] == ["c", "b", "e"]    # a and d lose to b; order is (y, x)
+    tie = [(5, 5, 1.0, "p"), (6, 5, 1.0, "q"), (20, 9, 1.0, "z")]
+    assert [t[3] for t in B.local_maxima(tie, 2)] == ["p", "z"]            # ties go to the lexicographically first
+    # the last occupied row is never searched: a stronger corner there does not suppress its neighbours
+    last = [(5, 5, 1.0, "w"), (6, 6, 9.0, "s")]
+    assert [t[3] for t in B.local_maxima(last, 3)] == ["w", "s"]
+    assert B.local_maxima([], 5) == []
+
+
+def test_add_points_and_tracked_features():
+    img = B.blur(_texture(96, 128, 4), 1.5)
+    first = B.add_points(img, [], 0.05, 7, 2.0)
+    assert len(first) >= 5 and first == sorted(first, key=lambda c: (c[1], c[0]))
+    assert all(7 <= x < 128 - 7 and 7 <= y < 96 - 7 for x, y in first)
+    for i, (x0, y0) in enumerate(first):                                   # kept corners are more than min_dist apart
+        for x1, y1 in first[i + 1:]:
+            assert max(abs(x0 - x1), abs(y0 - y1)) > 7 or y1 == first[-1][1]
+    again = B.add_points(img, [(x + 0.2, y - 0.3) for x, y in first], 0.05, 7, 2.0)
+    assert not set(again) & set(first)                                     # occupied neighbourhoods yield nothing new
+
+
+def test_feature_tracker_sequence():
+    h, w = 96, 128
+    ft = B.FeatureTracker(nlevels=3, preprocessing_blur_sigma=1.5, detection_threshold=0.02, detection_min_dist=9,
+                          detection_blur=2.0, optical_flow_max_iter=12)
+    assert ft.get_pyramid() is None
+    f0 = ft.process_frame(_texture(h, w, 21))
+    assert len(f0) >= 6 and [f[0] for f in f0] == list(range(len(f0)))
+    f1 = ft.process_frame(_texture(h, w, 21, dx=1.2, dy=-0.7))
+    p0 = {i: (x, y) for i, x, y in f0}
+    kept = [(i, x, y) for i, x, y in f1 if i in p0]
+    assert len(kept) >= len(f0) // 2
+    flow = np.array([[x - p0[i][0], y - p0[i][1]] for i, x, y in kept])
+    assert np.abs(np.median(flow, axis=0) - np.array([1.2, -0.7])).max() < 0.1
+    new_ids = [i for i, _, _ in f1 if i not in p0]
+    assert new_ids == list(range(len(f0), len(f0) + len(new_ids)))        # fresh ids, after the tracked features
+    assert [p.shape for p in ft.get_pyramid()] == [(96, 128), (48, 64), (24, 32)]
+
+
+def test_lssd_patch():
+    img = B.blur(_texture(64, 64, 7), 1.0)
+    p = B.Patch52Lssd(img, (30.3, 31.6), 0.1)
+    r = p.residuals(img, B.Iso2())
+    mean = np.float32(p.intensities.sum() / 52)
+    assert np.allclose(r, p.intensities / mean - p.intensities, atol=1e-5)   # the template stays raw, as in the reference
+    T = B.track_point([img], [(img * np.float32(0.7)).astype(np.float32)], (30.3, 31.6), 15, 0.1, "lssd")
+    assert T is not None

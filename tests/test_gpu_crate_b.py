@@ -87,3 +87,115 @@ def test_crate_b_pyramid_matches_oracle(rsvio):
     flow = np.stack([T[:, 0] * pts[:, 0] - T[:, 1] * pts[:, 1] + T[:, 2],
                      T[:, 1] * pts[:, 0] + T[:, 0] * pts[:, 1] + T[:, 3]], 1) - pts     # T p - p, not T's translation
     assert (st == 0).all() and np.abs(flow - np.array([1.3, -0.7])).max() < 0.05
+
+
+# ---- row f-2, the rest of crate B: blur, LSSD, Shi-Tomasi detection, stateful FeatureTracker ----------------------------
+def textured(h, w, seed, dx=0.0, dy=0.0):
+    """smooth texture + a few bright blobs (corner-like), values in [0, 1], shifted by (dx, dy)"""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:w].astype(np.float64)
+    x, y = x - dx, y - dy
+    v = 0.5 + 0.12 * np.sin(0.21 * x + 0.13 * y) + 0.1 * np.sin(0.09 * x - 0.17 * y + 1.0)
+    for _ in range(max(6, h * w // 900)):
+        cx, cy, s, a = rng.uniform(8, w - 8), rng.uniform(8, h - 8), rng.uniform(1.5, 3.5), rng.uniform(-0.3, 0.3)
+        v += a * np.exp(-((x - cx) ** 2 + (y - cy) ** 2) / (2 * s * s))
+    return np.clip(v, 0.0, 1.0).astype(np.float32)
+
+
+def test_crate_b_blur_is_bit_identical_to_the_oracle(rsvio):
+    rng = np.random.default_rng(5)
+    for (h, w, sigma) in ((61, 83, 2.0), (40, 50, 0.8), (33, 37, 3.3)):
+        img = rng.uniform(0.0, 1.0, (h, w)).astype(np.float32)
+        want, got = B.blur(img, sigma), rsvio.b_blur(img, sigma)
+        assert np.array_equal(got, want), (h, w, sigma, np.abs(got - want).max())
+    flat = np.full((24, 31), 0.25, np.float32)
+    assert np.abs(rsvio.b_blur(flat, 2.0) - 0.25).max() < 1e-6
+
+
+def test_crate_b_score_map_is_bit_identical_to_the_oracle(rsvio):
+    for (h, w, seed, dblur) in ((72, 96, 1, 6.0), (65, 51, 2, 2.0), (48, 160, 3, 1.0)):
+        img = B.blur(textured(h, w, seed), 2.0)
+        want, got = B.shi_tomasi_score(img, dblur), rsvio.b_shi_tomasi_score(img, dblur)
+        assert np.array_equal(got, want), (h, w, dblur, np.abs(got - want).max())
+    assert np.abs(rsvio.b_shi_tomasi_score(np.full((40, 40), 0.5, np.float32), 2.0)).max() == 0.0
+
+
+def test_crate_b_add_points_matches_the_oracle(rsvio):
+    for (h, w, seed, thr, md, dblur) in ((96, 128, 4, 0.05, 7, 2.0), (120, 90, 5, 0.02, 15, 3.0), (64, 64, 6, 0.0, 3, 1.0)):
+        img = B.blur(textured(h, w, seed), 1.5)
+        first = B.add_points(img, [], thr, md, dblur)
+        got = rsvio.b_add_points(img, np.zeros((0, 2), np.float32), thr, md, dblur)
+        assert len(first) >= 3, (h, w, len(first))
+        assert [tuple(int(v) for v in r) for r in got] == [tuple(c) for c in first]
+        # tracked features (some of the first corners, moved by sub-pixel amounts, plus one on the last row) suppress
+        # their neighbourhood
+        tracked = [(x + 0.3, y - 0.4) for x, y in first[::2]] + [(w - 6.2, h - 1.0)]
+        want = B.add_points(img, tracked, thr, md, dblur)
+        got = rsvio.b_add_points(img, np.array(tracked, np.float32), thr, md, dblur)
+        assert [tuple(int(v) for v in r) for r in got] == [tuple(c) for c in want]
+        assert len(want) < len(first)
+
+
+def test_crate_b_lssd_cost_matches_the_oracle(rsvio):
+    h, w = 96, 128
+    a, b = scene(h, w), (scene(h, w, 1.1, -0.6, 0.008) * np.float32(0.8)).astype(np.float32)   # gain change
+    pa, pb = B.build_image_pyramid(a, 3, 2.0), B.build_image_pyramid(b, 3, 2.0)
+    rng = np.random.default_rng(11)
+    pts = rng.uniform([24, 24], [w - 24, h - 24], (16, 2)).astype(np.float32)
+    got_T, got_st = rsvio.b_track_points_cost(pa, pb, pts, 10, 0.1, rsvio.B_COST_LSSD)
+    n_ok = 0
+    for k, p in enumerate(pts):
+        T0 = B.track_point(pa, pb, p, 10, 0.1, "lssd")
+        if T0 is None:
+            assert got_st[k] == 1
+            continue
+        q = T0.apply(p)
+        g = np.array([got_T[k, 0] * p[0] - got_T[k, 1] * p[1] + got_T[k, 2], got_T[k, 1] * p[0] + got_T[k, 0] * p[1] + got_T[k, 3]])
+        if got_st[k] != 1:
+            assert np.abs(g - q).max() < 1e-2, (k, g, q)
+            n_ok += 1
+    assert n_ok >= 12
+    # SSD through the same entry point equals the original one
+    T_a, st_a = rsvio.b_track_points_cost(pa, pa, pts, 10, 0.1, rsvio.B_COST_SSD)
+    T_b, st_b = rsvio.b_track_points(pa, pa, pts, 10, 0.1)
+    assert np.array_equal(T_a, T_b) and np.array_equal(st_a, st_b)
+
+
+def test_crate_b_stateful_tracker_matches_the_oracle(rsvio):
+    """FeatureTracker::process_frame over a short sequence: same ids in the same order, positions within 1e-3 px
+    (tracked) / identical (new corners)"""
+    h, w = 120, 160
+    kw = dict(nlevels=3, ratio=2.0, preprocessing_blur=True, preprocessing_blur_sigma=1.5, detection_threshold=0.02,
+              detection_min_dist=9, detection_blur=2.0, optical_flow_max_iter=12, optical_flow_lm_lambda=0.1)
+    ref = B.FeatureTracker(**kw)
+    gpu = rsvio.FeatureTrackerB(w, h, **kw)
+    assert gpu.get_pyramid() is None
+    stats = []
+    for t in range(4):
+        img = textured(h, w, 21, dx=1.2 * t, dy=-0.7 * t)
+        want = ref.process_frame(img)
+        got = gpu.process_frame(img, t)
+        ids_w, ids_g = [f[0] for f in want], [f[0] for f in got]
+        assert ids_g == ids_w, (t, len(ids_g), len(ids_w), sorted(set(ids_w) ^ set(ids_g))[:10])
+        d = np.abs(np.array([[f[1], f[2]] for f in got]) - np.array([[f[1], f[2]] for f in want]))
+        assert d.max() < 1e-3, (t, d.max())
+        stats.append((t, len(ids_g), gpu.n_new, float(d.max())))
+        for lg, lw in zip(gpu.get_pyramid(), ref.get_pyramid()):
+            assert np.array_equal(lg, lw)
+    assert stats[0][1] >= 10 and stats[0][1] == stats[0][2]            # first frame: everything is new
+    assert stats[-1][1] - stats[-1][2] >= stats[0][1] // 2             # most features survive the sequence
+    gpu.close()
+
+
+def test_crate_b_full_size_frame(rsvio):
+    """752x480 with the reference's config.yaml settings: detection runs, tracked features follow a known shift"""
+    h, w = 480, 752
+    gpu = rsvio.FeatureTrackerB(w, h, detection_threshold=0.02)
+    f0 = gpu.process_frame(textured(h, w, 33))
+    f1 = gpu.process_frame(textured(h, w, 33, dx=2.0, dy=1.0))
+    assert len(f0) >= 50
+    p0 = {i: (x, y) for i, x, y in f0}
+    flow = np.array([[x - p0[i][0], y - p0[i][1]] for i, x, y in f1 if i in p0])
+    assert len(flow) >= len(f0) // 2
+    assert np.abs(np.median(flow, axis=0) - np.array([2.0, 1.0])).max() < 0.1
+    assert gpu.last_frame_ms() > 0
