@@ -385,6 +385,44 @@ def per_config_results(torch, rsvio_b200, local_rank, stream, cores, which, step
     return out
 
 
+def crate_b_result(rsvio_b200, frames=40, warm=6):
+    """Row f-2 (`bench.py --config B1` in VERDICT's words; carried in per_config): the reference's second tracker
+    (`feature_tracker` crate, mono, f32 pyramid, bicubic LK, Shi-Tomasi) with its config.yaml settings on the EuRoC-size
+    left images of the C1 sequence, through the synchronous rsvio_b_tracker_process_frame (host image in, features on
+    the host out).  `value`: device time of a frame (events around the kernels), `e2e`: wall clock of the call."""
+    try:
+        p = CONFIGS["C1"]
+        ring = generate_frames("C1", [0], RING, 1)
+        imgs = [(ring[t, 0, 0].astype(np.float32) / np.float32(255.0)) for t in range(RING)]
+        tr = rsvio_b200.FeatureTrackerB(p["w"], p["h"], detection_threshold=0.02)
+        dev_ms, wall, tracks, n_feat = [], [], 0, []
+        for i in range(warm + frames):
+            img = imgs[ring_index(i)]
+            t0 = time.perf_counter()
+            feats = tr.process_frame(img, i)
+            t1 = time.perf_counter()
+            if i >= warm:
+                wall.append(t1 - t0)
+                dev_ms.append(tr.last_frame_ms())
+                tracks += len(feats) - tr.n_new          # features of the previous frame that were tracked + kept
+                n_feat.append(len(feats))
+        prev_total = sum(n_feat[:-1]) + n_feat[0]        # every feature of a previous frame is one forward+backward track
+        tr.close()
+        dsum, wsum = sum(dev_ms) * 1e-3, sum(wall)
+        return {"config": "B1", "shape": f"{p['w']}x{p['h']} mono, crate B (feature_tracker/config/config.yaml: 5 levels, "
+                                         "blur 2.0, min_dist 15, detection blur 6.0, 25 iterations; threshold 0.02)",
+                "streams": 1, "value": prev_total / dsum, "unit": "tracks/s", "ms_per_frame": 1e3 * dsum / frames,
+                "frames_per_sec": frames / dsum, "features_per_frame": float(np.mean(n_feat)),
+                "tracked_fraction": tracks / max(prev_total, 1),
+                "e2e": {"value": prev_total / wsum, "ms_per_frame": 1e3 * wsum / frames, "frames_per_sec": frames / wsum,
+                        "h2d_bytes_per_step": 4 * p["w"] * p["h"], "d2h_bytes_per_step": 16 * float(np.mean(n_feat))},
+                "cpu_baseline": None,
+                "note": "no CPU baseline: the crate B oracle is a pure-Python restatement (seconds per small frame), "
+                        "not a timing reference"}
+    except Exception as ex:
+        return {"config": "B1", "error": repr(ex)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -596,6 +634,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_per_config:
         per_config = per_config_results(torch, rsvio_b200, local_rank, stream, cores,
                                         ("C1", "C2", "C3", "C4", "EUROC_SHIPPED"))
+        per_config.append(crate_b_result(rsvio_b200))
 
     sampler.stop_flag = True
     clocks = sampler.summary()

@@ -213,4 +213,112 @@ class PatchTracker {
     detail::Handle h_;
 };
 
+// ---- crate B (the reference's standalone `feature_tracker` crate, row f-2) ----------------------------------------
+// FeatureTrackingConfig / Feature / FeatureTracker / ext::Frame of feature_tracker/src/feature_tracker.rs:24-69,
+// 77-193 and ext.rs:3-15, over rsvio_b_tracker_*.  Images are dense float arrays in [0, 1] (FloatGrayImage).
+namespace crate_b {
+
+struct FeatureTrackingConfig {
+    std::size_t nlevels = 5;
+    double ratio = 2.0;
+    bool preprocessing_blur = true;
+    float preprocessing_blur_sigma = 2.0f;
+    float detection_threshold = 2.5f;
+    std::uint32_t detection_min_dist = 15;
+    float detection_blur = 6.0f;
+    std::size_t optical_flow_max_iter = 25;
+    float optical_flow_lm_lambda = 0.1f;
+};
+
+struct Feature {
+    std::size_t feature_id;
+    float central_point[2];
+};
+
+struct Frame {
+    std::int64_t frame_id;
+    std::vector<Feature> features;
+    explicit Frame(std::int64_t id) : frame_id(id) {}
+};
+
+struct FloatGrayImageView {
+    const float *data;
+    std::int32_t width, height;
+};
+
+class FeatureTracker {
+  public:
+    explicit FeatureTracker(const FeatureTrackingConfig &config, int device = 0, int matching_cost = RSVIO_B_COST_SSD)
+        : config_(config), device_(device), cost_(matching_cost) {}
+    FeatureTracker(const FeatureTracker &) = delete;
+    FeatureTracker &operator=(const FeatureTracker &) = delete;
+    ~FeatureTracker() { rsvio_b_tracker_destroy(h_); }
+
+    // process_frame(&mut self, in_image, frame): the frame comes back with the tracked features (old order) followed
+    // by the new ones (fresh ids) and is kept as the previous frame
+    void process_frame(const FloatGrayImageView &image, Frame frame) {
+        ensure(image.width, image.height);
+        const rsvio_status st = rsvio_b_tracker_process_frame(h_, image.data, frame.frame_id);
+        if (st != RSVIO_OK && st != RSVIO_ERR_CAPACITY)  // a full table drops new corners, the frame is still valid
+            throw Error(st, std::string("rsvio_b_tracker_process_frame: ") + rsvio_status_string(st));
+        std::int32_t n = 0, n_new = 0;
+        rsvio_b_tracker_num_features(h_, &n, &n_new);
+        std::vector<std::uint64_t> ids((std::size_t)n);
+        std::vector<float> xy(2 * (std::size_t)n);
+        std::size_t got = 0;
+        rsvio_b_tracker_get_features(h_, ids.data(), xy.data(), (std::size_t)n, &got);
+        for (std::int32_t i = 0; i < n; ++i) frame.features.push_back(Feature{(std::size_t)ids[i], {xy[2 * i], xy[2 * i + 1]}});
+        previous_frame_.assign(1, std::move(frame));
+    }
+    const Frame *last_frame() const { return previous_frame_.empty() ? nullptr : &previous_frame_[0]; }
+
+    // get_pyramid(): levels of the last frame, finest first; empty before the first frame
+    std::vector<std::vector<float>> get_pyramid(std::vector<std::pair<int, int>> *dims = nullptr) {
+        std::vector<std::vector<float>> out;
+        if (previous_frame_.empty()) return out;
+        std::int32_t levels = 0, ws[RSVIO_MAX_LEVELS], hs[RSVIO_MAX_LEVELS];
+        rsvio_b_tracker_pyramid_dims(h_, &levels, ws, hs);
+        for (int l = 0; l < levels; ++l) {
+            out.emplace_back((std::size_t)ws[l] * hs[l]);
+            const rsvio_status st = rsvio_b_tracker_get_pyramid_level(h_, l, out.back().data());
+            if (st != RSVIO_OK) throw Error(st, std::string("rsvio_b_tracker_get_pyramid_level: ") + rsvio_status_string(st));
+            if (dims) dims->emplace_back(ws[l], hs[l]);
+        }
+        return out;
+    }
+
+  private:
+    void ensure(std::int32_t w, std::int32_t h) {  // the size is learnt from the first frame
+        if (h_ && w == w_ && h == hh_) return;
+        rsvio_b_tracker_destroy(h_);
+        h_ = nullptr;
+        rsvio_b_config c;
+        rsvio_b_config_default(&c);
+        c.width = w;
+        c.height = h;
+        c.nlevels = (std::int32_t)config_.nlevels;
+        c.ratio = config_.ratio;
+        c.preprocessing_blur = config_.preprocessing_blur ? 1 : 0;
+        c.preprocessing_blur_sigma = config_.preprocessing_blur_sigma;
+        c.detection_threshold = config_.detection_threshold;
+        c.detection_min_dist = config_.detection_min_dist;
+        c.detection_blur = config_.detection_blur;
+        c.optical_flow_max_iter = (std::int32_t)config_.optical_flow_max_iter;
+        c.optical_flow_lm_lambda = config_.optical_flow_lm_lambda;
+        c.matching_cost = cost_;
+        c.device = device_;
+        const rsvio_status st = rsvio_b_tracker_create(&c, &h_);
+        if (st != RSVIO_OK) throw Error(st, std::string("rsvio_b_tracker_create: ") + rsvio_status_string(st));
+        w_ = w;
+        hh_ = h;
+    }
+    FeatureTrackingConfig config_;
+    int device_, cost_;
+    rsvio_b_tracker *h_ = nullptr;
+    std::int32_t w_ = 0, hh_ = 0;
+    std::vector<Frame> previous_frame_;
+};
+
+}  // namespace crate_b
+
 }  // namespace rsvio

@@ -1,6 +1,7 @@
-"""GPU: first CUDA slice of row f-2 (crate B's tracking core, csrc/trackb.cu) against oracle/crate_b.py on the same
-f32 pyramids.  Tolerance: isometries to 1e-3 px / 1e-4 rad-ish (the 52-term sums are shuffle trees on the device and
-BLAS dot products in the numpy oracle), identical status except on a threshold edge."""
+"""GPU: row f-2 (crate B: csrc/trackb.cu, detectb.cu, apib.cu) against oracle/crate_b.py.  Bars: tracked positions
+within 1e-3 px and identical status (the 52-term sums are shuffle trees on the device and BLAS dot products in the
+numpy oracle); blur, chained pyramid, score map and corner lists bit-identical (same f32 operations in the same
+order)."""
 import os
 import sys
 
@@ -11,6 +12,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import crate_b as B  # noqa: E402
 
 pytestmark = pytest.mark.gpu
+
+
+def record(stats):
+    """append the parity statistics of a comparison to gpurun_out/parity_stats.jsonl (if the directory exists)"""
+    import json
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_stats.jsonl"), "a") as f:
+            f.write(json.dumps(stats) + "\n")
 
 
 def scene(h, w, dx=0.0, dy=0.0, rot=0.0):
@@ -54,16 +64,18 @@ def test_crate_b_tracking_core_matches_oracle(rsvio):
     want_T, want_st = oracle_track(pa, pb, pts, 10, 0.1)
     got_T, got_st = rsvio.b_track_points(pa, pb, pts, 10, 0.1)
     assert (want_st[:24] == 0).all()                                               # the scene is trackable
-    same = got_st == want_st
-    assert same.mean() >= 0.9, (got_st, want_st)
-    ok = same & (want_st != 1)
     moved_g = np.stack([got_T[:, 0] * pts[:, 0] - got_T[:, 1] * pts[:, 1] + got_T[:, 2],
                         got_T[:, 1] * pts[:, 0] + got_T[:, 0] * pts[:, 1] + got_T[:, 3]], 1)
     moved_w = np.stack([want_T[:, 0] * pts[:, 0] - want_T[:, 1] * pts[:, 1] + want_T[:, 2],
                         want_T[:, 1] * pts[:, 0] + want_T[:, 0] * pts[:, 1] + want_T[:, 3]], 1)
-    good = ok & (want_st == 0)
-    assert np.abs(moved_g[good] - moved_w[good]).max() < 1e-2
-    assert np.median(np.abs(moved_g[good] - moved_w[good])) < 1e-3
+    good = (got_st == want_st) & (want_st == 0)
+    err = np.abs(moved_g[good] - moved_w[good])
+    record({"tag": "crate B track_points 128x96 L3", "n": int(len(pts)), "status_equal": int((got_st == want_st).sum()),
+            "tracked": int(good.sum()), "max_err_px": float(err.max()), "median_err_px": float(np.median(err))})
+    # same bar as tracker A: identical status, positions within 1e-3 px (the interior points; the five border points
+    # exercise the out-of-bound exits and must agree in status)
+    assert (got_st == want_st).all(), (got_st, want_st)
+    assert err.max() < 1e-3, err.max()
     # and both recover the synthetic motion of the interior points
     flow = moved_g[:24] - pts[:24]
     assert np.abs(np.median(flow, axis=0) - np.array([1.3, -0.7])).max() < 0.1
@@ -182,6 +194,7 @@ def test_crate_b_stateful_tracker_matches_the_oracle(rsvio):
         stats.append((t, len(ids_g), gpu.n_new, float(d.max())))
         for lg, lw in zip(gpu.get_pyramid(), ref.get_pyramid()):
             assert np.array_equal(lg, lw)
+    record({"tag": "crate B FeatureTracker 160x120 L3, 4 frames", "per_frame": [list(x) for x in stats]})
     assert stats[0][1] >= 10 and stats[0][1] == stats[0][2]            # first frame: everything is new
     assert stats[-1][1] - stats[-1][2] >= stats[0][1] // 2             # most features survive the sequence
     gpu.close()
