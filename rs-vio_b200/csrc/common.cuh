@@ -197,6 +197,23 @@ cudaError_t remove_ids(const TableView &in, const TableView &out, int groups, in
 
 // ---- device helpers ---------------------------------------------------------------------
 #ifdef __CUDACC__
+// Bounds-check build (make VARIANT=check EXTRA=-DRSVIO_BOUNDS_CHECK): every unclamped gather, shared-memory tile index
+// and scratch index of the hot kernels is asserted; a violation prints its source line and traps the kernel.  This is
+// the repo's own stand-in for compute-sanitizer memcheck (closed on the GPU pool); tools/bounds_check.sh runs the
+// parity tests against that build.  The default build compiles the checks away.
+#ifdef RSVIO_BOUNDS_CHECK
+#include <cstdio>
+#define RSVIO_CHECK(cond)                                                                                       \
+    do {                                                                                                        \
+        if (!(cond)) {                                                                                          \
+            printf("rsvio bounds check failed: %s at %s:%d (block %d,%d thread %d)\n", #cond, __FILE__, __LINE__, \
+                   (int)blockIdx.x, (int)blockIdx.y, (int)threadIdx.x);                                         \
+            __trap();                                                                                           \
+        }                                                                                                       \
+    } while (0)
+#else
+#define RSVIO_CHECK(cond) ((void)0)
+#endif
 namespace rsvio {
 
 // Rust `f32 as u32`: saturating, NaN -> 0

@@ -97,6 +97,7 @@ __device__ __forceinline__ void image_grad(const Img &im, float x, float y, bool
     const float ddx = 1.0f - dx, ddy = 1.0f - dy;
     const float w00 = ddx * ddy, w01 = ddx * dy, w10 = dx * ddy, w11 = dx * dy;
     const uint32_t W = (uint32_t)im.w;
+    RSVIO_CHECK(ix >= 1u && ix + 2u < W && iy >= 1u && iy + 2u < (uint32_t)im.h);  // the 4x4 neighbourhood minus corners
     const uint8_t *__restrict__ r0 = im.p + (iy * W + ix);  // 32-bit offset inside one level
     const uint8_t *__restrict__ rm = r0 - W;
     const uint8_t *__restrict__ r1 = r0 + W;
@@ -426,6 +427,7 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
                 const uint32_t ix = ok ? __float2uint_rd(x) : 0u, iy = ok ? __float2uint_rd(y) : 0u;
                 const float dx = x - (float)ix, dy = y - (float)iy;
                 const float ddx = 1.0f - dx, ddy = 1.0f - dy;
+                RSVIO_CHECK(ix + 1u < ibw && iy + 1u < (uint32_t)ib.h);
                 const uint8_t *__restrict__ q0 = ibp + (iy * ibw + ix);
                 const uint8_t *__restrict__ q1 = q0 + ibw;
                 const float p00 = (float)__ldg(q0), p10 = (float)__ldg(q0 + 1);

@@ -142,6 +142,7 @@ __device__ __forceinline__ void generic_tile(const PyrDesc &pd, const PyrTaps &t
         const int top = ty.left[oy], n = ty.cnt[oy];
         const float *__restrict__ wy = ty.w + (size_t)oy * ty.kmax;
         const int x = xa + 4 * g;
+        RSVIO_CHECK(top >= 0 && top + n <= pd.lv[0].h && x >= 0 && x < w0 && cy * ncols + 4 * g + 3 < kGenSmemFloats);
         const uint8_t *__restrict__ p = src + (size_t)top * stride + x;
         float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
         if (vec4 && x + 4 <= w0) {
@@ -182,6 +183,7 @@ __device__ __forceinline__ void generic_tile(const PyrDesc &pd, const PyrTaps &t
         const int left = tx.left[ox] - xa, n = tx.cnt[ox];
         const float *__restrict__ wx = tx.w + (size_t)ox * tx.kmax;
         const float *__restrict__ vr = &v[cy * ncols + left];
+        RSVIO_CHECK(left >= 0 && left + n <= ncols && ox < wl && oy0 + cy < pd.lv[lev].h);
         float t = 0.0f;
         for (int k = 0; k < n; ++k) t = __fadd_rn(t, __fmul_rn(vr[k], __ldg(wx + k)));
         t = fminf(fmaxf(t, 0.0f), 255.0f);
@@ -217,6 +219,8 @@ pyr_generic_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ P
         const int left = __ldg(tx.left + ox), nx = __ldg(tx.cnt + ox), top = __ldg(ty.left + oy), ny = __ldg(ty.cnt + oy);
         const float *__restrict__ wy = ty.w + (size_t)oy * ty.kmax;
         const float *__restrict__ wx = tx.w + (size_t)ox * tx.kmax;
+        RSVIO_CHECK((lev == 4 || lev == 5) && nx <= 64 && ny <= 64 && left >= 0 && left + nx <= pd.lv[0].w && top >= 0 &&
+                    top + ny <= pd.lv[0].h && ox < pd.lv[lev].w && oy < pd.lv[lev].h);
         float vc[2], wc[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -440,6 +444,7 @@ struct RingTile {
     const uint8_t *a;
     int delta, X0, Y0, ytop;
     __device__ __forceinline__ const uint8_t *at(int ry, int col) const {
+        RSVIO_CHECK(ry >= 0 && col >= 0 && col < RB + RW);  // the caller's tap loops stay below the tile's row count
         return a + (col >= kSplitCol ? delta : 0) + ry * RW + col;
     }
 };
@@ -679,7 +684,10 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
     uint8_t *__restrict__ out = P.dst + (size_t)img * P.pd.pyr_stride;
     const uint8_t *__restrict__ tA = smem + S::off_tile + 2 * buf * S::region;   // tile columns [0, RW)
     const uint8_t *__restrict__ tB = tA + S::region - RB;                        // indexable by tile column >= RB
-    auto trow = [&](int ry, int col) -> const uint8_t * { return (col < kSplitCol ? tA : tB) + ry * RW + col; };
+    auto trow = [&](int ry, int col) -> const uint8_t * {
+        RSVIO_CHECK(ry >= 0 && ry < C::ROWS && col >= 0 && col < RB + RW);
+        return (col < kSplitCol ? tA : tB) + ry * RW + col;
+    };
     mbar_wait(mbar0 + 8u * buf, (dbl ? (it >> 1) : it) & 1);
 
     // ---- stage 0: level 0 == input, 16-byte copies from the staged tile.  A thread owns one 16-byte
@@ -777,6 +785,9 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
             grow += G2P / 4;
         };
         if (live) {
+            // rows read: 2 ts - 1 .. 2 te + 1 (+ 1 more without G); G rows written: ts .. te - 1
+            RSVIO_CHECK(2 * ts - 1 - (Y0 - C::ytop) >= 0 && 2 * te + 1 - (Y0 - C::ytop) < C::ROWS);
+            RSVIO_CHECK(!G || (ts - t_first >= 0 && te - 1 - t_first < C::G2ROWS && 4 * c + 3 < G2P));
             // O_t spans rows 2t-1..2t+2 (complete in iteration t+1, second row), G_t rows 2t..2t+3
             // (complete in iteration t+2, first row).  Iterations ts and ts+1 and te, te+1 are peeled:
             // they only feed the accumulators of rows this segment emits.
@@ -872,6 +883,7 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
                 // column 8q + 2k + 1 (odd): hi(A_i) + 2 lo(A_{i+1}) + hi(A_{i+1}), A_i = word 4q + k.
                 const int q = idx % OQ, ly = idx / OQ;
                 const int tc = 2 * ly + C::et;                 // centre row in g2
+                RSVIO_CHECK(tc - 1 >= 0 && tc + 1 < C::G2ROWS && 2 * (4 * q + 4) + 1 < G2P);
                 uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;
 #pragma unroll
                 for (int rr = 0; rr < 3; ++rr) {
@@ -904,6 +916,7 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
                 const int gq = k % GQ, gs = k / GQ;
                 const int gm = 2 * gq;
                 const int tc = 2 * gs + 1;                     // centre row = 2 (gs - 1) + et + 1 with et == 2
+                RSVIO_CHECK(tc - 1 >= 0 && tc + 1 < C::G2ROWS && 2 * (gm + 2) + 1 < G2P && gs < C::G4R);
                 uint32_t n0 = 0, n1 = 0;
 #pragma unroll
                 for (int rr = 0; rr < 3; ++rr) {
@@ -931,6 +944,7 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
             const int lx = k % (TW / 8), ly = k / (TW / 8);
             // g4[s - (Y0/4 - 1)][m - (X0/4 - 1)]:  O window centre m = 2*ox, G window centre m = 2*ox + 1
             const int mc = 2 * lx + 1 + (is_o ? 0 : 1), sc = 2 * ly + 1 + (is_o ? 0 : 1);
+            RSVIO_CHECK(sc + 1 < C::G4R && mc + 1 < C::G4C);
             const uint32_t *r0 = &g4[sc - 1][mc - 1], *r1 = &g4[sc][mc - 1], *r2 = &g4[sc + 1][mc - 1];
             const uint32_t n = r0[0] + 2u * r0[1] + r0[2] + 2u * (r1[0] + 2u * r1[1] + r1[2]) + r2[0] + 2u * r2[1] + r2[2];
             const int ox = X0 / 8 + lx, oy = Y0 / 8 + ly;
@@ -976,6 +990,7 @@ pyr_deep_kernel(const __grid_constant__ PyrDesc pd, const uint32_t *__restrict__
             lev = 4;
             ox = 1 + k % (w4 - 2);
             oy = 1 + k / (w4 - 2);
+            RSVIO_CHECK(2 * oy + 1 < h8 && 2 * ox + 1 < w8);
             const uint32_t *r0 = g + (size_t)(2 * oy - 1) * w8 + (2 * ox - 1), *r1 = r0 + w8, *r2 = r1 + w8;
             n = r0[0] + 2u * r0[1] + r0[2] + 2u * (r1[0] + 2u * r1[1] + r1[2]) + r2[0] + 2u * r2[1] + r2[2];
             shift = 18;  // D = 4 * 16^4
@@ -985,6 +1000,7 @@ pyr_deep_kernel(const __grid_constant__ PyrDesc pd, const uint32_t *__restrict__
             ox = 1 + k % (w5 - 2);
             oy = 1 + k / (w5 - 2);
             n = 0;
+            RSVIO_CHECK(4 * oy + 4 < h8 && 4 * ox + 4 < w8);
 #pragma unroll
             for (int a = 0; a < 7; ++a) {
                 const uint32_t *r = g + (size_t)(4 * oy - 2 + a) * w8 + (4 * ox - 2);
