@@ -1,6 +1,6 @@
 """Summarise ncu artefacts into small text files for profiles/.
   python tools/ncu_summary.py launches <launches.csv> <out.txt>     per-kernel launch count / avg / share
-  python tools/ncu_summary.py kernel   <report.ncu-rep> <out.txt>   key metrics of the first kernel in the report"""
+  python tools/ncu_summary.py kernel   <report.ncu-rep> <out.txt>   key metrics of the longest launch in the report"""
 import collections
 import csv
 import subprocess
@@ -46,7 +46,9 @@ def launches(src, dst):
 def kernel(src, dst):
     out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    H, U, D = rows[0], rows[1], rows[2]
+    H, U = rows[0], rows[1]
+    ti = H.index("gpu__time_duration.sum")
+    D = max(rows[2:], key=lambda r: float(r[ti].replace(",", "")) if len(r) > ti and r[ti] else 0.0)  # the longest launch captured
     with open(dst, "w") as f:
         f.write(f"# {src}: ncu --set full --clock-control none, kernel: {D[H.index('Kernel Name')]}\n")
         for k in KEYS:
