@@ -233,6 +233,43 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Sums of several per-lane values over the warp with fewer shuffles than one butterfly per value:
+// each xor step keeps half of the values and hands the other half to the partner lane, so 4 values
+// need 2 + 1 + 3 shuffles (instead of 20) and end up on lanes 0, 8, 16, 24, from where they are
+// broadcast.  Every lane returns the same bits.
+__device__ __forceinline__ void warp_sum4(float &v0, float &v1, float &v2, float &v3, int lane) {
+    const bool up16 = lane & 16, up8 = lane & 8;
+    float a = up16 ? v2 : v0, b = up16 ? v3 : v1;
+    a += __shfl_xor_sync(0xffffffffu, up16 ? v0 : v2, 16);
+    b += __shfl_xor_sync(0xffffffffu, up16 ? v1 : v3, 16);
+    float c = (up8 ? b : a) + __shfl_xor_sync(0xffffffffu, up8 ? a : b, 8);
+    c += __shfl_xor_sync(0xffffffffu, c, 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    v0 = __shfl_sync(0xffffffffu, c, 0);
+    v1 = __shfl_sync(0xffffffffu, c, 8);
+    v2 = __shfl_sync(0xffffffffu, c, 16);
+    v3 = __shfl_sync(0xffffffffu, c, 24);
+}
+
+// 8 values: 4 + 2 + 1 + 2 shuffles, results on lanes 0, 4, .., 28
+__device__ __forceinline__ void warp_sum8(float (&v)[8], int lane) {
+    const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
+    float a[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        a[k] = (up16 ? v[4 + k] : v[k]) + __shfl_xor_sync(0xffffffffu, up16 ? v[k] : v[4 + k], 16);
+    float b[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        b[k] = (up8 ? a[2 + k] : a[k]) + __shfl_xor_sync(0xffffffffu, up8 ? a[k] : a[2 + k], 8);
+    float c = (up4 ? b[1] : b[0]) + __shfl_xor_sync(0xffffffffu, up4 ? b[0] : b[1], 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = __shfl_sync(0xffffffffu, c, 4 * k);
+}
+
 // decoded frames (16-bit grey, RGB8) -> dense 8-bit luma (DynamicImage::to_luma8 of the dataset players)
 int pixel_bytes(int fmt);
 cudaError_t convert_to_luma8(const uint8_t *d_src, size_t stride_bytes, int w, int h, int fmt, uint8_t *d_dst,

@@ -746,7 +746,12 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
         // level-1 rows this thread stores: its segment, the tile's O range, the level's interior
         const int o_lo = max(max(ts, Y0 / 2), 1);
         const int o_hi = (j0 < w1 && j0 + 3 >= 1) ? min(min(te, Y0 / 2 + TH / 2), h1 - 1) : o_lo;
-        const bool o_edge = j0 < 1 || j0 + 3 > w1 - 2;  // group touches the first / last column
+        // which of the lane's four columns are interior columns of level 1 does not depend on the row: j0 = 2 (mod 4),
+        // so (j0, j0+1) and (j0+2, j0+3) are aligned byte pairs; only column 1 and column w1 - 2 end up alone in theirs
+        const bool ov0 = j0 + 0 >= 1 && j0 + 0 <= w1 - 2, ov1 = j0 + 1 >= 1 && j0 + 1 <= w1 - 2;
+        const bool ov2 = j0 + 2 >= 1 && j0 + 2 <= w1 - 2, ov3 = j0 + 3 >= 1 && j0 + 3 <= w1 - 2;
+        const bool pair_lo = ov0 && ov1, pair_hi = ov2 && ov3;
+        const unsigned lone = (ov0 && !ov1 ? 1u : 0u) | (ov1 && !ov0 ? 2u : 0u) | (ov2 && !ov3 ? 4u : 0u) | (ov3 && !ov2 ? 8u : 0u);
         uint32_t aOo[4] = {0, 0, 0, 0}, aOn[4] = {0, 0, 0, 0}, aGo[4] = {0, 0, 0, 0}, aGm[4] = {0, 0, 0, 0},
                  aGn[4] = {0, 0, 0, 0};
         uint8_t *__restrict__ orow = out + P.pd.lv[1].off + (ptrdiff_t)(ts - 1) * w1 + j0;  // row tau - 1
@@ -760,14 +765,14 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
             if (to >= o_lo && to < o_hi) {
                 constexpr uint32_t kR = 32u - kORound;  // what of the rounding constant is not in the accumulator yet
                 const uint32_t b0 = (aOo[0] + kR) >> 6, b1 = (aOo[1] + kR) >> 6, b2 = (aOo[2] + kR) >> 6, b3 = (aOo[3] + kR) >> 6;
-                if (!o_edge) {  // j0 = 2 (mod 4): two aligned 16-bit stores
-                    reinterpret_cast<uint16_t *>(orow)[0] = (uint16_t)(b0 | (b1 << 8));
-                    reinterpret_cast<uint16_t *>(orow)[1] = (uint16_t)(b2 | (b3 << 8));
-                } else {
-                    if (j0 + 0 >= 1 && j0 + 0 <= w1 - 2) orow[0] = (uint8_t)b0;
-                    if (j0 + 1 >= 1 && j0 + 1 <= w1 - 2) orow[1] = (uint8_t)b1;
-                    if (j0 + 2 >= 1 && j0 + 2 <= w1 - 2) orow[2] = (uint8_t)b2;
-                    if (j0 + 3 >= 1 && j0 + 3 <= w1 - 2) orow[3] = (uint8_t)b3;
+                // two aligned 16-bit stores, predicated per lane (no divergent second path for the tiles' edge lanes)
+                if (pair_lo) reinterpret_cast<uint16_t *>(orow)[0] = (uint16_t)(b0 | (b1 << 8));
+                if (pair_hi) reinterpret_cast<uint16_t *>(orow)[1] = (uint16_t)(b2 | (b3 << 8));
+                if (lone) {  // one lane of the first and of the last tile column
+                    if (lone & 1u) orow[0] = (uint8_t)b0;
+                    if (lone & 2u) orow[1] = (uint8_t)b1;
+                    if (lone & 4u) orow[2] = (uint8_t)b2;
+                    if (lone & 8u) orow[3] = (uint8_t)b3;
                 }
             }
         };

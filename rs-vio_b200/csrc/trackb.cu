@@ -29,9 +29,13 @@ struct PyrB {
 struct Iso {  // na::Isometry2<f32>: unit complex (c, s) and translation
     float c, s, tx, ty;
 };
+// FMA policy of this file (as lk.cu): the library is compiled with -fmad=false, the multiply-add chains of the
+// sampler and of the isometries are fused EXPLICITLY (one rounding instead of two per step).  The kernel is bound by
+// the issue rate of a single warp (77 k warp instructions per track before, a third of them in the two Horner
+// passes), the bar is 1e-3 px against an oracle that rounds every operation.
 __device__ __forceinline__ void iso_apply(const Iso &T, float x, float y, float &ox, float &oy) {
-    ox = T.c * x - T.s * y + T.tx;
-    oy = T.s * x + T.c * y + T.ty;
+    ox = fmaf(T.c, x, fmaf(-T.s, y, T.tx));
+    oy = fmaf(T.s, x, fmaf(T.c, y, T.ty));
 }
 
 // offsets of patch.rs:259-277: rows y = 7, 5, .., -7 with 4, 6, 8, 8, 8, 8, 6, 4 samples at odd x (not halved)
@@ -55,28 +59,27 @@ __device__ __forceinline__ void pattern_b(int i, float &ox, float &oy) {
 __device__ __forceinline__ void cubic_coeffs(const float f[4], float &a0, float &a1, float &a2, float &a3) {
     a0 = f[1];
     a1 = f[2] - f[0];
-    a2 = 2.0f * f[0] - 5.0f * f[1] + 4.0f * f[2] - f[3];
-    a3 = 3.0f * (f[1] - f[2]) + f[3] - f[0];
+    a2 = fmaf(4.0f, f[2], fmaf(-5.0f, f[1], 2.0f * f[0])) - f[3];
+    a3 = fmaf(3.0f, f[1] - f[2], f[3]) - f[0];
 }
 __device__ __forceinline__ float bicubic_1d(const float f[4], float t) {
     float a0, a1, a2, a3;
     cubic_coeffs(f, a0, a1, a2, a3);
-    return a0 + 0.5f * (t * (a1 + t * (a2 + t * a3)));
+    return fmaf(0.5f * t, fmaf(t, fmaf(t, a3, a2), a1), a0);
 }
 __device__ __forceinline__ float d_bicubic_1d(const float f[4], float t, float &dt) {
     float a0, a1, a2, a3;
     cubic_coeffs(f, a0, a1, a2, a3);
-    dt = 0.5f * (a1 + t * (2.0f * a2 + t * 3.0f * a3));
-    return a0 + 0.5f * (t * (a1 + t * (a2 + t * a3)));
+    dt = 0.5f * fmaf(t, fmaf(t, 3.0f * a3, 2.0f * a2), a1);
+    return fmaf(0.5f * t, fmaf(t, fmaf(t, a3, a2), a1), a0);
 }
 
 // window test of interpolate_bicubic: floor(x) in [1, w-3], floor(y) in [1, h-3] (`as u32` saturates)
 __device__ __forceinline__ bool window_b(int w, int h, float x, float y, int &xf, int &yf, float &tx, float &ty) {
-    if (!(isfinite(x) && isfinite(y))) return false;
-    const float fx = floorf(x), fy = floorf(y);
-    xf = fx < 0.0f ? 0 : (fx > 1e9f ? 1000000000 : (int)fx);
-    yf = fy < 0.0f ? 0 : (fy > 1e9f ? 1000000000 : (int)fy);
-    if (xf < 1 || xf > max(w - 3, 0) || yf < 1 || yf > max(h - 3, 0)) return false;
+    // floor(x) in [1, w - 3]  <=>  1 <= x < w - 2 (NaN and infinities fail the compares; w <= 3 leaves no window)
+    if (!(x >= 1.0f && x < (float)(w - 2) && y >= 1.0f && y < (float)(h - 2))) return false;
+    xf = (int)x;  // truncation == floor for x >= 1
+    yf = (int)y;
     tx = x - (float)xf;
     ty = y - (float)yf;
     return true;
@@ -130,18 +133,35 @@ __device__ __forceinline__ bool in_bounds_b(int w, int h, float x, float y) {
 }
 
 __device__ __forceinline__ Iso exp_se2_b(float theta, float v0, float v1) {
+    float sn, cs;
+    if (fabsf(theta) < 0.5f) {
+        // LM increments are small rotations: Taylor polynomials (truncation < 2e-11) instead of the general-range
+        // sinf / cosf (the reference's libm values are not reproducible bit for bit on a GPU anyway)
+        const float t2 = theta * theta;
+        float ps = fmaf(t2, 2.7557319e-06f, -1.9841270e-04f);
+        ps = fmaf(ps, t2, 8.3333333e-03f);
+        ps = fmaf(ps, t2, -1.6666667e-01f);
+        sn = fmaf(ps * t2, theta, theta);
+        float pc = fmaf(t2, -2.7557319e-07f, 2.4801587e-05f);
+        pc = fmaf(pc, t2, -1.3888889e-03f);
+        pc = fmaf(pc, t2, 4.1666667e-02f);
+        pc = fmaf(pc, t2, -0.5f);
+        cs = fmaf(pc, t2, 1.0f);
+    } else {
+        sincosf(theta, &sn, &cs);
+    }
     float diag, cross;
     if (fabsf(theta) > 1e-4f) {
-        diag = sinf(theta) / theta;
-        cross = (1.0f - cosf(theta)) / theta;
+        diag = sn / theta;
+        cross = (1.0f - cs) / theta;
     } else {
         const float theta_sq = theta * theta;
         diag = 1.0f - theta * theta / 6.0f;
         cross = (0.5f - theta_sq / 24.0f) * theta;
     }
     Iso E;
-    E.c = cosf(theta);
-    E.s = sinf(theta);
+    E.c = cs;
+    E.s = sn;
     E.tx = diag * v0 - cross * v1;
     E.ty = cross * v0 + diag * v1;
     return E;
@@ -216,8 +236,10 @@ __device__ bool track_level_b(const float *__restrict__ img0, const float *__res
         h12 += J[k][1] * J[k][2];
         h22 += J[k][2] * J[k][2];
     }
-    const float m11 = lambda + warp_sum(h00), m12 = warp_sum(h01), m13 = warp_sum(h02);
-    const float m22 = lambda + warp_sum(h11), m23 = warp_sum(h12), m33 = lambda + warp_sum(h22);
+    float hv[8] = {h00, h01, h02, h11, h12, h22, 0.0f, 0.0f};
+    warp_sum8(hv, lane);  // 9 shuffles for the six sums instead of 30
+    const float m11 = lambda + hv[0], m12 = hv[1], m13 = hv[2];
+    const float m22 = lambda + hv[3], m23 = hv[4], m33 = lambda + hv[5];
     const float m21 = m12, m31 = m13, m32 = m23;
     const float mn1 = m22 * m33 - m32 * m23, mn2 = m21 * m33 - m31 * m23, mn3 = m21 * m32 - m31 * m22;
     const float det = m11 * mn1 - m12 * mn2 + m13 * mn3;
@@ -242,18 +264,20 @@ __device__ bool track_level_b(const float *__restrict__ img0, const float *__res
             const bool ok = has[k] && interp_b(img1, w, h, px, py, v);
             tv[k] = ok ? v : 0.0f;
         }
-        float tmean = 1.0f;
-        if (cost == 1) tmean = warp_sum(tv[0] + tv[1]) / (float)kNP;
+        if (cost == 1) {  // residuals_lssd: target samples divided by their mean (warp-uniform branch)
+            const float tmean = warp_sum(tv[0] + tv[1]) / (float)kNP;
+            tv[0] = tv[0] / tmean;
+            tv[1] = tv[1] / tmean;
+        }
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-            const float res = has[k] ? (cost == 1 ? tv[k] / tmean : tv[k]) - inten[k] : 0.0f;
+            const float res = has[k] ? tv[k] - inten[k] : 0.0f;
             b0 += J[k][0] * res;
             b1 += J[k][1] * res;
             b2 += J[k][2] * res;
         }
-        b0 = warp_sum(b0);
-        b1 = warp_sum(b1);
-        b2 = warp_sum(b2);
+        float b3 = 0.0f;
+        warp_sum4(b0, b1, b2, b3, lane);  // 9 shuffles for the three sums instead of 15
         const float t0 = Hi[0][0] * b0 + Hi[0][1] * b1 + Hi[0][2] * b2;
         const float t1 = Hi[1][0] * b0 + Hi[1][1] * b1 + Hi[1][2] * b2;
         const float t2 = Hi[2][0] * b0 + Hi[2][1] * b1 + Hi[2][2] * b2;

@@ -258,3 +258,60 @@ impl<const LEVELS: u32> PatchTracker<LEVELS> {
         self.h.remove(ids);
     }
 }
+
+/// The reference's `image_utilities` module (src/feature_tracker/image_utilities.rs, `pub mod` at mod.rs:1) with the
+/// types of this crate: plain predicates on the host, `se2_exp_matrix` and `detect_key_points` evaluated by the device
+/// code through the stateless entry points (the same kernels the tracker runs).  `image_grad`, `Pattern52` and
+/// `track_point_at_level` (mod.rs:5, feature_tracker.rs:344) are internal to the fused LK kernel and have no
+/// standalone entry point: `rsvio_track_points` (ffi) runs the whole coarse-to-fine chain for a batch of points.
+pub mod image_utilities {
+    use crate::ffi;
+    use image::GrayImage;
+
+    /// imageproc::corners::Corner as the reference uses it (x, y, score)
+    #[derive(Copy, Clone, Debug, PartialEq)]
+    pub struct Corner {
+        pub x: u32,
+        pub y: u32,
+        pub score: f32,
+    }
+
+    /// image_utilities.rs:68-73
+    pub fn point_in_bound(keypoint: &Corner, height: u32, width: u32, radius: u32) -> bool {
+        keypoint.x >= radius && keypoint.x <= width - radius && keypoint.y >= radius && keypoint.y <= height - radius
+    }
+
+    /// image_utilities.rs:75-80 (`as u32` saturates: negatives and NaN become 0)
+    pub fn inbound(image: &GrayImage, x: f32, y: f32, radius: u32) -> bool {
+        let x = x.round() as u32;
+        let y = y.round() as u32;
+        x >= radius && y >= radius && x < image.width() - radius && y < image.height() - radius
+    }
+
+    /// image_utilities.rs:82-106: twist `[vx, vy, theta]` -> row-major 3x3 homogeneous matrix
+    pub fn se2_exp_matrix(a: &[f32; 3]) -> [[f32; 3]; 3] {
+        let mut out = [0f32; 9];
+        let st = unsafe { ffi::rsvio_se2_exp(0, a.as_ptr(), 1, out.as_mut_ptr()) };
+        assert!(st == ffi::RSVIO_OK, "rsvio_se2_exp: {}", crate::status_text(st));
+        [[out[0], out[1], out[2]], [out[3], out[4], out[5]], [out[6], out[7], out[8]]]
+    }
+
+    /// image_utilities.rs:108-175 with `num_points_in_cell == 1` (the only value the reference passes,
+    /// feature_tracker.rs:242): one FAST-9 corner per empty grid cell, in the reference's visiting order
+    pub fn detect_key_points(image: &GrayImage, grid_size: u32, current_corners: &Vec<Corner>, num_points_in_cell: u32) -> Vec<Corner> {
+        assert_eq!(num_points_in_cell, 1, "the device path implements one point per cell");
+        let (w, h) = image.dimensions();
+        let cur: Vec<u32> = current_corners.iter().flat_map(|c| [c.x, c.y]).collect();
+        let cap = ((w / grid_size + 1) * (h / grid_size + 1)) as usize;
+        let mut xy = vec![0u32; 2 * cap];
+        let mut score = vec![0f32; cap];
+        let mut n = 0usize;
+        let cur_ptr = if cur.is_empty() { std::ptr::null() } else { cur.as_ptr() };
+        let st = unsafe {
+            ffi::rsvio_detect_keypoints(0, image.as_raw().as_ptr(), w as i32, h as i32, w as usize, grid_size, cur_ptr,
+                                        current_corners.len() as i32, xy.as_mut_ptr(), score.as_mut_ptr(), cap, &mut n)
+        };
+        assert!(st == ffi::RSVIO_OK, "rsvio_detect_keypoints: {}", crate::status_text(st));
+        (0..n.min(cap)).map(|i| Corner { x: xy[2 * i], y: xy[2 * i + 1], score: score[i] }).collect()
+    }
+}
