@@ -82,6 +82,8 @@ constexpr int kBoxRMax = 40;  // sigma <= ~23
 constexpr int kBoxChunk = 64;
 constexpr int kBoxCols = kBoxChunk + 2 * kBoxRMax + 1;  // odd: lane * kBoxCols hits 32 different banks
 
+__device__ __noinline__ float ieee_div(float a, float b) { return a / b; }
+
 __global__ void __launch_bounds__(128)
 box_pass_kernel(const float *__restrict__ src, int w, int h, int r, size_t plane, float *__restrict__ dst) {
     __shared__ float tile[2][32][kBoxCols];
@@ -108,7 +110,7 @@ box_pass_kernel(const float *__restrict__ src, int w, int h, int r, size_t plane
     };
     const int row = row0 + lane;
     const bool live = row < h;
-    const float den = 2.0f * (float)r + 1.0f;
+    const float den = 2.0f * (float)r + 1.0f, rden = 1.0f / den;
     float v = 0.0f;
     if (warp == 0) {  // first window: columns -r .. r (clamped), summed left to right
         const float *__restrict__ p = src + (size_t)min(row, h - 1) * w;
@@ -123,10 +125,28 @@ box_pass_kernel(const float *__restrict__ src, int w, int h, int r, size_t plane
         } else if (live) {
             const int c0 = chunk * kBoxChunk, nc = min(kBoxChunk, w - c0);
             const float *__restrict__ t = tile[chunk & 1][lane];
+            // v / den, correctly rounded, without the IEEE division sequence (15 instructions with its range checks and
+            // a slow-path call -- control flow that would keep the next step's shared-memory loads behind it):
+            // q = RN(v y), r = v - q den (exact in the FMA), q' = RN(q + r y) equals RN(v / den) when y = RN(1 / den)
+            // (Markstein) and nothing underflows.  Tiny non-zero running sums (impossible for f32 images in [0, 1],
+            // whose squared differences are 0 or > 1e-15) are only flagged in the loop; a flagged chunk is redone with
+            // the real division.
+            const float v_start = v;
+            bool tiny = false;
 #pragma unroll 8  // the shared-memory loads run ahead of the two dependent adds per step
             for (int k = 0; k < nc; ++k) {
-                dst[(size_t)(c0 + k) * h + row] = fminf(fmaxf(v / den, 0.0f), 1.0f);
+                float q = v * rden;
+                q = fmaf(fmaf(-q, den, v), rden, q);
+                tiny = tiny || (!(fabsf(v) > 1e-30f) && v != 0.0f);
+                dst[(size_t)(c0 + k) * h + row] = fminf(fmaxf(q, 0.0f), 1.0f);
                 v = v - t[k] + t[k + 2 * r + 1];  // p[c - r], p[c + r + 1]
+            }
+            if (tiny) {
+                v = v_start;
+                for (int k = 0; k < nc; ++k) {
+                    dst[(size_t)(c0 + k) * h + row] = fminf(fmaxf(ieee_div(v, den), 0.0f), 1.0f);
+                    v = v - t[k] + t[k + 2 * r + 1];
+                }
             }
         }
         __syncthreads();
