@@ -598,7 +598,8 @@ class FeatureTracker:
 
     def __init__(self, nlevels=5, ratio=2.0, preprocessing_blur=True, preprocessing_blur_sigma=2.0,
                  detection_threshold=2.5, detection_min_dist=15, detection_blur=6.0, optical_flow_max_iter=25,
-                 optical_flow_lm_lambda=0.1):
+                 optical_flow_lm_lambda=0.1, matching_cost="ssd"):
+        self.cost = matching_cost   # process_frame hard-codes SSD (feature_tracker.rs:125); "lssd" mirrors the handle's option
         self.cfg = dict(nlevels=nlevels, ratio=ratio, blur=preprocessing_blur, sigma=preprocessing_blur_sigma,
                         thr=detection_threshold, min_dist=detection_min_dist, dblur=detection_blur,
                         max_iter=optical_flow_max_iter, lam=optical_flow_lm_lambda)
@@ -612,7 +613,7 @@ class FeatureTracker:
         if self.prev is not None:
             pf, pp = self.prev
             pts = [(x, y) for _, x, y in pf]
-            maps = track_points(pp, pyr, pts, c["max_iter"], c["lam"])
+            maps = track_points(pp, pyr, pts, c["max_iter"], c["lam"], self.cost)
             for k, (fid, x, y) in enumerate(pf):
                 if k in maps:
                     q = maps[k].apply((x, y))

@@ -94,3 +94,34 @@ def test_tools_and_entry_points_compile():
     assert len(files) > 8
     for f in files:
         py_compile.compile(f, doraise=True)
+
+
+def test_crate_b_invalid_arguments_are_rejected_without_touching_the_gpu(rsvio):
+    """row f-2 entry points: argument errors come back as RSVIO_ERR_INVALID_ARG (-1) before any CUDA call"""
+    import numpy as np
+    from rsvio_b200.binding import BConfig
+    L = rsvio.load_library()
+    cfg = BConfig()
+    L.rsvio_b_config_default(ctypes.byref(cfg))
+    assert (cfg.nlevels, cfg.ratio, cfg.preprocessing_blur, cfg.detection_min_dist, cfg.optical_flow_max_iter) == (5, 2.0, 1, 15, 25)
+    assert abs(cfg.detection_threshold - 2.5) < 1e-6 and abs(cfg.detection_blur - 6.0) < 1e-6 and cfg.matching_cost == 0
+    h = ctypes.c_void_p()
+    assert L.rsvio_b_tracker_create(None, ctypes.byref(h)) == -1
+    assert L.rsvio_b_tracker_create(ctypes.byref(cfg), ctypes.byref(h)) == -1            # width / height still 0
+    cfg.width, cfg.height = 64, 64
+    for field, bad in (("nlevels", 0), ("nlevels", 99), ("ratio", 1.0), ("detection_min_dist", 0), ("detection_blur", 0.0),
+                       ("matching_cost", 7), ("optical_flow_max_iter", -1), ("max_features", -5)):
+        c2 = BConfig.from_buffer_copy(cfg)
+        setattr(c2, field, bad)
+        assert L.rsvio_b_tracker_create(ctypes.byref(c2), ctypes.byref(h)) == -1, field
+    img = np.zeros((8, 8), np.float32)
+    assert L.rsvio_b_tracker_process_frame(None, img, 0) == -1
+    n = ctypes.c_int32(0)
+    assert L.rsvio_b_tracker_num_features(None, ctypes.byref(n), None) == -1
+    assert L.rsvio_b_blur(0, img, 0, 8, 2.0, img) == -1
+    assert L.rsvio_b_blur(0, img, 8, 8, 1000.0, img) == -1                             # kernel table holds sigma <= ~31
+    assert L.rsvio_b_shi_tomasi_score(0, img, 8, 8, 0.0, img) == -1
+    out = np.zeros((4, 2), np.uint32)
+    cnt = ctypes.c_size_t(0)
+    assert L.rsvio_b_add_points(0, img, 8, 8, img, 0, 0.0, 0, 2.0, out, 4, ctypes.byref(cnt)) == -1   # min_dist 0
+    L.rsvio_b_tracker_destroy(None)                                                    # a no-op

@@ -212,3 +212,46 @@ def test_crate_b_full_size_frame(rsvio):
     assert len(flow) >= len(f0) // 2
     assert np.abs(np.median(flow, axis=0) - np.array([2.0, 1.0])).max() < 0.1
     assert gpu.last_frame_ms() > 0
+
+
+def test_crate_b_edge_cases(rsvio):
+    """flat image -> no features and nothing to track; one level / no blur / LSSD configurations against the oracle;
+    a full feature table drops new corners but still returns the frame"""
+    h, w = 96, 128
+    flat = rsvio.FeatureTrackerB(w, h, nlevels=3, detection_min_dist=7, detection_blur=2.0)
+    assert flat.process_frame(np.full((h, w), 0.5, np.float32)) == [] and flat.n_new == 0
+    assert flat.process_frame(np.full((h, w), 0.25, np.float32)) == []
+    flat.close()
+    for kw in (dict(nlevels=1, preprocessing_blur=False), dict(nlevels=2, preprocessing_blur=False, ratio=1.5),
+               dict(nlevels=3, preprocessing_blur_sigma=0.8)):
+        cfg = dict(ratio=2.0, preprocessing_blur=True, preprocessing_blur_sigma=1.5, detection_threshold=0.02,
+                   detection_min_dist=9, detection_blur=2.0, optical_flow_max_iter=8, optical_flow_lm_lambda=0.1)
+        cfg.update(kw)
+        ref, gpu = B.FeatureTracker(**cfg), rsvio.FeatureTrackerB(w, h, **cfg)
+        for t in range(2):
+            img = textured(h, w, 9, dx=0.8 * t, dy=0.5 * t)
+            want, got = ref.process_frame(img), gpu.process_frame(img, t)
+            assert [f[0] for f in got] == [f[0] for f in want], (kw, t)
+            d = np.abs(np.array([[f[1], f[2]] for f in got]) - np.array([[f[1], f[2]] for f in want]))
+            assert len(got) >= 5 and d.max() < 1e-3, (kw, t, d.max())
+        gpu.close()
+    # LSSD through the stateful handle (the reference's LSSD compares mean-normalised target samples with a RAW
+    # template, so it loses most features -- what matters is that the device loses the same ones as the oracle)
+    cfg = dict(nlevels=3, preprocessing_blur_sigma=1.5, detection_threshold=0.02, detection_min_dist=9, detection_blur=2.0,
+               optical_flow_max_iter=8)
+    ref = B.FeatureTracker(matching_cost="lssd", **cfg)
+    lssd = rsvio.FeatureTrackerB(w, h, matching_cost=rsvio.B_COST_LSSD, **cfg)
+    for t in range(2):
+        img = (textured(h, w, 9, dx=0.6 * t) * np.float32(1.0 - 0.15 * t)).astype(np.float32)
+        want, got = ref.process_frame(img), lssd.process_frame(img, t)
+        assert [f[0] for f in got] == [f[0] for f in want], t
+        d = np.abs(np.array([[f[1], f[2]] for f in got]) - np.array([[f[1], f[2]] for f in want]))
+        assert d.max() < 1e-3, (t, d.max())
+    lssd.close()
+    # capacity: a table of 4 features
+    small = rsvio.FeatureTrackerB(w, h, nlevels=2, detection_threshold=0.02, detection_min_dist=9, detection_blur=2.0, max_features=4)
+    with pytest.raises(rsvio.RsvioError) as ei:
+        small.process_frame(textured(h, w, 9))
+    assert ei.value.status == -3                      # RSVIO_ERR_CAPACITY: the frame was processed, excess corners dropped
+    assert len(small.features()) == 4
+    small.close()
