@@ -269,3 +269,34 @@ def test_lssd_patch():
     assert np.allclose(r, p.intensities / mean - p.intensities, atol=1e-5)   # the template stays raw, as in the reference
     T = B.track_point([img], [(img * np.float32(0.7)).astype(np.float32)], (30.3, 31.6), 15, 0.1, "lssd")
     assert T is not None
+
+
+def test_crate_b_image_ops_against_independent_implementations():
+    """Third-party twins of the restated crate arithmetic (scipy / OpenCV / numpy.linalg share no code with the oracle):
+    they pin the ALGORITHMS as restated (box sizes, edge replication, kernel taps, the eigenvalue formula), not the
+    crates' own rounding order."""
+    import cv2
+    from scipy import ndimage
+    rng = np.random.default_rng(3)
+    img = B.blur(_texture(72, 96, 5), 1.0)
+    # fast_blur == three passes of a replicated-edge box filter of sizes boxes_for_gauss(sigma), both axes
+    for sigma in (1.0, 2.0, 6.0):
+        plane = rng.uniform(0.0, 1.0, (50, 64)).astype(np.float32)
+        want = plane.astype(np.float64)
+        for size in B.boxes_for_gauss(sigma):
+            want = ndimage.uniform_filter1d(want, size, axis=1, mode="nearest")
+            want = ndimage.uniform_filter1d(want, size, axis=0, mode="nearest")
+        assert np.abs(B.fast_blur(plane, sigma) - want).max() < 2e-6, sigma
+    # the score is 1000 x the smaller eigenvalue of the blurred structure tensor
+    p = np.pad(img, 1, mode="edge")
+    dx, dy = p[1:-1, 2:] - p[1:-1, :-2], p[2:, 1:-1] - p[:-2, 1:-1]
+    a, b, c = (B.fast_blur((u * v).astype(np.float32), 2.0).astype(np.float64) for u, v in ((dx, dx), (dy, dy), (dx, dy)))
+    lam = np.linalg.eigvalsh(np.stack([np.stack([a, c], -1), np.stack([c, b], -1)], -2))[..., 0]
+    assert np.abs(B.shi_tomasi_score(img, 2.0) - 1000.0 * np.abs(lam)).max() < 2e-3 * max(1.0, 1000.0 * np.abs(lam).max())
+    # blur == the normalised Gaussian taps -4 .. 4 (sigma 2) applied separably; interior only (truncated windows are
+    # renormalised at the border, OpenCV replicates instead)
+    k = np.exp(-np.arange(-4, 5, dtype=np.float64) ** 2 / (2 * 2.0 ** 2))
+    k /= k.sum()
+    tex = _texture(60, 80, 1)
+    ref = cv2.sepFilter2D(tex.astype(np.float64), -1, k, k, borderType=cv2.BORDER_REPLICATE)
+    assert np.abs(B.blur(tex, 2.0) - ref)[4:-4, 4:-4].max() < 1e-6
