@@ -469,7 +469,10 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
     return RSVIO_TRACK_OK;
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 8)
+#ifndef RSVIO_LK_MINB
+#define RSVIO_LK_MINB 8  // resident CTAs per SM the register budget is sized for (A/B: -DRSVIO_LK_MINB=10)
+#endif
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, RSVIO_LK_MINB)
 lk_track_fb_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ LkBatch b) {
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -611,7 +614,7 @@ cudaError_t lk_track(const PyrDesc &pd, const LkBatch &b, cudaStream_t st) {
     long long blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const bool dynamic = b.work_counter != nullptr && b.groups <= kMaxGroupsSmem;
     // dynamic scheduling: one resident wave (64 registers -> 8 CTAs per SM); static striding: up to 16 per SM
-    const long long max_blocks = (long long)sm_count() * (dynamic ? 8 : 16);
+    const long long max_blocks = (long long)sm_count() * (dynamic ? RSVIO_LK_MINB : 16);
     if (blocks > max_blocks) blocks = max_blocks;
     const size_t smem = dynamic ? sizeof(int) * (size_t)(b.groups + 1) : 0;
     lk_track_fb_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(pd, b);
