@@ -296,3 +296,56 @@ def test_capacity_error_is_reported(rsvio):
     assert st == -3 and tr.num_tracks(0) == 8 and tr.overflow_frames() == 1
     with pytest.warns(rsvio.CapacityWarning):        # the mirror delivers the frame and warns
         tr.process_frame(*seq.frame(1))
+
+
+def test_handles_on_concurrent_host_threads(rsvio):
+    """SURVEY 8b threading contract: distinct handles may be driven concurrently from distinct host threads (one handle
+    == one CUDA stream, no global mutable state in the library).  Four threads -- three tracker-A handles on different
+    sequences and one crate-B handle -- must reproduce, bit for bit, what the same handles produce one after the other."""
+    import threading
+    from rsvio_b200.synth import StereoSequence
+    w, h, levels, grid, frames = 376, 240, 3, 40, 5
+    seqs = [StereoSequence("C1", stream_id=s, w=w, h=h, grid=grid) for s in range(3)]
+    imgs = [[seq.frame(t) for t in range(frames)] for seq in seqs]
+    b_imgs = [(imgs[0][t][0].astype(np.float32) / np.float32(255.0)) for t in range(frames)]
+    b_cfg = dict(nlevels=3, preprocessing_blur_sigma=1.5, detection_threshold=0.02, detection_min_dist=9, detection_blur=2.0,
+                 optical_flow_max_iter=10)
+
+    def run_a(k, out):
+        tr = rsvio.StereoPatchTracker(grid, 20, 0.01, width=w, height=h, levels=levels)
+        res = []
+        for l, r in imgs[k]:
+            tr.process_frame(l, r)
+            res.append([tr.transforms(cam) for cam in (0, 1)])
+        out[k] = res
+
+    def run_b(out):
+        tr = rsvio.FeatureTrackerB(w, h, **b_cfg)
+        out["b"] = [tr.process_frame(im, t) for t, im in enumerate(b_imgs)]
+        tr.close()
+
+    serial, threaded = {}, {}
+    for k in range(3):
+        run_a(k, serial)
+    run_b(serial)
+    errors = []
+
+    def guarded(fn, *a):
+        try:
+            fn(*a)
+        except Exception as ex:  # surfaced below: an exception in a thread must fail the test
+            errors.append(repr(ex))
+
+    ths = [threading.Thread(target=guarded, args=(run_a, k, threaded)) for k in range(3)]
+    ths.append(threading.Thread(target=guarded, args=(run_b, threaded)))
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join(timeout=120)
+    assert not errors, errors
+    for k in range(3):
+        for t in range(frames):
+            for cam in (0, 1):
+                assert np.array_equal(serial[k][t][cam][0], threaded[k][t][cam][0]), (k, t, cam)
+                assert np.array_equal(serial[k][t][cam][1], threaded[k][t][cam][1]), (k, t, cam)
+    assert threaded["b"] == serial["b"] and len(serial["b"][-1]) >= 5
