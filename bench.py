@@ -394,6 +394,12 @@ def crate_b_result(rsvio_b200, frames=40, warm=6):
         p = CONFIGS["C1"]
         ring = generate_frames("C1", [0], RING, 1)
         imgs = [(ring[t, 0, 0].astype(np.float32) / np.float32(255.0)) for t in range(RING)]
+        try:  # pinned host images: the handle DMA-reads them in place (pageable ones go through its staging copy)
+            import torch
+            keep = [torch.from_numpy(a).pin_memory() for a in imgs]
+            imgs = [k.numpy() for k in keep]
+        except Exception:
+            pass
         tr = rsvio_b200.FeatureTrackerB(p["w"], p["h"], detection_threshold=0.02)
         dev_ms, wall, tracks, n_feat = [], [], 0, []
         for i in range(warm + frames):

@@ -262,15 +262,25 @@ rsvio_status rsvio_b_tracker_process_frame(rsvio_b_tracker *t, const float *imag
     const rsvio_b_config &c = t->cfg;
     const size_t n0 = (size_t)c.width * c.height;
     const int cur = t->cur ^ (t->have_prev ? 1 : 0), prev = cur ^ 1;
+    const float *h_src = image;
     CUB(ds.enter(c.device));
-    memcpy(t->h_img, image, n0 * sizeof(float));
+    // a caller's pinned (cudaHostAlloc / rsvio_host_alloc / registered) image is DMA-read in place; pageable memory
+    // goes through the handle's pinned staging copy (the call is synchronous: the buffer is free again on return)
+    {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, image) != cudaSuccess || pa.type != cudaMemoryTypeHost) {
+            cudaGetLastError();
+            memcpy(t->h_img, image, n0 * sizeof(float));
+            h_src = t->h_img;
+        }
+    }
     // build_image_pyramid: blur (optional), then level l = resize(level l - 1)
     if (c.preprocessing_blur) {
-        CUB(cudaMemcpyAsync(t->d_in, t->h_img, n0 * sizeof(float), cudaMemcpyHostToDevice, t->st));
+        CUB(cudaMemcpyAsync(t->d_in, h_src, n0 * sizeof(float), cudaMemcpyHostToDevice, t->st));
         CUB(cudaEventRecord(t->ev0, t->st));
         CUB(blurb_gaussian(t->d_in, c.width, c.height, t->gauss, t->d_tmp, t->d_lv[cur][0], t->st));
     } else {
-        CUB(cudaMemcpyAsync(t->d_lv[cur][0], t->h_img, n0 * sizeof(float), cudaMemcpyHostToDevice, t->st));
+        CUB(cudaMemcpyAsync(t->d_lv[cur][0], h_src, n0 * sizeof(float), cudaMemcpyHostToDevice, t->st));
         CUB(cudaEventRecord(t->ev0, t->st));
     }
     for (int l = 1; l < c.nlevels; ++l)

@@ -255,3 +255,26 @@ def test_crate_b_edge_cases(rsvio):
     assert ei.value.status == -3                      # RSVIO_ERR_CAPACITY: the frame was processed, excess corners dropped
     assert len(small.features()) == 4
     small.close()
+
+
+def test_crate_b_track_points_on_random_points(rsvio):
+    """96 random points (interior, near the border, outside) on a rotating, shifting scene: identical status, < 1e-3 px"""
+    h, w = 120, 160
+    a, b = scene(h, w), scene(h, w, -1.6, 0.9, -0.012)
+    pa, pb = B.build_image_pyramid(a, 3, 2.0, True, 1.0), B.build_image_pyramid(b, 3, 2.0, True, 1.0)
+    rng = np.random.default_rng(21)
+    pts = np.concatenate([rng.uniform([-4, -4], [w + 4, h + 4], (72, 2)), rng.uniform([0, 0], [w, 12], (12, 2)),
+                          rng.uniform([w - 12, 0], [w, h], (12, 2))]).astype(np.float32)
+    want_T, want_st = oracle_track(pa, pb, pts, 12, 0.1)
+    got_T, got_st = rsvio.b_track_points(pa, pb, pts, 12, 0.1)
+
+    def moved(T):
+        return np.stack([T[:, 0] * pts[:, 0] - T[:, 1] * pts[:, 1] + T[:, 2], T[:, 1] * pts[:, 0] + T[:, 0] * pts[:, 1] + T[:, 3]], 1)
+    good = (got_st == want_st) & (want_st == 0)
+    err = np.abs(moved(got_T)[good] - moved(want_T)[good])
+    record({"tag": "crate B track_points random 160x120 L3", "n": int(len(pts)), "status_equal": int((got_st == want_st).sum()),
+            "tracked": int(good.sum()), "status_hist": np.bincount(want_st, minlength=4).tolist(),
+            "max_err_px": float(err.max()) if good.any() else 0.0})
+    assert (got_st == want_st).all(), (np.flatnonzero(got_st != want_st), got_st[got_st != want_st], want_st[got_st != want_st])
+    assert good.sum() >= 40 and err.max() < 1e-3
+    assert (want_st != 0).sum() >= 5          # the failure exits are exercised too
