@@ -16,6 +16,8 @@
 // the library is built with -fmad=false); only the order of the 52-term sums differs (tree
 // instead of sequential), which is why positions agree with the CPU oracle to ~1e-5 px rather
 // than bit for bit.  Tensor cores are not used: nothing here is a dense contraction.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace rsvio {
@@ -614,7 +616,12 @@ cudaError_t lk_track(const PyrDesc &pd, const LkBatch &b, cudaStream_t st) {
     long long blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
     const bool dynamic = b.work_counter != nullptr && b.groups <= kMaxGroupsSmem;
     // dynamic scheduling: one resident wave (64 registers -> 8 CTAs per SM); static striding: up to 16 per SM
-    const long long max_blocks = (long long)sm_count() * (dynamic ? RSVIO_LK_MINB : 16);
+    // RSVIO_LK_BLOCKS_PER_SM (experiments): fewer persistent CTAs than the register file holds leave room for the
+    // kernels of another handle to run beside this launch
+    const char *env = getenv("RSVIO_LK_BLOCKS_PER_SM");
+    const int env_v = env ? atoi(env) : 0;
+    const int resident = (env_v >= 1 && env_v <= RSVIO_LK_MINB) ? env_v : RSVIO_LK_MINB;
+    const long long max_blocks = (long long)sm_count() * (dynamic ? resident : 16);
     if (blocks > max_blocks) blocks = max_blocks;
     const size_t smem = dynamic ? sizeof(int) * (size_t)(b.groups + 1) : 0;
     lk_track_fb_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(pd, b);

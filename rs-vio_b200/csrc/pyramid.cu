@@ -260,6 +260,9 @@ pyr_generic_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ P
 #ifndef PYR_OROUND
 #define PYR_OROUND 1        // 1: rounding constant folded into the O accumulators
 #endif
+#ifndef PYR_SPANSTORE
+#define PYR_SPANSTORE 1     // 1: level-1 store predicates as one unsigned compare against a per-lane row span
+#endif
 #ifndef PYR_TH
 #define PYR_TH 48
 #endif
@@ -750,8 +753,15 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
         // so (j0, j0+1) and (j0+2, j0+3) are aligned byte pairs; only column 1 and column w1 - 2 end up alone in theirs
         const bool ov0 = j0 + 0 >= 1 && j0 + 0 <= w1 - 2, ov1 = j0 + 1 >= 1 && j0 + 1 <= w1 - 2;
         const bool ov2 = j0 + 2 >= 1 && j0 + 2 <= w1 - 2, ov3 = j0 + 3 >= 1 && j0 + 3 <= w1 - 2;
-        const bool pair_lo = ov0 && ov1, pair_hi = ov2 && ov3;
         const unsigned lone = (ov0 && !ov1 ? 1u : 0u) | (ov1 && !ov0 ? 2u : 0u) | (ov2 && !ov3 ? 4u : 0u) | (ov3 && !ov2 ? 8u : 0u);
+        // Row range and column validity of a store folded into ONE unsigned compare each: row `to` is stored by this
+        // lane's low pair iff to - o_lo < span_lo (0 rows when the pair is not interior).  Opaque registers: the
+        // compiler otherwise re-derives the column predicates from j0 and w1 on every row (17 ISETP per level-1 row).
+        unsigned span = (unsigned)max(o_hi - o_lo, 0);
+        unsigned span_lo = (ov0 && ov1) ? span : 0u, span_hi = (ov2 && ov3) ? span : 0u, span_lone = lone ? span : 0u;
+        asm volatile("mov.u32 %0, %0;" : "+r"(span_lo));
+        asm volatile("mov.u32 %0, %0;" : "+r"(span_hi));
+        asm volatile("mov.u32 %0, %0;" : "+r"(span_lone));
         uint32_t aOo[4] = {0, 0, 0, 0}, aOn[4] = {0, 0, 0, 0}, aGo[4] = {0, 0, 0, 0}, aGm[4] = {0, 0, 0, 0},
                  aGn[4] = {0, 0, 0, 0};
         uint8_t *__restrict__ orow = out + P.pd.lv[1].off + (ptrdiff_t)(ts - 1) * w1 + j0;  // row tau - 1
@@ -761,14 +771,31 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
         uint2 *__restrict__ grow = reinterpret_cast<uint2 *>(&g2[0][4 * c]) + (ptrdiff_t)(ts - 2 - t_first) * (G2P / 4);
         constexpr bool G = NA >= 2;
         constexpr int RWW = RW / 8;  // row pitch in 8-byte units
+#if PYR_SPANSTORE
+        auto store_o = [&](int to) {  // O_{to} complete -> level 1, round half up: (N + 32) >> 6
+            constexpr uint32_t kR = 32u - kORound;  // what of the rounding constant is not in the accumulator yet
+            const unsigned dr = (unsigned)(to - o_lo);
+            // two aligned 16-bit stores, predicated per lane (no divergent second path for the tiles' edge lanes)
+            if (dr < span_lo)
+                reinterpret_cast<uint16_t *>(orow)[0] = (uint16_t)__byte_perm((aOo[0] + kR) >> 6, (aOo[1] + kR) >> 6, 0x0040);
+            if (dr < span_hi)
+                reinterpret_cast<uint16_t *>(orow)[1] = (uint16_t)__byte_perm((aOo[2] + kR) >> 6, (aOo[3] + kR) >> 6, 0x0040);
+            if (dr < span_lone) {  // one lane of the first and of the last tile column
+                if (lone & 1u) orow[0] = (uint8_t)((aOo[0] + kR) >> 6);
+                if (lone & 2u) orow[1] = (uint8_t)((aOo[1] + kR) >> 6);
+                if (lone & 4u) orow[2] = (uint8_t)((aOo[2] + kR) >> 6);
+                if (lone & 8u) orow[3] = (uint8_t)((aOo[3] + kR) >> 6);
+            }
+        };
+#else  // round-2 baseline: predicates re-derived per row
         auto store_o = [&](int to) {  // O_{to} complete -> level 1, round half up: (N + 32) >> 6
             if (to >= o_lo && to < o_hi) {
-                constexpr uint32_t kR = 32u - kORound;  // what of the rounding constant is not in the accumulator yet
+                constexpr uint32_t kR = 32u - kORound;
                 const uint32_t b0 = (aOo[0] + kR) >> 6, b1 = (aOo[1] + kR) >> 6, b2 = (aOo[2] + kR) >> 6, b3 = (aOo[3] + kR) >> 6;
-                // two aligned 16-bit stores, predicated per lane (no divergent second path for the tiles' edge lanes)
+                const bool pair_lo = ov0 && ov1, pair_hi = ov2 && ov3;
                 if (pair_lo) reinterpret_cast<uint16_t *>(orow)[0] = (uint16_t)(b0 | (b1 << 8));
                 if (pair_hi) reinterpret_cast<uint16_t *>(orow)[1] = (uint16_t)(b2 | (b3 << 8));
-                if (lone) {  // one lane of the first and of the last tile column
+                if (lone) {
                     if (lone & 1u) orow[0] = (uint8_t)b0;
                     if (lone & 2u) orow[1] = (uint8_t)b1;
                     if (lone & 4u) orow[2] = (uint8_t)b2;
@@ -776,6 +803,7 @@ pyr_fast_kernel(const __grid_constant__ FastParams P, const __grid_constant__ CU
                 }
             }
         };
+#endif
         auto rotate = [&]() {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {

@@ -22,6 +22,7 @@ constexpr int kWarps = kThreads / 32;
 
 // block-wide stable compaction helper: returns the output rank of this thread's element
 // (valid only when keep), advances *base by the number kept in this chunk.
+template <int NW = kWarps>
 __device__ __forceinline__ int block_rank(bool keep, int *warp_tot, int *base) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const unsigned m = __ballot_sync(0xffffffffu, keep);
@@ -33,20 +34,48 @@ __device__ __forceinline__ int block_rank(bool keep, int *warp_tot, int *base) {
     __syncthreads();
     if (threadIdx.x == 0) {
         int t = 0;
-        for (int k = 0; k < kWarps; ++k) t += warp_tot[k];
+        for (int k = 0; k < NW; ++k) t += warp_tot[k];
         *base += t;
     }
     __syncthreads();
     return rank;
 }
 
-__global__ void __launch_bounds__(kThreads)
+// block-wide exclusive offset of a per-thread count (0 .. E); advances *base by the block total
+template <int NW>
+__device__ __forceinline__ int block_offset(int cnt, int *warp_tot, int *base) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    int off = *base + incl - cnt;
+    for (int k = 0; k < wid; ++k) off += warp_tot[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int k = 0; k < NW; ++k) t += warp_tot[k];
+        *base += t;
+    }
+    __syncthreads();
+    return off;
+}
+
+// NT threads per CTA, E consecutive tracks per thread and round: 256 x 1 for the usual few hundred tracks per group;
+// 1024 x 4 for big tables (one high-resolution stream with 10 240 cells keeps ~27 k tracks per camera: a group is one
+// CTA, i.e. one SM's worth of memory latency per round -- 105 rounds at 256 x 1 were 105 us of a 690 us frame)
+template <int NT, int E>
+__global__ void __launch_bounds__(NT)
 compact_tracks_kernel(TableView in, const float *__restrict__ lk_T6, const int32_t *__restrict__ lk_status,
                       TableView out, int cap, int streams, GridDesc gd, uint8_t *__restrict__ occ, int have_prev,
                       unsigned long long *counters, int *__restrict__ err_clear, CellWork cw) {
     // the overflow flag the merge kernel of this frame may raise (its previous use, two frames ago, has been read)
     if (err_clear && blockIdx.x == 0 && threadIdx.x == 0) *err_clear = 0;
-    __shared__ int warp_tot[kWarps];
+    __shared__ int warp_tot[NT / 32];
     __shared__ int base;
     const int g = blockIdx.x;
     const int n = in.counts[g];
@@ -54,29 +83,39 @@ compact_tracks_kernel(TableView in, const float *__restrict__ lk_T6, const int32
     uint8_t *my_occ = occ + (size_t)g * gd.occ_rows * gd.occ_cols;  // only used when cam0
     if (threadIdx.x == 0) base = 0;
     if (cam0)
-        for (int i = threadIdx.x; i < gd.occ_rows * gd.occ_cols; i += kThreads) my_occ[i] = 0;
+        for (int i = threadIdx.x; i < gd.occ_rows * gd.occ_cols; i += NT) my_occ[i] = 0;
     __syncthreads();
     const uint32_t x_end = gd.x_start + gd.g * (uint32_t)gd.ncx + 1, y_end = gd.y_start + gd.g * (uint32_t)gd.ncy + 1;
-    for (int c0 = 0; c0 < n; c0 += kThreads) {
-        const int k = c0 + threadIdx.x;
-        const size_t src = (size_t)g * cap + k;
-        bool keep = false;
-        float T[6];
-        if (k < n) {
-            // first frame after create/reset: nothing was tracked, the table is carried over as is
-            keep = have_prev ? (lk_status[src] == RSVIO_TRACK_OK) : true;
-            const float *ps = have_prev ? lk_T6 + src * 6 : in.T6 + src * 6;
+    for (int c0 = 0; c0 < n; c0 += NT * E) {
+        const int k0 = c0 + (int)threadIdx.x * E;
+        bool keep[E];
+        float T[E][6];
+        int cnt = 0;
 #pragma unroll
-            for (int q = 0; q < 6; ++q) T[q] = ps[q];
+        for (int e = 0; e < E; ++e) {
+            const int k = k0 + e;
+            const size_t src = (size_t)g * cap + k;
+            keep[e] = false;
+            if (k < n) {
+                // first frame after create/reset: nothing was tracked, the table is carried over as is
+                keep[e] = have_prev ? (lk_status[src] == RSVIO_TRACK_OK) : true;
+                const float *ps = have_prev ? lk_T6 + src * 6 : in.T6 + src * 6;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) T[e][q] = ps[q];
+            }
+            cnt += keep[e] ? 1 : 0;
         }
-        const int rank = block_rank(keep, warp_tot, &base);
-        if (keep) {
-            const size_t dst = (size_t)g * cap + rank;
+        int rank = block_offset<NT / 32>(cnt, warp_tot, &base);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            if (!keep[e]) continue;
+            const size_t src = (size_t)g * cap + k0 + e;
+            const size_t dst = (size_t)g * cap + rank++;
             out.ids[dst] = in.ids[src];
 #pragma unroll
-            for (int q = 0; q < 6; ++q) out.T6[dst * 6 + q] = T[q];
+            for (int q = 0; q < 6; ++q) out.T6[dst * 6 + q] = T[e][q];
             if (cam0) {  // add_points: Corner::new(round(x) as u32, round(y) as u32)
-                const uint32_t x = sat_u32(roundf(T[2])), y = sat_u32(roundf(T[5]));
+                const uint32_t x = sat_u32(roundf(T[e][2])), y = sat_u32(roundf(T[e][5]));
                 if (x >= gd.x_start && y >= gd.y_start && x < x_end && y < y_end)
                     my_occ[(size_t)((y - gd.y_start) / gd.g) * gd.occ_cols + (x - gd.x_start) / gd.g] = 1;
             }
@@ -95,7 +134,7 @@ compact_tracks_kernel(TableView in, const float *__restrict__ lk_T6, const int32
         const int cells = gd.ncx * gd.ncy;
         const int lane = threadIdx.x & 31;
         int n_empty = 0;
-        for (int c0 = 0; c0 < cells; c0 += kThreads) {
+        for (int c0 = 0; c0 < cells; c0 += NT) {
             const int cell = c0 + threadIdx.x;
             bool empty = false;
             if (cell < cells) {
@@ -242,8 +281,12 @@ remove_ids_kernel(TableView in, TableView out, int cap, int streams, int stream,
 cudaError_t compact_tracks(const TableView &in, const float *lk_T6, const int32_t *lk_status, const TableView &out,
                            int groups, int cap, int streams, const GridDesc &gd, uint8_t *occ, int have_prev,
                            unsigned long long *counters, int *err_clear, const CellWork &cw, cudaStream_t st) {
-    compact_tracks_kernel<<<groups, kThreads, 0, st>>>(in, lk_T6, lk_status, out, cap, streams, gd, occ, have_prev,
-                                                       counters, err_clear, cw);
+    if (cap >= 4096)
+        compact_tracks_kernel<1024, 4><<<groups, 1024, 0, st>>>(in, lk_T6, lk_status, out, cap, streams, gd, occ, have_prev,
+                                                            counters, err_clear, cw);
+    else
+        compact_tracks_kernel<256, 1><<<groups, 256, 0, st>>>(in, lk_T6, lk_status, out, cap, streams, gd, occ, have_prev, counters,
+                                                           err_clear, cw);
     return cudaGetLastError();
 }
 
