@@ -76,7 +76,7 @@ struct rsvio_tracker {
     float *d_cell_score = nullptr;
     uint32_t *d_cell_list = nullptr;
     int *d_cell_list_n = nullptr;
-    int *d_cell_work = nullptr;  // [0, S): listed empty cells per stream, [S, 2S): finished ones (zero between frames)
+    int *d_cell_work = nullptr;  // [0, S): listed empty cells per stream, [S, 2S): finished ones, [2S, 3S): compaction chunks arrived (zero between frames)
     float *d_new_T6 = nullptr, *d_st_T6 = nullptr;
     int *d_new_count = nullptr;
     int32_t *d_st_status = nullptr;
@@ -225,7 +225,9 @@ rsvio_status clear_state(rsvio_tracker *t) {
     CU_TRY(t, cudaMemsetAsync(t->d_new_count, 0, sizeof(int) * t->S, t->st));
     CU_TRY(t, cudaMemsetAsync(t->d_work, 0, sizeof(unsigned) * 4, t->st));
     CU_TRY(t, cudaMemsetAsync(t->d_cell_list_n, 0, sizeof(int) * 2, t->st));
-    CU_TRY(t, cudaMemsetAsync(t->d_cell_work, 0, sizeof(int) * 2 * t->S, t->st));
+    CU_TRY(t, cudaMemsetAsync(t->d_cell_work, 0, sizeof(int) * 3 * t->S, t->st));
+    // the occupancy grids start clear; every compaction launch leaves them clear again (tracks.cu)
+    CU_TRY(t, cudaMemsetAsync(t->d_occ, 0, (size_t)t->S * t->gd.occ_rows * t->gd.occ_cols, t->st));
     t->lk_par[0] = t->lk_par[1] = t->det_par = 0;
     if (t->own_exp) CU_TRY(t, cudaStreamSynchronize(t->exp_st));
     if (t->own_pyr) CU_TRY(t, cudaStreamSynchronize(t->pyr_st));
@@ -309,6 +311,7 @@ rsvio_status frame_launches(rsvio_tracker *t, int slot, const uint8_t *src0, con
     cw.next_count = t->d_cell_list_n + (t->det_par ^ 1);
     cw.n_empty = t->d_cell_work;
     cw.done = t->d_cell_work + t->S;
+    cw.arrive = t->d_cell_work + 2 * t->S;
     cw.new_count = t->d_new_count;
     CU_TRY(t, compact_tracks(tin, t->d_lk_T6, t->d_lk_status, tout, t->groups, t->cap, t->S, t->gd, t->d_occ,
                              t->have_prev ? 1 : 0, t->d_counters, t->d_err + slot, cw, st));
@@ -644,7 +647,7 @@ rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) 
         CU_TRY(t, dmalloc(&t->d_cell_score, S * (size_t)t->new_cap));
         CU_TRY(t, dmalloc(&t->d_cell_list, S * (size_t)t->new_cap));
         CU_TRY(t, dmalloc(&t->d_cell_list_n, (size_t)2));
-        CU_TRY(t, dmalloc(&t->d_cell_work, 2 * S));
+        CU_TRY(t, dmalloc(&t->d_cell_work, 3 * S));
         CU_TRY(t, dmalloc(&t->d_new_T6, S * (size_t)t->new_cap * 6));
         CU_TRY(t, dmalloc(&t->d_st_T6, S * (size_t)t->new_cap * 6));
         CU_TRY(t, dmalloc(&t->d_new_count, S));

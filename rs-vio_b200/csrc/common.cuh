@@ -114,6 +114,8 @@ struct LkBatch {
     int groups, cap;
     int max_it;
     float thr;
+    uint32_t floor_bias;  // set by lk_track: the bit pattern of 2^23, passed as a launch parameter so that the
+                          // compiler cannot split the folded address constant back into per-load immediates
 };
 cudaError_t lk_track(const PyrDesc &pd, const LkBatch &b, cudaStream_t st);
 cudaError_t se2_exp_batch(const float *d_twists, int n, float *d_out9, cudaStream_t st);
@@ -155,6 +157,7 @@ struct CellWork {
     int *list_count, *next_count;
     int *n_empty, *done;
     int *new_count;  // [streams]
+    int *arrive;     // [streams] chunks of the compaction launch that have marked their part of the occupancy grid
 };
 // occ: [streams][occ_rows*occ_cols] bytes.  img of stream s = img0 + s * pitch.  Stateless form: lists the empty cells
 // itself (1 extra launch) before the detection launch.

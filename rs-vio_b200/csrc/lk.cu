@@ -46,6 +46,31 @@ __device__ __forceinline__ float bilin(float w00, float w01, float w10, float w1
                                        float p11) {
     return mad(w11, p11, mad(w10, p10, mad(w01, p01, w00 * p00)));
 }
+// u8 pixel -> f32.  Left to itself the compiler narrows the conversion to I2F.U16, which issues on the quarter-rate XU
+// pipe (the busiest pipe of this kernel: 45 % with F2I, MUFU and POPC); behind an opaque 32-bit value it is
+// I2FP.F32.U32 on the FMA pipe.  Exact either way.
+#ifndef RSVIO_LK_I2FP
+#define RSVIO_LK_I2FP 1
+#endif
+__device__ __forceinline__ float px_f32(const uint8_t *__restrict__ p) {
+#if RSVIO_LK_I2FP
+    uint32_t v = __ldg(p);
+    asm volatile("mov.b32 %0, %0;" : "+r"(v));
+    return __uint2float_rn(v);
+#else
+    return (float)__ldg(p);
+#endif
+}
+// floor(v) for 0 <= v < 2^23 without F2I / I2F: adding 2^23 with round-down leaves floor(v) in the low mantissa bits
+// (bit pattern 0x4B000000 + floor(v)), and subtracting 2^23 again gives floor(v) as a float, both exactly.
+// A/B on the C5 step (three interleaved runs each, one box): I2F.U16 baseline 368.7 us, pixels through I2FP 356.0 us,
+// I2FP + this floor 362.8 us -- taking F2I off the XU pipe buys nothing and the sequence is 2 instructions longer
+// per sample, so it is off; the code stays for the record (bit-identical results either way).
+#ifndef RSVIO_LK_FLOOR
+#define RSVIO_LK_FLOOR 0
+#endif
+constexpr float kTwo23 = 8388608.0f;
+[[maybe_unused]] __device__ __forceinline__ float floor_bits(float v) { return __fadd_rd(v, kTwo23); }
 constexpr int kWarpsPerBlock = 4;
 constexpr int kMaxGroupsSmem = 2048;  // groups whose live-point prefix fits the shared-memory table
 
@@ -94,21 +119,28 @@ __device__ __forceinline__ void image_grad(const Img &im, float x, float y, bool
     // floor; a sample that passed inbound(.., 2) has 1 <= ix <= w - 3 and 1 <= iy <= h - 3, so the 4x4
     // neighbourhood needs no clamping; rejected samples read the neighbourhood of (1, 1) (the caller
     // guarantees w, h >= 5)
+    const uint32_t W = (uint32_t)im.w;
+#if RSVIO_LK_FLOOR
+    // floor without the XU pipe (see floor_bits): the low mantissa bits of yx, yy are the pixel indices
+    const float yx = ok ? floor_bits(x) : kTwo23 + 1.0f, yy = ok ? floor_bits(y) : kTwo23 + 1.0f;
+    const float dx = x - (yx - kTwo23), dy = y - (yy - kTwo23);
+    const uint32_t ix = __float_as_uint(yx) & 0x7fffffu, iy = __float_as_uint(yy) & 0x7fffffu;
+#else
     const uint32_t ix = ok ? __float2uint_rd(x) : 1u, iy = ok ? __float2uint_rd(y) : 1u;
     const float dx = x - (float)ix, dy = y - (float)iy;
+#endif
     const float ddx = 1.0f - dx, ddy = 1.0f - dy;
     const float w00 = ddx * ddy, w01 = ddx * dy, w10 = dx * ddy, w11 = dx * dy;
-    const uint32_t W = (uint32_t)im.w;
     RSVIO_CHECK(ix >= 1u && ix + 2u < W && iy >= 1u && iy + 2u < (uint32_t)im.h);  // the 4x4 neighbourhood minus corners
     const uint8_t *__restrict__ r0 = im.p + (iy * W + ix);  // 32-bit offset inside one level
     const uint8_t *__restrict__ rm = r0 - W;
     const uint8_t *__restrict__ r1 = r0 + W;
     const uint8_t *__restrict__ r2 = r1 + W;
-    const float p00 = (float)__ldg(r0), p10 = (float)__ldg(r0 + 1), p01 = (float)__ldg(r1), p11 = (float)__ldg(r1 + 1);
-    const float pm0 = (float)__ldg(r0 - 1), pm1 = (float)__ldg(r1 - 1);
-    const float p20 = (float)__ldg(r0 + 2), p21 = (float)__ldg(r1 + 2);
-    const float p0m = (float)__ldg(rm), p1m = (float)__ldg(rm + 1);
-    const float p02 = (float)__ldg(r2), p12 = (float)__ldg(r2 + 1);
+    const float p00 = px_f32(r0), p10 = px_f32(r0 + 1), p01 = px_f32(r1), p11 = px_f32(r1 + 1);
+    const float pm0 = px_f32(r0 - 1), pm1 = px_f32(r1 - 1);
+    const float p20 = px_f32(r0 + 2), p21 = px_f32(r1 + 2);
+    const float p0m = px_f32(rm), p1m = px_f32(rm + 1);
+    const float p02 = px_f32(r2), p12 = px_f32(r2 + 1);
     v = bilin(w00, w01, w10, w11, p00, p01, p10, p11);
     const float res_mx = bilin(w00, w01, w10, w11, pm0, pm1, p00, p01);
     const float res_px = bilin(w00, w01, w10, w11, p10, p11, p20, p21);
@@ -234,8 +266,8 @@ struct Lane {
 // track_one_point (feature_tracker.rs:292-342): coarse-to-fine, template from pyramid A at the
 // un-rotated source position, running transform keeps its rotation across levels.
 __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A, const uint8_t *__restrict__ B,
-                               const float T0[6], float T1[6], int max_it, float thr, const Lane &ln, int lane,
-                               unsigned &n_iters, unsigned &n_templates) {
+                               const float T0[6], float T1[6], int max_it, float thr, uint32_t floor_bias, const Lane &ln,
+                               int lane, unsigned &n_iters, unsigned &n_templates) {
     T1[0] = 1.0f; T1[1] = 0.0f; T1[2] = T0[2];
     T1[3] = 0.0f; T1[4] = 1.0f; T1[5] = T0[5];
     for (int lev = pd.levels - 1; lev >= 0; --lev) {
@@ -368,7 +400,12 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
         // the level base and row pitch stay in registers across the iterations (opaque to rematerialisation)
         const uint8_t *ibp = ib.p;
         uint32_t ibw = (uint32_t)ib.w;
+#if RSVIO_LK_FLOOR
+        const uint8_t *ibq = ibp - (uint64_t)floor_bias * ((uint64_t)ibw + 1u);  // see the gather below
+        asm volatile("mov.u64 %0, %0;" : "+l"(ibq));
+#else
         asm volatile("mov.u64 %0, %0;" : "+l"(ibp));
+#endif
         asm volatile("mov.u32 %0, %0;" : "+r"(ibw));
         for (int it = 0; it < max_it; ++it) {
             ++n_iters;
@@ -389,14 +426,25 @@ __device__ int track_one_point(const PyrDesc &pd, const uint8_t *__restrict__ A,
                 const bool ok = ln.has[k] && x >= 2.0f && y >= 2.0f && x < wlim && y < hlim;
                 // branch-free gather: rejected samples read pixels (0,0)..(1,1), unused; accepted ones have
                 // ix + 1 <= w - 2 and iy + 1 <= h - 2, so nothing needs clamping
+#if RSVIO_LK_FLOOR
+                // floor_bits(v) = 2^23 + floor(v) as a float: its bit pattern is 0x4B000000 + floor(v).  The two
+                // constants are folded into the level base (ibq), so the pixel address is one wide multiply-add and one
+                // 64-bit add of the raw bit patterns: no F2I / I2F (XU pipe), no masks.
+                const float yx = ok ? floor_bits(x) : kTwo23, yy = ok ? floor_bits(y) : kTwo23;
+                const float dx = x - (yx - kTwo23), dy = y - (yy - kTwo23);
+                const float ddx = 1.0f - dx, ddy = 1.0f - dy;
+                RSVIO_CHECK((__float_as_uint(yx) & 0x7fffffu) + 1u < ibw && (__float_as_uint(yy) & 0x7fffffu) + 1u < (uint32_t)ib.h);
+                const uint8_t *__restrict__ q0 = ibq + ((uint64_t)__float_as_uint(yy) * ibw + __float_as_uint(yx));
+#else
                 const uint32_t ix = ok ? __float2uint_rd(x) : 0u, iy = ok ? __float2uint_rd(y) : 0u;
                 const float dx = x - (float)ix, dy = y - (float)iy;
                 const float ddx = 1.0f - dx, ddy = 1.0f - dy;
                 RSVIO_CHECK(ix + 1u < ibw && iy + 1u < (uint32_t)ib.h);
                 const uint8_t *__restrict__ q0 = ibp + (iy * ibw + ix);
+#endif
                 const uint8_t *__restrict__ q1 = q0 + ibw;
-                const float p00 = (float)__ldg(q0), p10 = (float)__ldg(q0 + 1);
-                const float p01 = (float)__ldg(q1), p11 = (float)__ldg(q1 + 1);
+                const float p00 = px_f32(q0), p10 = px_f32(q0 + 1);
+                const float p01 = px_f32(q1), p11 = px_f32(q1 + 1);
                 r[k] = bilin(ddx * ddy, ddx * dy, dx * ddy, dx * dy, p00, p01, p10, p11);
                 okk[k] = ok;
                 rsum = k == 0 ? (ok ? r[k] : 0.0f) : rsum + (ok ? r[k] : 0.0f);
@@ -564,7 +612,7 @@ lk_track_fb_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ L
 #pragma unroll 1
         for (int dir = 0; dir < 2; ++dir) {
             unsigned iters = 0;
-            st = track_one_point(pd, dir == 0 ? A : B, dir == 0 ? B : A, Tin, Tb, b.max_it, b.thr, ln, lane, iters,
+            st = track_one_point(pd, dir == 0 ? A : B, dir == 0 ? B : A, Tin, Tb, b.max_it, b.thr, b.floor_bias, ln, lane, iters,
                                  n_templates);
             if (dir == 0) it_f = iters; else it_b = iters;
             if (dir == 0) {
@@ -624,7 +672,9 @@ cudaError_t lk_track(const PyrDesc &pd, const LkBatch &b, cudaStream_t st) {
     const long long max_blocks = (long long)sm_count() * (dynamic ? resident : 16);
     if (blocks > max_blocks) blocks = max_blocks;
     const size_t smem = dynamic ? sizeof(int) * (size_t)(b.groups + 1) : 0;
-    lk_track_fb_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(pd, b);
+    LkBatch bb = b;
+    bb.floor_bias = 0x4B000000u;
+    lk_track_fb_kernel<<<(unsigned)blocks, kWarpsPerBlock * 32, smem, st>>>(pd, bb);
     return cudaGetLastError();
 }
 

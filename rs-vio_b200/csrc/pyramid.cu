@@ -44,6 +44,10 @@
 #include <cstring>
 #include <vector>
 
+#ifndef PYR_VEXACT
+#define PYR_VEXACT 1  // generic kernel: vertical pass of complete dyadic windows (levels 4, 5) as exact integer tents
+#endif
+
 namespace rsvio {
 
 namespace {
@@ -98,6 +102,27 @@ struct TileDesc {
 // a near-tie output of the deep dyadic kernel, queued for the faithful chains: x = image, y = lev << 28 | oy << 14 | ox
 typedef uint2 TieEntry;
 
+// Vertical pass of a COMPLETE window on an axis whose ratio is the power of two RY: the reference's weights are
+// (2k + 1) / (2 RY^2), mirrored -- exact in f32 -- and so is every product and partial sum of its chain (< 2^24 in units
+// of 1 / (2 RY^2) for RY <= 128), so the chain's value is the integer tent sum scaled by a power of two.  Four columns
+// per 32-bit load; the byte of column c is selected by putting the weight into byte c of the DP4A operand: one
+// instruction per column and tap instead of the chain's PRMT + FADD + FMUL + FADD.
+template <int RY>
+__device__ __forceinline__ float4 vtent_exact4(const uint8_t *__restrict__ p, size_t stride) {
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+    for (int k = 0; k < 2 * RY; ++k) {
+        const uint32_t q = __ldg(reinterpret_cast<const uint32_t *>(p + (size_t)k * stride));
+        const uint32_t wk = 2u * (uint32_t)(k < RY ? k : 2 * RY - 1 - k) + 1u;
+        a0 = __dp4a(q, wk, a0);
+        a1 = __dp4a(q, wk << 8, a1);
+        a2 = __dp4a(q, wk << 16, a2);
+        a3 = __dp4a(q, wk << 24, a3);
+    }
+    constexpr float sc = 1.0f / (2.0f * RY * RY);
+    return make_float4(__fmul_rn((float)a0, sc), __fmul_rn((float)a1, sc), __fmul_rn((float)a2, sc), __fmul_rn((float)a3, sc));
+}
+
 __device__ __forceinline__ void generic_tile(const PyrDesc &pd, const PyrTaps &taps, const TileDesc td, int img,
                                              const uint8_t *__restrict__ src0, const uint8_t *__restrict__ src1, int split,
                                              size_t stride, size_t pitch, uint8_t *__restrict__ dst, float *__restrict__ v) {
@@ -134,6 +159,8 @@ __device__ __forceinline__ void generic_tile(const PyrDesc &pd, const PyrTaps &t
     const int ngrp = (xr - xa + 3) >> 2;       // groups of 4 columns, one 32-bit load per tap
     const int ncols = ngrp * 4;                // intermediate columns kept (>= xr - xl)
     const bool vec4 = ((((size_t)src) | stride) & 3) == 0;
+    // vertical ratio 2^lev exactly (h0 divisible): complete windows (2 ry taps) take the exact integer path
+    const int ry = (pd.lv[0].h & ((1 << lev) - 1)) == 0 ? (1 << lev) : 0;
 
     // vertical pass: f32, tap order, multiply and add rounded separately; 4 columns per thread
     for (int idx = threadIdx.x; idx < ngrp * noy; idx += kGenThreads) {
@@ -145,7 +172,10 @@ __device__ __forceinline__ void generic_tile(const PyrDesc &pd, const PyrTaps &t
         RSVIO_CHECK(top >= 0 && top + n <= pd.lv[0].h && x >= 0 && x < w0 && cy * ncols + 4 * g + 3 < kGenSmemFloats);
         const uint8_t *__restrict__ p = src + (size_t)top * stride + x;
         float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f, t3 = 0.0f;
-        if (vec4 && x + 4 <= w0) {
+        if (PYR_VEXACT && vec4 && x + 4 <= w0 && n == 2 * ry && (ry == 16 || ry == 32)) {
+            const float4 t = ry == 32 ? vtent_exact4<32>(p, stride) : vtent_exact4<16>(p, stride);
+            t0 = t.x, t1 = t.y, t2 = t.z, t3 = t.w;
+        } else if (vec4 && x + 4 <= w0) {
             // u8 -> f32 without the quarter-rate I2F: one PRMT drops byte j into the mantissa of 2^23
             // (0x4B0000bb == 8388608 + b), one exact FADD removes the 2^23.  This loop is conversion-bound otherwise.
             constexpr float kTwo23 = 8388608.0f;
@@ -185,6 +215,7 @@ __device__ __forceinline__ void generic_tile(const PyrDesc &pd, const PyrTaps &t
         const float *__restrict__ vr = &v[cy * ncols + left];
         RSVIO_CHECK(left >= 0 && left + n <= ncols && ox < wl && oy0 + cy < pd.lv[lev].h);
         float t = 0.0f;
+#pragma unroll 16  // weights and column values of 16 taps in flight; only the adds are serial
         for (int k = 0; k < n; ++k) t = __fadd_rn(t, __fmul_rn(vr[k], __ldg(wx + k)));
         t = fminf(fmaxf(t, 0.0f), 255.0f);
         lo[(size_t)(oy0 + cy) * wl + ox] = (uint8_t)__float2uint_rz(roundf(t));
@@ -193,7 +224,7 @@ __device__ __forceinline__ void generic_tile(const PyrDesc &pd, const PyrTaps &t
 
 // One CTA per static tile descriptor (blockIdx.x < n_static, image blockIdx.y); the remaining CTAs of the grid drain
 // the tie queue of pyr_deep_kernel (any image).
-__global__ void __launch_bounds__(kGenThreads)
+__global__ void __launch_bounds__(kGenThreads, 5)
 pyr_generic_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ PyrTaps taps,
                    const TileDesc *__restrict__ tiles, int n_static, const TieEntry *__restrict__ tie_queue,
                    const unsigned *__restrict__ tie_count, const uint8_t *__restrict__ src0,

@@ -65,17 +65,15 @@ __device__ __forceinline__ int block_offset(int cnt, int *warp_tot, int *base) {
     return off;
 }
 
-// NT threads per CTA, E consecutive tracks per thread and round: 256 x 1 for the usual few hundred tracks per group;
-// 1024 x 4 for big tables (one high-resolution stream with 10 240 cells keeps ~27 k tracks per camera: a group is one
-// CTA, i.e. one SM's worth of memory latency per round -- 105 rounds at 256 x 1 were 105 us of a 690 us frame)
-template <int NT, int E>
-__global__ void __launch_bounds__(NT)
-compact_tracks_kernel(TableView in, const float *__restrict__ lk_T6, const int32_t *__restrict__ lk_status,
+// Tables of up to kThreads * 4 tracks per group (the usual few hundred tracks of a stream): one CTA per group walks the
+// table, builds the stream's occupancy grid and lists its empty cells -- the fewest dependent memory round trips.
+__global__ void __launch_bounds__(kThreads)
+compact_tracks_small_kernel(TableView in, const float *__restrict__ lk_T6, const int32_t *__restrict__ lk_status,
                       TableView out, int cap, int streams, GridDesc gd, uint8_t *__restrict__ occ, int have_prev,
                       unsigned long long *counters, int *__restrict__ err_clear, CellWork cw) {
     // the overflow flag the merge kernel of this frame may raise (its previous use, two frames ago, has been read)
     if (err_clear && blockIdx.x == 0 && threadIdx.x == 0) *err_clear = 0;
-    __shared__ int warp_tot[NT / 32];
+    __shared__ int warp_tot[kWarps];
     __shared__ int base;
     const int g = blockIdx.x;
     const int n = in.counts[g];
@@ -83,39 +81,29 @@ compact_tracks_kernel(TableView in, const float *__restrict__ lk_T6, const int32
     uint8_t *my_occ = occ + (size_t)g * gd.occ_rows * gd.occ_cols;  // only used when cam0
     if (threadIdx.x == 0) base = 0;
     if (cam0)
-        for (int i = threadIdx.x; i < gd.occ_rows * gd.occ_cols; i += NT) my_occ[i] = 0;
+        for (int i = threadIdx.x; i < gd.occ_rows * gd.occ_cols; i += kThreads) my_occ[i] = 0;
     __syncthreads();
     const uint32_t x_end = gd.x_start + gd.g * (uint32_t)gd.ncx + 1, y_end = gd.y_start + gd.g * (uint32_t)gd.ncy + 1;
-    for (int c0 = 0; c0 < n; c0 += NT * E) {
-        const int k0 = c0 + (int)threadIdx.x * E;
-        bool keep[E];
-        float T[E][6];
-        int cnt = 0;
+    for (int c0 = 0; c0 < n; c0 += kThreads) {
+        const int k = c0 + threadIdx.x;
+        const size_t src = (size_t)g * cap + k;
+        bool keep = false;
+        float T[6];
+        if (k < n) {
+            // first frame after create/reset: nothing was tracked, the table is carried over as is
+            keep = have_prev ? (lk_status[src] == RSVIO_TRACK_OK) : true;
+            const float *ps = have_prev ? lk_T6 + src * 6 : in.T6 + src * 6;
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const int k = k0 + e;
-            const size_t src = (size_t)g * cap + k;
-            keep[e] = false;
-            if (k < n) {
-                // first frame after create/reset: nothing was tracked, the table is carried over as is
-                keep[e] = have_prev ? (lk_status[src] == RSVIO_TRACK_OK) : true;
-                const float *ps = have_prev ? lk_T6 + src * 6 : in.T6 + src * 6;
-#pragma unroll
-                for (int q = 0; q < 6; ++q) T[e][q] = ps[q];
-            }
-            cnt += keep[e] ? 1 : 0;
+            for (int q = 0; q < 6; ++q) T[q] = ps[q];
         }
-        int rank = block_offset<NT / 32>(cnt, warp_tot, &base);
-#pragma unroll
-        for (int e = 0; e < E; ++e) {
-            if (!keep[e]) continue;
-            const size_t src = (size_t)g * cap + k0 + e;
-            const size_t dst = (size_t)g * cap + rank++;
+        const int rank = block_rank(keep, warp_tot, &base);
+        if (keep) {
+            const size_t dst = (size_t)g * cap + rank;
             out.ids[dst] = in.ids[src];
 #pragma unroll
-            for (int q = 0; q < 6; ++q) out.T6[dst * 6 + q] = T[e][q];
+            for (int q = 0; q < 6; ++q) out.T6[dst * 6 + q] = T[q];
             if (cam0) {  // add_points: Corner::new(round(x) as u32, round(y) as u32)
-                const uint32_t x = sat_u32(roundf(T[e][2])), y = sat_u32(roundf(T[e][5]));
+                const uint32_t x = sat_u32(roundf(T[2])), y = sat_u32(roundf(T[5]));
                 if (x >= gd.x_start && y >= gd.y_start && x < x_end && y < y_end)
                     my_occ[(size_t)((y - gd.y_start) / gd.g) * gd.occ_cols + (x - gd.x_start) / gd.g] = 1;
             }
@@ -134,7 +122,7 @@ compact_tracks_kernel(TableView in, const float *__restrict__ lk_T6, const int32
         const int cells = gd.ncx * gd.ncy;
         const int lane = threadIdx.x & 31;
         int n_empty = 0;
-        for (int c0 = 0; c0 < cells; c0 += NT) {
+        for (int c0 = 0; c0 < cells; c0 += kThreads) {
             const int cell = c0 + threadIdx.x;
             bool empty = false;
             if (cell < cells) {
@@ -153,6 +141,138 @@ compact_tracks_kernel(TableView in, const float *__restrict__ lk_T6, const int32
             cw.n_empty[g] = n_empty;
             if (n_empty == 0) cw.new_count[g] = 0;  // nobody will collect this stream
         }
+    }
+}
+
+
+// One CTA per chunk of kChunk consecutive tracks of a group (grid: chunks x groups).  The usual few hundred tracks of a
+// stream are one chunk; a high-resolution stream (10 240 cells keep ~13 k tracks per camera) spreads over a dozen SMs
+// instead of walking the table with one CTA (90 us of a 690 us frame, the SM's load/store queue the limiter:
+// lg_throttle 36 warps per issue).  A CTA finds its output offset by counting the survivors of the chunks before it
+// (coalesced int4 reads of the status array), ranks its own chunk, and then moves the rows as consecutive floats of
+// the OUTPUT (fully coalesced stores, near-coalesced loads: survivors are mostly neighbours).  The CTA that arrives
+// last at a camera-0 group (per-group counter, reset by that CTA) lists the stream's empty cells and clears the
+// occupancy grid for the next frame.
+constexpr int kCompactThreads = 256, kCompactE = 4, kChunk = kCompactThreads * kCompactE;
+__global__ void __launch_bounds__(kCompactThreads)
+compact_tracks_kernel(TableView in, const float *__restrict__ lk_T6, const int32_t *__restrict__ lk_status,
+                      TableView out, int cap, int streams, GridDesc gd, uint8_t *__restrict__ occ, int have_prev,
+                      unsigned long long *counters, int *__restrict__ err_clear, CellWork cw) {
+    constexpr int NT = kCompactThreads, E = kCompactE, NW = NT / 32;
+    const int g = blockIdx.y, chunk = blockIdx.x, n_chunks = gridDim.x;
+    const int tid = threadIdx.x;
+    // the overflow flag the merge kernel of this frame may raise (its previous use, two frames ago, has been read)
+    if (err_clear && g == 0 && chunk == 0 && tid == 0) *err_clear = 0;
+    __shared__ int s_src[kChunk];  // rank within the chunk -> index within the chunk
+    __shared__ int warp_tot[NW];
+    __shared__ int s_base;
+    __shared__ int s_last;
+    const int n = in.counts[g];
+    const int start = chunk * kChunk;
+    const bool cam0 = g < streams;
+    uint8_t *my_occ = occ + (size_t)g * gd.occ_rows * gd.occ_cols;  // only used when cam0
+    const size_t row0 = (size_t)g * cap;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    if (start < n) {
+        // survivors of the chunks before this one (first frame after create/reset: nothing was tracked, the table is
+        // carried over as is)
+        int before = start;
+        if (have_prev && start > 0) {
+            int c = 0;  // row0 and start are multiples of 4 (cap = 4 cells + 64): aligned int4 reads
+            const int4 *__restrict__ sp = reinterpret_cast<const int4 *>(lk_status + row0);
+            for (int i = tid; i < start / 4; i += NT) {
+                const int4 q = __ldg(sp + i);
+                c += (q.x == RSVIO_TRACK_OK) + (q.y == RSVIO_TRACK_OK) + (q.z == RSVIO_TRACK_OK) + (q.w == RSVIO_TRACK_OK);
+            }
+            block_offset<NW>(c, warp_tot, &s_base);
+            before = s_base;
+            __syncthreads();
+            if (tid == 0) s_base = 0;
+            __syncthreads();
+        }
+        const int m = min(kChunk, n - start);
+        bool keep[E];
+        int cnt = 0;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const int k = tid * E + e;
+            keep[e] = k < m && (have_prev ? (lk_status[row0 + start + k] == RSVIO_TRACK_OK) : true);
+            cnt += keep[e] ? 1 : 0;
+        }
+        int rank = block_offset<NW>(cnt, warp_tot, &s_base);
+#pragma unroll
+        for (int e = 0; e < E; ++e)
+            if (keep[e]) s_src[rank++] = tid * E + e;
+        __syncthreads();
+        const int kept = s_base;
+        const float *__restrict__ srcT = (have_prev ? lk_T6 : in.T6) + (row0 + start) * 6;
+        float *__restrict__ dstT = out.T6 + (row0 + before) * 6;
+        for (int f = tid; f < kept * 6; f += NT) {
+            const int r = f / 6, q = f - r * 6;
+            dstT[f] = srcT[s_src[r] * 6 + q];
+        }
+        const uint32_t x_end = gd.x_start + gd.g * (uint32_t)gd.ncx + 1, y_end = gd.y_start + gd.g * (uint32_t)gd.ncy + 1;
+        for (int r = tid; r < kept; r += NT) {
+            const int k = s_src[r];
+            out.ids[row0 + before + r] = in.ids[row0 + start + k];
+            if (cam0) {  // add_points: Corner::new(round(x) as u32, round(y) as u32)
+                const uint32_t x = sat_u32(roundf(srcT[k * 6 + 2])), y = sat_u32(roundf(srcT[k * 6 + 5]));
+                if (x >= gd.x_start && y >= gd.y_start && x < x_end && y < y_end)
+                    my_occ[(size_t)((y - gd.y_start) / gd.g) * gd.occ_cols + (x - gd.x_start) / gd.g] = 1;
+            }
+        }
+        if (tid == 0 && start + kChunk >= n) out.counts[g] = before + kept;  // the group's last chunk knows the total
+    } else if (chunk == 0 && tid == 0) {
+        out.counts[g] = 0;
+    }
+    if (tid == 0 && counters && g == 0 && chunk == 0) atomicAdd(counters + CNT_FRAMES, (unsigned long long)streams);
+    // The work list of the detection kernel (detect_key_points visits the cells without a tracked point,
+    // image_utilities.rs:141-149): the CTA that completes a stream's occupancy grid appends that stream's empty cells
+    // (any order: results are per cell) and initialises every cell to "no point".
+    if (cw.list && cam0) {
+        if (g == 0 && chunk == 0 && tid == 0) *cw.next_count = 0;  // the other counter of the pair, for the next frame
+        __threadfence();  // this CTA's occupancy marks are visible device-wide before it arrives
+        __syncthreads();
+        if (n_chunks > 1) {
+            if (tid == 0) {
+                s_last = atomicAdd(cw.arrive + g, 1) == n_chunks - 1;
+                if (s_last) cw.arrive[g] = 0;  // every chunk has arrived: ready for the next frame
+            }
+            __syncthreads();
+            if (!s_last) return;
+            __threadfence();
+        }
+        // every thread takes a run of consecutive cells: count its empty ones, ONE reservation in the list for the whole
+        // CTA (a reservation per warp and round was 40 dependent atomics for 10 240 cells), then append
+        const int cells = gd.ncx * gd.ncy;
+        const int per = (cells + NT - 1) / NT;
+        const int c_lo = min(tid * per, cells), c_hi = min(c_lo + per, cells);
+        int mine = 0;
+        for (int cell = c_lo; cell < c_hi; ++cell) {
+            const int cx = cell / gd.ncy, cy = cell - cx * gd.ncy;  // visiting order: x outer, y inner
+            mine += __ldcg(my_occ + (size_t)cy * gd.occ_cols + cx) == 0;  // L2: other CTAs wrote it
+            cw.cell_pt[(size_t)g * cells + cell] = 0xFFFFFFFFu;
+        }
+        if (tid == 0) s_base = 0;
+        __syncthreads();
+        int at = block_offset<NW>(mine, warp_tot, &s_base);
+        const int n_empty = s_base;
+        __syncthreads();
+        if (tid == 0) {
+            s_base = n_empty ? atomicAdd(cw.list_count, n_empty) : 0;
+            cw.n_empty[g] = n_empty;
+            if (n_empty == 0) cw.new_count[g] = 0;  // nobody will collect this stream
+        }
+        __syncthreads();
+        at += s_base;
+        for (int cell = c_lo; cell < c_hi; ++cell) {
+            const int cx = cell / gd.ncy, cy = cell - cx * gd.ncy;
+            if (__ldcg(my_occ + (size_t)cy * gd.occ_cols + cx) == 0) cw.list[at++] = (uint32_t)((size_t)g * cells + cell);
+        }
+        __syncthreads();
+        // every read of the grid is behind the barrier: clear it for the next frame's marks
+        for (int i = tid; i < gd.occ_rows * gd.occ_cols; i += NT) my_occ[i] = 0;
     }
 }
 
@@ -281,12 +401,14 @@ remove_ids_kernel(TableView in, TableView out, int cap, int streams, int stream,
 cudaError_t compact_tracks(const TableView &in, const float *lk_T6, const int32_t *lk_status, const TableView &out,
                            int groups, int cap, int streams, const GridDesc &gd, uint8_t *occ, int have_prev,
                            unsigned long long *counters, int *err_clear, const CellWork &cw, cudaStream_t st) {
-    if (cap >= 4096)
-        compact_tracks_kernel<1024, 4><<<groups, 1024, 0, st>>>(in, lk_T6, lk_status, out, cap, streams, gd, occ, have_prev,
-                                                            counters, err_clear, cw);
-    else
-        compact_tracks_kernel<256, 1><<<groups, 256, 0, st>>>(in, lk_T6, lk_status, out, cap, streams, gd, occ, have_prev, counters,
-                                                           err_clear, cw);
+    if (cap <= kChunk) {
+        compact_tracks_small_kernel<<<groups, kThreads, 0, st>>>(in, lk_T6, lk_status, out, cap, streams, gd, occ, have_prev,
+                                                               counters, err_clear, cw);
+    } else {
+        const int chunks = (cap + kChunk - 1) / kChunk;
+        compact_tracks_kernel<<<dim3((unsigned)chunks, (unsigned)groups, 1), kCompactThreads, 0, st>>>(
+            in, lk_T6, lk_status, out, cap, streams, gd, occ, have_prev, counters, err_clear, cw);
+    }
     return cudaGetLastError();
 }
 

@@ -1,0 +1,13 @@
+#!/bin/bash
+# session-3 experiment 3: small/chunked compaction split, generic pyramid kernel at 48 registers with the exact vertical path
+out=gpurun_out/r2/exp3; mkdir -p $out
+timeout 900 python -m pytest tests/test_gpu_tracker.py tests/test_gpu_pyramid.py tests/test_gpu_edge_cases.py -m gpu -x -q 2>&1 | tail -4 > $out/pytest.log
+for r in 1 2; do
+  for c in "EUROC6 128" "EUROC6 2" "C4 96" "C3 128"; do
+    for v in "" "_base"; do
+      RSVIO_LIB=$PWD/rs-vio_b200/lib/librsvio_b200$v.so timeout 300 python tools/pyr_bench.py $c 2>&1 | tail -1 | sed "s/^/[$v] /" >> $out/ab.log
+    done
+  done
+done
+for c in C4 C1 EUROC_SHIPPED; do timeout 200 python tools/config_stages.py $c >> $out/stages.log 2>&1; done
+cat $out/pytest.log $out/ab.log $out/stages.log
