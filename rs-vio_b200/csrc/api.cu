@@ -58,6 +58,15 @@ struct rsvio_tracker {
     cudaStream_t pyr_st = nullptr;  // pyramid of frame t+1 beside detection / stereo LK / merge of frame t (big batches), else == st
     bool own_pyr = false;
     cudaEvent_t ev_lk_done = nullptr, ev_pyr[kSlots]{};
+    // Batched handles split the temporal LK launch of a frame: the survivors of the previous frame's compaction (the
+    // bulk) are tracked on lk_st as soon as that compaction and this frame's pyramid are done -- beside the previous
+    // frame's detection / stereo LK / merge -- and only the points that merge appended wait for it (on st).
+    cudaStream_t lk_st = nullptr;
+    cudaEvent_t ev_compact = nullptr, ev_lk1 = nullptr;
+    int *d_surv = nullptr;     // [groups] survivors per group after the last compaction (rows before the merged new points)
+    bool split_lk = false;     // the handle may split (batched, own streams)
+    bool surv_valid = false;   // d_surv describes tab[tcur] (false after reset / remove_ids)
+    bool last_split = false;   // the frame just enqueued used the split launch
     bool own_stream = false;
     PyrPlan *plan = nullptr;
     PyrDesc pd{};
@@ -83,8 +92,8 @@ struct rsvio_tracker {
     unsigned long long *d_last_id = nullptr, *d_counters = nullptr, *d_rm = nullptr;
     int rm_cap = 0;
     int *d_err = nullptr;  // one overflow flag per slot: a full table is reported for the frame that overflowed only
-    unsigned *d_work = nullptr;  // [0,1] temporal LK counters, [2,3] stereo LK counters
-    int lk_par[2] = {0, 0}, det_par = 0;
+    unsigned *d_work = nullptr;  // [0,1] temporal LK counters, [2,3] stereo LK counters, [4,5] temporal LK of the new points (split launch)
+    int lk_par[3] = {0, 0, 0}, det_par = 0;
     // host-mapped output ring: records [groups][cap] and counts [groups] (+1 error flag)
     OutRecord *h_out[kSlots] = {nullptr, nullptr}, *d_out[kSlots] = {nullptr, nullptr};
     int *h_cnt[kSlots] = {nullptr, nullptr}, *d_cnt[kSlots] = {nullptr, nullptr};
@@ -166,6 +175,7 @@ void free_all(rsvio_tracker *t) {
     if (t->copy_st) cudaStreamSynchronize(t->copy_st);
     if (t->own_exp && t->exp_st) cudaStreamSynchronize(t->exp_st);
     if (t->own_pyr && t->pyr_st) cudaStreamSynchronize(t->pyr_st);
+    if (t->lk_st) cudaStreamSynchronize(t->lk_st);
     drop_graphs(t);
     pyr_plan_destroy(t->plan);
     for (int i = 0; i < kSlots; ++i) {
@@ -208,9 +218,13 @@ void free_all(rsvio_tracker *t) {
     cudaFree(t->d_rm);
     cudaFree(t->d_err);
     cudaFree(t->d_work);
+    cudaFree(t->d_surv);
     if (t->copy_st) cudaStreamDestroy(t->copy_st);
     if (t->own_exp && t->exp_st) cudaStreamDestroy(t->exp_st);
     if (t->own_pyr && t->pyr_st) cudaStreamDestroy(t->pyr_st);
+    if (t->lk_st) cudaStreamDestroy(t->lk_st);
+    if (t->ev_compact) cudaEventDestroy(t->ev_compact);
+    if (t->ev_lk1) cudaEventDestroy(t->ev_lk1);
     if (t->ev_lk_done) cudaEventDestroy(t->ev_lk_done);
     if (t->own_stream && t->st) cudaStreamDestroy(t->st);
     cudaGetLastError();
@@ -223,12 +237,15 @@ rsvio_status clear_state(rsvio_tracker *t) {
     CU_TRY(t, cudaMemsetAsync(t->d_counters, 0, sizeof(unsigned long long) * CNT_N, t->st));
     CU_TRY(t, cudaMemsetAsync(t->d_err, 0, sizeof(int) * kSlots, t->st));
     CU_TRY(t, cudaMemsetAsync(t->d_new_count, 0, sizeof(int) * t->S, t->st));
-    CU_TRY(t, cudaMemsetAsync(t->d_work, 0, sizeof(unsigned) * 4, t->st));
+    CU_TRY(t, cudaMemsetAsync(t->d_work, 0, sizeof(unsigned) * 6, t->st));
+    CU_TRY(t, cudaMemsetAsync(t->d_surv, 0, sizeof(int) * t->groups, t->st));
     CU_TRY(t, cudaMemsetAsync(t->d_cell_list_n, 0, sizeof(int) * 2, t->st));
     CU_TRY(t, cudaMemsetAsync(t->d_cell_work, 0, sizeof(int) * 3 * t->S, t->st));
     // the occupancy grids start clear; every compaction launch leaves them clear again (tracks.cu)
     CU_TRY(t, cudaMemsetAsync(t->d_occ, 0, (size_t)t->S * t->gd.occ_rows * t->gd.occ_cols, t->st));
-    t->lk_par[0] = t->lk_par[1] = t->det_par = 0;
+    t->lk_par[0] = t->lk_par[1] = t->lk_par[2] = t->det_par = 0;
+    t->surv_valid = false;
+    if (t->lk_st) CU_TRY(t, cudaStreamSynchronize(t->lk_st));
     if (t->own_exp) CU_TRY(t, cudaStreamSynchronize(t->exp_st));
     if (t->own_pyr) CU_TRY(t, cudaStreamSynchronize(t->pyr_st));
     CU_TRY(t, cudaStreamSynchronize(t->st));
@@ -282,6 +299,9 @@ rsvio_status frame_launches(rsvio_tracker *t, int slot, const uint8_t *src0, con
         CU_TRY(t, cudaStreamWaitEvent(st, t->ev_pyr[slot], 0));
     }
     mark(++stage);  // 2: temporal LK
+    // split launch (see lk_st): rows [0, surv) on lk_st behind the previous compaction, rows [surv, count) here
+    const bool split = t->split_lk && !prof && !capturing && t->have_prev && t->surv_valid;
+    t->last_split = split;
     if (t->have_prev) {
         LkBatch b{};
         b.pyr_a = prev;
@@ -298,8 +318,26 @@ rsvio_status frame_launches(rsvio_tracker *t, int slot, const uint8_t *src0, con
         b.cap = t->cap;
         b.max_it = t->cfg.max_iterations;
         b.thr = t->cfg.convergence_threshold;
-        CU_TRY(t, lk_track(t->pd, b, st));
-        count(2, 1);
+        if (split) {
+            // the bulk: one CTA slot per SM stays free for the previous frame's detection, stereo LK, merge and export
+            LkBatch b1 = b;
+            b1.counts = t->d_surv;
+            b1.blocks_per_sm = 7;
+            CU_TRY(t, cudaStreamWaitEvent(t->lk_st, t->ev_pyr[slot], 0));
+            CU_TRY(t, cudaStreamWaitEvent(t->lk_st, t->ev_compact, 0));
+            CU_TRY(t, lk_track(t->pd, b1, t->lk_st));
+            CU_TRY(t, cudaEventRecord(t->ev_lk1, t->lk_st));
+            // the points the previous frame's merge appended (st order: behind that merge)
+            b.first = t->d_surv;
+            b.work_counter = t->d_work + 4;
+            b.work_parity = t->lk_par[2];
+            CU_TRY(t, lk_track(t->pd, b, st));
+            CU_TRY(t, cudaStreamWaitEvent(st, t->ev_lk1, 0));
+            count(2, 2);
+        } else {
+            CU_TRY(t, lk_track(t->pd, b, st));
+            count(2, 1);
+        }
     }
     if (!capturing) CU_TRY(t, cudaEventRecord(t->ev_lk_done, st));  // `prev` may be overwritten from here on
     mark(++stage);  // 3: compaction + occupancy + the list of empty cells
@@ -314,11 +352,12 @@ rsvio_status frame_launches(rsvio_tracker *t, int slot, const uint8_t *src0, con
     cw.arrive = t->d_cell_work + 2 * t->S;
     cw.new_count = t->d_new_count;
     CU_TRY(t, compact_tracks(tin, t->d_lk_T6, t->d_lk_status, tout, t->groups, t->cap, t->S, t->gd, t->d_occ,
-                             t->have_prev ? 1 : 0, t->d_counters, t->d_err + slot, cw, st));
+                             t->have_prev ? 1 : 0, t->d_counters, t->d_err + slot, cw, t->d_surv, st));
+    if (t->split_lk && !capturing) CU_TRY(t, cudaEventRecord(t->ev_compact, st));
     count(3, 1);
     mark(++stage);  // 4: detection (level 0 of the current left pyramid is the input image) + ordered collection
     CU_TRY(t, detect_cells(t->gd, cur + t->pd.lv[0].off, (size_t)t->pd.lv[0].w, (size_t)t->pd.pyr_stride, t->S,
-                           t->d_occ, cw, t->d_new_T6, nullptr, t->new_cap, t->d_counters, false, st));
+                           t->d_occ, cw, t->d_new_T6, nullptr, t->new_cap, t->d_counters, false, t->split_lk && !prof, st));
     count(4, 1);
     mark(++stage);  // 5: stereo LK (left -> right of the current frame)
     if (t->stereo) {
@@ -369,6 +408,8 @@ rsvio_status frame_launches(rsvio_tracker *t, int slot, const uint8_t *src0, con
 // host state after the launches of a frame went out: the ping-pong sets and the counter pairs switch sides
 void frame_advance(rsvio_tracker *t) {
     if (t->have_prev) t->lk_par[0] ^= 1;  // only a launch that went out has cleared the other counter
+    if (t->last_split) t->lk_par[2] ^= 1;
+    t->surv_valid = true;  // the compaction of this frame wrote d_surv for the table the next frame tracks
     if (t->stereo) t->lk_par[1] ^= 1;
     t->det_par ^= 1;
     t->tcur ^= 1;
@@ -609,6 +650,13 @@ rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) 
                 CU_TRY(t, cudaStreamCreateWithPriority(&t->pyr_st, cudaStreamNonBlocking, lo));
             }
             t->own_pyr = true;
+            const char *ns = getenv("RSVIO_NO_SPLIT_LK");
+            if (!(ns && ns[0] == '1')) {
+                CU_TRY(t, cudaStreamCreateWithFlags(&t->lk_st, cudaStreamNonBlocking));
+                CU_TRY(t, cudaEventCreateWithFlags(&t->ev_compact, cudaEventDisableTiming));
+                CU_TRY(t, cudaEventCreateWithFlags(&t->ev_lk1, cudaEventDisableTiming));
+                t->split_lk = true;
+            }
         } else {
             t->exp_st = t->st;
             t->pyr_st = t->st;
@@ -655,7 +703,8 @@ rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) 
         CU_TRY(t, dmalloc(&t->d_last_id, S));
         CU_TRY(t, dmalloc(&t->d_counters, (size_t)CNT_N));
         CU_TRY(t, dmalloc(&t->d_err, (size_t)kSlots));
-        CU_TRY(t, dmalloc(&t->d_work, (size_t)4));
+        CU_TRY(t, dmalloc(&t->d_work, (size_t)6));
+        CU_TRY(t, dmalloc(&t->d_surv, G));
         return clear_state(t);
     };
     rs = body();
@@ -957,6 +1006,7 @@ rsvio_status rsvio_tracker_remove_ids(rsvio_tracker *t, int32_t stream, const ui
     CU_TRY(t, remove_ids(t->tab[t->tcur], t->tab[t->tcur ^ 1], t->groups, t->cap, t->S, stream, t->d_rm, (int)n, t->st));
     t->host_launches += 1;
     t->tcur ^= 1;
+    t->surv_valid = false;  // rows moved: the next frame tracks the whole table in one launch
     // refresh the host-visible result of the affected groups
     const int slot = t->result_slot < 0 ? 0 : t->result_slot;
     const TableView &tv = t->tab[t->tcur];
@@ -1263,7 +1313,7 @@ rsvio_status rsvio_detect_keypoints(int32_t device, const uint8_t *image, int32_
         cw.n_empty = d_list_n + 2;
         cw.done = d_list_n + 3;
         cw.new_count = d_cnt;
-        CU_TRY0(detect_cells(gd, d_img, (size_t)width, 0, 1, d_occ, cw, d_T6, d_nscore, cells, nullptr, true, cs.s));
+        CU_TRY0(detect_cells(gd, d_img, (size_t)width, 0, 1, d_occ, cw, d_T6, d_nscore, cells, nullptr, true, false, cs.s));
     }
     CU_TRY0(D2H(&cnt, d_cnt, sizeof(int)));
     CU_TRY0(cudaStreamSynchronize(cs.s));

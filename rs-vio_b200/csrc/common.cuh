@@ -103,7 +103,8 @@ cudaError_t pyr_build(const PyrPlan *p, const uint8_t *src0, const uint8_t *src1
 struct LkBatch {
     const uint8_t *pyr_a;   // slot 0 of the source pyramids
     const uint8_t *pyr_b;   // slot 0 of the target pyramids
-    const int *counts;      // [groups] points per group (device)
+    const int *counts;      // [groups] points per group (device): the launch tracks rows [first[g], counts[g])
+    const int *first;       // [groups] first row per group (device) or nullptr = 0
     const float *in_T6;     // [groups][cap][6]
     float *out_T6;          // [groups][cap][6]
     int32_t *status;        // [groups][cap]
@@ -114,6 +115,7 @@ struct LkBatch {
     int groups, cap;
     int max_it;
     float thr;
+    int blocks_per_sm;      // persistent CTAs per SM of a dynamically scheduled launch (0: as many as fit)
     uint32_t floor_bias;  // set by lk_track: the bit pattern of 2^23, passed as a launch parameter so that the
                           // compiler cannot split the folded address constant back into per-load immediates
 };
@@ -163,7 +165,7 @@ struct CellWork {
 // itself (1 extra launch) before the detection launch.
 cudaError_t detect_cells(const GridDesc &gd, const uint8_t *img0, size_t stride, size_t pitch, int streams,
                          const uint8_t *occ, const CellWork &cw, float *new_T6, float *new_score, int new_cap,
-                         unsigned long long *counters, bool list_first, cudaStream_t st);
+                         unsigned long long *counters, bool list_first, bool narrow, cudaStream_t st);
 // marks cells holding one of n (x, y) rounded positions (stateless API); occ must be zeroed
 cudaError_t mark_occupancy_xy(const GridDesc &gd, const uint32_t *d_xy, int n, uint8_t *occ, cudaStream_t st);
 
@@ -175,9 +177,10 @@ struct TableView {
 };
 // stable compaction of the surviving tracks of every group from `in` (+ lk results) into `out`;
 // groups < streams (camera 0) also rebuild the occupancy grid of their stream.
+// surv (optional): [groups] survivors per group, i.e. out.counts before the merge kernel appends the new points.
 cudaError_t compact_tracks(const TableView &in, const float *lk_T6, const int32_t *lk_status, const TableView &out,
                            int groups, int cap, int streams, const GridDesc &gd, uint8_t *occ, int have_prev,
-                           unsigned long long *counters, int *err_clear, const CellWork &cw, cudaStream_t st);
+                           unsigned long long *counters, int *err_clear, const CellWork &cw, int *surv, cudaStream_t st);
 // packed output record written to (mapped) host memory
 struct OutRecord {
     unsigned long long id;

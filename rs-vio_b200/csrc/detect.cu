@@ -105,11 +105,13 @@ list_empty_cells_kernel(GridDesc gd, int streams, const uint8_t *__restrict__ oc
     if (empty) atomicAdd(n_empty + (int)(item / cells), 1);  // stateless path only (one image): not on the frame path
 }
 
-constexpr int kDetThreads = 256;
+// CTA sizes of the detection kernel: 256 threads by default; 128 (64 registers x 128 threads = one CTA slot of a
+// temporal LK launch with 7 resident CTAs per SM) when the launch has to run beside the next frame's LK.
 constexpr int kDetChunk = 2048;  // candidates per compaction pass (a 40-px cell has 1156)
 
 // ordered compaction of one stream's cells (visiting order: x outer, y inner) into identity transforms, by one CTA.
 // The cell results were written by other CTAs of this launch (fenced before their `done` increment): read past L1.
+template <int NT>
 __device__ void collect_stream(const GridDesc &gd, int s, const uint32_t *cell_pt, const float *cell_score,
                                float *__restrict__ new_T6, float *__restrict__ new_score, int *__restrict__ new_count,
                                int new_cap, unsigned long long *counters, uint32_t *warp_tot /* >= 8 shared words */) {
@@ -118,7 +120,7 @@ __device__ void collect_stream(const GridDesc &gd, int s, const uint32_t *cell_p
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (threadIdx.x == 0) base = 0;
     __syncthreads();
-    for (int c0 = 0; c0 < cells; c0 += kDetThreads) {
+    for (int c0 = 0; c0 < cells; c0 += NT) {
         const int c = c0 + threadIdx.x;
         const uint32_t pt = c < cells ? __ldcg(cell_pt + (size_t)s * cells + c) : 0xFFFFFFFFu;
         const bool has = pt != 0xFFFFFFFFu;
@@ -137,7 +139,7 @@ __device__ void collect_stream(const GridDesc &gd, int s, const uint32_t *cell_p
         __syncthreads();
         if (threadIdx.x == 0) {
             int t = 0;
-            for (int k = 0; k < kDetThreads / 32; ++k) t += (int)warp_tot[k];
+            for (int k = 0; k < NT / 32; ++k) t += (int)warp_tot[k];
             base += t;
         }
         __syncthreads();
@@ -152,13 +154,14 @@ __device__ void collect_stream(const GridDesc &gd, int s, const uint32_t *cell_p
 // One CTA per empty cell: the (g-6)^2 candidates are spread over 256 threads, block-wide packed-key max.
 // (128 threads: 4 % slower on the bench step; one WARP per cell, no block barriers: 40 % slower -- a lane then
 // tests 36 candidates in sequence.)
-__global__ void __launch_bounds__(kDetThreads)
+template <int NT>
+__global__ void __launch_bounds__(NT)
 detect_list_kernel(GridDesc gd, const uint8_t *__restrict__ img0, size_t stride, size_t pitch, CellWork cw,
                    float *__restrict__ new_T6, float *__restrict__ new_score, int new_cap, unsigned long long *counters) {
     const uint32_t *__restrict__ list = cw.list;
     uint32_t *__restrict__ cell_pt = cw.cell_pt;
     float *__restrict__ cell_score = cw.cell_score;
-    __shared__ uint32_t wbest[kDetThreads / 32];
+    __shared__ uint32_t wbest[NT / 32];
     __shared__ uint32_t surv[kDetChunk];
     __shared__ int n_surv;
     __shared__ int s_last;
@@ -183,10 +186,10 @@ detect_list_kernel(GridDesc gd, const uint8_t *__restrict__ img0, size_t stride,
             const int c1 = min(c0 + kDetChunk, side * side);
             // tests first (independent loads of several candidates in flight), compaction afterwards
             uint32_t passbits = 0;
-            static_assert(kDetChunk / kDetThreads <= 32, "one pass bit per candidate of a thread");
+            static_assert(kDetChunk / NT <= 32, "one pass bit per candidate of a thread");
 #pragma unroll 4
-            for (int j = 0; j < kDetChunk / kDetThreads; ++j) {
-                const int idx = c0 + j * kDetThreads + (int)threadIdx.x;
+            for (int j = 0; j < kDetChunk / NT; ++j) {
+                const int idx = c0 + j * NT + (int)threadIdx.x;
                 if (idx < c1) {
                     const int ly = idx / side + 3, lx = idx - (idx / side) * side + 3;
                     const int gx = x0 + lx, gy = y0 + ly;
@@ -196,16 +199,16 @@ detect_list_kernel(GridDesc gd, const uint8_t *__restrict__ img0, size_t stride,
                         passbits |= 1u << j;
                 }
             }
-            for (int j = 0; c0 + j * kDetThreads < c1; ++j) {
+            for (int j = 0; c0 + j * NT < c1; ++j) {
                 const bool pass = (passbits >> j) & 1u;
                 const unsigned m = __ballot_sync(0xffffffffu, pass);
                 int at = 0;
                 if (lane == 0 && m) at = atomicAdd(&n_surv, __popc(m));
                 at = __shfl_sync(0xffffffffu, at, 0);
-                if (pass) surv[at + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(c0 + j * kDetThreads + (int)threadIdx.x);
+                if (pass) surv[at + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(c0 + j * NT + (int)threadIdx.x);
             }
             __syncthreads();
-            for (int k = threadIdx.x; k < n_surv; k += kDetThreads) {
+            for (int k = threadIdx.x; k < n_surv; k += NT) {
                 const int idx = (int)surv[k];
                 const int ly = idx / side + 3, lx = idx - (idx / side) * side + 3;
                 const int sc = fast9_score_full(base + (size_t)(y0 + ly) * stride + (x0 + lx), (int)stride);
@@ -221,7 +224,7 @@ detect_list_kernel(GridDesc gd, const uint8_t *__restrict__ img0, size_t stride,
         if (lane == 0) wbest[wid] = best;
         __syncthreads();
         if (threadIdx.x == 0) {
-            for (int k = 1; k < kDetThreads / 32; ++k) best = max(best, wbest[k]);
+            for (int k = 1; k < NT / 32; ++k) best = max(best, wbest[k]);
             if (best != 0) {
                 const int sc = 255 - (int)((best >> 20) & 0xFFu);
                 const uint32_t raster = 0xFFFFFu - (best & 0xFFFFFu);
@@ -237,7 +240,7 @@ detect_list_kernel(GridDesc gd, const uint8_t *__restrict__ img0, size_t stride,
         __syncthreads();
         if (s_last) {
             __threadfence();
-            collect_stream(gd, s, cell_pt, cell_score, new_T6, new_score, cw.new_count, new_cap, counters, wbest);
+            collect_stream<NT>(gd, s, cell_pt, cell_score, new_T6, new_score, cw.new_count, new_cap, counters, wbest);
             if (threadIdx.x == 0) cw.done[s] = 0;  // ready for the next frame
             __syncthreads();
         }
@@ -257,7 +260,7 @@ __global__ void mark_occupancy_xy_kernel(GridDesc gd, const uint32_t *__restrict
 
 cudaError_t detect_cells(const GridDesc &gd, const uint8_t *img0, size_t stride, size_t pitch, int streams,
                          const uint8_t *occ, const CellWork &cw, float *new_T6, float *new_score, int new_cap,
-                         unsigned long long *counters, bool list_first, cudaStream_t st) {
+                         unsigned long long *counters, bool list_first, bool narrow, cudaStream_t st) {
     const long long total = (long long)gd.ncx * gd.ncy * streams;
     if (total <= 0) return cudaSuccess;
     if (list_first)  // stateless path: the frame path gets its list from the compaction kernel
@@ -268,8 +271,10 @@ cudaError_t detect_cells(const GridDesc &gd, const uint8_t *img0, size_t stride,
     // them exiting at once, 31 us)
     const long long wave = (long long)sm_count() * 8;
     long long blocks = total < wave ? total : wave;
-    detect_list_kernel<<<(unsigned)blocks, kDetThreads, 0, st>>>(gd, img0, stride, pitch, cw, new_T6, new_score, new_cap,
-                                                                 counters);
+    if (narrow)
+        detect_list_kernel<128><<<(unsigned)blocks, 128, 0, st>>>(gd, img0, stride, pitch, cw, new_T6, new_score, new_cap, counters);
+    else
+        detect_list_kernel<256><<<(unsigned)blocks, 256, 0, st>>>(gd, img0, stride, pitch, cw, new_T6, new_score, new_cap, counters);
     return cudaGetLastError();
 }
 

@@ -554,7 +554,8 @@ lk_track_fb_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ L
         int base = 0;
         for (int g0 = 0; g0 < b.groups; g0 += blockDim.x) {
             const int g = g0 + threadIdx.x;
-            const int c = g < b.groups ? min(__ldg(b.counts + g), b.cap) : 0;
+            int c = g < b.groups ? min(__ldg(b.counts + g), b.cap) : 0;
+            if (b.first && g < b.groups) c = max(c - __ldg(b.first + g), 0);  // rows [first, count)
             int incl = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -589,12 +590,12 @@ lk_track_fb_kernel(const __grid_constant__ PyrDesc pd, const __grid_constant__ L
                 if (prefix[mid] <= w) lo = mid; else hi = mid;
             }
             g = lo;
-            k = w - prefix[g];
+            k = w - prefix[g] + (b.first ? __ldg(b.first + g) : 0);
         } else {
             if (it0 >= total) break;
             g = it0 / b.cap;
             k = it0 - g * b.cap;
-            if (k >= __ldg(b.counts + g)) continue;
+            if (k >= __ldg(b.counts + g) || (b.first && k < __ldg(b.first + g))) continue;
         }
         item = g * b.cap + k;
         const uint8_t *A = b.pyr_a + (size_t)g * pd.pyr_stride;
@@ -669,7 +670,7 @@ cudaError_t lk_track(const PyrDesc &pd, const LkBatch &b, cudaStream_t st) {
     const char *env = getenv("RSVIO_LK_BLOCKS_PER_SM");
     const int env_v = env ? atoi(env) : 0;
     const int resident = (env_v >= 1 && env_v <= RSVIO_LK_MINB) ? env_v : RSVIO_LK_MINB;
-    const long long max_blocks = (long long)sm_count() * (dynamic ? resident : 16);
+    const long long max_blocks = (long long)sm_count() * (dynamic ? (b.blocks_per_sm >= 1 && b.blocks_per_sm < resident ? b.blocks_per_sm : resident) : 16);
     if (blocks > max_blocks) blocks = max_blocks;
     const size_t smem = dynamic ? sizeof(int) * (size_t)(b.groups + 1) : 0;
     LkBatch bb = b;

@@ -70,7 +70,7 @@ __device__ __forceinline__ int block_offset(int cnt, int *warp_tot, int *base) {
 __global__ void __launch_bounds__(kThreads)
 compact_tracks_small_kernel(TableView in, const float *__restrict__ lk_T6, const int32_t *__restrict__ lk_status,
                       TableView out, int cap, int streams, GridDesc gd, uint8_t *__restrict__ occ, int have_prev,
-                      unsigned long long *counters, int *__restrict__ err_clear, CellWork cw) {
+                      unsigned long long *counters, int *__restrict__ err_clear, CellWork cw, int *__restrict__ surv) {
     // the overflow flag the merge kernel of this frame may raise (its previous use, two frames ago, has been read)
     if (err_clear && blockIdx.x == 0 && threadIdx.x == 0) *err_clear = 0;
     __shared__ int warp_tot[kWarps];
@@ -111,6 +111,7 @@ compact_tracks_small_kernel(TableView in, const float *__restrict__ lk_T6, const
     }
     if (threadIdx.x == 0) {
         out.counts[g] = base;
+        if (surv) surv[g] = base;
         if (counters && g == 0) atomicAdd(counters + CNT_FRAMES, (unsigned long long)streams);
     }
     // The work list of the detection kernel (detect_key_points visits the cells without a tracked point,
@@ -157,7 +158,7 @@ constexpr int kCompactThreads = 256, kCompactE = 4, kChunk = kCompactThreads * k
 __global__ void __launch_bounds__(kCompactThreads)
 compact_tracks_kernel(TableView in, const float *__restrict__ lk_T6, const int32_t *__restrict__ lk_status,
                       TableView out, int cap, int streams, GridDesc gd, uint8_t *__restrict__ occ, int have_prev,
-                      unsigned long long *counters, int *__restrict__ err_clear, CellWork cw) {
+                      unsigned long long *counters, int *__restrict__ err_clear, CellWork cw, int *__restrict__ surv) {
     constexpr int NT = kCompactThreads, E = kCompactE, NW = NT / 32;
     const int g = blockIdx.y, chunk = blockIdx.x, n_chunks = gridDim.x;
     const int tid = threadIdx.x;
@@ -181,6 +182,7 @@ compact_tracks_kernel(TableView in, const float *__restrict__ lk_T6, const int32
         if (have_prev && start > 0) {
             int c = 0;  // row0 and start are multiples of 4 (cap = 4 cells + 64): aligned int4 reads
             const int4 *__restrict__ sp = reinterpret_cast<const int4 *>(lk_status + row0);
+#pragma unroll 4
             for (int i = tid; i < start / 4; i += NT) {
                 const int4 q = __ldg(sp + i);
                 c += (q.x == RSVIO_TRACK_OK) + (q.y == RSVIO_TRACK_OK) + (q.z == RSVIO_TRACK_OK) + (q.w == RSVIO_TRACK_OK);
@@ -208,13 +210,17 @@ compact_tracks_kernel(TableView in, const float *__restrict__ lk_T6, const int32
         const int kept = s_base;
         const float *__restrict__ srcT = (have_prev ? lk_T6 : in.T6) + (row0 + start) * 6;
         float *__restrict__ dstT = out.T6 + (row0 + before) * 6;
+        RSVIO_CHECK(kept >= 0 && kept <= m && before >= 0 && before + kept <= cap);
+#pragma unroll 8  // independent gathers: 8 in flight per thread
         for (int f = tid; f < kept * 6; f += NT) {
             const int r = f / 6, q = f - r * 6;
             dstT[f] = srcT[s_src[r] * 6 + q];
         }
         const uint32_t x_end = gd.x_start + gd.g * (uint32_t)gd.ncx + 1, y_end = gd.y_start + gd.g * (uint32_t)gd.ncy + 1;
+#pragma unroll 2
         for (int r = tid; r < kept; r += NT) {
             const int k = s_src[r];
+            RSVIO_CHECK(k >= 0 && k < m);
             out.ids[row0 + before + r] = in.ids[row0 + start + k];
             if (cam0) {  // add_points: Corner::new(round(x) as u32, round(y) as u32)
                 const uint32_t x = sat_u32(roundf(srcT[k * 6 + 2])), y = sat_u32(roundf(srcT[k * 6 + 5]));
@@ -222,9 +228,13 @@ compact_tracks_kernel(TableView in, const float *__restrict__ lk_T6, const int32
                     my_occ[(size_t)((y - gd.y_start) / gd.g) * gd.occ_cols + (x - gd.x_start) / gd.g] = 1;
             }
         }
-        if (tid == 0 && start + kChunk >= n) out.counts[g] = before + kept;  // the group's last chunk knows the total
+        if (tid == 0 && start + kChunk >= n) {  // the group's last chunk knows the total
+            out.counts[g] = before + kept;
+            if (surv) surv[g] = before + kept;
+        }
     } else if (chunk == 0 && tid == 0) {
         out.counts[g] = 0;
+        if (surv) surv[g] = 0;
     }
     if (tid == 0 && counters && g == 0 && chunk == 0) atomicAdd(counters + CNT_FRAMES, (unsigned long long)streams);
     // The work list of the detection kernel (detect_key_points visits the cells without a tracked point,
@@ -249,6 +259,7 @@ compact_tracks_kernel(TableView in, const float *__restrict__ lk_T6, const int32
         const int per = (cells + NT - 1) / NT;
         const int c_lo = min(tid * per, cells), c_hi = min(c_lo + per, cells);
         int mine = 0;
+#pragma unroll 8
         for (int cell = c_lo; cell < c_hi; ++cell) {
             const int cx = cell / gd.ncy, cy = cell - cx * gd.ncy;  // visiting order: x outer, y inner
             mine += __ldcg(my_occ + (size_t)cy * gd.occ_cols + cx) == 0;  // L2: other CTAs wrote it
@@ -329,8 +340,10 @@ merge_new_kernel(TableView tab, int streams, int cap, int stereo, const float *_
 
 // packed output (mapped host memory): get_track_points / frame population (feature_tracker.rs:177-200).
 // Own kernel so that it can run beside the next frame: only live records cross PCIe.
-constexpr int kExportChunks = 4;
-__global__ void __launch_bounds__(kThreads)
+// 128-thread CTAs (x 8 chunks per group): 56 registers x 128 threads fit the one CTA slot per SM that a temporal LK
+// launch with 7 resident CTAs leaves free, so the export of frame t runs beside the LK launch of frame t + 1
+constexpr int kExportChunks = 8, kExportThreads = 128;
+__global__ void __launch_bounds__(kExportThreads)
 export_records_kernel(TableView tab, int cap, int streams, OutRecord *__restrict__ out_rec, int *__restrict__ out_counts,
                       const __grid_constant__ CameraModelDev cam0, const __grid_constant__ CameraModelDev cam1,
                       float2 *__restrict__ out_uxy, const int *__restrict__ err_flag) {
@@ -341,7 +354,7 @@ export_records_kernel(TableView tab, int cap, int streams, OutRecord *__restrict
     if (g == 0 && blockIdx.y == 0 && threadIdx.x == 0 && err_flag) out_counts[gridDim.x] = *err_flag;
     const CameraModelDev &cm = g < streams ? cam0 : cam1;
     const bool unproject = out_uxy != nullptr && cm.model != RSVIO_CAMERA_NONE;
-    for (int k = blockIdx.y * kThreads + threadIdx.x; k < n; k += kExportChunks * kThreads) {
+    for (int k = blockIdx.y * kExportThreads + threadIdx.x; k < n; k += kExportChunks * kExportThreads) {
         const size_t i = (size_t)g * cap + k;
         OutRecord r;
         r.id = tab.ids[i];
@@ -400,14 +413,14 @@ remove_ids_kernel(TableView in, TableView out, int cap, int streams, int stream,
 
 cudaError_t compact_tracks(const TableView &in, const float *lk_T6, const int32_t *lk_status, const TableView &out,
                            int groups, int cap, int streams, const GridDesc &gd, uint8_t *occ, int have_prev,
-                           unsigned long long *counters, int *err_clear, const CellWork &cw, cudaStream_t st) {
+                           unsigned long long *counters, int *err_clear, const CellWork &cw, int *surv, cudaStream_t st) {
     if (cap <= kChunk) {
         compact_tracks_small_kernel<<<groups, kThreads, 0, st>>>(in, lk_T6, lk_status, out, cap, streams, gd, occ, have_prev,
-                                                               counters, err_clear, cw);
+                                                               counters, err_clear, cw, surv);
     } else {
         const int chunks = (cap + kChunk - 1) / kChunk;
         compact_tracks_kernel<<<dim3((unsigned)chunks, (unsigned)groups, 1), kCompactThreads, 0, st>>>(
-            in, lk_T6, lk_status, out, cap, streams, gd, occ, have_prev, counters, err_clear, cw);
+            in, lk_T6, lk_status, out, cap, streams, gd, occ, have_prev, counters, err_clear, cw, surv);
     }
     return cudaGetLastError();
 }
@@ -423,7 +436,7 @@ cudaError_t merge_new_points(const TableView &tab, int streams, int cap, int ste
 cudaError_t export_records(const TableView &tab, int groups, int cap, int streams, OutRecord *out_rec, int *out_counts,
                            const CameraModelDev &cam0, const CameraModelDev &cam1, float *out_uxy, const int *err_flag,
                            cudaStream_t st) {
-    export_records_kernel<<<dim3((unsigned)groups, kExportChunks, 1), kThreads, 0, st>>>(
+    export_records_kernel<<<dim3((unsigned)groups, kExportChunks, 1), kExportThreads, 0, st>>>(
         tab, cap, streams, out_rec, out_counts, cam0, cam1, reinterpret_cast<float2 *>(out_uxy), err_flag);
     return cudaGetLastError();
 }
