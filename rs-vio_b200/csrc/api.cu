@@ -67,6 +67,7 @@ struct rsvio_tracker {
     bool split_lk = false;     // the handle may split (batched, own streams)
     bool surv_valid = false;   // d_surv describes tab[tcur] (false after reset / remove_ids)
     bool last_split = false;   // the frame just enqueued used the split launch
+    bool lk_helper = true;     // split launch: a third launch fills the free CTA slot once the previous frame's tail is done
     bool own_stream = false;
     PyrPlan *plan = nullptr;
     PyrDesc pd{};
@@ -332,8 +333,14 @@ rsvio_status frame_launches(rsvio_tracker *t, int slot, const uint8_t *src0, con
             b.work_counter = t->d_work + 4;
             b.work_parity = t->lk_par[2];
             CU_TRY(t, lk_track(t->pd, b, st));
+            // By now (st order) the previous frame's tail is done and the free CTA slot would idle until the bulk launch
+            // ends: one more persistent CTA per SM joins it, drawing from the same work counter (RSVIO_LK_HELPER=0: off)
+            if (t->lk_helper) {
+                b1.blocks_per_sm = 1;
+                CU_TRY(t, lk_track(t->pd, b1, st));
+            }
             CU_TRY(t, cudaStreamWaitEvent(st, t->ev_lk1, 0));
-            count(2, 2);
+            count(2, t->lk_helper ? 3 : 2);
         } else {
             CU_TRY(t, lk_track(t->pd, b, st));
             count(2, 1);
@@ -656,6 +663,8 @@ rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) 
                 CU_TRY(t, cudaEventCreateWithFlags(&t->ev_compact, cudaEventDisableTiming));
                 CU_TRY(t, cudaEventCreateWithFlags(&t->ev_lk1, cudaEventDisableTiming));
                 t->split_lk = true;
+                const char *hp = getenv("RSVIO_LK_HELPER");
+                t->lk_helper = !(hp && hp[0] == '0');
             }
         } else {
             t->exp_st = t->st;
