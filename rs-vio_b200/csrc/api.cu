@@ -68,6 +68,13 @@ struct rsvio_tracker {
     bool surv_valid = false;   // d_surv describes tab[tcur] (false after reset / remove_ids)
     bool last_split = false;   // the frame just enqueued used the split launch
     bool lk_helper = true;     // split launch: a third launch fills the free CTA slot once the previous frame's tail is done
+    // Host-fed frames arrive at PCIe rate, about half the rate the kernels could take them at EuRoC size: the device idles
+    // between frames, there is no tail to hide, and the split only adds latency (7 instead of 8 CTAs per SM at the start,
+    // narrower tail kernels) -- which matters with two frames in flight and a host loop that has to enqueue the next
+    // upload in time.  sync() looks whether the next frame's upload was still running when this frame finished; while
+    // that is so, frames are enqueued unsplit.
+    bool upload_bound = false;
+    bool slot_host[kSlots] = {false, false};  // the frame in this slot came through upload()
     bool own_stream = false;
     PyrPlan *plan = nullptr;
     PyrDesc pd{};
@@ -246,6 +253,7 @@ rsvio_status clear_state(rsvio_tracker *t) {
     CU_TRY(t, cudaMemsetAsync(t->d_occ, 0, (size_t)t->S * t->gd.occ_rows * t->gd.occ_cols, t->st));
     t->lk_par[0] = t->lk_par[1] = t->lk_par[2] = t->det_par = 0;
     t->surv_valid = false;
+    t->upload_bound = false;
     if (t->lk_st) CU_TRY(t, cudaStreamSynchronize(t->lk_st));
     if (t->own_exp) CU_TRY(t, cudaStreamSynchronize(t->exp_st));
     if (t->own_pyr) CU_TRY(t, cudaStreamSynchronize(t->pyr_st));
@@ -301,7 +309,7 @@ rsvio_status frame_launches(rsvio_tracker *t, int slot, const uint8_t *src0, con
     }
     mark(++stage);  // 2: temporal LK
     // split launch (see lk_st): rows [0, surv) on lk_st behind the previous compaction, rows [surv, count) here
-    const bool split = t->split_lk && !prof && !capturing && t->have_prev && t->surv_valid;
+    const bool split = t->split_lk && !prof && !capturing && t->have_prev && t->surv_valid && !t->upload_bound;
     t->last_split = split;
     if (t->have_prev) {
         LkBatch b{};
@@ -364,7 +372,7 @@ rsvio_status frame_launches(rsvio_tracker *t, int slot, const uint8_t *src0, con
     count(3, 1);
     mark(++stage);  // 4: detection (level 0 of the current left pyramid is the input image) + ordered collection
     CU_TRY(t, detect_cells(t->gd, cur + t->pd.lv[0].off, (size_t)t->pd.lv[0].w, (size_t)t->pd.pyr_stride, t->S,
-                           t->d_occ, cw, t->d_new_T6, nullptr, t->new_cap, t->d_counters, false, t->split_lk && !prof, st));
+                           t->d_occ, cw, t->d_new_T6, nullptr, t->new_cap, t->d_counters, false, t->split_lk && !prof && !t->upload_bound, st));
     count(4, 1);
     mark(++stage);  // 5: stereo LK (left -> right of the current frame)
     if (t->stereo) {
@@ -522,6 +530,7 @@ rsvio_status upload(rsvio_tracker *t, int slot, const uint8_t *const *left, cons
     if (t->profiling) cudaEventRecord(t->ev_up[slot][1], t->copy_st);
     t->up_valid[slot] = t->profiling;
     CU_TRY(t, cudaEventRecord(t->ev_h2d[slot], t->copy_st));
+    t->slot_host[slot] = true;
     CU_TRY(t, cudaStreamWaitEvent(t->st, t->ev_h2d[slot], 0));
     if (t->pyr_st != t->st) CU_TRY(t, cudaStreamWaitEvent(t->pyr_st, t->ev_h2d[slot], 0));
     return RSVIO_OK;
@@ -657,8 +666,10 @@ rsvio_status rsvio_tracker_create(const rsvio_config *cfg, rsvio_tracker **out) 
                 CU_TRY(t, cudaStreamCreateWithPriority(&t->pyr_st, cudaStreamNonBlocking, lo));
             }
             t->own_pyr = true;
+            // the split pays when the bulk launch outlasts the previous frame's latency-bound tail (~80 us, ~5.5 us
+            // of temporal LK per EuRoC-size stream): from about 24 streams up
             const char *ns = getenv("RSVIO_NO_SPLIT_LK");
-            if (!(ns && ns[0] == '1')) {
+            if (t->S >= 24 && !(ns && ns[0] == '1')) {
                 CU_TRY(t, cudaStreamCreateWithFlags(&t->lk_st, cudaStreamNonBlocking));
                 CU_TRY(t, cudaEventCreateWithFlags(&t->ev_compact, cudaEventDisableTiming));
                 CU_TRY(t, cudaEventCreateWithFlags(&t->ev_lk1, cudaEventDisableTiming));
@@ -768,6 +779,7 @@ rsvio_status rsvio_tracker_submit_device(rsvio_tracker *t, const void *d_left, c
     CU_TRY(t, dev_scope.enter(t->cfg.device));
     const int slot = t->next_slot;
     t->up_valid[slot] = false;
+    t->slot_host[slot] = false;
     rsvio_status rs = enqueue_frame(t, slot, (const uint8_t *)d_left, (const uint8_t *)d_right, stride, pitch);
     if (rs != RSVIO_OK) return rs;
     t->next_slot ^= 1;
@@ -788,6 +800,11 @@ rsvio_status rsvio_tracker_sync(rsvio_tracker *t) {
             t->inflight -= 1;
             return fail_cuda(t, e, "cudaEventSynchronize(ev_done)", __LINE__);
         }
+    }
+    if (t->split_lk && t->inflight >= 2) {  // a frame has been submitted behind this one: was the device waiting for it?
+        const int nslot = slot ^ 1;
+        t->upload_bound = t->slot_host[nslot] && cudaEventQuery(t->ev_h2d[nslot]) == cudaErrorNotReady;
+        cudaGetLastError();
     }
     if (t->stage_valid[slot]) {
         for (int k = 1; k < RSVIO_N_STAGES; ++k) {
@@ -870,6 +887,7 @@ rsvio_status rsvio_tracker_process_stereo_fmt(rsvio_tracker *t, const void *left
     if (t->profiling) cudaEventRecord(t->ev_up[slot][1], t->copy_st);
     t->up_valid[slot] = t->profiling;
     CU_TRY(t, cudaEventRecord(t->ev_h2d[slot], t->copy_st));
+    t->slot_host[slot] = true;
     CU_TRY(t, cudaStreamWaitEvent(t->st, t->ev_h2d[slot], 0));
     if (t->pyr_st != t->st) CU_TRY(t, cudaStreamWaitEvent(t->pyr_st, t->ev_h2d[slot], 0));
     rsvio_status rs = enqueue_frame(t, slot, t->d_in[slot], t->d_in[slot] + t->img_bytes, (size_t)w, t->img_bytes);

@@ -269,7 +269,7 @@ cudaError_t detect_cells(const GridDesc &gd, const uint8_t *img0, size_t stride,
                                                                                  cw.n_empty);
     // one resident wave of CTAs looping over the list (measured: 23 us; one CTA per candidate cell, most of
     // them exiting at once, 31 us)
-    const long long wave = (long long)sm_count() * 8;
+    const long long wave = (long long)sm_count() * (narrow ? 16 : 8);  // the same number of threads either way
     long long blocks = total < wave ? total : wave;
     if (narrow)
         detect_list_kernel<128><<<(unsigned)blocks, 128, 0, st>>>(gd, img0, stride, pitch, cw, new_T6, new_score, new_cap, counters);

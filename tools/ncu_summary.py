@@ -26,14 +26,27 @@ def launches(src, dst):
     H, data = rows[hdr], rows[hdr + 1:]
     ki, vi, gi = H.index("Kernel Name"), H.index("Metric Value"), H.index("Grid Size")
     agg = collections.defaultdict(list)
-    prev = ""
+    n_lk, after_detect = 0, False
     for r in data:
         if len(r) > vi:
             name = r[ki].replace("unnamed>::", "").replace("void ", "").replace("rsvio::<", "").split("(")[0]
-            if "lk_track_fb" in name:  # two launches per frame: after the pyramid (temporal), after collect (stereo)
-                name += " [temporal]" if "pyr_" in prev else " [stereo, new points]"
+            if "pyr_" in name:
+                n_lk, after_detect = 0, False
+            if "detect_list" in name:
+                after_detect = True
+            if "lk_track_fb" in name:
+                # launches of a frame in host order: temporal (split on batched handles: survivors of the previous
+                # compaction, then the newly merged points, then the helper that joins the first), stereo after detection
+                n_lk += 1
+                if after_detect:
+                    name += " [stereo, new points]"
+                elif n_lk == 1:
+                    name += " [temporal]"
+                elif n_lk == 2:
+                    name += " [temporal, points merged last frame]"
+                else:
+                    name += " [temporal, helper: queue already empty under ncu]"
             agg[f"{name} grid={r[gi]}"].append(float(r[vi].replace(",", "")))
-            prev = r[ki]
     tot = sum(sum(v) for v in agg.values())
     with open(dst, "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none (cold-cache, serialised: compare shares);\n"
