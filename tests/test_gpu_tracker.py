@@ -235,6 +235,71 @@ def test_pipelined_batch_with_side_stream_export(rsvio):
     assert want[-1][0][0][0].size > 5
 
 
+def test_split_temporal_lk_equals_single_handles(rsvio):
+    """Handles with >= 24 streams track the survivors of the previous compaction on their own CUDA stream beside the
+    previous frame's tail and the newly merged points behind it.  Pipelined (two frames in flight),
+    host-fed (the handle switches the split off while uploads are the bottleneck) and device-fed (always split), with
+    a remove_id in between (the next frame then tracks the whole table in one launch): every synced frame must equal
+    what independent 1-stream handles report, bit for bit."""
+    import ctypes as C
+    torch = pytest.importorskip("torch")
+    from rsvio_b200.synth import StereoSequence
+    S, frames, w, h = 26, 7, 256, 160
+    seqs = [StereoSequence("C5", stream_id=s, w=w, h=h) for s in range(S)]
+    data = [[q.frame(t) for q in seqs] for t in range(frames)]
+    t_rm = 3                                   # ids of stream 5 removed after frame t_rm has been synced
+    singles = [rsvio.StereoPatchTracker(40, 20, 0.01, width=w, height=h, levels=3) for _ in range(S)]
+    want, drop = [], None
+    for t in range(frames):
+        per = []
+        for s in range(S):
+            singles[s].process_frame(*data[t][s])
+            per.append([singles[s].tracks(c) for c in (0, 1)])
+        want.append(per)
+        if t == t_rm:
+            drop = singles[5].tracks(0)[0][::4]
+            singles[5].remove_id(drop)
+    assert drop is not None and len(drop) > 3
+
+    def check(batch, t):
+        rec, cnt = batch.result_view()
+        total = 0
+        for s in range(S):
+            for cam in (0, 1):
+                g = cam * S + s
+                ids, xy = want[t][s][cam]
+                assert cnt[g] == len(ids), (t, s, cam)
+                assert np.array_equal(rec["id"][g, :cnt[g]], ids), (t, s, cam)
+                assert np.array_equal(np.stack([rec["x"][g, :cnt[g]], rec["y"][g, :cnt[g]]], 1), xy), (t, s, cam)
+                total += len(ids)
+        assert total > S * 2 * 10
+
+    def run(batch, submit):
+        # frames 0..t_rm pipelined, remove_id on the idle handle, then the rest pipelined
+        for lo, hi in ((0, t_rm + 1), (t_rm + 1, frames)):
+            submit(batch, lo)
+            for t in range(lo + 1, hi):
+                submit(batch, t)
+                batch.sync()
+                check(batch, t - 1)
+            batch.sync()
+            check(batch, hi - 1)
+            if hi == t_rm + 1:
+                batch.remove_id(drop, stream=5)
+
+    # host-fed
+    ptrs = [((C.c_void_p * S)(*[f[0].ctypes.data for f in data[t]]), (C.c_void_p * S)(*[f[1].ctypes.data for f in data[t]]))
+            for t in range(frames)]
+    b1 = rsvio.StereoPatchTracker(40, 20, 0.01, width=w, height=h, levels=3, n_streams=S)
+    run(b1, lambda b, t: b.submit_batch_ptr(*ptrs[t]))
+    b1.close()
+    # device-fed: [frame][cam][stream][h][w]
+    dev = torch.from_numpy(np.stack([np.stack([np.stack([f[c] for f in data[t]]) for c in (0, 1)]) for t in range(frames)])).cuda()
+    b2 = rsvio.StereoPatchTracker(40, 20, 0.01, width=w, height=h, levels=3, n_streams=S)
+    run(b2, lambda b, t: b.submit_device(dev[t, 0].data_ptr(), dev[t, 1].data_ptr(), w, w * h))
+    b2.close()
+
+
 def test_async_submit_and_device_resident_paths(rsvio):
     import ctypes as C
     from rsvio_b200.synth import StereoSequence

@@ -1,5 +1,7 @@
 """Soak: a 16-stream handle over many frames with uploads from pinned memory; checks that track counts stay in
-range, ids keep increasing, no status errors, and device memory does not grow.  Usage: python tools/soak.py [frames]"""
+range, ids keep increasing, no status errors, and device memory does not grow.
+Usage: python tools/soak.py [frames] [streams] [device]   ("device": frames resident in HBM, submit_device -- with >= 24
+streams that is the split temporal LK pipeline running flat out)"""
 import os
 import sys
 
@@ -17,7 +19,8 @@ import bench  # noqa: E402
 def main():
     n_frames = int(sys.argv[1]) if len(sys.argv) > 1 else 3000
     p = CONFIGS["C5"]
-    w, h, S, ring = p["w"], p["h"], 16, 8
+    w, h, S, ring = p["w"], p["h"], (int(sys.argv[2]) if len(sys.argv) > 2 else 16), 8
+    on_device = len(sys.argv) > 3 and sys.argv[3] == "device"
     frames = bench.generate_frames("C5", list(range(S)), ring, 16)
     host = torch.from_numpy(frames).pin_memory()
     torch.cuda.init()
@@ -27,9 +30,17 @@ def main():
              (C.c_void_p * S)(*[host[k, 1, s].data_ptr() for s in range(S)])) for k in range(ring)]
     free0 = None
     last_max_id = -1
-    tr.submit_batch_ptr(*ptrs[0])
+    dev = host.cuda() if on_device else None
+
+    def submit(k):
+        if on_device:
+            tr.submit_device(dev[k, 0].data_ptr(), dev[k, 1].data_ptr(), w, w * h)
+        else:
+            tr.submit_batch_ptr(*ptrs[k])
+
+    submit(0)
     for i in range(1, n_frames):
-        tr.submit_batch_ptr(*ptrs[bench.ring_index(i)])
+        submit(bench.ring_index(i))
         tr.sync()
         if i % 500 == 0 or i == 50:
             rec, cnt = tr.result_view()
