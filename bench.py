@@ -203,7 +203,12 @@ def workload_config(args, S, n_gpus):
             "l2": "per step the kernels touch previous+current pyramids and the input ring slot "
                   "(> 230 MB at 64 streams), larger than the 126 MB L2; no explicit flush",
             "parallelism": f"{n_gpus} x independent replicas (streams sharded, no data-path collective; "
-                           "torch.distributed/NCCL carries only the timing barrier and the final counter reduction)"}
+                           "torch.distributed/NCCL carries only the timing barrier and the final counter reduction)",
+            "pipeline": "one handle per GPU, <= 2 frames in flight; with frames resident in HBM the temporal LK of a frame is "
+                        "launched in three parts (survivors of the previous compaction beside the previous frame's "
+                        "detection / stereo LK / merge; newly merged points; helper), host-fed frames are upload-bound "
+                        "and run unsplit; stage_ms_per_step / roofline are measured in profiling mode (one stream, "
+                        "one temporal launch, CUDA events between the stages)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -351,7 +356,9 @@ class Runner:
         """per-stage device ms per step: profiling mode puts everything on one stream with CUDA events between
         the stages, so a stage time is that stage's kernels alone on the device"""
         self.tr.set_profiling(True)
+        self.run(kind, first, 3)           # warm-up in profiling mode (one stream, events between the stages)
         self.tr.stage_times(reset=True)
+        first += 3
         self.run(kind, first, n)
         st = self.tr.stage_times(reset=True)
         self.tr.set_profiling(False)
