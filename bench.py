@@ -255,6 +255,17 @@ def bind_to_gpu_numa_node(local_rank):
     return None
 
 
+def sum_live_records(rec, cnt):
+    """sum of x and y over the live records of every group (records[group][k], k < cnt[group]) in ONE masked
+    reduction: a Python loop over the 128 groups of the bench handle took 0.86 ms per step -- the whole upload time of a
+    step -- and left the submit of the next-but-one upload late (two frames in flight), i.e. gaps in the DMA stream"""
+    cmax = int(cnt.max()) if cnt.size else 0
+    if cmax <= 0:
+        return 0.0
+    live = np.arange(cmax, dtype=np.int32)[None, :] < cnt[:, None]
+    return float(rec["x"][:, :cmax][live].sum(dtype=np.float64)) + float(rec["y"][:, :cmax][live].sum(dtype=np.float64))
+
+
 class Runner:
     """One tracker handle on one GPU fed from a ring of synthetic frames: device-resident steps (`value`),
     host-frame steps through the reference-facing submit/sync calls (`e2e`), per-stage profiling."""
@@ -308,13 +319,7 @@ class Runner:
     def _consume(self):
         """read the WHOLE result of the step on the host (zero-copy view of host-mapped pinned memory)"""
         rec, cnt = self.tr.result_view()
-        # one masked reduction over all groups: a Python loop over 128 groups took most of a step's 0.85 ms budget and
-        # left the submit of the next-but-one upload late (two frames in flight), i.e. gaps in the DMA stream
-        cmax = int(cnt.max()) if cnt.size else 0
-        if cmax:
-            live = np.arange(cmax, dtype=np.int32)[None, :] < cnt[:, None]
-            self.read_sum += float(rec["x"][:, :cmax][live].sum(dtype=np.float64)) + \
-                float(rec["y"][:, :cmax][live].sum(dtype=np.float64))
+        self.read_sum += sum_live_records(rec, cnt)
         return int(cnt.sum())
 
     def run(self, kind, first, n, consume=False):

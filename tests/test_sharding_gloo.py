@@ -66,3 +66,22 @@ def test_aggregate_world_size_2_gloo():
 
 def test_aggregate_single_process():
     assert sharding.aggregate(None, None, 10, 2, 5, 4.0) == (10.0, 2.0, 5.0, 4.0)
+
+
+def test_bench_reads_every_live_record():
+    """bench.sum_live_records (the e2e loop's consumer of the host-mapped result ring) equals the per-group loop it
+    replaced: every record k < counts[group] of every group, nothing beyond"""
+    import os
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    rng = np.random.default_rng(7)
+    dt = np.dtype([("id", "<u8"), ("x", "<f4"), ("y", "<f4")])
+    rec = np.zeros((12, 40), dt)
+    rec["x"] = rng.uniform(0, 752, rec.shape)
+    rec["y"] = rng.uniform(0, 480, rec.shape)
+    for cnt in (np.array([0] * 12, np.int32), rng.integers(0, 41, 12).astype(np.int32), np.full(12, 40, np.int32)):
+        want = sum(float(rec["x"][g, :c].astype(np.float64).sum()) + float(rec["y"][g, :c].astype(np.float64).sum())
+                   for g, c in enumerate(cnt))
+        assert abs(bench.sum_live_records(rec, cnt) - want) <= 1e-6 * max(1.0, abs(want))
