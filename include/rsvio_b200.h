@@ -16,7 +16,9 @@
  *  - images are row-major 8-bit luma, `stride` bytes between rows (GrayImage: stride == width).
  *  - a transform is the 6 free entries of the reference's `na::Affine2<f32>`:
  *    T = [m11, m12, m13(tx), m21, m22, m23(ty)]; the third row is (0, 0, 1).
- *  - one handle == one CUDA device + one CUDA stream; a handle is not re-entrant, distinct
+ *  - one handle == one CUDA device + one CUDA stream towards the caller (batched handles use further
+ *    internal streams to overlap consecutive frames; rsvio_tracker_sync orders everything the caller
+ *    can observe); a handle is not re-entrant, distinct
  *    handles may be driven from distinct threads (mirrors `&mut self`, feature_tracker.rs:116).
  *    Every call runs on the handle's device and restores the calling thread's current device.
  *  - there is no CPU fallback: without a usable CUDA device every entry point fails with
