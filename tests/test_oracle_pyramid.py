@@ -66,3 +66,39 @@ def test_pillow_bilinear_agrees_within_one_grey_level(oracle):
         ours = oracle.resize_triangle(img, nw, nh).astype(int)
         theirs = np.asarray(PIL.fromarray(img).resize((nw, nh), PIL.BILINEAR)).astype(int)
         assert np.abs(ours - theirs).max() <= 1
+
+
+def test_complete_dyadic_window_chain_is_an_exact_integer_tent():
+    """The claim behind `vtent_exact4` (csrc/pyramid.cu): on an axis whose ratio is r = 2^lev, an output whose window
+    is complete (2r taps) has the weights (2k+1)/(2r^2), mirrored, exactly in f32, and the reference's chain
+    `t += pix * w` in tap order never rounds -- so t == N / (2 r^2) bit for bit, N the integer tent sum.  Checked on
+    the numpy restatement of `image`'s sampler (oracle/np_crosscheck.py) for r = 16, 32, 64, 128 with worst-case
+    (all 255) and random columns; clamped border windows (1.5 r taps) are NOT exact and keep their chains."""
+    import math
+    import numpy as np
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import np_crosscheck as nc
+    F = np.float32
+    rng = np.random.default_rng(11)
+    for r in (16, 32, 64, 128):
+        n_out = 5
+        n_in = r * n_out
+        taps = nc._taps(n_in, n_out)
+        ks = np.arange(2 * r)
+        tent = np.where(ks < r, 2 * ks + 1, 4 * r - 2 * ks - 1).astype(np.int64)
+        for o, (left, w) in enumerate(taps):
+            if o in (0, n_out - 1):
+                assert len(w) == r + r // 2            # clamped: renormalised by a non-power-of-two sum
+                assert not np.array_equal(w * F(2 * r * r), np.round(w * F(2 * r * r)))
+                continue
+            assert left == o * r - r // 2 and len(w) == 2 * r
+            assert np.array_equal(w.astype(np.float64) * (2 * r * r), tent.astype(np.float64))   # exact weights
+            for col in (np.full(2 * r, 255, np.uint8), rng.integers(0, 256, 2 * r).astype(np.uint8),
+                        (np.arange(2 * r) % 2 * 255).astype(np.uint8)):
+                t = F(0)
+                for k in range(2 * r):                 # the reference's chain, every operation rounded to f32
+                    t = F(t + F(F(col[k]) * w[k]))
+                n = int((tent * col.astype(np.int64)).sum())
+                assert n < (1 << 24)
+                assert t == F(n) * F(1.0 / (2 * r * r)) and float(t) * (2 * r * r) == n, (r, o, n, t)
